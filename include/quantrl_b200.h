@@ -1,0 +1,209 @@
+/*
+ * quantrl_b200 — C ABI of the B200-native hot path of QuantRL (Sampreet/quantrl v0.0.8).
+ *
+ * The reference is pure Python and has no FFI; its plugin seams are the Python ABCs
+ * `BaseBackend` / `BaseIVPSolver` / `BaseEnv` and two registries.  This header is the boundary *beneath* those seams:
+ * each entry point names the reference code it replaces (paths relative to the reference root).  The Python host
+ * (quantrl_b200/*.py) binds it with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer to contiguous FP64 unless the name
+ *     starts with `h_` (host pointer).  Buffers are caller-owned; the library allocates nothing that outlives a call
+ *     except a small per-device scratch (qrl_release() frees it).
+ *   - every launch is an asynchronous enqueue on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream) on the CURRENT device; no host synchronisation unless stated.
+ *   - return value: 0 = ok, < 0 = invalid argument (QRL_E_*), > 0 = cudaError_t.  qrl_last_error() returns a
+ *     thread-local message.  Nothing throws, nothing exits.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns a cudaError_t.
+ *   - "strides" are in units of doubles; a stride of 0 broadcasts that axis.
+ *
+ * RNG stream (in-kernel noise, `rng_mode == QRL_RNG_PHILOX`), restated by oracle/em_oracle.py:philox_normals
+ *   (x0,x1,x2,x3) = Philox4x32-10(counter = (tau, episode, env_global, comp), key = (seed lo32, seed hi32))
+ *   d1 = bits(0x3FF<<52 | x1<<20 | x0>>12) in [1,2);  u1 = 2 - d1 in (0,1]
+ *   d2 = bits(0x3FF<<52 | x3<<20 | x2>>12) in [1,2);  u2 = d2 - 1 in [0,1)
+ *   r = sqrt(-2 ln u1);  z0 = r sin(2 pi u2);  z1 = r cos(2 pi u2)
+ *   z0 -> Wiener increment of sub-step tau -> tau+1 (scaled by sqrt(t_ssz));  z1 -> measurement noise at time
+ *   index tau (scaled by obs_std).  `env_global = env_offset + local env index` makes results independent of how
+ *   environments are sharded over GPUs.
+ */
+#ifndef QUANTRL_B200_H
+#define QUANTRL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QRL_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define QRL_API __attribute__((visibility("default")))
+#else
+#define QRL_API
+#endif
+
+#define QRL_E_INVALID   (-1)  /* bad argument (message in qrl_last_error) */
+#define QRL_E_UNSUPPORTED (-2) /* size/system not compiled in */
+
+#define QRL_RNG_FED    0
+#define QRL_RNG_PHILOX 1
+
+/* reward functors evaluated in the kernel epilogue (replace a user `get_reward` hook, quantrl/envs/base.py:307-317) */
+#define QRL_REWARD_NONE        0  /* leave `reward` untouched: the Python `get_reward()` hook fills it */
+#define QRL_REWARD_NEG_WSQ_OBS 1  /* r = -sum_c w_c * Observations_c^2 */
+#define QRL_REWARD_NEG_WSQ_STATE 2 /* r = -sum_c w_c * States_c^2 */
+
+/* deterministic system functors (replace user hooks get_mode_rates/get_A/get_D, quantrl/envs/deterministic.py:748-818);
+ * formulas in oracle/systems.py */
+#define QRL_SYS_OPTOMECH    1  /* m=2, q=4, 7 params/env, 1 action */
+#define QRL_SYS_KERR_CHAIN  2  /* m=N, q=2N (N = 1..4), 5+N params/env, 1 action */
+#define QRL_SYS_CONST_AD    3  /* m=0; A (E,q,q), D (E,q,q) constant over the interval (is_A_constant/is_D_constant) */
+
+#define QRL_ODE_RK4    0
+#define QRL_ODE_DOPRI5 1
+
+QRL_API int         qrl_abi_version(void);
+QRL_API const char* qrl_last_error(void);
+/* number of CUDA devices visible (0 if none / driver missing); never fails */
+QRL_API int         qrl_device_count(void);
+/* free the per-device scratch of the current device */
+QRL_API int         qrl_release(void);
+/* number of kernel launches this library has enqueued in this process (all entry points) */
+QRL_API uint64_t    qrl_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Euler–Maruyama action interval for E independent linear SDE environments.
+ * Replaces, fused into ONE launch: LinearEnv._update_states + func (quantrl/envs/stochastic.py:178-242; the Python
+ * `for` of backends/numpy.py:178-186), the Wiener draw of LinearEnv.reset (stochastic.py:157-170, philox mode), the
+ * measurement-noise draw and add of BaseEnv.reset/update (envs/base.py:408-426,462), the reward hook on all K+1 rows
+ * (base.py:471-473), `rewards += Reward[dim-1]` (base.py:1311) and the min/max reductions of check_truncation
+ * (base.py:485-499).
+ *
+ *   Y[0]   = x0
+ *   Y[i+1] = (I + A_i * t_ssz) @ Y[i] + nz_i * W_i            i = 0..K-1
+ *   Obs[i] = Y[i] + noise_i                                   i = 0..K
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct qrl_em_args {
+    int32_t  n;            /* state dimension (n_observations); 1..16 */
+    int32_t  n_envs;       /* E (local to this device) */
+    int32_t  K;            /* sub-steps in this interval = len(T_step) - 1 */
+    int32_t  rng_mode;     /* QRL_RNG_FED | QRL_RNG_PHILOX */
+    double   t_ssz;        /* step size */
+
+    const double* A;       /* drift A(t_idx+i, args): element [i,e,r,c] at A[i*A_stride_k + e*A_stride_e + r*n + c] */
+    int64_t  A_stride_k;   /* 0: constant over the interval */
+    int64_t  A_stride_e;   /* 0: shared by all envs, else n*n */
+    const double* nz;      /* noise prefixes: element [i,e,c] at nz[i*nz_stride_k + e*nz_stride_e + c] */
+    int64_t  nz_stride_k;
+    int64_t  nz_stride_e;
+
+    /* FED: the reference's own draws */
+    const double* W;         /* (K,E,n)   Ws[t_idx : t_idx+K], already scaled by sqrt(t_ssz) */
+    const double* obs_noise; /* (K+1,E,n) Observation_noises[t_idx : t_idx+K+1], already scaled; NULL = no noise */
+    /* PHILOX */
+    uint64_t seed;
+    uint32_t episode;
+    uint32_t _pad0;
+    int64_t  t_idx;          /* global time index of row 0 */
+    int64_t  env_offset;     /* global index of local env 0 */
+    const double* obs_std;   /* element [e,c] at obs_std[e*obs_std_stride_e + c]; NULL = no measurement noise */
+    int64_t  obs_std_stride_e;
+
+    const double* x0;        /* (E,n)  States[-1] of the previous interval */
+    double*  states;         /* (K+1,E,n) or NULL (trajectory off) */
+    double*  observations;   /* (K+1,E,n) or NULL */
+    double*  x_last;         /* (E,n) = Y[K]; may alias x0; or NULL */
+    double*  obs_last;       /* (E,n) = Obs[K]; or NULL */
+
+    int32_t  reward_kind;    /* QRL_REWARD_* */
+    int32_t  _pad1;
+    const double* reward_w;  /* (n,) weights */
+    double*  reward;         /* (K+1,E) or NULL */
+    double*  reward_last;    /* (E,) = Reward[K]; or NULL */
+    double*  rewards_cum;    /* (E,) in/out: += Reward[K]; or NULL */
+
+    double*  obs_minmax;     /* [min, max] running reduction (caller initialises to [+inf, -inf]); or NULL */
+    int32_t* nan_flag;       /* set to 1 if any state is NaN/Inf; or NULL */
+} qrl_em_args;
+
+QRL_API int qrl_em_step(const qrl_em_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Deterministic action interval: modes + Lyapunov covariance  dV/dt = A V + V A^T + D  for E environments.
+ * Replaces LinearizedHOVecEnv._update_states -> BaseIVPSolver.step -> integrate (quantrl/envs/deterministic.py:
+ * 646-651, quantrl/solvers/base.py:168-204, quantrl/solvers/numpy.py:87-178) together with the RHS `func` and the
+ * user hooks it calls (deterministic.py:653-746, 820-867), plus the same epilogue as qrl_em_step.
+ *   y = [Re a (m) | Im a (m) | vec(V) (q*q)],  d = 2m + q*q
+ * RK4: `substeps` classic RK4 steps per grid interval.  DOPRI5: per-env adaptive Dormand–Prince 5(4) with dense
+ * output on the grid, controller in oracle/lyap_oracle.py:dopri5_interval.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct qrl_ode_args {
+    int32_t  system;         /* QRL_SYS_* */
+    int32_t  num_modes;      /* m */
+    int32_t  num_quads;      /* q */
+    int32_t  n_envs;         /* E */
+    int32_t  K;              /* grid intervals = len(T_step) - 1 */
+    int32_t  method;         /* QRL_ODE_* */
+    int32_t  substeps;       /* RK4 steps per grid interval (>= 1) */
+    int32_t  n_actions;
+    double   t0;             /* T_step[0] */
+    double   t_ssz;          /* grid spacing */
+    double   atol, rtol;     /* DOPRI5 */
+
+    const double* params;    /* (E, n_params) system parameters, row stride params_stride_e (0 = shared) */
+    int64_t  params_stride_e;
+    const double* actions;   /* (E, n_actions) already multiplied by action_maximums */
+    const double* A;         /* QRL_SYS_CONST_AD: (E,q,q), stride A_stride_e */
+    int64_t  A_stride_e;
+    const double* D;
+    int64_t  D_stride_e;
+
+    const double* y0;        /* (E,d) */
+    double*  states;         /* (K+1,E,d) or NULL */
+    double*  observations;   /* (K+1,E,d) or NULL */
+    double*  y_last;         /* (E,d); may alias y0 */
+    double*  obs_last;       /* (E,d) or NULL */
+    const double* obs_noise; /* FED (K+1,E,d) or NULL */
+    double*  h_state;        /* DOPRI5: (E,) in/out carried step size (<= 0: start from t_ssz); or NULL */
+    int32_t* n_steps;        /* DOPRI5: (E,2) accepted, rejected counters (accumulated); or NULL */
+
+    double*  obs_minmax;     /* as in qrl_em_args */
+    int32_t* nan_flag;
+} qrl_ode_args;
+
+QRL_API int qrl_ode_step(const qrl_ode_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Packed trajectory-cache rows, BaseSB3Env.update_data (quantrl/envs/base.py:1314-1356):
+ *   packed[e, t, :] = [T_step[t], actions[e,:], Obs[t,e,:], Props[t,e,:], rewards_cum[e]]      (E, dim, n_data)
+ * and the host cache columns `data[:, t0:t1, :] = _data[:, :, data_idxs]` (base.py:1370-1372):
+ *   selected[e, t, j] = packed[e, t, idxs[j]]                                                  (E, dim, n_sel)
+ * Either output may be NULL.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct qrl_pack_args {
+    int32_t  n_envs, dim, n_actions, n_obs, n_props, n_sel;
+    const double*  T_step;      /* (dim,) */
+    const double*  actions;     /* (E,n_actions) */
+    const double*  observations;/* (dim,E,n_obs) */
+    const double*  properties;  /* (dim,E,n_props) or NULL */
+    const double*  rewards_cum; /* (E,) */
+    const int32_t* idxs;        /* (n_sel,) column indices into the n_data columns (negative = from the end) */
+    double*  packed;            /* element [e,t,c] at packed[e*packed_stride_e + t*n_data + c]; or NULL */
+    int64_t  packed_stride_e;   /* >= dim*n_data (lets the caller write straight into a (E, shape_T, n_data) cache) */
+    double*  selected;          /* element [e,t,j] at selected[e*selected_stride_e + t*n_sel + j]; or NULL */
+    int64_t  selected_stride_e; /* >= dim*n_sel */
+} qrl_pack_args;
+
+QRL_API int qrl_pack_rows(const qrl_pack_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Machine-peak micro-benchmarks used as roofline denominators (synchronous; return the measurement).
+ * ------------------------------------------------------------------------------------------------------------ */
+/* dependent-free DFMA stream on every SM: returns achieved FP64 TFLOP/s (FMA = 2 flop) in *tflops */
+QRL_API int qrl_measure_fp64_peak(int iters, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUANTRL_B200_H */

@@ -1,0 +1,136 @@
+"""ctypes binding of ``include/quantrl_b200.h`` (the C ABI of the CUDA hot path).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, a ``NativeError`` is raised.
+"""
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+ABI_VERSION = 1
+
+RNG_FED, RNG_PHILOX = 0, 1
+REWARD_NONE, REWARD_NEG_WSQ_OBS, REWARD_NEG_WSQ_STATE = 0, 1, 2
+SYS_OPTOMECH, SYS_KERR_CHAIN, SYS_CONST_AD = 1, 2, 3
+ODE_RK4, ODE_DOPRI5 = 0, 1
+
+_dp = C.c_void_p  # device pointers travel as integers
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class EmArgs(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("n_envs", C.c_int32), ("K", C.c_int32), ("rng_mode", C.c_int32), ("t_ssz", C.c_double),
+        ("A", _dp), ("A_stride_k", C.c_int64), ("A_stride_e", C.c_int64),
+        ("nz", _dp), ("nz_stride_k", C.c_int64), ("nz_stride_e", C.c_int64),
+        ("W", _dp), ("obs_noise", _dp),
+        ("seed", C.c_uint64), ("episode", C.c_uint32), ("_pad0", C.c_uint32), ("t_idx", C.c_int64),
+        ("env_offset", C.c_int64), ("obs_std", _dp), ("obs_std_stride_e", C.c_int64),
+        ("x0", _dp), ("states", _dp), ("observations", _dp), ("x_last", _dp), ("obs_last", _dp),
+        ("reward_kind", C.c_int32), ("_pad1", C.c_int32), ("reward_w", _dp), ("reward", _dp), ("reward_last", _dp),
+        ("rewards_cum", _dp), ("obs_minmax", _dp), ("nan_flag", _dp),
+    ]
+
+
+class OdeArgs(C.Structure):
+    _fields_ = [
+        ("system", C.c_int32), ("num_modes", C.c_int32), ("num_quads", C.c_int32), ("n_envs", C.c_int32),
+        ("K", C.c_int32), ("method", C.c_int32), ("substeps", C.c_int32), ("n_actions", C.c_int32),
+        ("t0", C.c_double), ("t_ssz", C.c_double), ("atol", C.c_double), ("rtol", C.c_double),
+        ("params", _dp), ("params_stride_e", C.c_int64), ("actions", _dp),
+        ("A", _dp), ("A_stride_e", C.c_int64), ("D", _dp), ("D_stride_e", C.c_int64),
+        ("y0", _dp), ("states", _dp), ("observations", _dp), ("y_last", _dp), ("obs_last", _dp), ("obs_noise", _dp),
+        ("h_state", _dp), ("n_steps", _dp), ("obs_minmax", _dp), ("nan_flag", _dp),
+    ]
+
+
+class PackArgs(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int32), ("dim", C.c_int32), ("n_actions", C.c_int32), ("n_obs", C.c_int32),
+        ("n_props", C.c_int32), ("n_sel", C.c_int32),
+        ("T_step", _dp), ("actions", _dp), ("observations", _dp), ("properties", _dp), ("rewards_cum", _dp),
+        ("idxs", _dp), ("packed", _dp), ("packed_stride_e", C.c_int64), ("selected", _dp),
+        ("selected_stride_e", C.c_int64),
+    ]
+
+
+# every symbol include/quantrl_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "qrl_abi_version": (C.c_int, []),
+    "qrl_last_error": (C.c_char_p, []),
+    "qrl_device_count": (C.c_int, []),
+    "qrl_release": (C.c_int, []),
+    "qrl_launch_count": (C.c_uint64, []),
+    "qrl_em_step": (C.c_int, [C.POINTER(EmArgs), C.c_void_p]),
+    "qrl_ode_step": (C.c_int, [C.POINTER(OdeArgs), C.c_void_p]),
+    "qrl_pack_rows": (C.c_int, [C.POINTER(PackArgs), C.c_void_p]),
+    "qrl_measure_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library; raises NativeError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                f"{LIB_PATH} is missing: build it with `python -m quantrl_b200.build` (nvcc, sm_100a). "
+                "quantrl_b200 has no CPU or PyTorch fallback for its hot path.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)  # AttributeError if the .so does not export a declared symbol
+            fn.restype, fn.argtypes = res, args
+        if handle.qrl_abi_version() != ABI_VERSION:
+            raise NativeError(f"ABI mismatch: library {handle.qrl_abi_version()} vs binding {ABI_VERSION}")
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().qrl_last_error().decode(errors="replace")
+        kind = "invalid argument" if rc < 0 else f"CUDA error {rc}"
+        raise NativeError(f"{what} failed ({kind}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch CUDA tensor (None -> NULL).  The tensor must be contiguous float64/int32."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NativeError("expected a CUDA tensor (quantrl_b200 has no CPU path)")
+    if not t.is_contiguous():
+        raise NativeError("expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def current_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def em_step(args: EmArgs, stream=None):
+    check(lib().qrl_em_step(C.byref(args), stream if stream is not None else current_stream()), "qrl_em_step")
+
+
+def ode_step(args: OdeArgs, stream=None):
+    check(lib().qrl_ode_step(C.byref(args), stream if stream is not None else current_stream()), "qrl_ode_step")
+
+
+def pack_rows(args: PackArgs, stream=None):
+    check(lib().qrl_pack_rows(C.byref(args), stream if stream is not None else current_stream()), "qrl_pack_rows")
+
+
+def launch_count() -> int:
+    return int(lib().qrl_launch_count())
+
+
+def measure_fp64_peak(iters=4096) -> float:
+    out = C.c_double(0.0)
+    check(lib().qrl_measure_fp64_peak(int(iters), C.byref(out)), "qrl_measure_fp64_peak")
+    return float(out.value)

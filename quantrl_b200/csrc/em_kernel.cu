@@ -1,0 +1,144 @@
+// Fused Euler–Maruyama action interval (qrl_em_step) — sm_100a.
+//
+// One launch replaces K iterations of the reference's Python loop
+//   Y[i+1] = (I + A dt) @ Y[i] + n * Ws[t_idx+i]            quantrl/envs/stochastic.py:218-242
+// plus the noise draws (stochastic.py:162-170, envs/base.py:408-424), Observations = States + noise (base.py:462),
+// the reward hook on all K+1 rows (base.py:471-473), rewards += Reward[-1] (base.py:1311) and the truncation
+// reductions (base.py:485-499).
+//
+// Mapping: LPE (= next power of two >= n) lanes cooperate on one environment; lane c owns state component c, row c of
+// M = I + A dt (registers) and generates its own pair of normals (Wiener increment + measurement noise).  The n
+// components are exchanged with warp shuffles each sub-step, rows of States/Observations are written with fully
+// coalesced 8-byte-per-lane stores (one warp = 32 consecutive doubles of the (K+1,E,n) block).
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace qrl {
+
+template <int LPE>
+__global__ void __launch_bounds__(128) em_step_kernel(const qrl_em_args a) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = tid / LPE;
+    const int c = tid % LPE;
+    const int n = a.n;
+    const int E = a.n_envs;
+    const int K = a.K;
+    const bool live = (e < E) && (c < n);
+    const int el = e < E ? e : E - 1;      // clamped indices keep dead lanes' loads in bounds
+    const int cl = c < n ? c : n - 1;
+    const int lane_base = (threadIdx.x & 31) & ~(LPE - 1);
+
+    const double dt = a.t_ssz;
+    const double sqrt_dt = sqrt(dt);
+    const bool philox = a.rng_mode == QRL_RNG_PHILOX;
+    const uint32_t env_g = (uint32_t)(a.env_offset + el);
+    const double std_c = (philox && a.obs_std) ? a.obs_std[(int64_t)el * a.obs_std_stride_e + cl] : 0.0;
+    const double w_c = (a.reward_kind != QRL_REWARD_NONE && live) ? a.reward_w[cl] : 0.0;
+    const int64_t row = (int64_t)E * n;           // doubles per time row
+    const int64_t off = (int64_t)el * n + cl;     // this lane's element within a row
+
+    double x = live ? a.x0[off] : 0.0;
+    double M[LPE];
+    double nzc = 0.0;
+    auto load_coeffs = [&](int i) {
+        const double* Ar = a.A + (int64_t)i * a.A_stride_k + (int64_t)el * a.A_stride_e + (int64_t)cl * n;
+#pragma unroll
+        for (int j = 0; j < LPE; ++j) {
+            const double aij = (live && j < n) ? Ar[j] : 0.0;
+            // M = I + A * t_ssz, unfused like the reference (stochastic.py:219-222)
+            M[j] = __dadd_rn((j == c) ? 1.0 : 0.0, __dmul_rn(aij, dt));
+        }
+        nzc = live ? a.nz[(int64_t)i * a.nz_stride_k + (int64_t)el * a.nz_stride_e + cl] : 0.0;
+    };
+    const bool coeffs_vary = (a.A_stride_k != 0) || (a.nz_stride_k != 0);
+    load_coeffs(0);
+
+    double lo = INFINITY, hi = -INFINITY;
+    double r_last = 0.0, obs = 0.0;
+
+#pragma unroll 2
+    for (int i = 0; i <= K; ++i) {
+        // ---- noise for time index tau = t_idx + i ----
+        double w, v;
+        if (philox) {
+            double z0, z1;
+            philox_normal2(a.seed, (uint32_t)(a.t_idx + i), a.episode, env_g, (uint32_t)c, z0, z1);
+            w = sqrt_dt * z0;
+            v = std_c * z1;
+        } else {
+            w = (i < K) ? a.W[(int64_t)i * row + off] : 0.0;
+            v = a.obs_noise ? a.obs_noise[(int64_t)i * row + off] : 0.0;
+        }
+        // ---- outputs of row i ----
+        obs = x + v;
+        if (live) {
+            if (a.states) a.states[(int64_t)i * row + off] = x;
+            if (a.observations) a.observations[(int64_t)i * row + off] = obs;
+            lo = fmin(lo, obs);
+            hi = fmax(hi, obs);
+        }
+        if (a.reward_kind != QRL_REWARD_NONE) {
+            const double s = (a.reward_kind == QRL_REWARD_NEG_WSQ_OBS) ? obs : x;
+            double r = w_c * s * s;
+#pragma unroll
+            for (int o = LPE >> 1; o > 0; o >>= 1) r += shfl_xor_d(r, o);
+            r_last = -r;
+            if (live && c == 0 && a.reward) a.reward[(int64_t)i * E + e] = r_last;
+        }
+        if (i == K) break;
+        // ---- recurrence ----
+        if (coeffs_vary && i > 0) load_coeffs(i);
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < LPE; ++j) {
+            const double xj = shfl_d(x, lane_base + j);
+            acc = (j == 0) ? __dmul_rn(M[0], xj) : fma(M[j], xj, acc);
+        }
+        x = fma(nzc, w, acc);
+    }
+
+    if (live) {
+        if (a.x_last) a.x_last[off] = x;
+        if (a.obs_last) a.obs_last[off] = obs;
+        if (c == 0 && a.reward_kind != QRL_REWARD_NONE) {
+            if (a.reward_last) a.reward_last[e] = r_last;
+            if (a.rewards_cum) a.rewards_cum[e] += r_last;
+        }
+        if (a.nan_flag && !isfinite(x)) *a.nan_flag = 1;
+    }
+    if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
+}
+
+template <int LPE>
+static int launch_em(const qrl_em_args& a, cudaStream_t st) {
+    const int threads = 128;
+    const int64_t total = (int64_t)a.n_envs * LPE;
+    const int blocks = (int)((total + threads - 1) / threads);
+    em_step_kernel<LPE><<<blocks, threads, 0, st>>>(a);
+    return after_launch("em_step_kernel");
+}
+
+}  // namespace qrl
+
+extern "C" int qrl_em_step(const qrl_em_args* args, void* stream) {
+    using namespace qrl;
+    QRL_REQUIRE(args != nullptr, "qrl_em_step: args is NULL");
+    const qrl_em_args& a = *args;
+    QRL_REQUIRE(a.n >= 1 && a.n <= 16, "qrl_em_step: n must be in 1..16");
+    QRL_REQUIRE(a.n_envs >= 0 && a.K >= 0, "qrl_em_step: n_envs and K must be non-negative");
+    QRL_REQUIRE(a.rng_mode == QRL_RNG_FED || a.rng_mode == QRL_RNG_PHILOX, "qrl_em_step: bad rng_mode");
+    QRL_REQUIRE(a.reward_kind >= QRL_REWARD_NONE && a.reward_kind <= QRL_REWARD_NEG_WSQ_STATE,
+                "qrl_em_step: bad reward_kind");
+    if (a.n_envs == 0) return 0;
+    QRL_REQUIRE(a.x0 != nullptr, "qrl_em_step: x0 is NULL");
+    QRL_REQUIRE(a.K == 0 || (a.A != nullptr && a.nz != nullptr), "qrl_em_step: A / nz is NULL");
+    QRL_REQUIRE(a.rng_mode != QRL_RNG_FED || a.K == 0 || a.W != nullptr, "qrl_em_step: fed mode needs W");
+    QRL_REQUIRE(a.reward_kind == QRL_REWARD_NONE || a.reward_w != nullptr, "qrl_em_step: reward_w is NULL");
+    QRL_REQUIRE(a.t_idx >= 0 && a.env_offset >= 0, "qrl_em_step: negative t_idx / env_offset");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a.n <= 1) return launch_em<1>(a, st);
+    if (a.n <= 2) return launch_em<2>(a, st);
+    if (a.n <= 4) return launch_em<4>(a, st);
+    if (a.n <= 8) return launch_em<8>(a, st);
+    return launch_em<16>(a, st);
+}

@@ -1,0 +1,2 @@
+from .base import BaseVecEnv, PartCacheWriter  # noqa: F401
+from .stochastic import LinearVecEnv  # noqa: F401

@@ -1,0 +1,446 @@
+"""Host-side mirror of the reference's vectorized env surface for the ``'b200'`` backend.
+
+``BaseVecEnv`` restates, from scratch, the lock-step semantics of ``BaseEnv`` + ``BaseSB3Env``
+(quantrl/envs/base.py:30-667, 999-1492): the same constructor arguments and ``kwargs`` (base.py:92-111), the same
+public attributes (``T``, ``t_idx``, ``States``, ``Observations``, ``Reward``, ``Properties``, ``actions``,
+``rewards``, ``data``, ``data_rewards``, ``batch_idx`` …), the same user hooks (``reset_states``, ``get_reward``,
+``get_properties``) and the Stable-Baselines3 ``VecEnv`` protocol (``reset/step_async/step_wait/step/close`` and the
+``env_is_wrapped/env_method/get_attr/set_attr`` replication helpers, base.py:1097-1183).
+
+What differs is where the work happens: ``_update_states`` of the subclasses is ONE launch of the fused CUDA kernel
+(through the C ABI) that also produces the noisy observations, the reward rows, the cumulative-reward update and
+the truncation reductions; ``update_data`` is one launch of the pack kernel that writes the ``(E, dim, n_data)``
+cache rows and the selected ``data`` columns straight into a device-resident ``(E, shape_T, n_sel)`` cache that is
+copied to the host lazily.  Index conventions follow SURVEY.md Appendix A line by line.
+"""
+import math
+import os
+import queue
+import threading
+
+import numpy as np
+import torch
+
+from .. import _native as N
+from ..backends import get_backend_instance
+
+try:  # the real SB3 base class when it is installed, else a protocol-compatible stand-in
+    from stable_baselines3.common.vec_env import VecEnv as _SB3VecEnv
+except Exception:  # noqa: BLE001
+    _SB3VecEnv = None
+
+
+class _Box:
+    """Stand-in for ``gymnasium.spaces.Box`` (only the attributes the reference touches, base.py:173-206)."""
+
+    def __init__(self, low, high, shape, dtype):
+        self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), dtype
+
+    def sample(self):
+        lo, hi = max(self.low, -1e3), min(self.high, 1e3)
+        return np.random.uniform(lo, hi, self.shape).astype(self.dtype)
+
+
+class _MultiDiscrete:
+    def __init__(self, nvec):
+        self.nvec = np.asarray(nvec)
+        self.shape = self.nvec.shape
+
+    def sample(self):
+        return np.array([np.random.randint(k) for k in self.nvec])
+
+
+def _spaces():
+    try:
+        from gymnasium.spaces import Box, MultiDiscrete
+        return Box, MultiDiscrete
+    except Exception:  # noqa: BLE001
+        return _Box, _MultiDiscrete
+
+
+class PartCacheWriter:
+    """Trajectory part files in the reference's on-disk format (quantrl/io.py:56-80): one ``.npz`` per action step,
+    named ``{b*E}_{(b+1)*E-1}_{part}.npz`` with the array under ``arr_0``.  Unlike the reference (whose "async" dump
+    joins its thread immediately, io.py:74-80) the write really happens on a background thread."""
+
+    def __init__(self, disk_cache_dir, cache_dump_interval, compressed=True):
+        self.disk_cache_dir = disk_cache_dir
+        self.cache_dump_interval = cache_dump_interval
+        self.compressed = compressed
+        self._q = None
+        self._thread = None
+
+    def _start(self):
+        os.makedirs(self.disk_cache_dir, exist_ok=True)
+        self._q = queue.Queue(maxsize=8)
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def _run(self):
+        while True:
+            item = self._q.get()
+            if item is None:
+                return
+            path, data = item
+            (np.savez_compressed if self.compressed else np.savez)(path, data)
+
+    def dump_part_async(self, data, batch_idx, part_idx):
+        if self._thread is None:
+            self._start()
+        name = "_".join([str(batch_idx * self.cache_dump_interval),
+                         str((batch_idx + 1) * self.cache_dump_interval - 1), str(part_idx)])
+        self._q.put((os.path.join(self.disk_cache_dir, name + ".npz"), data))
+
+    def close(self, dump_cache=True):
+        if self._thread is not None:
+            self._q.put(None)
+            self._thread.join()
+            self._thread = None
+
+
+class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
+    """Vectorized, lock-stepped environment batch on one B200 (mirror of ``BaseSB3Env``, base.py:999-1492)."""
+
+    base_env_kwargs = {
+        "has_delay": False,
+        "observation_space_range": [-1e12, 1e12],
+        "observation_stds": None,
+        "action_space_range": [-1.0, 1.0],
+        "action_space_type": "box",
+        "seed": None,
+        "cache_all_data": True,
+        "cache_dump_interval": 100,
+        "average_over": 100,
+        "plot": False,              # matplotlib live plots are out of scope
+        # ---- additions of the b200 backend ----
+        "rng": "philox",            # 'philox': in-kernel Philox4x32-10 noise; 'fed': pre-drawn tensors (reference layout)
+        "return_numpy": False,      # step()/reset() return NumPy (pinned D2H) instead of device tensors
+        "env_offset": 0,            # global index of local env 0 (multi-GPU sharding)
+        "store_trajectory": True,   # keep the (K+1,E,n) States/Observations/Reward blocks (reference semantics)
+        "cache_compressed": True,
+    }
+
+    def __init__(self, backend, t_norm_max, t_norm_ssz, t_norm_mul, n_envs, n_observations, n_properties, n_actions,
+                 action_maximums, action_interval, data_idxs, dir_prefix, file_prefix, **kwargs):
+        for key, val in self.base_env_kwargs.items():
+            kwargs.setdefault(key, val)
+        # same validation as base.py:135-148
+        assert t_norm_max > t_norm_ssz, "maximum normalized time should be greater than the normalized step size"
+        assert n_properties >= 0, "parameter ``n_properties`` should be non-negative"
+        assert action_interval > 0, "parameter ``action_interval`` should be a positive integer"
+        assert len(data_idxs) > 0, "parameter ``data_idxs`` should be a list containing at least one element"
+        assert kwargs["observation_stds"] is None or isinstance(kwargs["observation_stds"], (list, np.ndarray, torch.Tensor)), \
+            "parameter ``observation_stds`` should be a list"
+        assert kwargs["seed"] is None or isinstance(kwargs["seed"], int), "parameter ``seed`` should be an integer or ``None``"
+        assert isinstance(kwargs["cache_all_data"], bool), "parameter ``cache_all_data`` should be a boolean"
+        assert len(kwargs["observation_space_range"]) == 2 and len(kwargs["action_space_range"]) == 2
+        assert kwargs["action_space_type"] in ["binary", "box"], "parameter ``action_space_type`` can be either ``'binary'`` or ``'box'``"
+        assert kwargs["rng"] in ["philox", "fed"], "parameter ``rng`` can be either ``'philox'`` or ``'fed'``"
+        assert not kwargs["has_delay"], "delay (DDE) support is out of scope of the b200 backend (SURVEY.md §2 #19)"
+
+        N.lib()  # fail loudly, now, if the CUDA extension is missing
+        self.backend = backend
+        self.device = backend.device
+        self.numpy_int = backend.dtypes["numpy"][backend.precision]["integer"]
+        self.numpy_real = backend.dtypes["numpy"][backend.precision]["real"]
+        assert backend.precision == "double", "the b200 hot path computes in FP64 (backend_precision='double')"
+        f64 = torch.float64
+
+        # time grid (base.py:157-168)
+        self.t_norm_max, self.t_norm_ssz, self.t_norm_mul = t_norm_max, t_norm_ssz, t_norm_mul
+        self.shape_T = (int(self.numpy_int(t_norm_max / t_norm_ssz)) + 1,)
+        self.T_norm = np.arange(self.shape_T[0], dtype=self.numpy_real) * t_norm_ssz
+        self._T_host = self.T_norm * t_norm_mul
+        self.T = torch.as_tensor(self._T_host, device=self.device)
+        self.t_ssz = t_norm_ssz * t_norm_mul
+
+        # spaces (base.py:170-212)
+        Box, MultiDiscrete = _spaces()
+        self.n_envs = int(n_envs)
+        self.n_observations = int(n_observations)
+        self.observation_space_range = kwargs["observation_space_range"]
+        self.observation_space = Box(low=self.observation_space_range[0], high=self.observation_space_range[1],
+                                     shape=(self.n_observations,), dtype=self.numpy_real)
+        self.n_properties = int(n_properties)
+        self.n_actions = int(n_actions)
+        self.action_space_type = kwargs["action_space_type"]
+        if self.action_space_type == "binary":
+            self.action_space_range = [0, 1]
+            self.action_space = MultiDiscrete(nvec=[2] * self.n_actions)
+        else:
+            self.action_space_range = kwargs["action_space_range"]
+            self.action_space = Box(low=self.action_space_range[0], high=self.action_space_range[1],
+                                    shape=(self.n_actions,), dtype=self.numpy_real)
+        self.action_maximums = torch.as_tensor(np.asarray(action_maximums, dtype=np.float64), device=self.device)
+        self.action_maximums_batch = self.action_maximums.reshape(1, self.n_actions).repeat(self.n_envs, 1).contiguous()
+        self.action_interval = int(action_interval)
+        self.action_steps = int(math.ceil((self.shape_T[0] - 1) / self.action_interval))
+        self.has_delay = False
+
+        # measurement noise: per-env stds (E,n_obs) or shared (n_obs,) (base.py:179-184, 417-424)
+        stds = kwargs["observation_stds"]
+        self.observation_stds = None
+        if stds is not None:
+            stds = torch.as_tensor(np.asarray(stds, dtype=np.float64), device=self.device)
+            assert stds.shape in [(self.n_observations,), (self.n_envs, self.n_observations)], \
+                "``observation_stds`` should have shape (n_observations,) or (n_envs, n_observations)"
+            self.observation_stds = stds.contiguous()
+
+        self.seed_value = kwargs["seed"]
+        self.seed = kwargs["seed"]
+        self._philox_seed = int(np.random.SeedSequence(kwargs["seed"]).generate_state(1, dtype=np.uint64)[0])
+        self.rng = kwargs["rng"]
+        self.env_offset = int(kwargs["env_offset"])
+        self.return_numpy = bool(kwargs["return_numpy"])
+        self.store_trajectory = bool(kwargs["store_trajectory"])
+
+        # data / cache constants (base.py:221-240)
+        self.dir_path = dir_prefix + "/" + "_".join(
+            [str(t_norm_max), str(t_norm_ssz), str(t_norm_mul), str(list(np.asarray(action_maximums).tolist())),
+             str(action_interval)])
+        self.file_path_prefix = self.dir_path + "/" + file_prefix
+        self.n_data = 1 + self.n_actions + self.n_observations + self.n_properties + 1
+        self.average_over = int(kwargs["average_over"])
+        self.data_idxs = list(data_idxs)
+        self.cache_all_data = kwargs["cache_all_data"]
+        self.cache_dump_interval = self.n_envs  # n_envs overrides cache_dump_interval (base.py:1040)
+        self.io = PartCacheWriter(self.file_path_prefix + "_cache", self.cache_dump_interval,
+                                  compressed=kwargs["cache_compressed"])
+        self.plot = False
+
+        if _SB3VecEnv is not None:
+            _SB3VecEnv.__init__(self, num_envs=self.n_envs, observation_space=self.observation_space,
+                                action_space=self.action_space)
+        self.num_envs = self.n_envs
+        self.render_mode = None
+
+        # device buffers (base.py:1063-1084)
+        K1, E, no = self.action_interval + 1, self.n_envs, self.n_observations
+        self.t_idx, self.t, self.action_idx, self._idx_s = 0, self.numpy_real(0.0), 0, 0
+        self.batch_idx = -1
+        self.actions = None
+        self.T_step = None
+        self._States = torch.empty((K1, E, no), dtype=f64, device=self.device)
+        self._Observations = torch.empty((K1, E, no), dtype=f64, device=self.device)
+        self._Reward = torch.zeros((K1, E), dtype=f64, device=self.device)
+        self._Properties = torch.empty((K1, E, self.n_properties), dtype=f64, device=self.device)
+        self.States, self.Observations, self.Reward, self.Properties = \
+            self._States, self._Observations, self._Reward, self._Properties
+        self.Observation_noises = None
+        self._x_last = torch.empty((E, no), dtype=f64, device=self.device)
+        self._step_out = torch.empty((E * (no + 1) + 4,), dtype=f64, device=self.device)  # obs_last|reward_last|min,max|nan
+        self._obs_last = self._step_out[:E * no].view(E, no)
+        self._reward_last = self._step_out[E * no:E * (no + 1)]
+        self._minmax = self._step_out[E * (no + 1):E * (no + 1) + 2]
+        self._minmax_init = torch.tensor([float("inf"), float("-inf")], dtype=f64, device=self.device)
+        self._nan = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        self._h_out = torch.empty(self._step_out.shape, dtype=f64).pin_memory()
+        self._h_actions = torch.empty((E, self.n_actions), dtype=f64).pin_memory()
+        self.rewards = None
+        self.data_rewards = []
+        self._data_dev = None
+        self._data_host = None
+        self._sel_idxs = torch.as_tensor(np.asarray(self.data_idxs, dtype=np.int32), device=self.device)
+        self._packed = torch.empty((E, K1, self.n_data), dtype=f64, device=self.device) if self.cache_all_data else None
+        self._reward_fused = False
+        self._cum_fused = False
+
+    # ---- hooks the interfaced environment implements (base.py:272-317) ------------------------------------------
+    def _update_states(self):
+        raise NotImplementedError
+
+    def _initial_observations(self, states_0):
+        """obs_0 = states_0 + noise[0] (base.py:426)."""
+        raise NotImplementedError
+
+    def reset_states(self):
+        raise NotImplementedError
+
+    def get_properties(self):
+        raise NotImplementedError
+
+    def get_reward(self):
+        raise NotImplementedError
+
+    # ---- SB3 replication helpers (base.py:1097-1183) ------------------------------------------------------------
+    def _n_indices(self, indices):
+        return indices if isinstance(indices, int) else (self.n_envs if indices is None else len(indices))
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        return [False for _ in range(self._n_indices(indices))]
+
+    def env_method(self, method_name, *method_args, indices=None, **method_kwargs):
+        return [getattr(self, method_name)(*method_args, **method_kwargs) for _ in range(self._n_indices(indices))]
+
+    def get_attr(self, attr_name, indices=None):
+        return [getattr(self, attr_name) for _ in range(self._n_indices(indices))]
+
+    def set_attr(self, attr_name, value, indices=None):
+        return [setattr(self, attr_name, value) for _ in range(self._n_indices(indices))]
+
+    def validate(self):
+        """Shape checks of the user hooks (base.py:319-376, 1088-1095)."""
+        states_0 = self.backend.convert_to_typed(tensor=self.reset_states(), dtype="real")
+        assert tuple(states_0.shape) == (self.n_envs, self.n_observations), \
+            f"``reset_states`` should return an array with shape ``{(self.n_envs, self.n_observations)}``"
+
+    # ---- reset (base.py:378-438, 1185-1231) ------------------------------------------------------------------
+    def reset(self, seed=None, options=None):
+        obs = self._reset()
+        return self._out(obs)
+
+    def _reset(self):
+        self.batch_idx += 1
+        self.rewards = torch.zeros((self.n_envs,), dtype=torch.float64, device=self.device)
+        n_sel = len(self.data_idxs)
+        if self._data_dev is None:
+            self._data_dev = torch.zeros((self.n_envs, self.shape_T[0], n_sel), dtype=torch.float64, device=self.device)
+        else:
+            self._data_dev.zero_()
+        self._data_host = None
+        self.t_idx, self.t, self.action_idx = 0, self.numpy_real(0.0), 0
+        states_0 = self.backend.convert_to_typed(tensor=self.reset_states(), dtype="real").contiguous()
+        self._x_last.copy_(states_0)
+        self._States[:] = states_0.unsqueeze(0)
+        self.States = self._States
+        self._minmax.copy_(self._minmax_init, non_blocking=True)
+        observations_0 = self._initial_observations(states_0)
+        self._Observations[:] = observations_0.unsqueeze(0)
+        self.Observations = self._Observations
+        return observations_0
+
+    # ---- one action interval (base.py:440-483, 1233-1293) --------------------------------------------------------
+    def step_async(self, actions):
+        if isinstance(actions, torch.Tensor):
+            a = actions.to(device=self.device, dtype=torch.float64)
+        else:
+            self._h_actions.copy_(torch.as_tensor(np.asarray(actions, dtype=np.float64)).reshape(self.n_envs, self.n_actions))
+            a = self._h_actions.to(self.device, non_blocking=True)
+        self.actions = (a.reshape(self.n_envs, self.n_actions) * self.action_maximums_batch).contiguous()
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def update(self):
+        S1 = self.shape_T[0]
+        K = self.action_interval
+        dim = K + 1 if self.t_idx + K < S1 else S1 - self.t_idx
+        self._dim = dim
+        self._T_step_host = self._T_host[self.t_idx:self.t_idx + dim]
+        self.T_step = self.T[self.t_idx:self.t_idx + dim]
+
+        self._minmax.copy_(self._minmax_init, non_blocking=True)
+        self.States = self._update_states()        # ONE fused launch: States, Observations (+Reward, rewards, min/max)
+        self.Observations = self._Observations[:dim]
+        if self.n_properties > 0:
+            self.Properties = self.backend.convert_to_typed(tensor=self.get_properties(), dtype="real")
+        if not self._reward_fused:
+            self.Reward = self.backend.convert_to_typed(tensor=self.get_reward(), dtype="real")
+            self._reward_last.copy_(self.Reward[dim - 1])
+        else:
+            self.Reward = self._Reward[:dim]
+
+        self.t_idx += dim - 1
+        self.t = self._T_host[self.t_idx]
+        self.action_idx += 1
+        terminated = not self.t_idx + 1 < S1
+        return self._obs_last, self._reward_last, terminated
+
+    def update_data(self):
+        """Packed rows ``[t, actions, obs, props, cumulative reward]`` (base.py:1295-1380) — one pack-kernel launch."""
+        dim = self._dim
+        if not self._cum_fused:
+            self.rewards += self._reward_last
+        if not self.store_trajectory:
+            return  # learner-only mode: no (K+1,E,n) blocks exist, nothing to pack
+        a = N.PackArgs()
+        a.n_envs, a.dim, a.n_actions, a.n_obs, a.n_props = self.n_envs, dim, self.n_actions, self.n_observations, self.n_properties
+        a.n_sel = len(self.data_idxs)
+        a.T_step = N.ptr(self.T) + 8 * (self.t_idx - dim + 1)
+        a.actions = N.ptr(self.actions)
+        a.observations = N.ptr(self._Observations)
+        a.properties = N.ptr(self.Properties.contiguous()) if self.n_properties > 0 else None
+        a.rewards_cum = N.ptr(self.rewards)
+        a.idxs = N.ptr(self._sel_idxs)
+        if self._packed is not None:
+            a.packed, a.packed_stride_e = N.ptr(self._packed), (self.action_interval + 1) * self.n_data
+        # rows t_idx-dim+1 .. t_idx of the (E, shape_T, n_sel) cache; row 0 of a block overwrites the last row of
+        # the previous one exactly as in the reference (base.py:1370-1372)
+        a.selected = N.ptr(self._data_dev) + 8 * (self.t_idx - dim + 1) * a.n_sel
+        a.selected_stride_e = self.shape_T[0] * a.n_sel
+        N.pack_rows(a)
+        self._data_host = None
+        if self.cache_all_data:
+            part = self._packed[:, :dim].cpu().numpy()
+            self.io.dump_part_async(data=part, batch_idx=self.batch_idx, part_idx=self.action_idx - 1)
+
+    def _fetch_step_outputs(self):
+        """One D2H of [obs_last | reward_last | min,max] into pinned memory, then a stream sync."""
+        self._h_out.copy_(self._step_out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._h_out
+
+    def check_truncation(self, host=None):
+        """``max(Observations) > range[1] or min(Observations) < range[0]`` over the whole block (base.py:485-499)."""
+        h = self._fetch_step_outputs() if host is None else host
+        E, no = self.n_envs, self.n_observations
+        lo, hi = float(h[E * (no + 1)]), float(h[E * (no + 1) + 1])
+        return bool(hi > self.observation_space_range[1] or lo < self.observation_space_range[0])
+
+    def step_wait(self):
+        observations, reward, terminated = self.update()
+        self.update_data()
+        host = self._fetch_step_outputs()
+        truncated = self.check_truncation(host)
+        if truncated:
+            print(f"Batch #{self.batch_idx} truncated")
+        E, no = self.n_envs, self.n_observations
+        if self.return_numpy:
+            reward_out = host[E * no:E * (no + 1)].numpy().copy()
+            obs_out = host[:E * no].view(E, no).numpy().copy()
+        else:
+            reward_out, obs_out = reward.clone(), observations.clone()
+        done = bool(terminated or truncated)
+        if done:
+            self.data_rewards.append(self.rewards)
+            obs_reset = self._reset()
+            obs_out = self._out(obs_reset)
+        return obs_out, reward_out, [done] * self.n_envs, [{}] * self.n_envs
+
+    def _out(self, t):
+        return t.detach().cpu().numpy() if self.return_numpy else t
+
+    @property
+    def data(self):
+        """Host view of the selected-column cache ``(n_envs, shape_T, len(data_idxs))`` (base.py:1226, 1372)."""
+        if self._data_host is None and self._data_dev is not None:
+            self._data_host = self._data_dev.cpu().numpy()
+        return self._data_host
+
+    def evolve(self, show_progress=False, close=True, save=False):
+        """Free evolution with ``actions = action_maximums`` (base.py:1382-1449)."""
+        self.reset()
+        for _ in range(self.action_steps):
+            self.actions = self.action_maximums_batch
+            self.update()
+            self.update_data()
+            if self.check_truncation():
+                print("Batch truncated")
+                break
+        self.data_rewards.append(self.rewards)
+        if close:
+            self.close(save=save)
+
+    def close(self, save=False, axis_args=None):
+        if save:
+            os.makedirs(self.dir_path, exist_ok=True)
+            rewards = self.backend.convert_to_numpy(tensor=self.data_rewards, dtype="real").ravel()
+            np.savez_compressed(self.file_path_prefix + "_" + "_".join(
+                ["learning_curve", str(self._idx_s), str(self._idx_s + rewards.shape[0] - 1)]) + ".npz", rewards)
+        self.io.close(dump_cache=True)
+
+
+def default_backend(backend_library="b200", backend_precision="double", backend_device="gpu"):
+    assert "b200" in backend_library, "parameter ``backend_library`` should be ``'b200'``"
+    return get_backend_instance(library=backend_library, precision=backend_precision, device=backend_device)

@@ -1,0 +1,167 @@
+"""``LinearVecEnv`` — vectorized stochastic linear environments (Euler–Maruyama with Wiener increments) on a B200.
+
+The reference's stochastic env is single-env only (``LinearEnv(BaseGymEnv)``, quantrl/envs/stochastic.py:21-284).
+This class keeps its per-env semantics and user hooks, batched over ``n_envs`` independent environments behind the
+``BaseSB3Env``-style vectorized surface:
+
+* ``get_A(t_idx, args) -> (n_envs, n, n)`` or ``(n, n)``      (stochastic.py:244-263; ``args = (actions, None, None)``)
+* ``get_noise_prefixes(t_idx, args) -> (n_envs, n)`` or ``(n,)`` (stochastic.py:265-284)
+* ``reset_states() -> (n_envs, n)``, ``get_reward() -> (K+1, n_envs)`` (optional when a fused ``reward_functor`` is set)
+
+Per sub-step (stochastic.py:218-242):  ``Y[i+1] = (I + A(t_idx+i) * t_ssz) @ Y[i] + n(t_idx+i) * Ws[t_idx+i]``,
+``Ws = sqrt(t_ssz) * N(0,1)`` (stochastic.py:162-170); observations add measurement noise
+``N(0,1) * observation_stds`` (envs/base.py:408-426, 462).
+
+The hooks are batched torch on the device and — because they depend only on ``(t_idx, actions)`` — are evaluated
+once per action interval (``is_A_time_dependent=False``) or once per sub-step of the interval and stacked
+(``True``); all ``K`` sub-steps then run in ONE launch of ``qrl_em_step``.
+
+``rng='philox'``: increments and measurement noise are generated inside the kernel (no ``O(shape_T*E*n)`` tensors).
+``rng='fed'``: ``Ws`` ``(shape_T-1, E, n)`` and ``Observation_noises`` ``(shape_T, E, n)`` are drawn at ``reset`` exactly
+like the reference (or assigned by the caller) and fed to the kernel — used for pathwise parity with the reference.
+"""
+import numpy as np
+import torch
+
+from .. import _native as N
+from .base import BaseVecEnv, default_backend
+
+_REWARD_KINDS = {None: N.REWARD_NONE, "neg_wsq_obs": N.REWARD_NEG_WSQ_OBS, "neg_wsq_state": N.REWARD_NEG_WSQ_STATE}
+
+
+class LinearVecEnv(BaseVecEnv):
+    default_params = {}
+    backend_libraries = ["b200"]
+
+    def __init__(self, name, desc, params, t_norm_max, t_norm_ssz, t_norm_mul, n_envs, n_observations, n_properties,
+                 n_actions, action_maximums, action_interval, data_idxs, backend_library="b200",
+                 backend_precision="double", backend_device="gpu", dir_prefix="data", **kwargs):
+        assert backend_library in self.backend_libraries, \
+            f"parameter ``backend_library`` should be one of ``{self.backend_libraries}``"
+        backend = default_backend(backend_library, backend_precision, backend_device)
+        self.name, self.desc = name, desc
+        self.params = {key: params.get(key, val) for key, val in self.default_params.items()}
+        self.is_A_time_dependent = bool(kwargs.pop("is_A_time_dependent", False))
+        self.reward_functor = kwargs.pop("reward_functor", None)
+        reward_weights = kwargs.pop("reward_weights", None)
+        assert self.reward_functor in _REWARD_KINDS, f"``reward_functor`` should be one of {list(_REWARD_KINDS)}"
+        self.Ws = None
+        super().__init__(
+            backend=backend, t_norm_max=t_norm_max, t_norm_ssz=t_norm_ssz, t_norm_mul=t_norm_mul, n_envs=n_envs,
+            n_observations=n_observations, n_properties=n_properties, n_actions=n_actions,
+            action_maximums=action_maximums, action_interval=action_interval, data_idxs=data_idxs,
+            dir_prefix=(dir_prefix if dir_prefix != "data" else ("data/" + self.name.lower()) + "/env") + "_" + "_".join(
+                [str(val) for _, val in self.params.items()]),
+            file_prefix="lin_vec_env", **kwargs)
+        n = self.n_observations
+        assert 1 <= n <= 16, "qrl_em_step supports 1 <= n_observations <= 16"
+        assert (self.shape_T[0] - 1) % self.action_interval == 0 or True  # tails are supported (dim < K+1)
+        self.I = torch.eye(n, dtype=torch.float64, device=self.device)
+        self._reward_fused = self.reward_functor is not None
+        self._cum_fused = self._reward_fused
+        self._reward_w = None
+        if self._reward_fused:
+            w = np.ones(n) if reward_weights is None else np.asarray(reward_weights, dtype=np.float64)
+            assert w.shape == (n,), "``reward_weights`` should have shape (n_observations,)"
+            self._reward_w = torch.as_tensor(w, device=self.device)
+
+    # ---- user hooks ---------------------------------------------------------------------------------------
+    def get_A(self, t_idx, args):
+        raise NotImplementedError
+
+    def get_noise_prefixes(self, t_idx, args):
+        raise NotImplementedError
+
+    def get_reward(self):
+        raise NotImplementedError("override ``get_reward`` or pass ``reward_functor=``")
+
+    # ---- reset: noise bookkeeping (stochastic.py:157-176, base.py:408-426) --------------------------------------
+    def _reset(self):
+        if self.rng == "fed" and not getattr(self, "_fed_assigned", False):
+            S1, E, n = self.shape_T[0], self.n_envs, self.n_observations
+            self.Ws = np.sqrt(self.t_ssz) * self.backend.normal(
+                generator=self.backend.generator(seed=self.seed), shape=(S1 - 1, E, n), mean=0.0, std=1.0, dtype="real")
+            if self.observation_stds is not None:
+                self.Observation_noises = self.backend.normal(
+                    generator=self.backend.generator(seed=self.seed), shape=(S1, E, n), mean=0.0, std=1.0,
+                    dtype="real") * self.observation_stds.reshape(1, -1, n)
+        return super()._reset()
+
+    def set_fed_noise(self, Ws, Observation_noises=None):
+        """Use caller-supplied draws (e.g. the reference's own) for the next episode(s): ``Ws (shape_T-1, E, n)``
+        already scaled by ``sqrt(t_ssz)``; ``Observation_noises (shape_T, E, n)`` already scaled by the stds."""
+        assert self.rng == "fed"
+        S1, E, n = self.shape_T[0], self.n_envs, self.n_observations
+        self.Ws = self.backend.convert_to_typed(tensor=Ws, dtype="real").contiguous()
+        assert tuple(self.Ws.shape) == (S1 - 1, E, n)
+        self.Observation_noises = None
+        if Observation_noises is not None:
+            self.Observation_noises = self.backend.convert_to_typed(tensor=Observation_noises, dtype="real").contiguous()
+            assert tuple(self.Observation_noises.shape) == (S1, E, n)
+        self._fed_assigned = True
+
+    def _coefficients(self, K):
+        args = (self.actions, None, None)
+        E, n = self.n_envs, self.n_observations
+        if self.is_A_time_dependent and K > 0:
+            A = torch.stack([self._as_A(self.get_A(self.t_idx + i, args)) for i in range(K)]).contiguous()
+            nz = torch.stack([self._as_nz(self.get_noise_prefixes(self.t_idx + i, args)) for i in range(K)]).contiguous()
+            return A, E * n * n, n * n, nz, E * n, n
+        A = self.backend.convert_to_typed(tensor=self.get_A(self.t_idx, args), dtype="real").contiguous()
+        nz = self.backend.convert_to_typed(tensor=self.get_noise_prefixes(self.t_idx, args), dtype="real").contiguous()
+        assert tuple(A.shape) in [(n, n), (E, n, n)], "``get_A`` should return (n, n) or (n_envs, n, n)"
+        assert tuple(nz.shape) in [(n,), (E, n)], "``get_noise_prefixes`` should return (n,) or (n_envs, n)"
+        return A, 0, (n * n if A.dim() == 3 else 0), nz, 0, (n if nz.dim() == 2 else 0)
+
+    def _as_A(self, A):
+        A = self.backend.convert_to_typed(tensor=A, dtype="real")
+        return A.expand(self.n_envs, -1, -1) if A.dim() == 2 else A
+
+    def _as_nz(self, nz):
+        nz = self.backend.convert_to_typed(tensor=nz, dtype="real")
+        return nz.expand(self.n_envs, -1) if nz.dim() == 1 else nz
+
+    def _launch(self, K, x0, write_traj=True):
+        E, n = self.n_envs, self.n_observations
+        a = N.EmArgs()
+        a.n, a.n_envs, a.K, a.t_ssz = n, E, K, self.t_ssz
+        keep = []
+        if K > 0:
+            A, a.A_stride_k, a.A_stride_e, nz, a.nz_stride_k, a.nz_stride_e = self._coefficients(K)
+            keep += [A, nz]
+            a.A, a.nz = N.ptr(A), N.ptr(nz)
+        if self.rng == "philox":
+            a.rng_mode = N.RNG_PHILOX
+            a.seed, a.episode, a.t_idx, a.env_offset = self._philox_seed, self.batch_idx & 0xFFFFFFFF, self.t_idx, self.env_offset
+            if self.observation_stds is not None:
+                a.obs_std = N.ptr(self.observation_stds)
+                a.obs_std_stride_e = n if self.observation_stds.dim() == 2 else 0
+        else:
+            a.rng_mode = N.RNG_FED
+            if K > 0:
+                a.W = N.ptr(self.Ws) + 8 * self.t_idx * E * n
+            if self.Observation_noises is not None:
+                a.obs_noise = N.ptr(self.Observation_noises) + 8 * self.t_idx * E * n
+        a.x0 = N.ptr(x0)
+        if write_traj and self.store_trajectory:
+            a.states, a.observations = N.ptr(self._States), N.ptr(self._Observations)
+        a.x_last, a.obs_last = N.ptr(self._x_last), N.ptr(self._obs_last)
+        if self._reward_fused and K > 0:
+            a.reward_kind = _REWARD_KINDS[self.reward_functor]
+            a.reward_w = N.ptr(self._reward_w)
+            a.reward = N.ptr(self._Reward) if self.store_trajectory else None
+            a.reward_last = N.ptr(self._reward_last)
+            a.rewards_cum = N.ptr(self.rewards)
+        a.obs_minmax = N.ptr(self._minmax)
+        a.nan_flag = N.ptr(self._nan)
+        N.em_step(a)
+        return keep
+
+    def _initial_observations(self, states_0):
+        self._launch(0, states_0, write_traj=False)  # row 0 only: obs_0 = states_0 + noise[0]
+        return self._obs_last.clone()
+
+    def _update_states(self):
+        dim = self._dim
+        self._launch(dim - 1, self._x_last)
+        return self._States[:dim]

@@ -1,0 +1,42 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/quantrl_b200.h declares (no compute)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol(native):
+    header = open(os.path.join(ROOT, "include", "quantrl_b200.h")).read()
+    declared = set(re.findall(r"QRL_API\s+[\w\s\*]+?\b(qrl_\w+)\s*\(", header))
+    assert declared, "no QRL_API declarations found"
+    assert declared == set(native.SYMBOLS), (declared ^ set(native.SYMBOLS))
+    lib = native.lib()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.qrl_abi_version() == native.ABI_VERSION == int(re.search(r"#define QRL_ABI_VERSION (\d+)", header).group(1))
+
+
+def test_struct_sizes_match_header(native):
+    # natural alignment, all members 4 or 8 bytes: ctypes and nvcc must agree
+    assert ctypes.sizeof(native.EmArgs) % 8 == 0 and ctypes.sizeof(native.OdeArgs) % 8 == 0
+    assert native.EmArgs.t_ssz.offset == 16 and native.EmArgs.A.offset == 24
+    assert native.EmArgs.seed.offset % 8 == 0 and native.EmArgs.t_idx.offset == native.EmArgs.seed.offset + 16
+
+
+def test_invalid_arguments_are_reported_without_a_gpu(native):
+    a = native.EmArgs()
+    a.n, a.n_envs, a.K = 99, 1, 1
+    with pytest.raises(native.NativeError, match="n must be in 1..16"):
+        native.em_step(a, ctypes.c_void_p(0))
+    assert native.lib().qrl_device_count() >= 0
+
+
+def test_missing_library_fails_loudly(native, monkeypatch):
+    import quantrl_b200._native as N
+    monkeypatch.setattr(N, "_lib", None)
+    monkeypatch.setattr(N, "LIB_PATH", "/nonexistent/libquantrl_b200.so")
+    with pytest.raises(N.NativeError, match="no CPU or PyTorch fallback"):
+        N.lib()

@@ -1,0 +1,56 @@
+"""Scratch timing of qrl_em_step at BASELINE config sizes (CUDA events on the launch stream)."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np, torch
+from quantrl_b200 import _native as N
+
+def bench(E, n, K, philox=True, traj=True, reps=50):
+    dev = "cuda"
+    rng = np.random.default_rng(0)
+    A = torch.as_tensor(0.3 * rng.standard_normal((E, n, n)), device=dev)
+    nz = torch.full((n,), 0.05, dtype=torch.float64, device=dev)
+    std = torch.full((n,), 0.01, dtype=torch.float64, device=dev)
+    x = torch.ones((E, n), dtype=torch.float64, device=dev)
+    S = torch.empty((K + 1, E, n), dtype=torch.float64, device=dev)
+    O = torch.empty((K + 1, E, n), dtype=torch.float64, device=dev)
+    R = torch.empty((K + 1, E), dtype=torch.float64, device=dev)
+    rl = torch.empty((E,), dtype=torch.float64, device=dev); rc = torch.zeros((E,), dtype=torch.float64, device=dev)
+    xl = torch.empty((E, n), dtype=torch.float64, device=dev); ol = torch.empty((E, n), dtype=torch.float64, device=dev)
+    w = torch.ones((n,), dtype=torch.float64, device=dev)
+    mm = torch.tensor([float("inf"), float("-inf")], dtype=torch.float64, device=dev)
+    nan = torch.zeros((1,), dtype=torch.int32, device=dev)
+    a = N.EmArgs()
+    a.n, a.n_envs, a.K, a.t_ssz = n, E, K, 0.01
+    a.A, a.A_stride_e, a.nz = N.ptr(A), n * n, N.ptr(nz)
+    if philox:
+        a.rng_mode, a.seed, a.obs_std = N.RNG_PHILOX, 1, N.ptr(std)
+    else:
+        W = torch.as_tensor(0.1 * rng.standard_normal((K, E, n)), device=dev)
+        ON = torch.as_tensor(0.01 * rng.standard_normal((K + 1, E, n)), device=dev)
+        a.rng_mode, a.W, a.obs_noise = N.RNG_FED, N.ptr(W), N.ptr(ON)
+    a.x0, a.x_last, a.obs_last = N.ptr(x), N.ptr(xl), N.ptr(ol)
+    if traj:
+        a.states, a.observations, a.reward = N.ptr(S), N.ptr(O), N.ptr(R)
+    a.reward_kind, a.reward_w, a.reward_last, a.rewards_cum = N.REWARD_NEG_WSQ_OBS, N.ptr(w), N.ptr(rl), N.ptr(rc)
+    a.obs_minmax, a.nan_flag = N.ptr(mm), N.ptr(nan)
+    for _ in range(5):
+        N.em_step(a)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        a.t_idx = i * K
+        N.em_step(a)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    sub = E * K / (ms * 1e-3)
+    return dict(E=E, n=n, K=K, philox=philox, traj=traj, ms=round(ms, 4), substeps_per_s=f"{sub:.3e}",
+                hbm_GBs=round(sub * 8 * (2 * n + 1) / 1e9, 1) if traj else 0)
+
+if __name__ == "__main__":
+    print("fp64 peak TFLOP/s:", N.measure_fp64_peak(8192))
+    for E, n in ((4096, 4), (8192, 4), (65536, 4), (65536, 8), (262144, 4)):
+        for philox in (True, False):
+            for traj in (True, False):
+                print(json.dumps(bench(E, n, 100, philox, traj)))
