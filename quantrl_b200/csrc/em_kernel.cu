@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(128) em_step_kernel(const qrl_em_args a) {
         nzc = live ? a.nz[(int64_t)i * a.nz_stride_k + (int64_t)el * a.nz_stride_e + cl] : 0.0;
     };
     const bool coeffs_vary = (a.A_stride_k != 0) || (a.nz_stride_k != 0);
-    load_coeffs(0);
+    if (K > 0) load_coeffs(0);   // K == 0 (reset row only): A / nz may be NULL
 
     double lo = INFINITY, hi = -INFINITY;
     double r_last = 0.0, obs = 0.0;

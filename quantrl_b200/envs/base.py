@@ -322,7 +322,7 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         self.step_async(actions)
         return self.step_wait()
 
-    def update(self):
+    def update(self, reset_minmax=True):
         S1 = self.shape_T[0]
         K = self.action_interval
         dim = K + 1 if self.t_idx + K < S1 else S1 - self.t_idx
@@ -330,7 +330,8 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         self._T_step_host = self._T_host[self.t_idx:self.t_idx + dim]
         self.T_step = self.T[self.t_idx:self.t_idx + dim]
 
-        self._minmax.copy_(self._minmax_init, non_blocking=True)
+        if reset_minmax:
+            self._minmax.copy_(self._minmax_init, non_blocking=True)
         self.States = self._update_states()        # ONE fused launch: States, Observations (+Reward, rewards, min/max)
         self.Observations = self._Observations[:dim]
         if self.n_properties > 0:
@@ -407,6 +408,21 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
             obs_reset = self._reset()
             obs_out = self._out(obs_reset)
         return obs_out, reward_out, [done] * self.n_envs, [{}] * self.n_envs
+
+    def step_device(self, actions):
+        """Device-resident step for on-GPU learners: same work as ``step`` (integration, observations, reward,
+        cumulative reward, packed cache rows) but no host round trip — actions are a CUDA tensor, the returned
+        ``(observations, reward)`` are views of device buffers that the next step overwrites, and the truncation
+        reduction stays on the device (``truncation_pending()`` reads it).  Returns ``(obs, reward, terminated)``."""
+        self.actions = (actions.reshape(self.n_envs, self.n_actions) * self.action_maximums_batch)
+        observations, reward, terminated = self.update(reset_minmax=False)  # min/max accumulate over the episode
+        self.update_data()
+        if terminated:
+            self.data_rewards.append(self.rewards)
+        return observations, reward, terminated
+
+    def truncation_pending(self):
+        return self.check_truncation()
 
     def _out(self, t):
         return t.detach().cpu().numpy() if self.return_numpy else t

@@ -154,7 +154,15 @@ class LinearVecEnv(BaseVecEnv):
             a.rewards_cum = N.ptr(self.rewards)
         a.obs_minmax = N.ptr(self._minmax)
         a.nan_flag = N.ptr(self._nan)
-        N.em_step(a)
+        ev = getattr(self, "_em_events", None)
+        if ev is not None and K > 0:  # live per-launch timing on the launch stream (bench.py roofline)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            N.em_step(a)
+            e1.record()
+            ev.append((e0, e1))
+        else:
+            N.em_step(a)
         return keep
 
     def _initial_observations(self, states_0):

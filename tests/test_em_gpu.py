@@ -173,6 +173,13 @@ def test_edge_cases(native, cuda):
     out = em_step(x0, A, nz, 0.01, 0, obs_noise=np.full((1, 2, 4), 0.5))
     np.testing.assert_array_equal(out["obs_last"].cpu().numpy(), x0 + 0.5)
     np.testing.assert_array_equal(out["x_last"].cpu().numpy(), x0)
+    # K = 0 with A = nz = NULL (how reset() asks for observations_0)
+    xk = dev(x0)
+    ol = torch.empty_like(xk)
+    a = N.EmArgs(); a.n, a.n_envs, a.K, a.rng_mode, a.seed = 4, 2, 0, N.RNG_PHILOX, 3
+    a.x0, a.obs_last = N.ptr(xk), N.ptr(ol)
+    N.em_step(a); torch.cuda.synchronize()
+    np.testing.assert_array_equal(ol.cpu().numpy(), x0)   # obs_std NULL -> no measurement noise
     # E = 0: nothing to do, no launch, no error
     before = N.launch_count()
     a = N.EmArgs(); a.n, a.n_envs, a.K = 4, 0, 5
