@@ -164,7 +164,16 @@ typedef struct qrl_ode_args {
     double*  observations;   /* (K+1,E,d) or NULL */
     double*  y_last;         /* (E,d); may alias y0 */
     double*  obs_last;       /* (E,d) or NULL */
-    const double* obs_noise; /* FED (K+1,E,d) or NULL */
+    const double* obs_noise; /* FED measurement noise (K+1,E,d), already scaled; or NULL */
+    /* PHILOX measurement noise (used when obs_noise is NULL and obs_std is not):
+     * counter = (t_idx + row, episode, env_global, 0x10000 + d/2), component d takes z[d & 1] */
+    uint64_t seed;
+    uint32_t episode;
+    uint32_t _pad0;
+    int64_t  t_idx;
+    int64_t  env_offset;
+    const double* obs_std;   /* element [e,d] at obs_std[e*obs_std_stride_e + d]; or NULL */
+    int64_t  obs_std_stride_e;
     double*  h_state;        /* DOPRI5: (E,) in/out carried step size (<= 0: start from t_ssz); or NULL */
     int32_t* n_steps;        /* DOPRI5: (E,2) accepted, rejected counters (accumulated); or NULL */
 

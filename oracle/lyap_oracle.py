@@ -14,7 +14,7 @@ Third-party arithmetic: the adaptive integrators are SciPy's (``scipy`` unpinned
 pyproject.toml:26; 1.18.1 in this image).  They are *called*, not restated.
 
 Fixed-step RK4 and the per-env dopri5 do not exist in the reference; they are defined by the
-north_star.  ``rk4_interval`` is the classic tableau applied to the restated RHS; ``dopri5_interval`` is
+north_star.  ``rk4_interval`` is the classic tableau applied to the restated RHS; ``dopri5_dense_interval`` is
 Dormand–Prince 5(4) (Hairer, Nørsett & Wanner, *Solving ODEs I*, II.5; same tableau/controller family as SciPy's
 ``RK45``/``dopri5``) with ONE controller PER ENV.  Both are pinned two ways in ``tests/test_oracle_golden.py``:
 (1) RK4 driven by the *reference's own* ``env.func`` (fixture G2) must equal ``rk4_interval`` to ~1e-13, and
@@ -85,7 +85,7 @@ def scipy_interval(func, T_step, y0, args, method="vode", atol=1e-9, rtol=1e-6):
     return Y.reshape((len(T_step),) + shape)
 
 
-# Dormand–Prince 5(4) tableau
+# Dormand–Prince 5(4) tableau + Shampine's 4th-order dense output (the interpolant behind SciPy's ``RK45``)
 _C = np.array([0.0, 1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0])
 _A = [
     [],
@@ -96,82 +96,95 @@ _A = [
     [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656],
     [35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84],
 ]
-_B5 = np.array([35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84, 0.0])
 _E = np.array([71 / 57600, 0.0, -71 / 16695, 71 / 1920, -17253 / 339200, 22 / 525, -1 / 40])
+_P = np.array([
+    [1.0, -8048581381 / 2820520608, 8663915743 / 2820520608, -12715105075 / 11282082432],
+    [0.0, 0.0, 0.0, 0.0],
+    [0.0, 131558114200 / 32700410799, -68118460800 / 10900136933, 87487479700 / 32700410799],
+    [0.0, -1754552775 / 470086768, 14199869525 / 1410260304, -10690763975 / 1880347072],
+    [0.0, 127303824393 / 49829197408, -318862633887 / 49829197408, 701980252875 / 199316789632],
+    [0.0, -282668133 / 205662961, 2019193451 / 616988883, -1453857185 / 822651844],
+    [0.0, 40617522 / 29380423, -110615467 / 29380423, 69997945 / 29380423]])
 
 DOPRI5_SAFETY = 0.9
 DOPRI5_MIN_FACTOR = 0.2
 DOPRI5_MAX_FACTOR = 10.0
-DOPRI5_MAX_STEPS = 100000
+DOPRI5_MAX_STEPS = 1000000
 
 
-def dopri5_interval(func_single, T_step, y0, args_per_env, atol, rtol, h0=None):
-    """Per-env adaptive DP5(4): each env integrates from T_step[i] to T_step[i+1] *landing on the grid*
-    (the step is clipped to the grid point, as SciPy's old ``ode`` interface does when asked to integrate to
-    ``T_step[i]``), carrying its own step size across grid points.
+def dopri5_dense_interval(func_single, t0, t_ssz, K, y0, args_per_env, atol, rtol, h0=None):
+    """Per-env adaptive DP5(4) over one action interval with dense output on the grid ``t0 + i * t_ssz``.
 
-    func_single(t, y (d,), args, e) -> (d,) evaluates env ``e`` alone.  Returns Y (len(T_step),E,d),
-    n_accepted (E,), n_rejected (E,), h_last (E,).
+    Each env runs its own controller; steps are free-running (not clipped to grid points), grid rows inside an
+    accepted step come from the 4th-order interpolant, the interval end ``t0 + K * t_ssz`` is hit exactly (the action
+    changes there) and the step size is carried to the next interval through ``h0``/``h_last``.
 
-    Controller (what the CUDA kernel implements; Hairer's DOPRI5 without PI stabilisation / SciPy ``RK45``):
-      err = sqrt(mean(((y5 - y4) / (atol + rtol * max(|y|, |y5|)))^2))
-      accept iff err <= 1;  h_new = h * clip(0.9 * err^(-1/5), 0.2, 10)   (err == 0 -> factor 10)
-      after a rejection the growth factor is capped at 1 for the next step.
+    func_single(t, y (d,), args, e) -> (d,).  Returns Y (K+1,E,d), n_accepted (E,), n_rejected (E,), h_last (E,).
+
+    Controller (= the CUDA kernel; SciPy ``RK45``'s rule):
+      err = sqrt(mean(((y5 - y4) / (atol + rtol * max(|y|, |y5|)))^2));  accept iff err <= 1
+      accepted: h <- h * min(10, max(0.2, 0.9 err^(-1/5)))  (err == 0 -> 10; capped at 1 right after a rejection)
+      rejected: h <- h * max(0.2, 0.9 err^(-1/5))
+      a step clipped to the interval end never shrinks the carried step size.
     """
     E, d = y0.shape
-    Y = np.empty((len(T_step), E, d))
+    Y = np.empty((K + 1, E, d))
     Y[0] = y0
     n_acc = np.zeros(E, dtype=np.int64)
     n_rej = np.zeros(E, dtype=np.int64)
     h_last = np.zeros(E)
+    t_end = t0 + K * t_ssz
     for e in range(E):
         y = y0[e].copy()
         args = args_per_env(e)
-        h = (T_step[1] - T_step[0]) if h0 is None else float(h0[e])
+        t = t0
+        h = float(h0[e]) if (h0 is not None and h0[e] > 0.0) else t_ssz
         k = [None] * 7
-        k[0] = func_single(T_step[0], y, args, e)
+        k[0] = func_single(t, y, args, e)
         rejected = False
-        for i in range(len(T_step) - 1):
-            t, t_end = T_step[i], T_step[i + 1]
-            steps = 0
-            while t < t_end:
-                steps += 1
-                assert steps < DOPRI5_MAX_STEPS
-                h_try = h
-                last = False
-                if t + h_try >= t_end or (t_end - (t + h_try)) < 1e-14 * abs(t_end):
-                    h_try = t_end - t
-                    last = True
-                for s in range(1, 7):
-                    ys = y.copy()
-                    for j, a in enumerate(_A[s]):
-                        if a != 0.0:
-                            ys = ys + (h_try * a) * k[j]
-                    k[s] = func_single(t + _C[s] * h_try, ys, args, e)
-                y5 = ys  # stage 7 argument is the 5th-order solution (FSAL)
-                errv = h_try * sum(_E[s] * k[s] for s in range(7))
-                sc = atol + rtol * np.maximum(np.abs(y), np.abs(y5))
-                err = np.sqrt(np.mean((errv / sc) ** 2))
-                if err <= 1.0:
-                    fac = DOPRI5_MAX_FACTOR if err == 0.0 else min(DOPRI5_MAX_FACTOR,
-                                                                  max(DOPRI5_MIN_FACTOR,
-                                                                      DOPRI5_SAFETY * err ** (-0.2)))
-                    if rejected:
-                        fac = min(1.0, fac)
-                    rejected = False
-                    n_acc[e] += 1
-                    t = t_end if last else t + h_try
-                    y = y5
-                    k[0] = k[6]
-                    if not last or fac < 1.0:
-                        h = h_try * fac
+        next_row = 1
+        steps = 0
+        while next_row <= K:
+            steps += 1
+            assert steps < DOPRI5_MAX_STEPS
+            remaining = t_end - t
+            last = h >= remaining * (1.0 - 1e-12)
+            ht = remaining if last else h
+            for s in range(1, 7):
+                ys = y + ht * sum(a * k[j] for j, a in enumerate(_A[s]))
+                if s < 6:
+                    k[s] = func_single(t + _C[s] * ht, ys, args, e)
+            y5 = ys
+            k[6] = func_single(t + ht, y5, args, e)
+            errv = ht * sum(_E[s] * k[s] for s in range(7))
+            sc = atol + rtol * np.maximum(np.abs(y), np.abs(y5))
+            err = np.sqrt(np.mean((errv / sc) ** 2))
+            if err <= 1.0:
+                fac = DOPRI5_MAX_FACTOR if err == 0.0 else min(DOPRI5_MAX_FACTOR,
+                                                              max(DOPRI5_MIN_FACTOR, DOPRI5_SAFETY * err ** (-0.2)))
+                if rejected:
+                    fac = min(1.0, fac)
+                rejected = False
+                n_acc[e] += 1
+                t_new = t_end if last else t + ht
+                while next_row <= K:
+                    tg = t_end if next_row == K else t0 + next_row * t_ssz
+                    if tg > t_new:
+                        break
+                    if tg == t_new:
+                        Y[next_row, e] = y5
                     else:
-                        h = max(h, h_try * fac) if h_try * fac > h else h
-                else:
-                    fac = max(DOPRI5_MIN_FACTOR, DOPRI5_SAFETY * err ** (-0.2))
-                    h = h_try * fac
-                    rejected = True
-                    n_rej[e] += 1
-            Y[i + 1, e] = y
+                        x = (tg - t) / ht
+                        pw = np.array([1.0, x, x * x, x * x * x])
+                        Y[next_row, e] = y + ht * x * sum(k[s] * (_P[s] @ pw) for s in range(7))
+                    next_row += 1
+                t = t_new
+                y = y5
+                k[0] = k[6]
+                h = max(h, ht * fac) if (last and fac >= 1.0) else ht * fac
+            else:
+                h = ht * max(DOPRI5_MIN_FACTOR, DOPRI5_SAFETY * err ** (-0.2))
+                rejected = True
+                n_rej[e] += 1
         h_last[e] = h
     return Y, n_acc, n_rej, h_last

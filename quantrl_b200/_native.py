@@ -43,6 +43,8 @@ class OdeArgs(C.Structure):
         ("params", _dp), ("params_stride_e", C.c_int64), ("actions", _dp),
         ("A", _dp), ("A_stride_e", C.c_int64), ("D", _dp), ("D_stride_e", C.c_int64),
         ("y0", _dp), ("states", _dp), ("observations", _dp), ("y_last", _dp), ("obs_last", _dp), ("obs_noise", _dp),
+        ("seed", C.c_uint64), ("episode", C.c_uint32), ("_pad0", C.c_uint32), ("t_idx", C.c_int64),
+        ("env_offset", C.c_int64), ("obs_std", _dp), ("obs_std_stride_e", C.c_int64),
         ("h_state", _dp), ("n_steps", _dp), ("obs_minmax", _dp), ("nan_flag", _dp),
     ]
 

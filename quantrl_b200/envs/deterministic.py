@@ -1,0 +1,178 @@
+"""``LinearizedHOVecEnv`` for the ``'b200'`` backend — deterministic linearized harmonic-oscillator environments.
+
+Mirror of the reference class of the same name (quantrl/envs/deterministic.py:439-867): same constructor arguments
+(``num_modes``, ``num_quads``, time grid, ``n_envs``, spaces, ``ode_method/ode_atol/ode_rtol`` kwargs), same state
+layout ``y = [Re a | Im a | vec(V)]`` (deterministic.py:667), same ``_update_states = solver.step(T_step, States[-1],
+actions)`` (deterministic.py:646-651) and the same user hooks.
+
+* With ``system='optomech' | 'kerr_chain' | 'const_AD'`` (+ ``system_params``) the hooks are CUDA device functors and a
+  whole action interval is one kernel launch.
+* Without ``system`` the reference's Python hooks ``get_mode_rates / get_A / get_D`` (deterministic.py:748-818) are
+  used, written in torch on the device, through the solver's stage-callback mode; ``func`` below restates
+  deterministic.py:653-746 for that case.
+"""
+import torch
+
+from .. import _native as N
+from ..solvers import SYSTEM_NPARAMS, SYSTEMS, get_IVP_solver
+from .base import BaseVecEnv, default_backend
+
+
+class LinearizedHOVecEnv(BaseVecEnv):
+    default_params = {}
+    default_ode_solver_params = {"ode_method": "rk4", "ode_atol": 1e-9, "ode_rtol": 1e-6, "ode_substeps": 1}
+    backend_libraries = ["b200"]
+
+    def __init__(self, name, desc, params, num_modes, num_quads, t_norm_max, t_norm_ssz, t_norm_mul, n_envs,
+                 n_observations, n_properties, n_actions, action_maximums, action_interval, data_idxs,
+                 backend_library="b200", backend_precision="double", backend_device="gpu", dir_prefix="data", **kwargs):
+        assert backend_library in self.backend_libraries, \
+            f"parameter ``backend_library`` should be one of ``{self.backend_libraries}``"
+        backend = default_backend(backend_library, backend_precision, backend_device)
+        IVPSolver = get_IVP_solver(library=backend_library)
+        self.name, self.desc = name, desc
+        self.num_modes = int(num_modes)
+        self.dim_corrs = (int(num_quads), int(num_quads))
+        self.num_corrs = int(num_quads) ** 2
+        self.params = {key: params.get(key, val) for key, val in self.default_params.items()}
+        for key, val in self.default_ode_solver_params.items():
+            kwargs.setdefault(key, val)
+        ode = {k: kwargs.pop(k) for k in list(self.default_ode_solver_params)}
+        system = kwargs.pop("system", None)
+        system_params = kwargs.pop("system_params", None)
+        assert n_observations == 2 * self.num_modes + self.num_corrs, \
+            "``n_observations`` should equal 2 * num_modes + num_quads**2"
+        self.is_A_constant = False
+        self.is_D_constant = False
+        super().__init__(
+            backend=backend, t_norm_max=t_norm_max, t_norm_ssz=t_norm_ssz, t_norm_mul=t_norm_mul, n_envs=n_envs,
+            n_observations=n_observations, n_properties=n_properties, n_actions=n_actions,
+            action_maximums=action_maximums, action_interval=action_interval, data_idxs=data_idxs,
+            dir_prefix=(dir_prefix if dir_prefix != "data" else ("data/" + self.name.lower()) + "/env"),
+            file_prefix="lho_vec_env", **kwargs)
+        E, q = self.n_envs, self.dim_corrs[0]
+        self.A = torch.zeros((E, q, q), dtype=torch.float64, device=self.device)
+        self.D = torch.zeros((E, q, q), dtype=torch.float64, device=self.device)
+
+        sysd = None
+        if system is not None:
+            assert system in SYSTEMS, f"``system`` should be one of {list(SYSTEMS)}"
+            sysd = {"system": system, "num_modes": self.num_modes, "num_quads": q, "t_ssz": self.t_ssz}
+            if system == "const_AD":
+                sysd["A"], sysd["D"] = self.A, self.D   # filled by the user (is_A_constant / is_D_constant semantics)
+                self.is_A_constant = self.is_D_constant = True
+            else:
+                P = self.backend.convert_to_typed(tensor=system_params, dtype="real").contiguous()
+                npar = SYSTEM_NPARAMS[system](self.num_modes)
+                assert tuple(P.shape) in [(npar,), (E, npar)], f"``system_params`` should have shape ({npar},) or (n_envs, {npar})"
+                sysd["params"] = P
+        self.system = sysd
+        self.solver = IVPSolver(
+            func=self.func, y_0=self._States[-1], T=self.T,
+            solver_params={"method": ode["ode_method"], "atol": ode["ode_atol"], "rtol": ode["ode_rtol"], "is_stiff": False,
+                           "step_interval": self.action_interval, "substeps": ode["ode_substeps"]},
+            func_controls=getattr(self, "func_controls", None), has_delay=False,
+            func_delay=getattr(self, "func_delay", None), delay_interval=self.action_interval, backend=self.backend,
+            system=sysd)
+
+    # ---- user hooks (deterministic.py:748-818) ------------------------------------------------------------------
+    def get_A(self, t, modes, args):
+        raise NotImplementedError
+
+    def get_D(self, t, modes, args):
+        raise NotImplementedError
+
+    def get_mode_rates(self, t, modes, args):
+        raise NotImplementedError
+
+    def get_mode_rates_real(self, t, modes_real, args):
+        m = self.num_modes
+        rates = self.get_mode_rates(t=t, modes=torch.complex(modes_real[:, :m], modes_real[:, m:]), args=args)
+        return torch.cat((rates.real, rates.imag), dim=1)
+
+    def func(self, t, y, args):
+        """RHS for the stage-callback mode (restates deterministic.py:653-746 in torch)."""
+        m, q, E = self.num_modes, self.dim_corrs[0], self.n_envs
+        parts, modes = [], None
+        if m != 0:
+            modes = torch.complex(y[:, :m], y[:, m:2 * m])
+            parts.append(self.get_mode_rates_real(t=t, modes_real=y[:, :2 * m], args=args))
+        if self.num_corrs != 0:
+            V = y[:, 2 * m:].reshape(E, q, q)
+            A = self.A if self.is_A_constant else self.get_A(t=t, modes=modes, args=args)
+            D = self.D if self.is_D_constant else self.get_D(t=t, modes=modes, args=args)
+            parts.append(((torch.matmul(A, V) + torch.matmul(V, A.transpose(1, 2))) + D).reshape(E, q * q))
+        return torch.cat(parts, dim=1)
+
+    # ---- engine hooks ---------------------------------------------------------------------------------------
+    def _noise_epilogue(self, t_idx):
+        """Measurement-noise source for the launch: fed tensor slice or the in-kernel Philox stream."""
+        ep = {}
+        E, d = self.n_envs, self.n_observations
+        if self.observation_stds is None:
+            return ep
+        if self.rng == "fed":
+            ep["obs_noise"] = N.ptr(self.Observation_noises) + 8 * t_idx * E * d
+        else:
+            ep.update(obs_std=N.ptr(self.observation_stds), obs_std_stride_e=(d if self.observation_stds.dim() == 2 else 0),
+                      seed=self._philox_seed, episode=self.batch_idx & 0xFFFFFFFF, t_idx=t_idx, env_offset=self.env_offset)
+        return ep
+
+    def _reset(self):
+        if self.rng == "fed" and self.observation_stds is not None and not getattr(self, "_fed_assigned", False):
+            S1, E, d = self.shape_T[0], self.n_envs, self.n_observations
+            self.Observation_noises = self.backend.normal(
+                generator=self.backend.generator(seed=self.seed), shape=(S1, E, d), mean=0.0, std=1.0,
+                dtype="real") * self.observation_stds.reshape(1, -1, d)
+        self.solver.reset_controller()
+        return super()._reset()
+
+    def set_fed_noise(self, Observation_noises):
+        assert self.rng == "fed"
+        self.Observation_noises = self.backend.convert_to_typed(tensor=Observation_noises, dtype="real").contiguous()
+        assert tuple(self.Observation_noises.shape) == (self.shape_T[0], self.n_envs, self.n_observations)
+        self._fed_assigned = True
+
+    def _initial_observations(self, states_0):
+        if self.observation_stds is None:
+            self._obs_last.copy_(states_0)
+            return states_0.clone()
+        if self.system is None:
+            noise0 = self.Observation_noises[0] if self.rng == "fed" else \
+                self.backend.normal(generator=self.backend.generator(seed=self.seed), shape=tuple(states_0.shape),
+                                    mean=0.0, std=1.0, dtype="real") * self.observation_stds
+            obs = states_0 + noise0
+            self._obs_last.copy_(obs)
+            return obs
+        # K = 0 launch of the fused kernel: row 0 only
+        self.system["T_host"] = self._T_host[:1]
+        self.solver.epilogue = dict(self._noise_epilogue(0), obs_last=N.ptr(self._obs_last))
+        self.solver.integrate(T_step=self.T[:1], y_0=states_0, params=self.action_maximums_batch, out=self._States[:1])
+        return self._obs_last.clone()
+
+    def _update_states(self):
+        dim = self._dim
+        t0 = self.t_idx
+        if self.system is not None:
+            self.system["T_host"] = self._T_step_host
+            self.solver.epilogue = dict(
+                self._noise_epilogue(t0), observations=N.ptr(self._Observations), y_last=N.ptr(self._x_last),
+                obs_last=N.ptr(self._obs_last), obs_minmax=N.ptr(self._minmax), nan_flag=N.ptr(self._nan))
+            return self.solver.integrate(T_step=self.T_step, y_0=self._x_last, params=self.actions,
+                                         out=self._States[:dim])
+        # stage-callback mode: integrate with torch hooks, then the (unfused) noise add / reductions
+        Y = self.solver.step(T_step=self.T_step, y_0=self._x_last.clone(), params=self.actions)
+        self._States[:dim] = Y
+        obs = Y
+        if self.observation_stds is not None:
+            noise = self.Observation_noises[t0:t0 + dim] if self.rng == "fed" else \
+                self.backend.normal(generator=self.backend.generator(seed=self.seed), shape=tuple(Y.shape), mean=0.0,
+                                    std=1.0, dtype="real") * self.observation_stds
+            obs = Y + noise
+        self._Observations[:dim] = obs
+        self._x_last.copy_(Y[dim - 1])
+        self._obs_last.copy_(obs[dim - 1])
+        finite = obs[torch.isfinite(obs)]
+        if finite.numel() > 0:
+            self._minmax[0], self._minmax[1] = torch.minimum(self._minmax[0], finite.min()), torch.maximum(self._minmax[1], finite.max())
+        return self._States[:dim]

@@ -6,6 +6,8 @@ from quantrl_b200 import _native as N
 
 
 def dev(x, device="cuda"):
+    if isinstance(x, torch.Tensor):
+        return x.to(device).contiguous()
     return torch.as_tensor(np.ascontiguousarray(x), device=device)
 
 
@@ -60,3 +62,63 @@ def em_step(x0, A, nz, t_ssz, K, W=None, obs_noise=None, philox=None, obs_std=No
     N.em_step(a)
     torch.cuda.synchronize()
     return out
+
+
+def ode_step(system, m, q, y0, K, t0, t_ssz, params=None, actions=None, A=None, D=None, method="rk4", substeps=1,
+             atol=1e-9, rtol=1e-6, obs_noise=None, h_state=None, philox=None, obs_std=None):
+    """Run qrl_ode_step once; returns dict of torch tensors."""
+    y0 = dev(y0).double()
+    E, d = y0.shape
+    a = N.OdeArgs()
+    a.system = {"optomech": N.SYS_OPTOMECH, "kerr_chain": N.SYS_KERR_CHAIN, "const_AD": N.SYS_CONST_AD}[system]
+    a.num_modes, a.num_quads, a.n_envs, a.K = m, q, E, K
+    a.method = N.ODE_RK4 if method == "rk4" else N.ODE_DOPRI5
+    a.substeps, a.t0, a.t_ssz, a.atol, a.rtol = substeps, t0, t_ssz, atol, rtol
+    keep = [y0]
+    if params is not None:
+        params = dev(params).double(); keep.append(params)
+        a.params, a.params_stride_e = N.ptr(params), (params.shape[-1] if params.dim() == 2 else 0)
+    if actions is not None:
+        actions = dev(actions).double().reshape(E, -1).contiguous(); keep.append(actions)
+        a.actions, a.n_actions = N.ptr(actions), actions.shape[1]
+    if A is not None:
+        A, D = dev(A).double(), dev(D).double(); keep += [A, D]
+        a.A, a.A_stride_e, a.D, a.D_stride_e = N.ptr(A), (q * q if A.dim() == 3 else 0), N.ptr(D), (q * q if D.dim() == 3 else 0)
+    out = {
+        "states": torch.full((K + 1, E, d), float("nan"), dtype=torch.float64, device="cuda"),
+        "observations": torch.full((K + 1, E, d), float("nan"), dtype=torch.float64, device="cuda"),
+        "y_last": torch.empty((E, d), dtype=torch.float64, device="cuda"),
+        "obs_last": torch.empty((E, d), dtype=torch.float64, device="cuda"),
+        "h_state": torch.zeros((E,), dtype=torch.float64, device="cuda") if h_state is None else dev(h_state).double(),
+        "n_steps": torch.zeros((E, 2), dtype=torch.int32, device="cuda"),
+        "minmax": torch.tensor([float("inf"), float("-inf")], dtype=torch.float64, device="cuda"),
+        "nan": torch.zeros((1,), dtype=torch.int32, device="cuda"),
+    }
+    if obs_noise is not None:
+        obs_noise = dev(obs_noise).double(); keep.append(obs_noise); a.obs_noise = N.ptr(obs_noise)
+    if philox is not None:
+        obs_std = dev(obs_std).double(); keep.append(obs_std)
+        a.obs_std, a.obs_std_stride_e = N.ptr(obs_std), (d if obs_std.dim() == 2 else 0)
+        a.seed, a.episode, a.t_idx, a.env_offset = philox["seed"], philox.get("episode", 0), philox.get("t_idx", 0), philox.get("env_offset", 0)
+    a.y0, a.states, a.observations = N.ptr(y0), N.ptr(out["states"]), N.ptr(out["observations"])
+    a.y_last, a.obs_last = N.ptr(out["y_last"]), N.ptr(out["obs_last"])
+    a.h_state, a.n_steps = N.ptr(out["h_state"]), N.ptr(out["n_steps"])
+    a.obs_minmax, a.nan_flag = N.ptr(out["minmax"]), N.ptr(out["nan"])
+    N.ode_step(a)
+    torch.cuda.synchronize()
+    return out
+
+
+def ode_smoke():
+    """One RK4 Lyapunov interval on cuda:0 vs oracle/lyap_oracle.py (used by __graft_entry__.smoke)."""
+    import lyap_oracle as lo
+    import systems as sy
+    E, K, dt = 48, 10, 0.01
+    p = sy.optomech_default_params(E, seed=2)
+    y0 = sy.optomech_y0(p)
+    u = np.random.default_rng(0).uniform(-1, 1, E)
+    func = lo.make_func(2, 4, lambda t, mo, uu: sy.optomech_mode_rates(p, t, mo, uu), lambda t, mo, uu: sy.optomech_A(p, t, mo, uu),
+                        lambda t, mo, uu: sy.optomech_D(p, t, mo, uu), E)
+    ref = lo.rk4_interval(func, np.arange(K + 1) * dt, y0, u)
+    out = ode_step("optomech", 2, 4, y0, K, 0.0, dt, params=p, actions=u)
+    np.testing.assert_allclose(out["states"].cpu().numpy(), ref, rtol=1e-11, atol=1e-13)
