@@ -1,0 +1,232 @@
+"""GPU: the public env surface (LinearVecEnv / LinearizedHOVecEnv, mirrors of the reference's env classes) against
+reference-generated fixtures: step()/reset() returns, lock-step episode bookkeeping, the packed ``data`` cache of
+BaseSB3Env.update_data, auto-reset, truncation."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import em_oracle as eo
+import systems as sy
+
+pytestmark = pytest.mark.gpu
+
+
+def _em_env(g, tag, **kw):
+    from quantrl_b200.systems import AffineLinearVecEnv
+    K, S, ssz = int(g[f"{tag}_K"]), int(g[f"{tag}_S"]), float(g[f"{tag}_ssz"])
+    E, n = g[f"{tag}_x0"].shape
+    return AffineLinearVecEnv(
+        n_envs=E, n=n, A0=g[f"{tag}_A0"], Au=g[f"{tag}_Au"], noise_prefixes=g[f"{tag}_nz"], x0=g[f"{tag}_x0"],
+        t_norm_max=S * ssz + ssz / 2, t_norm_ssz=ssz, action_interval=K, observation_stds=list(g[f"{tag}_stds"]),
+        reward_weights=g[f"{tag}_weights"], dir_prefix="/tmp/qrl_test", **kw)
+
+
+@pytest.mark.parametrize("tag", ["n4", "n8"])
+def test_linear_vec_env_fed_matches_reference_linear_env(native, cuda, golden_dir, tag):
+    """Each row of the vectorized env == the reference's single LinearEnv fed the same draws (fixture G3)."""
+    g = np.load(os.path.join(golden_dir, "em_linear_env.npz"))
+    env = _em_env(g, tag, rng="fed")
+    K, S = int(g[f"{tag}_K"]), int(g[f"{tag}_S"])
+    env.set_fed_noise(np.transpose(g[f"{tag}_Ws"], (1, 0, 2)), np.transpose(g[f"{tag}_obs_noises"], (1, 0, 2)))
+    obs0 = env.reset()
+    np.testing.assert_allclose(obs0.cpu().numpy(), g[f"{tag}_Observations"][:, 0], rtol=1e-13, atol=1e-15)
+    assert env.action_steps == S // K and env.shape_T == (S + 1,)
+    cum = 0.0
+    for a in range(S // K):
+        acts = g[f"{tag}_actions"][:, a]
+        obs, rew, done, info = env.step(acts)
+        t1 = (a + 1) * K
+        ref_R = g[f"{tag}_Reward"][:, t1]
+        np.testing.assert_allclose(rew.cpu().numpy(), ref_R, rtol=1e-12, atol=1e-14)
+        cum = cum + ref_R
+        last = a == S // K - 1
+        assert done == [last] * env.n_envs and info == [{}] * env.n_envs
+        if not last:
+            np.testing.assert_allclose(obs.cpu().numpy(), g[f"{tag}_Observations"][:, t1], rtol=1e-12, atol=1e-14)
+            np.testing.assert_allclose(env.States.cpu().numpy(), np.transpose(g[f"{tag}_States"][:, t1 - K:t1 + 1], (1, 0, 2)),
+                                       rtol=1e-12, atol=1e-14)
+            np.testing.assert_allclose(env.rewards.cpu().numpy(), cum, rtol=1e-12)
+            assert env.t_idx == t1 and env.action_idx == a + 1
+        else:  # auto-reset: the reset observation is returned, no terminal_observation (base.py:1277-1293)
+            np.testing.assert_allclose(obs.cpu().numpy(), g[f"{tag}_Observations"][:, 0], rtol=1e-13, atol=1e-15)
+            assert env.t_idx == 0 and env.batch_idx == 1 and len(env.data_rewards) == 1
+            np.testing.assert_allclose(env.data_rewards[0].cpu().numpy(), cum, rtol=1e-12)
+    env.close()
+
+
+def test_linear_vec_env_data_cache_rows(native, cuda, golden_dir):
+    """env.data == BaseSB3Env.update_data's rows [t, actions, obs, cumulative reward] incl. the overlap rule
+    (row 0 of a block overwrites the last row of the previous block, base.py:1370-1372), via the oracle's pack_rows."""
+    g = np.load(os.path.join(golden_dir, "em_linear_env.npz"))
+    tag = "n4"
+    env = _em_env(g, tag, rng="fed")
+    K, S, ssz = int(g[f"{tag}_K"]), int(g[f"{tag}_S"]), float(g[f"{tag}_ssz"])
+    E = env.n_envs
+    env.set_fed_noise(np.transpose(g[f"{tag}_Ws"], (1, 0, 2)), np.transpose(g[f"{tag}_obs_noises"], (1, 0, 2)))
+    env.reset()
+    T = np.arange(S + 1) * ssz
+    Obs = np.transpose(g[f"{tag}_Observations"], (1, 0, 2))
+    ref = np.zeros((E, S + 1, 7))
+    cum = np.zeros(E)
+    n_steps = S // K - 1     # stop before the terminating step (its auto-reset zeroes ``data``)
+    for a in range(n_steps):
+        env.step(g[f"{tag}_actions"][:, a])
+        t0 = a * K
+        cum = cum + g[f"{tag}_Reward"][:, t0 + K]
+        ref[:, t0:t0 + K + 1] = eo.pack_rows(T[t0:t0 + K + 1], g[f"{tag}_actions"][:, a], Obs[t0:t0 + K + 1], None, cum)
+    np.testing.assert_allclose(env.data, ref, rtol=1e-12, atol=1e-14)
+    # the reference's own Gym-env data agrees on the time / action / observation columns of the surviving rows
+    gd = g[f"{tag}_data"]
+    np.testing.assert_allclose(env.data[:, 1:n_steps * K, 0], gd[:, 1:n_steps * K, 0], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(env.data[:, :n_steps * K, 2:6], gd[:, :n_steps * K, 2:6], rtol=1e-12, atol=1e-14)
+    env.close()
+
+
+def test_linear_vec_env_philox_numpy_api_and_truncation(native, cuda):
+    from quantrl_b200.systems import AffineLinearVecEnv, affine_matrices
+    A0, Au = affine_matrices(4, 1, seed=0)
+    E, K = 100, 10
+    kw = dict(n_envs=E, n=4, A0=A0, Au=Au, noise_prefixes=0.05, x0=1.0, t_norm_max=0.305, t_norm_ssz=0.01,
+              action_interval=K, observation_stds=[0.01] * 4, seed=9, dir_prefix="/tmp/qrl_test", return_numpy=True)
+    env = AffineLinearVecEnv(**kw)
+    obs0 = env.reset()
+    assert isinstance(obs0, np.ndarray) and obs0.shape == (E, 4)
+    u = np.random.default_rng(0).uniform(-1, 1, (E, 1))
+    obs, rew, done, _ = env.step(u)
+    assert isinstance(obs, np.ndarray) and isinstance(rew, np.ndarray) and rew.shape == (E,) and done == [False] * E
+    z_w, z_o = eo.philox_noise_block(env._philox_seed, 0, 0, K, 0, E, 4)
+    ref = eo.em_interval_vec(np.ones((E, 4)), sy.affine_A(A0, Au, u), np.full((E, 4), 0.05), np.sqrt(0.01) * z_w, 0.01)
+    np.testing.assert_allclose(obs, ref[-1] + 0.01 * z_o[-1], rtol=1e-10, atol=1e-12)
+    # same seed -> same episode; the second episode of one env differs from its first (episode counter in the stream)
+    env_b = AffineLinearVecEnv(**kw)
+    env_b.reset()
+    obs_b, _, _, _ = env_b.step(u)
+    np.testing.assert_array_equal(obs, obs_b)
+    env.step(u); o3, _, done3, _ = env.step(u)
+    assert done3 == [True] * E and env.batch_idx == 1
+    obs_e2, _, _, _ = env.step(u)
+    assert not np.array_equal(obs_e2, obs)
+    # truncation: any observation outside the range ends the episode for ALL envs (base.py:485-499, 1271-1293)
+    env_t = AffineLinearVecEnv(**dict(kw, observation_space_range=[-1.05, 1.05]))
+    env_t.reset()
+    _, _, done_t, _ = env_t.step(u)
+    assert done_t == [True] * E and env_t.batch_idx == 1 and env_t.t_idx == 0
+    for e in (env, env_b, env_t):
+        e.close()
+
+
+def _optomech_env(g, tag, method, atol=1e-9, rtol=1e-6, fused=True, **kw):
+    from quantrl_b200.envs import LinearizedHOVecEnv
+    p, y0 = g[f"{tag}_p"], g[f"{tag}_y0"]
+    K, S, ssz = int(g[f"{tag}_K"]), int(g[f"{tag}_S"]), float(g[f"{tag}_ssz"])
+    E, d = y0.shape
+
+    class Env(LinearizedHOVecEnv):
+        def reset_states(self):
+            return torch.as_tensor(y0, device="cuda")
+
+        def get_reward(self):
+            V = self.Observations[..., 4:].reshape(*self.Observations.shape[:-1], 4, 4)
+            return -torch.diagonal(V, dim1=-2, dim2=-1).sum(-1)
+
+        # torch hooks for the stage-callback mode (same formulas as oracle/systems.py)
+        def get_mode_rates(self, t, modes, args):
+            P, u = self._P, args[0][:, 0]
+            a, b = modes[:, 0], modes[:, 1]
+            da = -(P[:, 0] / 2 - 1j * P[:, 3]) * a + 1j * P[:, 4] * a * (b + b.conj()) + P[:, 6] * (1.0 + u)
+            db = -(P[:, 1] / 2 + 1j * P[:, 2]) * b + 1j * P[:, 4] * (a.real ** 2 + a.imag ** 2)
+            return torch.stack([da, db], dim=1)
+
+        def get_A(self, t, modes, args):
+            P = self._P
+            a, b = modes[:, 0], modes[:, 1]
+            Dl, GR, GI = P[:, 3] + 2 * P[:, 4] * b.real, 2 * P[:, 4] * a.real, 2 * P[:, 4] * a.imag
+            A = torch.zeros((E, 4, 4), dtype=torch.float64, device="cuda")
+            A[:, 0, 0] = A[:, 1, 1] = -P[:, 0] / 2
+            A[:, 2, 2] = A[:, 3, 3] = -P[:, 1] / 2
+            A[:, 0, 1], A[:, 1, 0], A[:, 0, 2], A[:, 1, 2] = -Dl, Dl, -GI, GR
+            A[:, 2, 3], A[:, 3, 2], A[:, 3, 0], A[:, 3, 1] = P[:, 2], -P[:, 2], GR, GI
+            return A
+
+        def get_D(self, t, modes, args):
+            P = self._P
+            D = torch.zeros((E, 4, 4), dtype=torch.float64, device="cuda")
+            D[:, 0, 0] = D[:, 1, 1] = P[:, 0] / 2
+            D[:, 2, 2] = D[:, 3, 3] = P[:, 1] * (P[:, 5] + 0.5)
+            return D
+
+    env = Env(name="optomech", desc="test", params={}, num_modes=2, num_quads=4, t_norm_max=(S + K) * ssz + ssz / 2,
+              t_norm_ssz=ssz, t_norm_mul=1.0, n_envs=E, n_observations=d, n_properties=0, n_actions=1,
+              action_maximums=[1.0], action_interval=K, data_idxs=[0, 1, 2, 2 + d], cache_all_data=False,
+              dir_prefix="/tmp/qrl_test", ode_method=method, ode_atol=atol, ode_rtol=rtol,
+              **(dict(system="optomech", system_params=p) if fused else {}), **kw)
+    env._P = torch.as_tensor(p, device="cuda")
+    return env
+
+
+def test_lho_vec_env_matches_reference_vec_env(native, cuda, golden_dir):
+    """Fused LinearizedHOVecEnv (dopri5, tight) vs the reference's LinearizedHOVecEnv + SciPy dop853 (fixture G1):
+    States, per-step reward and the packed ``data`` cache produced by BaseSB3Env.update_data."""
+    g = np.load(os.path.join(golden_dir, "lyap_optomech.npz"))
+    tag = "E5"
+    env = _optomech_env(g, tag, "dopri5", atol=1e-14, rtol=1e-13)
+    K, S = int(g[f"{tag}_K"]), int(g[f"{tag}_S"])
+    env.reset()
+    ref = g[f"{tag}_States_dop853_tight"]
+    scale = np.abs(ref).max(axis=(0, 1)) + 1e-300
+    for a in range(S // K):
+        obs, rew, done, _ = env.step(g[f"{tag}_actions"][a])
+        np.testing.assert_allclose(rew.cpu().numpy(), g[f"{tag}_Reward_dop853_tight"][a], rtol=1e-9)
+        assert np.max(np.abs(env.States.cpu().numpy() - ref[a * K:(a + 1) * K + 1]) / scale) < 1e-10
+        assert done == [False] * env.n_envs
+    np.testing.assert_allclose(env.data[:, :S + 1], g[f"{tag}_data_dop853_tight"], rtol=1e-9, atol=1e-10)
+    env.close()
+
+
+def test_lho_vec_env_stage_callback_equals_fused(native, cuda, golden_dir):
+    """The same env with torch hooks (no device functor; RK4 stages call ``func``) == the fused kernel == fixture G2."""
+    g = np.load(os.path.join(golden_dir, "lyap_optomech.npz"))
+    tag = "E5"
+    fused, cb = _optomech_env(g, tag, "rk4"), _optomech_env(g, tag, "rk4", fused=False)
+    fused.reset(); cb.reset()
+    K = int(g[f"{tag}_K"])
+    for a in range(3):
+        of, rf, _, _ = fused.step(g[f"{tag}_actions"][a])
+        oc, rc, _, _ = cb.step(g[f"{tag}_actions"][a])
+        torch.testing.assert_close(of, oc, rtol=1e-11, atol=1e-13)
+        torch.testing.assert_close(rf, rc, rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(fused.States.cpu().numpy(), g[f"{tag}_States_rk4_reffunc"][a * K:(a + 1) * K + 1],
+                                   rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(fused.data, cb.data, rtol=1e-11, atol=1e-13)
+    fused.close(); cb.close()
+
+
+def test_lho_vec_env_evolve_tail_interval_and_noise(native, cuda, golden_dir):
+    """``evolve`` (actions = action_maximums, base.py:1382-1449) with an episode length that is not a multiple of the
+    action interval (tail slice, base.py:455) and in-kernel measurement noise."""
+    g = np.load(os.path.join(golden_dir, "lyap_optomech.npz"))
+    from quantrl_b200.envs import LinearizedHOVecEnv
+    p, y0 = g["E5_p"], g["E5_y0"]
+
+    class Env(LinearizedHOVecEnv):
+        def reset_states(self):
+            return torch.as_tensor(y0, device="cuda")
+
+        def get_reward(self):
+            return -self.Observations[..., 4]
+
+    env = Env(name="optomech", desc="t", params={}, num_modes=2, num_quads=4, t_norm_max=0.255, t_norm_ssz=0.01,
+              t_norm_mul=2.0, n_envs=5, n_observations=20, n_properties=0, n_actions=1, action_maximums=[0.5],
+              action_interval=10, data_idxs=[0, -1], cache_all_data=False, dir_prefix="/tmp/qrl_test",
+              system="optomech", system_params=p, observation_stds=[1e-3] * 20, seed=3)
+    assert env.shape_T == (26,) and env.action_steps == 3 and env.t_ssz == 0.02
+    env.evolve(close=False)
+    assert env.t_idx == 25 and env.States.shape[0] == 6          # the tail interval has 5 sub-steps
+    d = env.data
+    np.testing.assert_allclose(d[0, :, 0], np.arange(26) * 0.02, rtol=0, atol=1e-15)
+    assert np.all(d[:, 21:, 1] == d[:, 25:26, 1]) and len(env.data_rewards) == 1
+    noise = (env.Observations - env.States).flatten()
+    assert 0.5e-3 < noise.std().item() < 2e-3
+    env.close()
