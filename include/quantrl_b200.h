@@ -19,12 +19,17 @@
  *
  * RNG stream (in-kernel noise, `rng_mode == QRL_RNG_PHILOX`), restated by oracle/em_oracle.py:philox_normals
  *   (x0,x1,x2,x3) = Philox4x32-10(counter = (tau, episode, env_global, comp), key = (seed lo32, seed hi32))
- *   d1 = bits(0x3FF<<52 | x1<<20 | x0>>12) in [1,2);  u1 = 2 - d1 in (0,1]
- *   d2 = bits(0x3FF<<52 | x3<<20 | x2>>12) in [1,2);  u2 = d2 - 1 in [0,1)
- *   r = sqrt(-2 ln u1);  z0 = r sin(2 pi u2);  z1 = r cos(2 pi u2)
- *   z0 -> Wiener increment of sub-step tau -> tau+1 (scaled by sqrt(t_ssz));  z1 -> measurement noise at time
- *   index tau (scaled by obs_std).  `env_global = env_offset + local env index` makes results independent of how
- *   environments are sharded over GPUs.
+ *   u1 = 2 - bits(0x3FF<<52 | x1<<20 | x0>>12 | 1) in (0,1);  r = sqrt(-2 ln u1)
+ *   B = x3<<20 | x2>>12 (52 bits);  alpha = (B mod 2^49) / 2^49 * pi/4;  (s, c) = (sin alpha, cos alpha);
+ *   bit 49 of B swaps (s, c), bit 50 negates the first, bit 51 the second (the octant symmetries: a uniform direction);
+ *   z0 = r s;  z1 = r c     (Box-Muller; ln/sqrt/sin/cos are evaluated by polynomial kernels accurate to < 1e-15)
+ *   Stochastic path (qrl_em_step): the call with tau = global sub-step index k gives z0 -> Wiener increment of sub-step
+ *   k -> k+1 (scaled by sqrt(t_ssz)) and z1 -> measurement noise of time index k+1 (scaled by obs_std), so every
+ *   trajectory row after the first depends on exactly one call; the measurement noise of time index 0 (the reset
+ *   observation) is z1 of the call with tau = 0xFFFFFFFF.
+ *   Deterministic path (qrl_ode_step): measurement noise of time index t, component d = z[d & 1] of the call with
+ *   counter (t, episode, env_global, 0x10000 + d/2).
+ *   `env_global = env_offset + local env index` makes results independent of how environments are sharded over GPUs.
  */
 #ifndef QUANTRL_B200_H
 #define QUANTRL_B200_H
@@ -117,7 +122,7 @@ typedef struct qrl_em_args {
     double*  obs_last;       /* (E,n) = Obs[K]; or NULL */
 
     int32_t  reward_kind;    /* QRL_REWARD_* */
-    int32_t  _pad1;
+    int32_t  flags;          /* QRL_EM_* bits */
     const double* reward_w;  /* (n,) weights */
     double*  reward;         /* (K+1,E) or NULL */
     double*  reward_last;    /* (E,) = Reward[K]; or NULL */
@@ -125,7 +130,20 @@ typedef struct qrl_em_args {
 
     double*  obs_minmax;     /* [min, max] running reduction (caller initialises to [+inf, -inf]); or NULL */
     int32_t* nan_flag;       /* set to 1 if any state is NaN/Inf; or NULL */
+
+    /* fused trajectory-cache rows (BaseSB3Env.update_data, quantrl/envs/base.py:1314-1372), n_properties == 0 only:
+     *   packed[e, t, j] = column sel_idxs[j] of [T_step[t], actions[e,:], Obs[t,e,:], rewards_cum[e] (after this step)]
+     * requires reward_kind != QRL_REWARD_NONE and rewards_cum != NULL.  NULL = no packing. */
+    double*  packed;         /* element [e,t,j] at packed[e*packed_stride_e + t*n_sel + j], t = 0..K */
+    int64_t  packed_stride_e;
+    const double*  T_step;   /* (K+1,) */
+    const double*  actions;  /* (E,n_actions) */
+    const int32_t* sel_idxs; /* (n_sel,) indices into the n_data = 1 + n_actions + n + 1 columns (negative = from end) */
+    int32_t  n_actions;
+    int32_t  n_sel;
 } qrl_em_args;
+
+#define QRL_EM_FORCE_GENERIC 1  /* flags: always use the generic lane-per-component kernel (A/B testing) */
 
 QRL_API int qrl_em_step(const qrl_em_args* args, void* stream);
 

@@ -154,28 +154,54 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
-def _unit_12(hi, lo):
-    """52 random mantissa bits -> double in [1, 2): bits = 0x3FF<<52 | (hi<<20) | (lo>>12)."""
-    bits = (np.uint64(0x3FF) << np.uint64(52)) | (hi << np.uint64(20)) | (lo >> np.uint64(12))
+def _bits_to_double(hi20, lo32):
+    """double with exponent 0 (value in [1,2)) from a 20-bit high and a 32-bit low mantissa word."""
+    bits = (np.uint64(0x3FF) << np.uint64(52)) | (hi20 << np.uint64(32)) | lo32
     return bits.view(np.float64)
 
 
 def philox_normals(seed, episode, tau, env, comp):
-    """Two N(0,1) per (tau, episode, env, comp): z0 drives the Wiener increment tau -> tau+1, z1 is the
-    measurement noise at time index tau.  counter = (tau, episode, env, comp), key = (seed lo, seed hi)."""
+    """Two N(0,1) per counter (tau, episode, env, comp), key = (seed lo, seed hi): the stream of
+    include/quantrl_b200.h ("RNG stream"), evaluated with NumPy's libm instead of the kernel's polynomial kernels.
+
+      u1 = 2 - bits(0x3FF<<52 | x1<<20 | x0>>12 | 1)   in (0,1);   radius = sqrt(-2 ln u1)
+      B  = x3<<20 | x2>>12 (52 bits);  alpha = (B mod 2^49) / 2^49 * pi/4;  (s, c) = (sin alpha, cos alpha)
+      bit 49 of B swaps (s, c), bit 50 negates the first, bit 51 the second;  z0 = radius * s,  z1 = radius * c
+    """
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     x0, x1, x2, x3 = philox4x32_10(tau, episode, env, comp, seed & 0xFFFFFFFF, seed >> 32)
-    u1 = 2.0 - _unit_12(x1, x0)          # (0, 1]
-    u2 = _unit_12(x3, x2) - 1.0          # [0, 1)
-    r = np.sqrt(-2.0 * np.log(u1))
-    ang = 2.0 * np.pi * u2
-    return r * np.sin(ang), r * np.cos(ang)
+    u64 = np.uint64
+    d1 = _bits_to_double(x1 >> u64(12), ((x1 << u64(20)) & _MASK) | (x0 >> u64(12)) | u64(1))
+    radius = np.sqrt(-2.0 * np.log(2.0 - d1))
+    mant_hi = ((x3 << u64(3)) & _MASK) >> u64(12)
+    mant_lo = ((x3 << u64(23)) & _MASK) | ((x2 >> u64(9)) & u64(0xFFFFFFF8))
+    alpha = (_bits_to_double(mant_hi, mant_lo) - 1.0) * (np.pi / 4)
+    sn, cs = np.sin(alpha), np.cos(alpha)
+    swap = ((x3 >> u64(29)) & u64(1)) == 1
+    s0, c0 = np.where(swap, cs, sn), np.where(swap, sn, cs)
+    s0 = np.where(((x3 >> u64(30)) & u64(1)) == 1, -s0, s0)
+    c0 = np.where(((x3 >> u64(31)) & u64(1)) == 1, -c0, c0)
+    return radius * s0, radius * c0
 
 
 def philox_noise_block(seed, episode, t_idx, K, env0, E, n):
-    """(z_w (K,E,n), z_obs (K+1,E,n)) for the interval starting at global time index ``t_idx``."""
-    tau = np.arange(t_idx, t_idx + K + 1, dtype=np.uint64).reshape(-1, 1, 1)
+    """(z_w (K,E,n), z_obs (K+1,E,n)) for the interval starting at global time index ``t_idx``.
+
+    Stochastic-path convention: the call with tau = k gives z0 -> Wiener increment of sub-step k -> k+1 and
+    z1 -> measurement noise of time index k+1; the measurement noise of time index 0 is z1 of tau = 0xFFFFFFFF."""
     env = (np.uint64(env0) + np.arange(E, dtype=np.uint64)).reshape(1, -1, 1)
     comp = np.arange(n, dtype=np.uint64).reshape(1, 1, -1)
+    first = np.uint64(t_idx - 1) if t_idx > 0 else np.uint64(0xFFFFFFFF)
+    tau = np.concatenate([[first], np.arange(t_idx, t_idx + K, dtype=np.uint64)]).reshape(-1, 1, 1)
     z0, z1 = philox_normals(seed, episode, tau, env, comp)
-    return z0[:K], z1
+    return z0[1:], z1
+
+
+def philox_obs_noise_ode(seed, episode, t_idx, K, env0, E, d):
+    """Deterministic-path measurement noise (K+1,E,d): component c of time index t = z[c & 1] of the call with
+    counter (t, episode, env, 0x10000 + c // 2)."""
+    tau = np.arange(t_idx, t_idx + K + 1, dtype=np.uint64).reshape(-1, 1, 1)
+    env = (np.uint64(env0) + np.arange(E, dtype=np.uint64)).reshape(1, -1, 1)
+    comp = np.arange(d, dtype=np.uint64).reshape(1, 1, -1)
+    z0, z1 = philox_normals(seed, episode, tau, env, np.uint64(0x10000) + comp // np.uint64(2))
+    return np.where(comp % np.uint64(2) == 1, z1, z0)

@@ -13,6 +13,7 @@ RNG_FED, RNG_PHILOX = 0, 1
 REWARD_NONE, REWARD_NEG_WSQ_OBS, REWARD_NEG_WSQ_STATE = 0, 1, 2
 SYS_OPTOMECH, SYS_KERR_CHAIN, SYS_CONST_AD = 1, 2, 3
 ODE_RK4, ODE_DOPRI5 = 0, 1
+EM_FORCE_GENERIC = 1
 
 _dp = C.c_void_p  # device pointers travel as integers
 
@@ -30,8 +31,10 @@ class EmArgs(C.Structure):
         ("seed", C.c_uint64), ("episode", C.c_uint32), ("_pad0", C.c_uint32), ("t_idx", C.c_int64),
         ("env_offset", C.c_int64), ("obs_std", _dp), ("obs_std_stride_e", C.c_int64),
         ("x0", _dp), ("states", _dp), ("observations", _dp), ("x_last", _dp), ("obs_last", _dp),
-        ("reward_kind", C.c_int32), ("_pad1", C.c_int32), ("reward_w", _dp), ("reward", _dp), ("reward_last", _dp),
+        ("reward_kind", C.c_int32), ("flags", C.c_int32), ("reward_w", _dp), ("reward", _dp), ("reward_last", _dp),
         ("rewards_cum", _dp), ("obs_minmax", _dp), ("nan_flag", _dp),
+        ("packed", _dp), ("packed_stride_e", C.c_int64), ("T_step", _dp), ("actions", _dp), ("sel_idxs", _dp),
+        ("n_actions", C.c_int32), ("n_sel", C.c_int32),
     ]
 
 

@@ -1,4 +1,5 @@
-// Fused Euler–Maruyama action interval (qrl_em_step) — sm_100a.
+// Fused Euler–Maruyama action interval (qrl_em_step) — sm_100a: dispatcher + the generic lane-per-component kernel
+// (any n <= 16, time-dependent coefficients, K = 0 reset rows).  The tiled fast path lives in em_tile_kernel.cu.
 //
 // One launch replaces K iterations of the reference's Python loop
 //   Y[i+1] = (I + A dt) @ Y[i] + n * Ws[t_idx+i]            quantrl/envs/stochastic.py:218-242
@@ -16,7 +17,7 @@
 namespace qrl {
 
 template <int LPE>
-__global__ void __launch_bounds__(128) em_step_kernel(const qrl_em_args a) {
+__global__ void __launch_bounds__(128) em_step_kernel(const qrl_em_args a, const PhiloxKeys keys) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int e = tid / LPE;
     const int c = tid % LPE;
@@ -55,22 +56,20 @@ __global__ void __launch_bounds__(128) em_step_kernel(const qrl_em_args a) {
 
     double lo = INFINITY, hi = -INFINITY;
     double r_last = 0.0, obs = 0.0;
+    // measurement noise of row 0 = time index t_idx: z1 of the previous sub-step's call (or of the reset call)
+    double v = 0.0;
+    if (philox && a.obs_std) {
+        double z0, z1;
+        const uint32_t tau = a.t_idx > 0 ? (uint32_t)(a.t_idx - 1) : 0xFFFFFFFFu;
+        philox_normal2(keys, tau, a.episode, env_g, (uint32_t)c, z0, z1);
+        v = __dmul_rn(std_c, z1);
+    }
 
 #pragma unroll 2
     for (int i = 0; i <= K; ++i) {
-        // ---- noise for time index tau = t_idx + i ----
-        double w, v;
-        if (philox) {
-            double z0, z1;
-            philox_normal2(a.seed, (uint32_t)(a.t_idx + i), a.episode, env_g, (uint32_t)c, z0, z1);
-            w = sqrt_dt * z0;
-            v = std_c * z1;
-        } else {
-            w = (i < K) ? a.W[(int64_t)i * row + off] : 0.0;
-            v = a.obs_noise ? a.obs_noise[(int64_t)i * row + off] : 0.0;
-        }
+        if (!philox) v = a.obs_noise ? a.obs_noise[(int64_t)i * row + off] : 0.0;
         // ---- outputs of row i ----
-        obs = x + v;
+        obs = __dadd_rn(x, v);
         if (live) {
             if (a.states) a.states[(int64_t)i * row + off] = x;
             if (a.observations) a.observations[(int64_t)i * row + off] = obs;
@@ -86,6 +85,16 @@ __global__ void __launch_bounds__(128) em_step_kernel(const qrl_em_args a) {
             if (live && c == 0 && a.reward) a.reward[(int64_t)i * E + e] = r_last;
         }
         if (i == K) break;
+        // ---- noise of sub-step t_idx + i: Wiener increment now, measurement noise of the next row ----
+        double w;
+        if (philox) {
+            double z0, z1;
+            philox_normal2(keys, (uint32_t)(a.t_idx + i), a.episode, env_g, (uint32_t)c, z0, z1);
+            w = __dmul_rn(sqrt_dt, z0);
+            v = __dmul_rn(std_c, z1);
+        } else {
+            w = a.W[(int64_t)i * row + off];
+        }
         // ---- recurrence ----
         if (coeffs_vary && i > 0) load_coeffs(i);
         double acc = 0.0;
@@ -114,9 +123,11 @@ static int launch_em(const qrl_em_args& a, cudaStream_t st) {
     const int threads = 128;
     const int64_t total = (int64_t)a.n_envs * LPE;
     const int blocks = (int)((total + threads - 1) / threads);
-    em_step_kernel<LPE><<<blocks, threads, 0, st>>>(a);
+    em_step_kernel<LPE><<<blocks, threads, 0, st>>>(a, make_philox_keys(a.seed));
     return after_launch("em_step_kernel");
 }
+
+int em_tile_launch(const qrl_em_args& a, cudaStream_t st);  // em_tile_kernel.cu
 
 }  // namespace qrl
 
@@ -135,10 +146,29 @@ extern "C" int qrl_em_step(const qrl_em_args* args, void* stream) {
     QRL_REQUIRE(a.rng_mode != QRL_RNG_FED || a.K == 0 || a.W != nullptr, "qrl_em_step: fed mode needs W");
     QRL_REQUIRE(a.reward_kind == QRL_REWARD_NONE || a.reward_w != nullptr, "qrl_em_step: reward_w is NULL");
     QRL_REQUIRE(a.t_idx >= 0 && a.env_offset >= 0, "qrl_em_step: negative t_idx / env_offset");
+    if (a.packed) {
+        QRL_REQUIRE(a.reward_kind != QRL_REWARD_NONE && a.rewards_cum != nullptr,
+                    "qrl_em_step: packed rows need a fused reward functor and rewards_cum");
+        QRL_REQUIRE(a.T_step && a.sel_idxs && a.n_sel >= 1 && a.n_actions >= 0 && (a.n_actions == 0 || a.actions),
+                    "qrl_em_step: packed rows need T_step, actions and sel_idxs");
+        QRL_REQUIRE(a.packed_stride_e >= (int64_t)(a.K + 1) * a.n_sel, "qrl_em_step: packed_stride_e too small");
+    }
     cudaStream_t st = (cudaStream_t)stream;
-    if (a.n <= 1) return launch_em<1>(a, st);
-    if (a.n <= 2) return launch_em<2>(a, st);
-    if (a.n <= 4) return launch_em<4>(a, st);
-    if (a.n <= 8) return launch_em<8>(a, st);
-    return launch_em<16>(a, st);
+    const bool tiled = a.K >= 1 && a.n <= 8 && a.A_stride_k == 0 && a.nz_stride_k == 0 && !(a.flags & QRL_EM_FORCE_GENERIC);
+    if (tiled) return em_tile_launch(a, st);
+    QRL_REQUIRE(!a.packed || a.observations != nullptr, "qrl_em_step: the generic kernel packs from the observations block");
+    int rc;
+    if (a.n <= 1) rc = launch_em<1>(a, st);
+    else if (a.n <= 2) rc = launch_em<2>(a, st);
+    else if (a.n <= 4) rc = launch_em<4>(a, st);
+    else if (a.n <= 8) rc = launch_em<8>(a, st);
+    else rc = launch_em<16>(a, st);
+    if (rc != 0 || !a.packed) return rc;
+    // generic path: the cache rows are written by the pack kernel right behind the integration (same stream)
+    qrl_pack_args p;
+    memset(&p, 0, sizeof(p));
+    p.n_envs = a.n_envs; p.dim = a.K + 1; p.n_actions = a.n_actions; p.n_obs = a.n; p.n_props = 0; p.n_sel = a.n_sel;
+    p.T_step = a.T_step; p.actions = a.actions; p.observations = a.observations; p.rewards_cum = a.rewards_cum;
+    p.idxs = a.sel_idxs; p.selected = a.packed; p.selected_stride_e = a.packed_stride_e;
+    return qrl_pack_rows(&p, stream);
 }

@@ -355,6 +355,9 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
             self.rewards += self._reward_last
         if not self.store_trajectory:
             return  # learner-only mode: no (K+1,E,n) blocks exist, nothing to pack
+        if getattr(self, "_packed_by_kernel", False):
+            self._data_host = None
+            return  # the integration kernel already wrote this interval's cache rows
         a = N.PackArgs()
         a.n_envs, a.dim, a.n_actions, a.n_obs, a.n_props = self.n_envs, dim, self.n_actions, self.n_observations, self.n_properties
         a.n_sel = len(self.data_idxs)

@@ -42,6 +42,8 @@ class LinearVecEnv(BaseVecEnv):
         self.name, self.desc = name, desc
         self.params = {key: params.get(key, val) for key, val in self.default_params.items()}
         self.is_A_time_dependent = bool(kwargs.pop("is_A_time_dependent", False))
+        self.fuse_cache_rows = bool(kwargs.pop("fuse_cache_rows", True))
+        self.force_generic_kernel = bool(kwargs.pop("force_generic_kernel", False))
         self.reward_functor = kwargs.pop("reward_functor", None)
         reward_weights = kwargs.pop("reward_weights", None)
         assert self.reward_functor in _REWARD_KINDS, f"``reward_functor`` should be one of {list(_REWARD_KINDS)}"
@@ -154,6 +156,19 @@ class LinearVecEnv(BaseVecEnv):
             a.rewards_cum = N.ptr(self.rewards)
         a.obs_minmax = N.ptr(self._minmax)
         a.nan_flag = N.ptr(self._nan)
+        self._packed_by_kernel = False
+        if (self._reward_fused and K > 0 and self.n_properties == 0 and self.store_trajectory
+                and not self.cache_all_data and self.fuse_cache_rows):
+            # the (E, shape_T, n_sel) ``data`` cache rows of this interval are written by the same launch
+            n_sel = len(self.data_idxs)
+            a.packed = N.ptr(self._data_dev) + 8 * self.t_idx * n_sel
+            a.packed_stride_e = self.shape_T[0] * n_sel
+            a.T_step = N.ptr(self.T) + 8 * self.t_idx
+            a.actions, a.n_actions = N.ptr(self.actions), self.n_actions
+            a.sel_idxs, a.n_sel = N.ptr(self._sel_idxs), n_sel
+            self._packed_by_kernel = True
+        if self.force_generic_kernel:
+            a.flags = N.EM_FORCE_GENERIC
         ev = getattr(self, "_em_events", None)
         if ev is not None and K > 0:  # live per-launch timing on the launch stream (bench.py roofline)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -12,7 +12,7 @@ def dev(x, device="cuda"):
 
 
 def em_step(x0, A, nz, t_ssz, K, W=None, obs_noise=None, philox=None, obs_std=None, reward_kind=N.REWARD_NONE,
-            reward_w=None, rewards_cum=None, traj=True):
+            reward_w=None, rewards_cum=None, traj=True, flags=0, pack=None):
     """Run qrl_em_step once.  x0 (E,n) numpy/torch; A (n,n)|(E,n,n)|(K,E,n,n); nz (n,)|(E,n)|(K,E,n).
     philox = dict(seed, episode, t_idx, env_offset).  Returns dict of torch tensors."""
     x0 = dev(x0).double()
@@ -59,6 +59,17 @@ def em_step(x0, A, nz, t_ssz, K, W=None, obs_noise=None, philox=None, obs_std=No
         a.reward_w = N.ptr(reward_w)
         a.reward, a.reward_last, a.rewards_cum = N.ptr(out["reward"]), N.ptr(out["reward_last"]), N.ptr(out["rewards_cum"])
     a.obs_minmax, a.nan_flag = N.ptr(out["minmax"]), N.ptr(out["nan"])
+    a.flags = flags
+    if pack is not None:   # dict(T_step (K+1,), actions (E,na), idxs list, rows_total, row0)
+        T_step, actions = dev(pack["T_step"]).double(), dev(pack["actions"]).double().reshape(E, -1).contiguous()
+        idxs = torch.as_tensor(np.asarray(pack["idxs"], dtype=np.int32), device="cuda")
+        rows_total, row0 = pack.get("rows_total", K + 1), pack.get("row0", 0)
+        out["packed"] = torch.full((E, rows_total, len(pack["idxs"])), float("nan"), dtype=torch.float64, device="cuda")
+        keep += [T_step, actions, idxs]
+        a.packed = N.ptr(out["packed"]) + 8 * row0 * len(pack["idxs"])
+        a.packed_stride_e = rows_total * len(pack["idxs"])
+        a.T_step, a.actions, a.n_actions = N.ptr(T_step), N.ptr(actions), actions.shape[1]
+        a.sel_idxs, a.n_sel = N.ptr(idxs), len(pack["idxs"])
     N.em_step(a)
     torch.cuda.synchronize()
     return out

@@ -208,3 +208,48 @@ def test_invalid_arguments_raise(native, cuda):
         N.em_step(a)
     with pytest.raises(N.NativeError, match="CUDA tensor"):
         N.ptr(torch.zeros(3))
+
+
+@pytest.mark.parametrize("E,n,K", [(4096, 4, 100), (300, 8, 37), (65, 3, 12), (1000, 2, 64), (33, 5, 7), (5000, 4, 20)])
+def test_tiled_kernel_equals_generic_kernel_bitwise(native, cuda, E, n, K):
+    """The tiled warp-specialised kernel and the generic lane-per-component kernel run the same operations in the
+    same order: States/Observations must agree bit for bit (Philox and fed), rewards to rounding."""
+    rng = np.random.default_rng(E + n)
+    A = 0.4 * rng.standard_normal((E, n, n))
+    nz = rng.uniform(0.01, 0.1, (E, n))
+    std = rng.uniform(0.01, 0.02, (E, n))
+    x0 = rng.standard_normal((E, n))
+    w = rng.uniform(0.5, 1.5, n)
+    for mode in ("philox", "fed"):
+        kw = dict(philox=dict(seed=99, episode=1, t_idx=300, env_offset=17), obs_std=std) if mode == "philox" else \
+            dict(W=0.1 * rng.standard_normal((K, E, n)), obs_noise=0.01 * rng.standard_normal((K + 1, E, n)))
+        t = em_step(x0, A, nz, 0.01, K, reward_kind=N.REWARD_NEG_WSQ_OBS, reward_w=w, **kw)
+        g = em_step(x0, A, nz, 0.01, K, reward_kind=N.REWARD_NEG_WSQ_OBS, reward_w=w, flags=N.EM_FORCE_GENERIC, **kw)
+        for key in ("states", "observations", "x_last", "obs_last", "minmax"):
+            assert torch.equal(t[key], g[key]), (mode, key)
+        for key in ("reward", "reward_last", "rewards_cum"):
+            torch.testing.assert_close(t[key], g[key], rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("flags", [0, N.EM_FORCE_GENERIC])
+@pytest.mark.parametrize("idxs", [[0, 1, 2, 3, 4, 5, 6], [-1], [0, 3, -1, 1]])
+def test_fused_cache_rows_match_oracle_pack_rows(native, cuda, flags, idxs):
+    """Packed rows written by the integration launch == oracle pack_rows (BaseSB3Env.update_data layout), written
+    at a row offset of a larger (E, shape_T, n_sel) cache like the env does."""
+    rng = np.random.default_rng(21)
+    E, n, K = 77, 4, 23
+    A = 0.4 * rng.standard_normal((E, n, n))
+    nz = rng.uniform(0.01, 0.1, (E, n))
+    x0 = rng.standard_normal((E, n))
+    W, ON = 0.1 * rng.standard_normal((K, E, n)), 0.01 * rng.standard_normal((K + 1, E, n))
+    T_step = 0.5 + np.arange(K + 1) * 0.01
+    acts = rng.uniform(-1, 1, (E, 1))
+    cum0 = rng.standard_normal(E)
+    out = em_step(x0, A, nz, 0.01, K, W=W, obs_noise=ON, reward_kind=N.REWARD_NEG_WSQ_OBS, reward_w=np.ones(n),
+                  rewards_cum=cum0, flags=flags, pack=dict(T_step=T_step, actions=acts, idxs=idxs, rows_total=K + 11, row0=5))
+    obs = eo.em_interval_vec(x0, A, nz, W, 0.01) + ON
+    cum = cum0 - np.sum(obs[-1] ** 2, -1)
+    full = eo.pack_rows(T_step, acts, obs, None, cum)
+    got = out["packed"].cpu().numpy()
+    np.testing.assert_allclose(got[:, 5:5 + K + 1], full[:, :, idxs], rtol=1e-12, atol=1e-14)
+    assert np.isnan(got[:, :5]).all() and np.isnan(got[:, 5 + K + 1:]).all()   # nothing outside the block is touched
