@@ -143,7 +143,9 @@ typedef struct qrl_em_args {
     int32_t  n_sel;
 } qrl_em_args;
 
-#define QRL_EM_FORCE_GENERIC 1  /* flags: always use the generic lane-per-component kernel (A/B testing) */
+#define QRL_EM_FORCE_GENERIC 1   /* flags: always use the generic lane-per-component kernel (A/B testing) */
+#define QRL_EM_FORCE_TILED   16  /* flags: use the tiled kernel whenever it supports the case, whatever the batch size */
+/* flag bits 2, 4, 8 are diagnostics of the tiled kernel (skip produce / recurrence / output stage); results invalid */
 
 QRL_API int qrl_em_step(const qrl_em_args* args, void* stream);
 
@@ -229,6 +231,8 @@ QRL_API int qrl_pack_rows(const qrl_pack_args* args, void* stream);
  * ------------------------------------------------------------------------------------------------------------ */
 /* dependent-free DFMA stream on every SM: returns achieved FP64 TFLOP/s (FMA = 2 flop) in *tflops */
 QRL_API int qrl_measure_fp64_peak(int iters, double* tflops);
+/* one warp, one dependent DFMA chain: returns the FP64 FMA pipeline latency in SM cycles */
+QRL_API int qrl_measure_fp64_latency(double* cycles_per_dfma);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ RNG_FED, RNG_PHILOX = 0, 1
 REWARD_NONE, REWARD_NEG_WSQ_OBS, REWARD_NEG_WSQ_STATE = 0, 1, 2
 SYS_OPTOMECH, SYS_KERR_CHAIN, SYS_CONST_AD = 1, 2, 3
 ODE_RK4, ODE_DOPRI5 = 0, 1
-EM_FORCE_GENERIC = 1
+EM_FORCE_GENERIC, EM_FORCE_TILED = 1, 16
 
 _dp = C.c_void_p  # device pointers travel as integers
 
@@ -73,6 +73,7 @@ SYMBOLS = {
     "qrl_ode_step": (C.c_int, [C.POINTER(OdeArgs), C.c_void_p]),
     "qrl_pack_rows": (C.c_int, [C.POINTER(PackArgs), C.c_void_p]),
     "qrl_measure_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    "qrl_measure_fp64_latency": (C.c_int, [C.POINTER(C.c_double)]),
 }
 
 _lib = None
@@ -82,11 +83,12 @@ def lib():
     """Load (once) and return the shared library; raises NativeError if it has not been built."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("QRL_B200_LIB", LIB_PATH)   # development override (kernel variants)
+        if not os.path.exists(path):
             raise NativeError(
-                f"{LIB_PATH} is missing: build it with `python -m quantrl_b200.build` (nvcc, sm_100a). "
+                f"{path} is missing: build it with `python -m quantrl_b200.build` (nvcc, sm_100a). "
                 "quantrl_b200 has no CPU or PyTorch fallback for its hot path.")
-        handle = C.CDLL(LIB_PATH)
+        handle = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(handle, name)  # AttributeError if the .so does not export a declared symbol
             fn.restype, fn.argtypes = res, args
@@ -138,4 +140,10 @@ def launch_count() -> int:
 def measure_fp64_peak(iters=4096) -> float:
     out = C.c_double(0.0)
     check(lib().qrl_measure_fp64_peak(int(iters), C.byref(out)), "qrl_measure_fp64_peak")
+    return float(out.value)
+
+
+def measure_fp64_latency() -> float:
+    out = C.c_double(0.0)
+    check(lib().qrl_measure_fp64_latency(C.byref(out)), "qrl_measure_fp64_latency")
     return float(out.value)

@@ -20,6 +20,16 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, 
     const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
     if (s == 123.456) out[0] = s;  // never true; keeps the chains alive
 }
+// one warp, one dependent DFMA chain: cycles per dependent FP64 FMA (pipeline latency)
+__global__ void dfma_latency_kernel(double* out, long long* cycles, int n) {
+    double a = 1.0 + threadIdx.x * 1e-9;
+    const double m = 0.999999, b = 1e-9;
+    long long t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < n; ++i) a = fma(a, m, b);
+    long long t1 = clock64();
+    if (threadIdx.x == 0) { cycles[0] = t1 - t0; out[0] = a; }
+}
 }  // namespace qrl
 
 extern "C" int qrl_abi_version(void) { return QRL_ABI_VERSION; }
@@ -31,6 +41,27 @@ extern "C" int qrl_device_count(void) {
     return n;
 }
 extern "C" int qrl_release(void) { return 0; }
+
+extern "C" int qrl_measure_fp64_latency(double* cycles_per_dfma) {
+    using namespace qrl;
+    QRL_REQUIRE(cycles_per_dfma != nullptr, "qrl_measure_fp64_latency: NULL output");
+    double* d_out = nullptr;
+    long long* d_cyc = nullptr;
+    QRL_CUDA(cudaMalloc(&d_out, sizeof(double)));
+    QRL_CUDA(cudaMalloc(&d_cyc, sizeof(long long)));
+    const int n = 1 << 14;
+    long long h = 0;
+    for (int rep = 0; rep < 2; ++rep) {
+        dfma_latency_kernel<<<1, 32>>>(d_out, d_cyc, n);
+        int rc = after_launch("dfma_latency_kernel");
+        if (rc) return rc;
+        QRL_CUDA(cudaMemcpy(&h, d_cyc, sizeof(h), cudaMemcpyDeviceToHost));
+    }
+    *cycles_per_dfma = (double)h / n;
+    cudaFree(d_out);
+    cudaFree(d_cyc);
+    return 0;
+}
 
 extern "C" int qrl_measure_fp64_peak(int iters, double* tflops) {
     using namespace qrl;

@@ -154,7 +154,12 @@ extern "C" int qrl_em_step(const qrl_em_args* args, void* stream) {
         QRL_REQUIRE(a.packed_stride_e >= (int64_t)(a.K + 1) * a.n_sel, "qrl_em_step: packed_stride_e too small");
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const bool tiled = a.K >= 1 && a.n <= 8 && a.A_stride_k == 0 && a.nz_stride_k == 0 && !(a.flags & QRL_EM_FORCE_GENERIC);
+    // Tiled kernel: one CTA per SM, noise generation spread over 15 warps -> best while the batch cannot fill the chip
+    // with one lane per component (measured crossover on B200: E*n ~ 32k, tools/size_sweep.py).  Beyond that the
+    // generic kernel has enough warps per scheduler and no shared-memory round trip.
+    const bool small_batch = (int64_t)a.n_envs * a.n <= 32768 || (a.flags & QRL_EM_FORCE_TILED);
+    const bool tiled = a.K >= 1 && a.n <= 8 && a.A_stride_k == 0 && a.nz_stride_k == 0 && small_batch &&
+                       !(a.flags & QRL_EM_FORCE_GENERIC);
     if (tiled) return em_tile_launch(a, st);
     QRL_REQUIRE(!a.packed || a.observations != nullptr, "qrl_em_step: the generic kernel packs from the observations block");
     int rc;

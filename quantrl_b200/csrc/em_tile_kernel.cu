@@ -7,10 +7,17 @@
 //
 // One CTA owns G <= 32 environments for the whole interval; time is cut into chunks of C sub-steps that flow through
 // double-buffered shared-memory tiles in a 3-stage pipeline, one __syncthreads per chunk:
-//   iteration it:  workers   produce noise(chunk it)        -> Wt/Vt[it & 1]       (Philox or fed loads)
-//                  warp 0    recurrence(chunk it-1)          Wt/Vt[(it-1) & 1] -> Xt/Ot[(it-1) & 1]
-//                  workers   output(chunk it-2)              Xt/Ot[it & 1] -> States, Observations, Reward,
-//                                                            packed cache rows, min/max  (coalesced 16-byte stores)
+//   iteration it:  workers   produce noise(chunk it)      -> Wt/Vt[it & 1]          (Philox, or fed loads)
+//                  warp 0    recurrence(chunk it-1)        Wt[(it-1) & 1] -> Xt[(it-1) & 1]   (x-update only: the warp
+//                                                          is the sequential critical path, ncu r1b)
+//                  workers   output(chunk it-2)            Ot = Xt[it & 1] + Vt[it & 1], then -> global:
+//                              * Observations rows: lane-contiguous (fully coalesced) 8-byte stores;
+//                              * States rows: each tile row is one contiguous run of the (K+1,E,n) block and
+//                                leaves through the TMA engine (cp.async.bulk shared -> global), no LSU work;
+//                              * Reward rows: one coalesced 8-byte store per (row, env);
+//                              * packed cache rows [t, actions, obs, cum. reward] (env-major): element-wise,
+//                                lane-contiguous 8-byte stores;
+//                              * min/max of the observations (truncation check).
 // Replaces the same reference code as em_kernel.cu (quantrl/envs/stochastic.py:178-242, envs/base.py:408-426,462,
 // 471-473,485-499) plus the packed rows of BaseSB3Env.update_data (envs/base.py:1314-1372).
 #include "common.cuh"
@@ -18,96 +25,135 @@
 
 namespace qrl {
 
-constexpr int EM_TILE_THREADS = 512;
+#ifndef QRL_EM_TILE_THREADS
+#define QRL_EM_TILE_THREADS 512
+#endif
+#ifndef QRL_EM_TILE_ILP
+#define QRL_EM_TILE_ILP 1
+#endif
+constexpr int EM_TILE_THREADS = QRL_EM_TILE_THREADS;
 constexpr int EM_TILE_WORKERS = EM_TILE_THREADS - 32;
+constexpr int EM_TILE_ILP = QRL_EM_TILE_ILP;
+
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make generic-proxy shared-memory writes visible to the async proxy (TMA) before the barrier that precedes the copy
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, %0;" :: "n"(EM_TILE_WORKERS) : "memory"); }
 
 template <int N>
-__global__ void __launch_bounds__(EM_TILE_THREADS, 1) em_tile_kernel(const qrl_em_args a, const PhiloxKeys keys, const int G, const int C) {
-    extern __shared__ double sm[];
+__global__ void __launch_bounds__(EM_TILE_THREADS, 1)
+em_tile_kernel(const qrl_em_args a, const PhiloxKeys keys, const int G, const int C) {
+    extern __shared__ __align__(128) double sm[];
     const int E = a.n_envs, K = a.K;
     const int e0 = blockIdx.x * G;
     const int Gl = min(G, E - e0);             // live environments of this CTA
     const int RP = Gl * N;                     // doubles per tile row
-    const int tile = C * G * N;                // doubles per tile buffer
-    double* Wt = sm;                           // [2][tile]
-    double* Vt = Wt + 2 * tile;
-    double* Xt = Vt + 2 * tile;
-    double* Ot = Xt + 2 * tile;
-    double* stdS = Ot + 2 * tile;              // [G*N] measurement-noise std per (env, comp)
+    const int tile = C * G * N;                // doubles per tile buffer (even: G is even, see plan_tiles)
+    double* Wt = sm;                           // [2][tile] Wiener increments (scaled), produced by the workers
+    double* Vt = Wt + 2 * tile;                // [2][tile] measurement noise (scaled)
+    double* Xt = Vt + 2 * tile;                // [2][tile] states, written by the recurrence warp
+    double* Ot = Xt + 2 * tile;                // [tile]    observations = states + noise, written by the workers
+    double* x0S = Ot + tile;                   // [G*N] initial state (row 0)
+    double* stdS = x0S + G * N;                // [G*N] measurement-noise std per (env, comp)
     double* cumS = stdS + G * N;               // [G]   cumulative reward after this interval
-    int* selS = reinterpret_cast<int*>(cumS + G);  // [n_sel]
+    double* wS = cumS + G;                     // [N]   reward weights
+    int* selS = reinterpret_cast<int*>(wS + N);  // [n_sel]
 
     const int tid = threadIdx.x;
     const bool is_rec = tid < 32;
     const int wt = tid - 32;                   // worker lane id (0..EM_TILE_WORKERS-1)
     const bool philox = a.rng_mode == QRL_RNG_PHILOX;
+    const bool has_reward = a.reward_kind != QRL_REWARD_NONE;
     const double sqrt_dt = sqrt(a.t_ssz);
     const int NC = (K + C - 1) / C;
     const int64_t row = (int64_t)E * N;
     const int n_data = 1 + a.n_actions + N + 1;
+    const int n_sel = a.n_sel;
 
     for (int i = tid; i < RP; i += EM_TILE_THREADS) {
         const int el = i / N, c = i - el * N;
         stdS[i] = (philox && a.obs_std) ? a.obs_std[(int64_t)(e0 + el) * a.obs_std_stride_e + c] : 0.0;
+        x0S[i] = a.x0[(int64_t)e0 * N + i];
     }
+    if (tid < N) wS[tid] = has_reward ? a.reward_w[tid] : 0.0;
     if (a.packed)
-        for (int i = tid; i < a.n_sel; i += EM_TILE_THREADS) {
+        for (int i = tid; i < n_sel; i += EM_TILE_THREADS) {
             const int s = a.sel_idxs[i];
             selS[i] = s < 0 ? s + n_data : s;
         }
     __syncthreads();
 
+    // TMA eligibility: 16-byte aligned sources/destinations and sizes
+    const bool tma_x = (RP % 2 == 0) && (row % 2 == 0) && (((int64_t)e0 * N) % 2 == 0) && ((uintptr_t)a.states % 16 == 0);
+
     double lo = INFINITY, hi = -INFINITY;
 
-    // ---- per-row outputs shared by the prologue (row 0) and the output stage -------------------------------------
-    auto emit_row = [&](int r, int el, const double* x, const double* o) {
-        const int e = e0 + el;
-        const int64_t off = (int64_t)r * row + (int64_t)e * N;
-        if (a.states) {
+    // ---- worker helpers: everything derived from a finished observation row block in Ot ------------------------
+    // reward rows, last-row outputs and packed cache rows for rows r_first .. r_first+ns-1 whose states/observations
+    // sit in Xb/Ob (row-major [slot][env][comp])
+    auto emit_derived = [&](const double* Xb, const double* Ob, int r_first, int ns) {
+        if (has_reward || a.x_last || a.obs_last) {
+            for (int item = wt; item < ns * Gl; item += EM_TILE_WORKERS) {
+                const int sl = item / Gl, el = item - sl * Gl;
+                const int r = r_first + sl, e = e0 + el;
+                const double* xr = Xb + sl * RP + el * N;
+                const double* orow = Ob + sl * RP + el * N;
+                double rv = 0.0;
+                if (has_reward) {
+                    const double* s = (a.reward_kind == QRL_REWARD_NEG_WSQ_OBS) ? orow : xr;
+                    double acc = 0.0;
 #pragma unroll
-            for (int c = 0; c < N; ++c) a.states[off + c] = x[c];
-        }
-        if (a.observations) {
+                    for (int c = 0; c < N; ++c) acc = fma(wS[c] * s[c], s[c], acc);
+                    rv = -acc;
+                    if (a.reward) a.reward[(int64_t)r * E + e] = rv;
+                }
+                if (r == K) {
+                    if (has_reward) {
+                        if (a.reward_last) a.reward_last[e] = rv;
+                        double cum = rv;
+                        if (a.rewards_cum) { cum += a.rewards_cum[e]; a.rewards_cum[e] = cum; }
+                        cumS[el] = cum;
+                    }
 #pragma unroll
-            for (int c = 0; c < N; ++c) a.observations[off + c] = o[c];
-        }
-#pragma unroll
-        for (int c = 0; c < N; ++c) { lo = fmin(lo, o[c]); hi = fmax(hi, o[c]); }
-        if (a.reward_kind != QRL_REWARD_NONE) {
-            const double* s = (a.reward_kind == QRL_REWARD_NEG_WSQ_OBS) ? o : x;
-            double acc = 0.0;
-#pragma unroll
-            for (int c = 0; c < N; ++c) acc = fma(a.reward_w[c] * s[c], s[c], acc);
-            const double rv = -acc;
-            if (a.reward) a.reward[(int64_t)r * E + e] = rv;
-            if (r == K) {
-                if (a.reward_last) a.reward_last[e] = rv;
-                double cum = rv;
-                if (a.rewards_cum) { cum += a.rewards_cum[e]; a.rewards_cum[e] = cum; }
-                cumS[el] = cum;
+                    for (int c = 0; c < N; ++c) {
+                        if (a.x_last) a.x_last[(int64_t)e * N + c] = xr[c];
+                        if (a.obs_last) a.obs_last[(int64_t)e * N + c] = orow[c];
+                    }
+                }
             }
         }
-        if (r == K) {
-#pragma unroll
-            for (int c = 0; c < N; ++c) {
-                if (a.x_last) a.x_last[(int64_t)e * N + c] = x[c];
-                if (a.obs_last) a.obs_last[(int64_t)e * N + c] = o[c];
+        if (a.packed) {
+            // q runs over [env][slot][column]: consecutive lanes write consecutive doubles of one env's contiguous run
+            const int per_env = ns * n_sel;
+            int el = wt / per_env, rr = wt - el * per_env;
+            int sl = rr / n_sel, j = rr - sl * n_sel;
+            const int d_el = EM_TILE_WORKERS / per_env, d_rr = EM_TILE_WORKERS - d_el * per_env;
+            const int d_sl = d_rr / n_sel, d_j = d_rr - d_sl * n_sel;
+            while (el < Gl) {
+                const int col = selS[j];
+                const int r = r_first + sl;
+                double val = 0.0;  // cumulative-reward column: only known after the last sub-step, patched at the end
+                if (col == 0) val = a.T_step[r];
+                else if (col <= a.n_actions) val = a.actions[(int64_t)(e0 + el) * a.n_actions + (col - 1)];
+                else if (col <= a.n_actions + N) val = Ob[sl * RP + el * N + (col - 1 - a.n_actions)];
+                a.packed[(int64_t)(e0 + el) * a.packed_stride_e + (int64_t)r * n_sel + j] = val;
+                el += d_el;
+                sl += d_sl;
+                j += d_j;
+                if (j >= n_sel) { j -= n_sel; ++sl; }
+                if (sl >= ns) { sl -= ns; ++el; }
             }
-        }
-    };
-    auto pack_row = [&](int r, int el, const double* o) {
-        const int e = e0 + el;
-        double* dst = a.packed + (int64_t)e * a.packed_stride_e + (int64_t)r * a.n_sel;
-        for (int j = 0; j < a.n_sel; ++j) {
-            const int col = selS[j];
-            if (col == 0) dst[j] = a.T_step[r];
-            else if (col <= a.n_actions) dst[j] = a.actions[(int64_t)e * a.n_actions + (col - 1)];
-            else if (col <= a.n_actions + N) dst[j] = o[col - 1 - a.n_actions];
-            // the cumulative-reward column is only known after the last sub-step: patched below
         }
     };
 
-    // ---- recurrence warp state ---------------------------------------------------------------------------------
+    // ---- recurrence warp: coefficients and state in registers ----------------------------------------------------
     double M[N][N], nz[N], x[N];
     const int el_r = tid;                      // env handled by this recurrence lane
     const bool rec_live = is_rec && el_r < Gl;
@@ -119,105 +165,178 @@ __global__ void __launch_bounds__(EM_TILE_THREADS, 1) em_tile_kernel(const qrl_e
 #pragma unroll
             for (int c = 0; c < N; ++c) M[r][c] = __dadd_rn((r == c) ? 1.0 : 0.0, __dmul_rn(Ar[r * N + c], a.t_ssz));
             nz[r] = a.nz[(int64_t)e * a.nz_stride_e + r];
-            x[r] = a.x0[(int64_t)e * N + r];
+            x[r] = x0S[el_r * N + r];
         }
-        // row 0: Observations[0] = States[0] + noise[t_idx]  (envs/base.py:462)
-        double o[N];
-#pragma unroll
-        for (int c = 0; c < N; ++c) {
+    } else if (!is_rec) {
+        // ---- workers: row 0, Observations[0] = States[0] + noise[t_idx]  (envs/base.py:462) ----
+        for (int i = wt; i < RP; i += EM_TILE_WORKERS) {
+            const int el = i / N, c = i - el * N;
             double v = 0.0;
             if (philox) {
                 if (a.obs_std) {
                     double z0, z1;
                     const uint32_t tau = a.t_idx > 0 ? (uint32_t)(a.t_idx - 1) : 0xFFFFFFFFu;
-                    philox_normal2(keys, tau, a.episode, (uint32_t)(a.env_offset + e), (uint32_t)c, z0, z1);
-                    v = __dmul_rn(stdS[el_r * N + c], z1);
+                    philox_normal2(keys, tau, a.episode, (uint32_t)(a.env_offset + e0 + el), (uint32_t)c, z0, z1);
+                    v = __dmul_rn(stdS[i], z1);
                 }
             } else if (a.obs_noise) {
-                v = a.obs_noise[(int64_t)e * N + c];
+                v = a.obs_noise[(int64_t)e0 * N + i];
             }
-            o[c] = __dadd_rn(x[c], v);
+            const double xv = x0S[i], o = __dadd_rn(xv, v);
+            Ot[i] = o;
+            if (a.states) a.states[(int64_t)e0 * N + i] = xv;
+            if (a.observations) a.observations[(int64_t)e0 * N + i] = o;
+            lo = fmin(lo, o);
+            hi = fmax(hi, o);
         }
-        emit_row(0, el_r, x, o);
-        if (a.packed) pack_row(0, el_r, o);
+        worker_barrier();
+        emit_derived(x0S, Ot, 0, 1);
     }
 
     // incremental (slot, rem) walkers avoid runtime integer divisions in the hot loops
     const int p_dslot = EM_TILE_WORKERS / RP, p_drem = EM_TILE_WORKERS - p_dslot * RP;
-    const int o_dslot = EM_TILE_WORKERS / Gl, o_drem = EM_TILE_WORKERS - o_dslot * Gl;
+    const bool dbg_no_prod = a.flags & 2, dbg_no_rec = a.flags & 4, dbg_no_out = a.flags & 8;  // diagnostics only
 
     for (int it = 0; it < NC + 2; ++it) {
         if (!is_rec) {
+            const bool out_now = it >= 2;
+            const int co = it - 2;
+            // ---------------- output chunk `it - 2`, part A: observations = states + noise ----------------
+            if (out_now) {
+                const int ns = min(C, K - co * C);
+                const double* Xb = Xt + (co & 1) * tile;
+                const double* Vb = Vt + (co & 1) * tile;
+                const int r0 = co * C;
+                if (!dbg_no_out) {
+                    if (tma_x && a.states && wt < 32) {
+                        // one bulk store per tile row = one contiguous run of the (K+1,E,n) States block
+                        for (int slot = wt; slot < ns; slot += 32)
+                            bulk_store(a.states + (int64_t)(r0 + slot + 1) * row + (int64_t)e0 * N, Xb + slot * RP, RP * 8);
+                        bulk_commit();
+                    }
+                    // observations leave through the LSU right here (lane-contiguous 8-byte stores = fully coalesced
+                    // runs of the (K+1,E,n) block); the states tile goes out through the TMA engine below
+                    int s2 = wt / RP, rem = wt - s2 * RP;
+                    const int64_t gbase = (int64_t)(r0 + 1) * row + (int64_t)e0 * N;
+                    while (s2 < ns) {
+                        const int idx = s2 * RP + rem;
+                        const double o = __dadd_rn(Xb[idx], Vb[idx]);
+                        Ot[idx] = o;
+                        if (a.observations) a.observations[gbase + (int64_t)s2 * row + rem] = o;
+                        if (!tma_x && a.states) a.states[gbase + (int64_t)s2 * row + rem] = Xb[idx];
+                        lo = fmin(lo, o);
+                        hi = fmax(hi, o);
+                        s2 += p_dslot;
+                        rem += p_drem;
+                        if (rem >= RP) { rem -= RP; ++s2; }
+                    }
+                }
+                worker_barrier();   // Ot complete; every read of Vt[it & 1] is done before it is refilled below
+                // ---------------- part B: reward rows, last-row outputs, packed rows ----------------
+                if (!dbg_no_out) {
+                    emit_derived(Xb, Ot, r0 + 1, ns);
+                }
+            }
             // ---------------- produce noise of chunk `it` ----------------
-            if (it < NC) {
+            if (it < NC && !dbg_no_prod) {
                 const int j0 = it * C;
                 const int ns = min(C, K - j0);
                 double* Wb = Wt + (it & 1) * tile;
                 double* Vb = Vt + (it & 1) * tile;
                 int slot = wt / RP, rem = wt - slot * RP;
-                while (slot < ns) {
-                    const int el = rem / N, c = rem - el * N;
-                    const int idx = slot * RP + rem;
-                    if (philox) {
-                        double z0, z1;
-                        philox_normal2(keys, (uint32_t)(a.t_idx + j0 + slot), a.episode, (uint32_t)(a.env_offset + e0 + el),
-                                       (uint32_t)c, z0, z1);
-                        Wb[idx] = __dmul_rn(sqrt_dt, z0);
-                        Vb[idx] = __dmul_rn(stdS[rem], z1);
-                    } else {
-                        const int64_t g = (int64_t)(j0 + slot) * row + (int64_t)e0 * N + rem;
-                        Wb[idx] = a.W[g];
-                        Vb[idx] = a.obs_noise ? a.obs_noise[g + row] : 0.0;
+                if (philox) {
+                    // Software pipeline: the Philox rounds (integer ALU / IMAD pipes) of the NEXT pair are issued inside
+                    // the same straight-line block as the Box-Muller polynomials (FP64 pipe) of the CURRENT pair, so the
+                    // half-rate pipes overlap instead of all warps sitting in the same phase (ncu r1c: issue slots 50 %
+                    // busy with ALU 31 %, FMA-heavy 29 %, FP64 20 % when the phases ran back to back).
+                    // EM_TILE_ILP pairs per trip give that many independent DFMA chains (DFMA latency 8.4 cycles, measured).
+                    const uint32_t envg0 = (uint32_t)(a.env_offset + e0);
+                    const uint32_t tau0 = (uint32_t)(a.t_idx + j0);
+                    int sl[EM_TILE_ILP], rm[EM_TILE_ILP];
+                    uint4 bits[EM_TILE_ILP];
+#pragma unroll
+                    for (int u = 0; u < EM_TILE_ILP; ++u) {
+                        sl[u] = slot;
+                        rm[u] = rem;
+                        bits[u] = philox4x32_10(make_uint4(tau0 + slot, a.episode, envg0 + rem / N, (uint32_t)(rem % N)), keys);
+                        slot += p_dslot;
+                        rem += p_drem;
+                        if (rem >= RP) { rem -= RP; ++slot; }
                     }
-                    slot += p_dslot;
-                    rem += p_drem;
-                    if (rem >= RP) { rem -= RP; ++slot; }
+                    while (sl[0] < ns) {
+                        uint4 cur[EM_TILE_ILP];
+                        int idx[EM_TILE_ILP];
+                        double sd[EM_TILE_ILP];
+                        bool ok[EM_TILE_ILP];
+#pragma unroll
+                        for (int u = 0; u < EM_TILE_ILP; ++u) {
+                            cur[u] = bits[u];
+                            ok[u] = sl[u] < ns;
+                            idx[u] = sl[u] * RP + rm[u];
+                            sd[u] = stdS[rm[u]];
+                            // next pair of this chain: unconditional (a pair past the end of the chunk is computed and
+                            // dropped), so the whole trip is one basic block the scheduler can interleave freely
+                            sl[u] = slot;
+                            rm[u] = rem;
+                            bits[u] = philox4x32_10(make_uint4(tau0 + slot, a.episode, envg0 + rem / N, (uint32_t)(rem % N)), keys);
+                            slot += p_dslot;
+                            rem += p_drem;
+                            if (rem >= RP) { rem -= RP; ++slot; }
+                        }
+                        double z0[EM_TILE_ILP], z1[EM_TILE_ILP];
+#pragma unroll
+                        for (int u = 0; u < EM_TILE_ILP; ++u) normal_pair(cur[u], z0[u], z1[u]);
+#pragma unroll
+                        for (int u = 0; u < EM_TILE_ILP; ++u) {
+                            if (ok[u]) {
+                                Wb[idx[u]] = __dmul_rn(sqrt_dt, z0[u]);
+                                Vb[idx[u]] = __dmul_rn(sd[u], z1[u]);
+                            }
+                        }
+                    }
+                } else {
+                    // fed noise: 4 independent loads in flight per lane (the loop is global-latency bound otherwise)
+                    const int total = ns * RP;
+                    const int64_t g0 = (int64_t)j0 * row + (int64_t)e0 * N;
+                    for (int base = wt; base < total; base += 4 * EM_TILE_WORKERS) {
+                        double wv[4], vv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int idx = base + u * EM_TILE_WORKERS;
+                            wv[u] = vv[u] = 0.0;
+                            if (idx < total) {
+                                const int s2 = idx / RP;
+                                const int64_t g = g0 + (int64_t)s2 * row + (idx - s2 * RP);
+                                wv[u] = a.W[g];
+                                if (a.obs_noise) vv[u] = a.obs_noise[g + row];
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int idx = base + u * EM_TILE_WORKERS;
+                            if (idx < total) { Wb[idx] = wv[u]; Vb[idx] = vv[u]; }
+                        }
+                    }
                 }
             }
-            // ---------------- output chunk `it - 2` ----------------
-            if (it >= 2) {
-                const int co = it - 2;
-                const int r0 = co * C;
-                const int ns = min(C, K - r0);
-                const double* Xb = Xt + (co & 1) * tile;
-                const double* Ob = Ot + (co & 1) * tile;
-                // (a) time-major blocks: item = (slot, env), env fastest -> consecutive lanes write consecutive
-                //     N*8-byte pieces of one row of the (K+1,E,N) blocks
-                int slot = wt / Gl, el = wt - slot * Gl;
-                while (slot < ns) {
-                    double xs[N], os[N];
-#pragma unroll
-                    for (int c = 0; c < N; ++c) { xs[c] = Xb[slot * RP + el * N + c]; os[c] = Ob[slot * RP + el * N + c]; }
-                    emit_row(r0 + slot + 1, el, xs, os);
-                    slot += o_dslot;
-                    el += o_drem;
-                    if (el >= Gl) { el -= Gl; ++slot; }
-                }
-                // (b) env-major packed cache rows: item = (env, slot), slot fastest -> consecutive lanes write
-                //     consecutive rows of one env's contiguous run
-                if (a.packed) {
-                    for (int item = wt; item < Gl * ns; item += EM_TILE_WORKERS) {
-                        const int el2 = item / ns, sl = item - el2 * ns;
-                        double os[N];
-#pragma unroll
-                        for (int c = 0; c < N; ++c) os[c] = Ob[sl * RP + el2 * N + c];
-                        pack_row(r0 + sl + 1, el2, os);
-                    }
-                }
-            }
-        } else if (it >= 1 && it <= NC && rec_live) {
-            // ---------------- recurrence of chunk `it - 1` ----------------
+            // the TMA source tiles are rewritten in the next iteration: wait until they have been read
+            if (out_now && tma_x && a.states && wt < 32) bulk_wait_read();
+        } else if (it >= 1 && it <= NC && rec_live && !dbg_no_rec) {
+            // ---------------- recurrence of chunk `it - 1` (the only sequential part) ----------------
             const int cr = it - 1;
             const int ns = min(C, K - cr * C);
-            const double* Wb = Wt + (cr & 1) * tile;
-            const double* Vb = Vt + (cr & 1) * tile;
-            double* Xb = Xt + (cr & 1) * tile;
-            double* Ob = Ot + (cr & 1) * tile;
+            const double* Wb = Wt + (cr & 1) * tile + el_r * N;
+            double* Xb = Xt + (cr & 1) * tile + el_r * N;
             for (int slot = 0; slot < ns; ++slot) {
-                const int base = slot * RP + el_r * N;
-                double w[N], v[N], xn[N];
+                double w[N], xn[N];
+                if constexpr (N % 2 == 0) {   // RP even and 16-byte aligned tiles: 128-bit shared-memory accesses
+                    const double2* wp = reinterpret_cast<const double2*>(Wb + slot * RP);
 #pragma unroll
-                for (int c = 0; c < N; ++c) { w[c] = Wb[base + c]; v[c] = Vb[base + c]; }
+                    for (int c = 0; c < N / 2; ++c) { const double2 t = wp[c]; w[2 * c] = t.x; w[2 * c + 1] = t.y; }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < N; ++c) w[c] = Wb[slot * RP + c];
+                }
 #pragma unroll
                 for (int r = 0; r < N; ++r) {
                     double acc = __dmul_rn(M[r][0], x[0]);
@@ -226,12 +345,17 @@ __global__ void __launch_bounds__(EM_TILE_THREADS, 1) em_tile_kernel(const qrl_e
                     xn[r] = fma(nz[r], w[r], acc);
                 }
 #pragma unroll
-                for (int c = 0; c < N; ++c) {
-                    x[c] = xn[c];
-                    Xb[base + c] = xn[c];
-                    Ob[base + c] = __dadd_rn(xn[c], v[c]);
+                for (int c = 0; c < N; ++c) x[c] = xn[c];
+                if constexpr (N % 2 == 0) {
+                    double2* xp = reinterpret_cast<double2*>(Xb + slot * RP);
+#pragma unroll
+                    for (int c = 0; c < N / 2; ++c) xp[c] = make_double2(xn[2 * c], xn[2 * c + 1]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < N; ++c) Xb[slot * RP + c] = xn[c];
                 }
             }
+            fence_async_smem();
         }
         __syncthreads();
     }
@@ -244,14 +368,15 @@ __global__ void __launch_bounds__(EM_TILE_THREADS, 1) em_tile_kernel(const qrl_e
     }
     // cumulative-reward column of every packed row of this interval (envs/base.py:1311, 1342-1349)
     if (a.packed) {
-        for (int j = 0; j < a.n_sel; ++j) {
+        for (int j = 0; j < n_sel; ++j) {
             if (selS[j] != n_data - 1) continue;
             for (int item = tid; item < Gl * (K + 1); item += EM_TILE_THREADS) {
                 const int el = item / (K + 1), r = item - el * (K + 1);
-                a.packed[(int64_t)(e0 + el) * a.packed_stride_e + (int64_t)r * a.n_sel + j] = cumS[el];
+                a.packed[(int64_t)(e0 + el) * a.packed_stride_e + (int64_t)r * n_sel + j] = cumS[el];
             }
         }
     }
+    if (!is_rec && wt < 32 && tma_x && a.states) bulk_wait_all();   // the bulk stores have reached global memory
     if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
 }
 
@@ -260,19 +385,22 @@ struct TilePlan { int G, C, grid; size_t smem; };
 static TilePlan plan_tiles(int E, int N, int K, int n_sel, int sms) {
     TilePlan p;
     p.G = E <= 32 * sms ? (E + sms - 1) / sms : 32;
-    if (p.G < 1) p.G = 1;
+    if (p.G & 1) ++p.G;                        // even G keeps every tile row 16-byte aligned for the bulk stores
+    if (p.G > 32) p.G = 32;
+    if (p.G < 2) p.G = 2;
     p.grid = (E + p.G - 1) / p.G;
     const size_t budget = 200 * 1024;
-    const size_t fixed = (size_t)(p.G * N + p.G) * sizeof(double) + (size_t)n_sel * sizeof(int) + 64;
-    int C = (int)((budget - fixed) / ((size_t)8 * p.G * N * sizeof(double)));
+    const size_t fixed = (size_t)(2 * p.G * N + p.G + N) * sizeof(double) + (size_t)n_sel * sizeof(int) + 256;
+    const size_t per_c = (size_t)(7 * p.G * N) * sizeof(double);
+    int C = (int)((budget - fixed) / per_c);
     if (C > K) C = K;
     if (C > 32) C = 32;
     if (C < 1) C = 1;
-    // balance the chunks (K = 100, C = 32 -> 4 chunks of 25)
+    // balance the chunks (K = 100, C = 27 -> 4 chunks of 25)
     const int nc = (K + C - 1) / C;
     C = (K + nc - 1) / nc;
     p.C = C;
-    p.smem = (size_t)8 * C * p.G * N * sizeof(double) + fixed;
+    p.smem = per_c * C + fixed;
     return p;
 }
 

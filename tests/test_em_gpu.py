@@ -210,7 +210,8 @@ def test_invalid_arguments_raise(native, cuda):
         N.ptr(torch.zeros(3))
 
 
-@pytest.mark.parametrize("E,n,K", [(4096, 4, 100), (300, 8, 37), (65, 3, 12), (1000, 2, 64), (33, 5, 7), (5000, 4, 20)])
+@pytest.mark.parametrize("E,n,K", [(4096, 4, 100), (300, 8, 37), (65, 3, 12), (1000, 2, 64), (33, 5, 7), (5000, 4, 20),
+                                   (9001, 4, 30), (31, 7, 3), (2, 6, 1)])
 def test_tiled_kernel_equals_generic_kernel_bitwise(native, cuda, E, n, K):
     """The tiled warp-specialised kernel and the generic lane-per-component kernel run the same operations in the
     same order: States/Observations must agree bit for bit (Philox and fed), rewards to rounding."""
@@ -223,7 +224,7 @@ def test_tiled_kernel_equals_generic_kernel_bitwise(native, cuda, E, n, K):
     for mode in ("philox", "fed"):
         kw = dict(philox=dict(seed=99, episode=1, t_idx=300, env_offset=17), obs_std=std) if mode == "philox" else \
             dict(W=0.1 * rng.standard_normal((K, E, n)), obs_noise=0.01 * rng.standard_normal((K + 1, E, n)))
-        t = em_step(x0, A, nz, 0.01, K, reward_kind=N.REWARD_NEG_WSQ_OBS, reward_w=w, **kw)
+        t = em_step(x0, A, nz, 0.01, K, reward_kind=N.REWARD_NEG_WSQ_OBS, reward_w=w, flags=N.EM_FORCE_TILED, **kw)
         g = em_step(x0, A, nz, 0.01, K, reward_kind=N.REWARD_NEG_WSQ_OBS, reward_w=w, flags=N.EM_FORCE_GENERIC, **kw)
         for key in ("states", "observations", "x_last", "obs_last", "minmax"):
             assert torch.equal(t[key], g[key]), (mode, key)

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import numpy as np, torch
 from quantrl_b200 import _native as N
 
-def bench(E, n, K, philox=True, traj=True, reps=50):
+def bench(E, n, K, philox=True, traj=True, reps=50, flags=0, graph=True):
     dev = "cuda"
     rng = np.random.default_rng(0)
     A = torch.as_tensor(0.3 * rng.standard_normal((E, n, n)), device=dev)
@@ -34,18 +34,34 @@ def bench(E, n, K, philox=True, traj=True, reps=50):
         a.states, a.observations, a.reward = N.ptr(S), N.ptr(O), N.ptr(R)
     a.reward_kind, a.reward_w, a.reward_last, a.rewards_cum = N.REWARD_NEG_WSQ_OBS, N.ptr(w), N.ptr(rl), N.ptr(rc)
     a.obs_minmax, a.nan_flag = N.ptr(mm), N.ptr(nan)
+    a.flags = flags
     for _ in range(5):
         N.em_step(a)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(reps):
-        a.t_idx = i * K
-        N.em_step(a)
-    e1.record(); torch.cuda.synchronize()
+    if graph:
+        # back-to-back launches replayed from a CUDA graph: pure device time, no CPU launch-rate floor
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            N.em_step(a)
+        torch.cuda.current_stream().wait_stream(s)
+        with torch.cuda.graph(g):
+            for i in range(reps):
+                a.t_idx = i * K
+                N.em_step(a)
+        g.replay(); torch.cuda.synchronize()
+        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+    else:
+        e0.record()
+        for i in range(reps):
+            a.t_idx = i * K
+            N.em_step(a)
+        e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     sub = E * K / (ms * 1e-3)
-    return dict(E=E, n=n, K=K, philox=philox, traj=traj, ms=round(ms, 4), substeps_per_s=f"{sub:.3e}",
+    return dict(E=E, n=n, K=K, philox=philox, traj=traj, flags=flags, ms=round(ms, 4), substeps_per_s=f"{sub:.3e}",
                 hbm_GBs=round(sub * 8 * (2 * n + 1) / 1e9, 1) if traj else 0)
 
 if __name__ == "__main__":
