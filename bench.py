@@ -145,13 +145,14 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------------
-def make_env(rank, return_numpy):
+def make_env(rank, return_numpy, use_cuda_graph=True):
     from quantrl_b200.systems import AffineLinearVecEnv, affine_matrices
     A0, Au = affine_matrices(N_STATE, 1, seed=0)
     return AffineLinearVecEnv(
         n_envs=E_PER_GPU, n=N_STATE, A0=A0, Au=Au, noise_prefixes=0.05, x0=1.0, t_norm_max=S_EPISODE * T_SSZ + T_SSZ / 2,
         t_norm_ssz=T_SSZ, action_interval=K_SUB, observation_stds=[0.01] * N_STATE, seed=1, rng="philox",
-        env_offset=rank * E_PER_GPU, return_numpy=return_numpy, dir_prefix="/tmp/qrl_bench")
+        env_offset=rank * E_PER_GPU, return_numpy=return_numpy, use_cuda_graph=use_cuda_graph, data_idxs=[-1],
+        dir_prefix="/tmp/qrl_bench")
 
 
 def main():
@@ -197,14 +198,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_device(n_steps, events=None):
+    def run_device(n_steps):
         """n_steps action intervals, everything resident in HBM; multi-GPU: obs|reward all-gathered every step."""
         pending = []
         for i in range(n_steps):
             if env.t_idx + 1 >= env.shape_T[0] or env.batch_idx < 0:
                 env.reset()
-            if events is not None:
-                env._em_events = events
             obs, rew, _ = env.step_device(actions_dev[i % n_act_bufs])
             if world > 1:
                 local_or[:, :n].copy_(obs)
@@ -218,19 +217,32 @@ def main():
     # ---- value: device-resident ----
     run_device(args.warmup)
     barrier()
-    launches0 = N.launch_count()
-    events = []
+    launches0, replays0 = N.launch_count(), env.graph_replays
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         barrier()
         e0.record()
-        run_device(args.steps, events)
+        run_device(args.steps)
         e1.record()
         barrier()
-    env._em_events = None
     ms = e0.elapsed_time(e1)
-    launches = N.launch_count() - launches0
+    # kernels of libquantrl_b200.so launched in the timed region: eager launches + graph replays x kernels per graph
+    launches = (N.launch_count() - launches0) + (env.graph_replays - replays0) * env.graph_native_launches
+
+    # dominant kernel (the fused integration launch): per-launch CUDA events on its stream, same env configuration
+    # launched eagerly (events cannot be recorded inside a replayed graph)
+    env_k = make_env(rank, return_numpy=False, use_cuda_graph=False)
+    env_k.reset()
+    for i in range(args.warmup):
+        env_k.step_device(actions_dev[i % n_act_bufs])
+    events = []
+    env_k._em_events = events
+    for i in range(min(args.steps, 90 - args.warmup if args.warmup < 80 else 10)):
+        env_k.step_device(actions_dev[i % n_act_bufs])
+    torch.cuda.synchronize()
+    env_k._em_events = None
     em_ms = sum(a.elapsed_time(b) for a, b in events) / max(1, len(events))
+    del env_k
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -268,7 +280,8 @@ def main():
             pass
         hbm_peak, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured)") if "hbm_gbs" in peaks else \
             (6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)")
-        bytes_per_substep = 8 * (2 * n + 1)               # States + Observations + Reward rows
+        # States + Observations + Reward rows + the selected cache column (cumulative reward, data_idxs=[-1])
+        bytes_per_substep = 8 * (2 * n + 1) + 8
         alg_bytes = bytes_per_substep * E * K
         achieved = alg_bytes / (em_ms * 1e-3) / 1e9
         fp64_peak = N.measure_fp64_peak(8192)
@@ -277,9 +290,10 @@ def main():
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": E, "n": n, "action_interval": K,
-                       "rng": "philox4x32-10 in-kernel", "trajectory": "States+Observations+Reward blocks and packed cache rows kept on device",
-                       "l2": "outputs rotate through a device-resident (E, shape_T, n_data) episode cache of 2.3 GB (> L2); "
-                             "inputs per step are < 1 MB", "parallelism": f"env-sharded dp{world}",
+                       "rng": "philox4x32-10 in-kernel", "trajectory": "States+Observations+Reward blocks kept on device; data cache column data_idxs=[-1] (cumulative reward) "
+                                     "written by the same launch into a device-resident (E, shape_T, 1) episode cache",
+                       "l2": "inputs per step are < 1 MB (no reuse to exploit); the 33 MB of trajectory rows per step are rewritten "
+                             "every step and stay L2-resident (126 MB L2), the episode cache (655 MB) streams to HBM", "parallelism": f"env-sharded dp{world}",
                        "collective": "all_gather(obs|reward) per step (NCCL, overlapped with the next interval)" if world > 1 else "none"},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * 1 * 8, "d2h_bytes_per_step": (E * (n + 1) + 4) * 8,

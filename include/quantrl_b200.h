@@ -134,17 +134,27 @@ typedef struct qrl_em_args {
     /* fused trajectory-cache rows (BaseSB3Env.update_data, quantrl/envs/base.py:1314-1372), n_properties == 0 only:
      *   packed[e, t, j] = column sel_idxs[j] of [T_step[t], actions[e,:], Obs[t,e,:], rewards_cum[e] (after this step)]
      * requires reward_kind != QRL_REWARD_NONE and rewards_cum != NULL.  NULL = no packing. */
-    double*  packed;         /* element [e,t,j] at packed[e*packed_stride_e + t*n_sel + j], t = 0..K */
+    double*  packed;         /* element [e,t,j] at packed[e*packed_stride_e + t*packed_row_pitch + j], t = 0..K */
     int64_t  packed_stride_e;
+    int64_t  packed_row_pitch; /* doubles per cache row, >= n_sel (0 = n_sel).  An even pitch and stride keep every env's
+                                * run 16-byte aligned, which lets the tiled kernel write it with TMA bulk stores */
     const double*  T_step;   /* (K+1,) */
     const double*  actions;  /* (E,n_actions) */
     const int32_t* sel_idxs; /* (n_sel,) indices into the n_data = 1 + n_actions + n + 1 columns (negative = from end) */
     int32_t  n_actions;
     int32_t  n_sel;
+
+    /* CUDA-graph replay: optional DEVICE pointer to {int64 t_idx, int64 episode}.  When non-NULL the kernel reads the
+     * two scalars from there instead of `t_idx` / `episode`, and treats W, obs_noise, T_step and packed as the bases
+     * of the WHOLE episode (time index 0): it adds t_idx rows itself.  The launch is then identical from step to step
+     * and can be captured once and replayed (the caller advances dyn[0] by K on the same stream). */
+    const int64_t* dyn;
 } qrl_em_args;
 
 #define QRL_EM_FORCE_GENERIC 1   /* flags: always use the generic lane-per-component kernel (A/B testing) */
 #define QRL_EM_FORCE_TILED   16  /* flags: use the tiled kernel whenever it supports the case, whatever the batch size */
+#define QRL_EM_PACK_TMA     128 /* flags: tiled kernel stages the packed rows in shared memory and writes each env's run
+                                 * with one TMA bulk store (needs an even packed_row_pitch / packed_stride_e) */
 /* flag bits 2, 4, 8 are diagnostics of the tiled kernel (skip produce / recurrence / output stage); results invalid */
 
 QRL_API int qrl_em_step(const qrl_em_args* args, void* stream);
@@ -220,8 +230,11 @@ typedef struct qrl_pack_args {
     const int32_t* idxs;        /* (n_sel,) column indices into the n_data columns (negative = from the end) */
     double*  packed;            /* element [e,t,c] at packed[e*packed_stride_e + t*n_data + c]; or NULL */
     int64_t  packed_stride_e;   /* >= dim*n_data (lets the caller write straight into a (E, shape_T, n_data) cache) */
-    double*  selected;          /* element [e,t,j] at selected[e*selected_stride_e + t*n_sel + j]; or NULL */
-    int64_t  selected_stride_e; /* >= dim*n_sel */
+    double*  selected;          /* element [e,t,j] at selected[e*selected_stride_e + t*selected_row_pitch + j]; or NULL */
+    int64_t  selected_stride_e; /* >= dim*selected_row_pitch */
+    int64_t  selected_row_pitch;/* doubles per row, >= n_sel (0 = n_sel) */
+    const int64_t* dyn;         /* optional DEVICE pointer {int64 t_idx, ...} (CUDA-graph replay): when non-NULL, T_step,
+                                 * packed and selected are the bases of the whole episode and t_idx rows are added here */
 } qrl_pack_args;
 
 QRL_API int qrl_pack_rows(const qrl_pack_args* args, void* stream);

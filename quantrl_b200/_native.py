@@ -13,7 +13,7 @@ RNG_FED, RNG_PHILOX = 0, 1
 REWARD_NONE, REWARD_NEG_WSQ_OBS, REWARD_NEG_WSQ_STATE = 0, 1, 2
 SYS_OPTOMECH, SYS_KERR_CHAIN, SYS_CONST_AD = 1, 2, 3
 ODE_RK4, ODE_DOPRI5 = 0, 1
-EM_FORCE_GENERIC, EM_FORCE_TILED = 1, 16
+EM_FORCE_GENERIC, EM_FORCE_TILED, EM_PACK_TMA = 1, 16, 128
 
 _dp = C.c_void_p  # device pointers travel as integers
 
@@ -33,8 +33,8 @@ class EmArgs(C.Structure):
         ("x0", _dp), ("states", _dp), ("observations", _dp), ("x_last", _dp), ("obs_last", _dp),
         ("reward_kind", C.c_int32), ("flags", C.c_int32), ("reward_w", _dp), ("reward", _dp), ("reward_last", _dp),
         ("rewards_cum", _dp), ("obs_minmax", _dp), ("nan_flag", _dp),
-        ("packed", _dp), ("packed_stride_e", C.c_int64), ("T_step", _dp), ("actions", _dp), ("sel_idxs", _dp),
-        ("n_actions", C.c_int32), ("n_sel", C.c_int32),
+        ("packed", _dp), ("packed_stride_e", C.c_int64), ("packed_row_pitch", C.c_int64), ("T_step", _dp), ("actions", _dp), ("sel_idxs", _dp),
+        ("n_actions", C.c_int32), ("n_sel", C.c_int32), ("dyn", _dp),
     ]
 
 
@@ -58,7 +58,7 @@ class PackArgs(C.Structure):
         ("n_props", C.c_int32), ("n_sel", C.c_int32),
         ("T_step", _dp), ("actions", _dp), ("observations", _dp), ("properties", _dp), ("rewards_cum", _dp),
         ("idxs", _dp), ("packed", _dp), ("packed_stride_e", C.c_int64), ("selected", _dp),
-        ("selected_stride_e", C.c_int64),
+        ("selected_stride_e", C.c_int64), ("selected_row_pitch", C.c_int64), ("dyn", _dp),
     ]
 
 

@@ -42,6 +42,22 @@ inline int after_launch(const char* name) {
 }
 
 // ---- device helpers ---------------------------------------------------------------------------------------
+// CUDA-graph replay support: fold the device-resident {t_idx, episode} into a private copy of the arguments
+__device__ __forceinline__ qrl_em_args resolve_dyn(const qrl_em_args& in) {
+    qrl_em_args a = in;
+    if (in.dyn) {
+        const int64_t t = in.dyn[0];
+        const int64_t rows = t * (int64_t)in.n_envs * in.n;
+        a.t_idx = t;
+        a.episode = (uint32_t)in.dyn[1];
+        if (a.W) a.W += rows;
+        if (a.obs_noise) a.obs_noise += rows;
+        if (a.T_step) a.T_step += t;
+        if (a.packed) a.packed += t * (in.packed_row_pitch > 0 ? in.packed_row_pitch : (int64_t)in.n_sel);
+    }
+    return a;
+}
+
 __device__ __forceinline__ double shfl_d(double v, int src, int width = 32) {
     return __shfl_sync(0xffffffffu, v, src, width);
 }

@@ -17,7 +17,8 @@
 namespace qrl {
 
 template <int LPE>
-__global__ void __launch_bounds__(128) em_step_kernel(const qrl_em_args a, const PhiloxKeys keys) {
+__global__ void __launch_bounds__(128) em_step_kernel(const qrl_em_args a_in, const PhiloxKeys keys) {
+    const qrl_em_args a = resolve_dyn(a_in);
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int e = tid / LPE;
     const int c = tid % LPE;
@@ -151,7 +152,9 @@ extern "C" int qrl_em_step(const qrl_em_args* args, void* stream) {
                     "qrl_em_step: packed rows need a fused reward functor and rewards_cum");
         QRL_REQUIRE(a.T_step && a.sel_idxs && a.n_sel >= 1 && a.n_actions >= 0 && (a.n_actions == 0 || a.actions),
                     "qrl_em_step: packed rows need T_step, actions and sel_idxs");
-        QRL_REQUIRE(a.packed_stride_e >= (int64_t)(a.K + 1) * a.n_sel, "qrl_em_step: packed_stride_e too small");
+        QRL_REQUIRE(a.packed_row_pitch == 0 || a.packed_row_pitch >= a.n_sel, "qrl_em_step: packed_row_pitch < n_sel");
+        QRL_REQUIRE(a.packed_stride_e >= (int64_t)(a.K + 1) * (a.packed_row_pitch > 0 ? a.packed_row_pitch : a.n_sel),
+                    "qrl_em_step: packed_stride_e too small");
     }
     cudaStream_t st = (cudaStream_t)stream;
     // Tiled kernel: one CTA per SM, noise generation spread over 15 warps -> best while the batch cannot fill the chip
@@ -175,5 +178,6 @@ extern "C" int qrl_em_step(const qrl_em_args* args, void* stream) {
     p.n_envs = a.n_envs; p.dim = a.K + 1; p.n_actions = a.n_actions; p.n_obs = a.n; p.n_props = 0; p.n_sel = a.n_sel;
     p.T_step = a.T_step; p.actions = a.actions; p.observations = a.observations; p.rewards_cum = a.rewards_cum;
     p.idxs = a.sel_idxs; p.selected = a.packed; p.selected_stride_e = a.packed_stride_e;
+    p.selected_row_pitch = a.packed_row_pitch; p.dyn = a.dyn;
     return qrl_pack_rows(&p, stream);
 }

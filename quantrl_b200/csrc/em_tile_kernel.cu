@@ -20,6 +20,7 @@
 //                              * min/max of the observations (truncation check).
 // Replaces the same reference code as em_kernel.cu (quantrl/envs/stochastic.py:178-242, envs/base.py:408-426,462,
 // 471-473,485-499) plus the packed rows of BaseSB3Env.update_data (envs/base.py:1314-1372).
+#include <stdlib.h>
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -49,18 +50,22 @@ __device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, %0;
 
 template <int N>
 __global__ void __launch_bounds__(EM_TILE_THREADS, 1)
-em_tile_kernel(const qrl_em_args a, const PhiloxKeys keys, const int G, const int C) {
+em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const int C) {
+    const qrl_em_args a = resolve_dyn(a_in);
     extern __shared__ __align__(128) double sm[];
     const int E = a.n_envs, K = a.K;
     const int e0 = blockIdx.x * G;
     const int Gl = min(G, E - e0);             // live environments of this CTA
     const int RP = Gl * N;                     // doubles per tile row
     const int tile = C * G * N;                // doubles per tile buffer (even: G is even, see plan_tiles)
-    double* Wt = sm;                           // [2][tile] Wiener increments (scaled), produced by the workers
-    double* Vt = Wt + 2 * tile;                // [2][tile] measurement noise (scaled)
-    double* Xt = Vt + 2 * tile;                // [2][tile] states, written by the recurrence warp
+    double* NB = sm;                           // [2][2][tile] noise buffers {W, V}[b]: Wiener increments and measurement
+                                               // noise (scaled) of one chunk sit next to each other, so that the pair
+                                               // doubles as the staging area of the packed cache rows once consumed
+    double* Xt = NB + 4 * tile;                // [2][tile] states, written by the recurrence warp
     double* Ot = Xt + 2 * tile;                // [tile]    observations = states + noise, written by the workers
-    double* x0S = Ot + tile;                   // [G*N] initial state (row 0)
+    double* Pt = Ot + tile;                    // [G][C][pitch] packed cache rows of one chunk, in each env's global layout
+    const int pitch = a.packed ? (int)(a.packed_row_pitch > 0 ? a.packed_row_pitch : a.n_sel) : 0;
+    double* x0S = Pt + (size_t)C * G * pitch;  // [G*N] initial state (row 0)
     double* stdS = x0S + G * N;                // [G*N] measurement-noise std per (env, comp)
     double* cumS = stdS + G * N;               // [G]   cumulative reward after this interval
     double* wS = cumS + G;                     // [N]   reward weights
@@ -89,16 +94,80 @@ em_tile_kernel(const qrl_em_args a, const PhiloxKeys keys, const int G, const in
             selS[i] = s < 0 ? s + n_data : s;
         }
     __syncthreads();
+    bool sel_identity = a.packed != nullptr && n_sel == n_data;
+    if (sel_identity)
+        for (int j = 0; j < n_sel; ++j) sel_identity &= (selS[j] == j);
 
-    // TMA eligibility: 16-byte aligned sources/destinations and sizes
-    const bool tma_x = (RP % 2 == 0) && (row % 2 == 0) && (((int64_t)e0 * N) % 2 == 0) && ((uintptr_t)a.states % 16 == 0);
+    // TMA eligibility of the packed rows: every env's run of this CTA starts 16-byte aligned and has a 16-byte size
+    const bool tma_p = a.packed != nullptr && (pitch % 2 == 0) && (a.packed_stride_e % 2 == 0) &&
+                       ((uintptr_t)a.packed % 16 == 0);
 
     double lo = INFINITY, hi = -INFINITY;
 
     // ---- worker helpers: everything derived from a finished observation row block in Ot ------------------------
     // reward rows, last-row outputs and packed cache rows for rows r_first .. r_first+ns-1 whose states/observations
     // sit in Xb/Ob (row-major [slot][env][comp])
-    auto emit_derived = [&](const double* Xb, const double* Ob, int r_first, int ns) {
+    auto emit_derived = [&](const double* Xb, const double* Ob, int r_first, int ns, double* stage) {
+        if (a.packed) {
+            // Rows are built in shared memory as [env][slot][pitch] = the global layout of each env's run, then leave
+            // as ONE TMA bulk store per env (ns * pitch * 8 contiguous bytes) when the 16-byte rules hold, else through
+            // lane-contiguous 8-byte stores.  (Direct per-row stores from the lanes cost +12 us per launch at config 3:
+            // ~300 instructions per row of address arithmetic and 8-byte pieces of 7 different sectors.)
+            const int per_env = ns * pitch;
+            const bool staged = stage != nullptr;
+            int el = wt / ns, sl = wt - el * ns;
+            const int d_el = EM_TILE_WORKERS / ns, d_sl = EM_TILE_WORKERS - d_el * ns;
+            while (el < Gl) {
+                const int r = r_first + sl, e = e0 + el;
+                const double* orow = Ob + sl * RP + el * N;
+                double* dst = staged ? stage + (el * ns + sl) * pitch
+                                     : a.packed + (int64_t)e * a.packed_stride_e + (int64_t)r * pitch;
+                if (sel_identity) {
+                    // all n_data columns in their natural order (the reference's cache_all_data layout): straight copy
+                    dst[0] = a.T_step[r];
+                    for (int k = 0; k < a.n_actions; ++k) dst[1 + k] = a.actions[(int64_t)e * a.n_actions + k];
+#pragma unroll
+                    for (int c = 0; c < N; ++c) dst[1 + a.n_actions + c] = orow[c];
+                    dst[n_data - 1] = 0.0;   // cumulative reward: patched after the last sub-step
+                } else {
+                    for (int j = 0; j < n_sel; ++j) {
+                        const int col = selS[j];
+                        double val = 0.0;  // cumulative-reward column: only known after the last sub-step, patched below
+                        if (col == 0) val = a.T_step[r];
+                        else if (col <= a.n_actions) val = a.actions[(int64_t)e * a.n_actions + (col - 1)];
+                        else if (col <= a.n_actions + N) val = orow[col - 1 - a.n_actions];
+                        dst[j] = val;
+                    }
+                }
+                if (staged)
+                    for (int j = n_sel; j < pitch; ++j) dst[j] = 0.0;   // padding columns travel with the bulk store
+                el += d_el;
+                sl += d_sl;
+                if (sl >= ns) { sl -= ns; ++el; }
+            }
+            if (staged) {
+                const bool tma_now = tma_p && (((int64_t)r_first * pitch) % 2 == 0) && (per_env % 2 == 0);
+                if (tma_now) fence_async_smem();
+                worker_barrier();
+                if (tma_now) {
+                    if (wt < 32) {
+                        for (int e2 = wt; e2 < Gl; e2 += 32)
+                            bulk_store(a.packed + (int64_t)(e0 + e2) * a.packed_stride_e + (int64_t)r_first * pitch,
+                                       stage + e2 * per_env, per_env * 8);
+                        bulk_commit();
+                    }
+                } else {
+                    int e2 = wt / per_env, off = wt - e2 * per_env;
+                    const int d_e2 = EM_TILE_WORKERS / per_env, d_off = EM_TILE_WORKERS - d_e2 * per_env;
+                    while (e2 < Gl) {
+                        a.packed[(int64_t)(e0 + e2) * a.packed_stride_e + (int64_t)r_first * pitch + off] = stage[e2 * per_env + off];
+                        e2 += d_e2;
+                        off += d_off;
+                        if (off >= per_env) { off -= per_env; ++e2; }
+                    }
+                }
+            }
+        }
         if (has_reward || a.x_last || a.obs_last) {
             for (int item = wt; item < ns * Gl; item += EM_TILE_WORKERS) {
                 const int sl = item / Gl, el = item - sl * Gl;
@@ -127,28 +196,6 @@ em_tile_kernel(const qrl_em_args a, const PhiloxKeys keys, const int G, const in
                         if (a.obs_last) a.obs_last[(int64_t)e * N + c] = orow[c];
                     }
                 }
-            }
-        }
-        if (a.packed) {
-            // q runs over [env][slot][column]: consecutive lanes write consecutive doubles of one env's contiguous run
-            const int per_env = ns * n_sel;
-            int el = wt / per_env, rr = wt - el * per_env;
-            int sl = rr / n_sel, j = rr - sl * n_sel;
-            const int d_el = EM_TILE_WORKERS / per_env, d_rr = EM_TILE_WORKERS - d_el * per_env;
-            const int d_sl = d_rr / n_sel, d_j = d_rr - d_sl * n_sel;
-            while (el < Gl) {
-                const int col = selS[j];
-                const int r = r_first + sl;
-                double val = 0.0;  // cumulative-reward column: only known after the last sub-step, patched at the end
-                if (col == 0) val = a.T_step[r];
-                else if (col <= a.n_actions) val = a.actions[(int64_t)(e0 + el) * a.n_actions + (col - 1)];
-                else if (col <= a.n_actions + N) val = Ob[sl * RP + el * N + (col - 1 - a.n_actions)];
-                a.packed[(int64_t)(e0 + el) * a.packed_stride_e + (int64_t)r * n_sel + j] = val;
-                el += d_el;
-                sl += d_sl;
-                j += d_j;
-                if (j >= n_sel) { j -= n_sel; ++sl; }
-                if (sl >= ns) { sl -= ns; ++el; }
             }
         }
     };
@@ -190,7 +237,7 @@ em_tile_kernel(const qrl_em_args a, const PhiloxKeys keys, const int G, const in
             hi = fmax(hi, o);
         }
         worker_barrier();
-        emit_derived(x0S, Ot, 0, 1);
+        emit_derived(x0S, Ot, 0, 1, nullptr);
     }
 
     // incremental (slot, rem) walkers avoid runtime integer divisions in the hot loops
@@ -205,17 +252,14 @@ em_tile_kernel(const qrl_em_args a, const PhiloxKeys keys, const int G, const in
             if (out_now) {
                 const int ns = min(C, K - co * C);
                 const double* Xb = Xt + (co & 1) * tile;
-                const double* Vb = Vt + (co & 1) * tile;
+                const double* Vb = NB + (co & 1) * 2 * tile + tile;
                 const int r0 = co * C;
+                if (wt < 32) bulk_wait_read();   // the bulk stores of the previous chunk have read Pt by now (long ago)
                 if (!dbg_no_out) {
-                    if (tma_x && a.states && wt < 32) {
-                        // one bulk store per tile row = one contiguous run of the (K+1,E,n) States block
-                        for (int slot = wt; slot < ns; slot += 32)
-                            bulk_store(a.states + (int64_t)(r0 + slot + 1) * row + (int64_t)e0 * N, Xb + slot * RP, RP * 8);
-                        bulk_commit();
-                    }
-                    // observations leave through the LSU right here (lane-contiguous 8-byte stores = fully coalesced
-                    // runs of the (K+1,E,n) block); the states tile goes out through the TMA engine below
+                    // states and observations leave through the LSU right here: lane-contiguous 8-byte stores = fully
+                    // coalesced runs of the (K+1,E,n) blocks.  (TMA bulk stores of the state rows were tried: the
+                    // recurrence warp may not overwrite its tile before the engine has read it, and waiting for that
+                    // at the end of every iteration cost more barrier time than the stores cost issue slots.)
                     int s2 = wt / RP, rem = wt - s2 * RP;
                     const int64_t gbase = (int64_t)(r0 + 1) * row + (int64_t)e0 * N;
                     while (s2 < ns) {
@@ -223,7 +267,7 @@ em_tile_kernel(const qrl_em_args a, const PhiloxKeys keys, const int G, const in
                         const double o = __dadd_rn(Xb[idx], Vb[idx]);
                         Ot[idx] = o;
                         if (a.observations) a.observations[gbase + (int64_t)s2 * row + rem] = o;
-                        if (!tma_x && a.states) a.states[gbase + (int64_t)s2 * row + rem] = Xb[idx];
+                        if (a.states) a.states[gbase + (int64_t)s2 * row + rem] = Xb[idx];
                         lo = fmin(lo, o);
                         hi = fmax(hi, o);
                         s2 += p_dslot;
@@ -234,15 +278,18 @@ em_tile_kernel(const qrl_em_args a, const PhiloxKeys keys, const int G, const in
                 worker_barrier();   // Ot complete; every read of Vt[it & 1] is done before it is refilled below
                 // ---------------- part B: reward rows, last-row outputs, packed rows ----------------
                 if (!dbg_no_out) {
-                    emit_derived(Xb, Ot, r0 + 1, ns);
+                    // Packed rows: direct per-row stores by default.  The shared-memory-staged variant (one TMA bulk
+                    // store per env run, flag QRL_EM_PACK_TMA) moves the bytes for free but needs a proxy fence and a
+                    // second worker barrier per chunk and measured slower on B200 (49.7 vs 43.3 us at config 3).
+                    emit_derived(Xb, Ot, r0 + 1, ns, (a.flags & QRL_EM_PACK_TMA) ? Pt : nullptr);
                 }
             }
             // ---------------- produce noise of chunk `it` ----------------
             if (it < NC && !dbg_no_prod) {
                 const int j0 = it * C;
                 const int ns = min(C, K - j0);
-                double* Wb = Wt + (it & 1) * tile;
-                double* Vb = Vt + (it & 1) * tile;
+                double* Wb = NB + (it & 1) * 2 * tile;
+                double* Vb = NB + (it & 1) * 2 * tile + tile;
                 int slot = wt / RP, rem = wt - slot * RP;
                 if (philox) {
                     // Software pipeline: the Philox rounds (integer ALU / IMAD pipes) of the NEXT pair are issued inside
@@ -319,13 +366,11 @@ em_tile_kernel(const qrl_em_args a, const PhiloxKeys keys, const int G, const in
                     }
                 }
             }
-            // the TMA source tiles are rewritten in the next iteration: wait until they have been read
-            if (out_now && tma_x && a.states && wt < 32) bulk_wait_read();
         } else if (it >= 1 && it <= NC && rec_live && !dbg_no_rec) {
             // ---------------- recurrence of chunk `it - 1` (the only sequential part) ----------------
             const int cr = it - 1;
             const int ns = min(C, K - cr * C);
-            const double* Wb = Wt + (cr & 1) * tile + el_r * N;
+            const double* Wb = NB + (cr & 1) * 2 * tile + el_r * N;
             double* Xb = Xt + (cr & 1) * tile + el_r * N;
             for (int slot = 0; slot < ns; ++slot) {
                 double w[N], xn[N];
@@ -355,7 +400,6 @@ em_tile_kernel(const qrl_em_args a, const PhiloxKeys keys, const int G, const in
                     for (int c = 0; c < N; ++c) Xb[slot * RP + c] = xn[c];
                 }
             }
-            fence_async_smem();
         }
         __syncthreads();
     }
@@ -372,17 +416,17 @@ em_tile_kernel(const qrl_em_args a, const PhiloxKeys keys, const int G, const in
             if (selS[j] != n_data - 1) continue;
             for (int item = tid; item < Gl * (K + 1); item += EM_TILE_THREADS) {
                 const int el = item / (K + 1), r = item - el * (K + 1);
-                a.packed[(int64_t)(e0 + el) * a.packed_stride_e + (int64_t)r * n_sel + j] = cumS[el];
+                a.packed[(int64_t)(e0 + el) * a.packed_stride_e + (int64_t)r * pitch + j] = cumS[el];
             }
         }
     }
-    if (!is_rec && wt < 32 && tma_x && a.states) bulk_wait_all();   // the bulk stores have reached global memory
+    if (!is_rec && wt < 32) bulk_wait_all();   // the bulk stores have reached global memory
     if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
 }
 
 struct TilePlan { int G, C, grid; size_t smem; };
 
-static TilePlan plan_tiles(int E, int N, int K, int n_sel, int sms) {
+static TilePlan plan_tiles(int E, int N, int K, int n_sel, int pitch, int sms) {
     TilePlan p;
     p.G = E <= 32 * sms ? (E + sms - 1) / sms : 32;
     if (p.G & 1) ++p.G;                        // even G keeps every tile row 16-byte aligned for the bulk stores
@@ -391,7 +435,7 @@ static TilePlan plan_tiles(int E, int N, int K, int n_sel, int sms) {
     p.grid = (E + p.G - 1) / p.G;
     const size_t budget = 200 * 1024;
     const size_t fixed = (size_t)(2 * p.G * N + p.G + N) * sizeof(double) + (size_t)n_sel * sizeof(int) + 256;
-    const size_t per_c = (size_t)(7 * p.G * N) * sizeof(double);
+    const size_t per_c = (size_t)(7 * p.G * N + p.G * pitch) * sizeof(double);
     int C = (int)((budget - fixed) / per_c);
     if (C > K) C = K;
     if (C > 32) C = 32;
@@ -401,12 +445,14 @@ static TilePlan plan_tiles(int E, int N, int K, int n_sel, int sms) {
     C = (K + nc - 1) / nc;
     p.C = C;
     p.smem = per_c * C + fixed;
+    if (const char* pad = getenv("QRL_DEBUG_SMEM_PAD")) p.smem += (size_t)atoi(pad);
     return p;
 }
 
 template <int N>
 static int launch_tile(const qrl_em_args& a, cudaStream_t st, int sms) {
-    const TilePlan p = plan_tiles(a.n_envs, N, a.K, a.packed ? a.n_sel : 0, sms);
+    const int pitch = a.packed ? (int)(a.packed_row_pitch > 0 ? a.packed_row_pitch : a.n_sel) : 0;
+    const TilePlan p = plan_tiles(a.n_envs, N, a.K, a.packed ? a.n_sel : 0, pitch, sms);
     static bool attr_set = false;
     if (!attr_set) {
         QRL_CUDA(cudaFuncSetAttribute(em_tile_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));

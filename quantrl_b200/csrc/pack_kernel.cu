@@ -12,7 +12,14 @@ namespace qrl {
 constexpr int PACK_G = 8;    // envs per tile
 constexpr int PACK_TT = 32;  // time rows per tile
 
-__global__ void __launch_bounds__(256) pack_rows_kernel(const qrl_pack_args a) {
+__global__ void __launch_bounds__(256) pack_rows_kernel(const qrl_pack_args a_in) {
+    qrl_pack_args a = a_in;
+    if (a_in.dyn) {   // CUDA-graph replay: episode bases + device-resident time index
+        const int64_t t = a_in.dyn[0];
+        a.T_step += t;
+        if (a.packed) a.packed += t * (2 + a.n_actions + a.n_obs + a.n_props);
+        if (a.selected) a.selected += t * (a.selected_row_pitch > 0 ? a.selected_row_pitch : (int64_t)a.n_sel);
+    }
     extern __shared__ double tile[];  // [PACK_TT][PACK_G][n_src], n_src = n_obs + n_props
     const int E = a.n_envs, dim = a.dim, na = a.n_actions, no = a.n_obs, np = a.n_props;
     const int n_src = no + np;
@@ -52,13 +59,14 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const qrl_pack_args a) {
     }
     if (a.selected && a.n_sel > 0) {
         const int ns = a.n_sel;
+        const int64_t pitch = a.selected_row_pitch > 0 ? a.selected_row_pitch : ns;
         const int per_env = gt * ns;
         for (int idx = threadIdx.x; idx < ge * per_env; idx += blockDim.x) {
             const int el = idx / per_env, r = idx % per_env;
-            const int t = r / ns;
-            int col = a.idxs[r % ns];
+            const int t = r / ns, j = r % ns;
+            int col = a.idxs[j];
             if (col < 0) col += n_data;
-            a.selected[(int64_t)(e0 + el) * a.selected_stride_e + (int64_t)t0 * ns + r] = column(el, t, col);
+            a.selected[(int64_t)(e0 + el) * a.selected_stride_e + (int64_t)(t0 + t) * pitch + j] = column(el, t, col);
         }
     }
 }
@@ -78,7 +86,8 @@ extern "C" int qrl_pack_rows(const qrl_pack_args* args, void* stream) {
     QRL_REQUIRE(a.n_sel == 0 || !a.selected || a.idxs, "qrl_pack_rows: idxs is NULL");
     QRL_REQUIRE(!a.packed || a.packed_stride_e >= (int64_t)a.dim * (2 + a.n_actions + a.n_obs + a.n_props),
                 "qrl_pack_rows: packed_stride_e too small");
-    QRL_REQUIRE(!a.selected || a.selected_stride_e >= (int64_t)a.dim * a.n_sel,
+    QRL_REQUIRE(a.selected_row_pitch == 0 || a.selected_row_pitch >= a.n_sel, "qrl_pack_rows: selected_row_pitch < n_sel");
+    QRL_REQUIRE(!a.selected || a.selected_stride_e >= (int64_t)a.dim * (a.selected_row_pitch > 0 ? a.selected_row_pitch : a.n_sel),
                 "qrl_pack_rows: selected_stride_e too small");
     const size_t smem = (size_t)PACK_TT * PACK_G * (a.n_obs + a.n_props) * sizeof(double);
     QRL_REQUIRE(smem <= 200 * 1024, "qrl_pack_rows: n_obs + n_props too large for the staging tile");

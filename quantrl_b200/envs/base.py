@@ -291,10 +291,18 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
 
     def _reset(self):
         self.batch_idx += 1
-        self.rewards = torch.zeros((self.n_envs,), dtype=torch.float64, device=self.device)
+        # zeroed in place: the buffer address is baked into captured CUDA graphs (use_cuda_graph)
+        if self.rewards is None:
+            self.rewards = torch.zeros((self.n_envs,), dtype=torch.float64, device=self.device)
+        else:
+            self.rewards.zero_()
         n_sel = len(self.data_idxs)
         if self._data_dev is None:
-            self._data_dev = torch.zeros((self.n_envs, self.shape_T[0], n_sel), dtype=torch.float64, device=self.device)
+            # row pitch rounded up to an even number of doubles: every env's run of rows then starts 16-byte aligned
+            # and the integration kernel can write it with TMA bulk stores; ``data`` drops the padding column
+            self._data_pitch = n_sel + (n_sel & 1)
+            self._data_dev = torch.zeros((self.n_envs, self.shape_T[0], self._data_pitch), dtype=torch.float64,
+                                         device=self.device)
         else:
             self._data_dev.zero_()
         self._data_host = None
@@ -315,8 +323,17 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
             a = actions.to(device=self.device, dtype=torch.float64)
         else:
             self._h_actions.copy_(torch.as_tensor(np.asarray(actions, dtype=np.float64)).reshape(self.n_envs, self.n_actions))
-            a = self._h_actions.to(self.device, non_blocking=True)
-        self.actions = (a.reshape(self.n_envs, self.n_actions) * self.action_maximums_batch).contiguous()
+            a = self._h_actions
+        self._set_actions(a)
+
+    def _set_actions(self, a):
+        """``actions = float(action) * action_maximums`` (base.py:1244-1248).  With ``use_cuda_graph`` the raw actions
+        land in the graph's static input buffer and the scaling is part of the captured graph."""
+        if getattr(self, "use_cuda_graph", False):
+            self._actions_in.copy_(a.reshape(self.n_envs, self.n_actions), non_blocking=True)
+        else:
+            a = a.to(self.device, non_blocking=True) if not a.is_cuda else a
+            self.actions = (a.reshape(self.n_envs, self.n_actions) * self.action_maximums_batch).contiguous()
 
     def step(self, actions):
         self.step_async(actions)
@@ -371,8 +388,9 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
             a.packed, a.packed_stride_e = N.ptr(self._packed), (self.action_interval + 1) * self.n_data
         # rows t_idx-dim+1 .. t_idx of the (E, shape_T, n_sel) cache; row 0 of a block overwrites the last row of
         # the previous one exactly as in the reference (base.py:1370-1372)
-        a.selected = N.ptr(self._data_dev) + 8 * (self.t_idx - dim + 1) * a.n_sel
-        a.selected_stride_e = self.shape_T[0] * a.n_sel
+        a.selected = N.ptr(self._data_dev) + 8 * (self.t_idx - dim + 1) * self._data_pitch
+        a.selected_stride_e = self.shape_T[0] * self._data_pitch
+        a.selected_row_pitch = self._data_pitch
         N.pack_rows(a)
         self._data_host = None
         if self.cache_all_data:
@@ -407,7 +425,7 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
             reward_out, obs_out = reward.clone(), observations.clone()
         done = bool(terminated or truncated)
         if done:
-            self.data_rewards.append(self.rewards)
+            self.data_rewards.append(self.rewards.clone())
             obs_reset = self._reset()
             obs_out = self._out(obs_reset)
         return obs_out, reward_out, [done] * self.n_envs, [{}] * self.n_envs
@@ -417,11 +435,11 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         cumulative reward, packed cache rows) but no host round trip — actions are a CUDA tensor, the returned
         ``(observations, reward)`` are views of device buffers that the next step overwrites, and the truncation
         reduction stays on the device (``truncation_pending()`` reads it).  Returns ``(obs, reward, terminated)``."""
-        self.actions = (actions.reshape(self.n_envs, self.n_actions) * self.action_maximums_batch)
+        self._set_actions(actions)
         observations, reward, terminated = self.update(reset_minmax=False)  # min/max accumulate over the episode
         self.update_data()
         if terminated:
-            self.data_rewards.append(self.rewards)
+            self.data_rewards.append(self.rewards.clone())
         return observations, reward, terminated
 
     def truncation_pending(self):
@@ -434,20 +452,20 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
     def data(self):
         """Host view of the selected-column cache ``(n_envs, shape_T, len(data_idxs))`` (base.py:1226, 1372)."""
         if self._data_host is None and self._data_dev is not None:
-            self._data_host = self._data_dev.cpu().numpy()
+            self._data_host = self._data_dev[:, :, :len(self.data_idxs)].cpu().numpy()
         return self._data_host
 
     def evolve(self, show_progress=False, close=True, save=False):
         """Free evolution with ``actions = action_maximums`` (base.py:1382-1449)."""
         self.reset()
         for _ in range(self.action_steps):
-            self.actions = self.action_maximums_batch
+            self._set_actions(torch.ones((self.n_envs, self.n_actions), dtype=torch.float64, device=self.device))
             self.update()
             self.update_data()
             if self.check_truncation():
                 print("Batch truncated")
                 break
-        self.data_rewards.append(self.rewards)
+        self.data_rewards.append(self.rewards.clone())
         if close:
             self.close(save=save)
 

@@ -44,6 +44,9 @@ class LinearVecEnv(BaseVecEnv):
         self.is_A_time_dependent = bool(kwargs.pop("is_A_time_dependent", False))
         self.fuse_cache_rows = bool(kwargs.pop("fuse_cache_rows", True))
         self.force_generic_kernel = bool(kwargs.pop("force_generic_kernel", False))
+        # replay one captured CUDA graph per action interval (hooks + integration launch) instead of launching eagerly;
+        # requires hooks that do not depend on ``t_idx`` (``is_A_time_dependent=False``)
+        self.use_cuda_graph = bool(kwargs.pop("use_cuda_graph", False))
         self.reward_functor = kwargs.pop("reward_functor", None)
         reward_weights = kwargs.pop("reward_weights", None)
         assert self.reward_functor in _REWARD_KINDS, f"``reward_functor`` should be one of {list(_REWARD_KINDS)}"
@@ -61,6 +64,13 @@ class LinearVecEnv(BaseVecEnv):
         self.I = torch.eye(n, dtype=torch.float64, device=self.device)
         self._reward_fused = self.reward_functor is not None
         self._cum_fused = self._reward_fused
+        assert not (self.use_cuda_graph and self.is_A_time_dependent), \
+            "``use_cuda_graph`` needs coefficient hooks that do not depend on the time index"
+        self._dyn = torch.zeros((2,), dtype=torch.int64, device=self.device)      # {t_idx, episode} read by the kernel
+        self._dyn_host = torch.zeros((2,), dtype=torch.int64).pin_memory()
+        self._actions_in = torch.zeros((self.n_envs, self.n_actions), dtype=torch.float64, device=self.device)
+        self._graph = None
+        self.graph_replays, self.graph_native_launches = 0, 0
         self._reward_w = None
         if self._reward_fused:
             w = np.ones(n) if reward_weights is None else np.asarray(reward_weights, dtype=np.float64)
@@ -87,6 +97,9 @@ class LinearVecEnv(BaseVecEnv):
                 self.Observation_noises = self.backend.normal(
                     generator=self.backend.generator(seed=self.seed), shape=(S1, E, n), mean=0.0, std=1.0,
                     dtype="real") * self.observation_stds.reshape(1, -1, n)
+        if self.use_cuda_graph:
+            self._dyn_host[0], self._dyn_host[1] = 0, (self.batch_idx + 1) & 0xFFFFFFFF
+            self._dyn.copy_(self._dyn_host, non_blocking=True)
         return super()._reset()
 
     def set_fed_noise(self, Ws, Observation_noises=None):
@@ -135,15 +148,20 @@ class LinearVecEnv(BaseVecEnv):
         if self.rng == "philox":
             a.rng_mode = N.RNG_PHILOX
             a.seed, a.episode, a.t_idx, a.env_offset = self._philox_seed, self.batch_idx & 0xFFFFFFFF, self.t_idx, self.env_offset
+            if self.use_cuda_graph:
+                a.dyn = N.ptr(self._dyn)
             if self.observation_stds is not None:
                 a.obs_std = N.ptr(self.observation_stds)
                 a.obs_std_stride_e = n if self.observation_stds.dim() == 2 else 0
         else:
             a.rng_mode = N.RNG_FED
+            t_off = 0 if self.use_cuda_graph else self.t_idx      # graph mode: the kernel adds dyn[0] rows itself
+            if self.use_cuda_graph:
+                a.dyn = N.ptr(self._dyn)
             if K > 0:
-                a.W = N.ptr(self.Ws) + 8 * self.t_idx * E * n
+                a.W = N.ptr(self.Ws) + 8 * t_off * E * n
             if self.Observation_noises is not None:
-                a.obs_noise = N.ptr(self.Observation_noises) + 8 * self.t_idx * E * n
+                a.obs_noise = N.ptr(self.Observation_noises) + 8 * t_off * E * n
         a.x0 = N.ptr(x0)
         if write_traj and self.store_trajectory:
             a.states, a.observations = N.ptr(self._States), N.ptr(self._Observations)
@@ -161,9 +179,11 @@ class LinearVecEnv(BaseVecEnv):
                 and not self.cache_all_data and self.fuse_cache_rows):
             # the (E, shape_T, n_sel) ``data`` cache rows of this interval are written by the same launch
             n_sel = len(self.data_idxs)
-            a.packed = N.ptr(self._data_dev) + 8 * self.t_idx * n_sel
-            a.packed_stride_e = self.shape_T[0] * n_sel
-            a.T_step = N.ptr(self.T) + 8 * self.t_idx
+            t_off = 0 if self.use_cuda_graph else self.t_idx
+            a.packed = N.ptr(self._data_dev) + 8 * t_off * self._data_pitch
+            a.packed_stride_e = self.shape_T[0] * self._data_pitch
+            a.packed_row_pitch = self._data_pitch
+            a.T_step = N.ptr(self.T) + 8 * t_off
             a.actions, a.n_actions = N.ptr(self.actions), self.n_actions
             a.sel_idxs, a.n_sel = N.ptr(self._sel_idxs), n_sel
             self._packed_by_kernel = True
@@ -186,5 +206,34 @@ class LinearVecEnv(BaseVecEnv):
 
     def _update_states(self):
         dim = self._dim
-        self._launch(dim - 1, self._x_last)
+        if not self.use_cuda_graph:
+            self._launch(dim - 1, self._x_last)
+        elif dim == self.action_interval + 1:
+            self._replay_interval()
+        else:  # tail interval (fewer sub-steps): eager launch, then advance the device-side time index
+            self.actions = (self._actions_in * self.action_maximums_batch)
+            self._launch(dim - 1, self._x_last)
+            self._dyn[0] += dim - 1
         return self._States[:dim]
+
+    def _replay_interval(self):
+        """One full action interval as ONE graph launch: actions scaling, the coefficient hooks (batched torch), the
+        fused integration kernel and the advance of the device-side time index are captured once and replayed."""
+        if self._graph is None:
+            K = self.action_interval
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            graph = torch.cuda.CUDAGraph()
+            n0 = N.launch_count()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(graph, stream=side):
+                    self.actions = self._actions_in * self.action_maximums_batch
+                    self._graph_keep = self._launch(K, self._x_last)
+                    self._dyn[0] += K
+            torch.cuda.current_stream().wait_stream(side)
+            self._graph = graph
+            self._graph_packs = self._packed_by_kernel
+            self.graph_native_launches = N.launch_count() - n0   # kernels of libquantrl_b200.so inside one replay
+        self.graph_replays += 1
+        self._packed_by_kernel = self._graph_packs
+        self._graph.replay()

@@ -64,10 +64,11 @@ def em_step(x0, A, nz, t_ssz, K, W=None, obs_noise=None, philox=None, obs_std=No
         T_step, actions = dev(pack["T_step"]).double(), dev(pack["actions"]).double().reshape(E, -1).contiguous()
         idxs = torch.as_tensor(np.asarray(pack["idxs"], dtype=np.int32), device="cuda")
         rows_total, row0 = pack.get("rows_total", K + 1), pack.get("row0", 0)
-        out["packed"] = torch.full((E, rows_total, len(pack["idxs"])), float("nan"), dtype=torch.float64, device="cuda")
+        pitch = pack.get("pitch", len(pack["idxs"]))
+        out["packed"] = torch.full((E, rows_total, pitch), float("nan"), dtype=torch.float64, device="cuda")
         keep += [T_step, actions, idxs]
-        a.packed = N.ptr(out["packed"]) + 8 * row0 * len(pack["idxs"])
-        a.packed_stride_e = rows_total * len(pack["idxs"])
+        a.packed = N.ptr(out["packed"]) + 8 * row0 * pitch
+        a.packed_stride_e, a.packed_row_pitch = rows_total * pitch, pitch
         a.T_step, a.actions, a.n_actions = N.ptr(T_step), N.ptr(actions), actions.shape[1]
         a.sel_idxs, a.n_sel = N.ptr(idxs), len(pack["idxs"])
     N.em_step(a)

@@ -232,9 +232,10 @@ def test_tiled_kernel_equals_generic_kernel_bitwise(native, cuda, E, n, K):
             torch.testing.assert_close(t[key], g[key], rtol=1e-13, atol=1e-15)
 
 
-@pytest.mark.parametrize("flags", [0, N.EM_FORCE_GENERIC])
-@pytest.mark.parametrize("idxs", [[0, 1, 2, 3, 4, 5, 6], [-1], [0, 3, -1, 1]])
-def test_fused_cache_rows_match_oracle_pack_rows(native, cuda, flags, idxs):
+@pytest.mark.parametrize("flags", [0, N.EM_FORCE_GENERIC, N.EM_PACK_TMA])
+@pytest.mark.parametrize("idxs,pitch", [([0, 1, 2, 3, 4, 5, 6], 7), ([0, 1, 2, 3, 4, 5, 6], 8), ([-1], 1), ([-1], 2),
+                                        ([0, 3, -1, 1], 4), ([0, 3, -1, 1], 6)])
+def test_fused_cache_rows_match_oracle_pack_rows(native, cuda, flags, idxs, pitch):
     """Packed rows written by the integration launch == oracle pack_rows (BaseSB3Env.update_data layout), written
     at a row offset of a larger (E, shape_T, n_sel) cache like the env does."""
     rng = np.random.default_rng(21)
@@ -247,10 +248,15 @@ def test_fused_cache_rows_match_oracle_pack_rows(native, cuda, flags, idxs):
     acts = rng.uniform(-1, 1, (E, 1))
     cum0 = rng.standard_normal(E)
     out = em_step(x0, A, nz, 0.01, K, W=W, obs_noise=ON, reward_kind=N.REWARD_NEG_WSQ_OBS, reward_w=np.ones(n),
-                  rewards_cum=cum0, flags=flags, pack=dict(T_step=T_step, actions=acts, idxs=idxs, rows_total=K + 11, row0=5))
+                  rewards_cum=cum0, flags=flags,
+                  pack=dict(T_step=T_step, actions=acts, idxs=idxs, rows_total=K + 11, row0=5 + (pitch & 1), pitch=pitch))
     obs = eo.em_interval_vec(x0, A, nz, W, 0.01) + ON
     cum = cum0 - np.sum(obs[-1] ** 2, -1)
     full = eo.pack_rows(T_step, acts, obs, None, cum)
     got = out["packed"].cpu().numpy()
-    np.testing.assert_allclose(got[:, 5:5 + K + 1], full[:, :, idxs], rtol=1e-12, atol=1e-14)
-    assert np.isnan(got[:, :5]).all() and np.isnan(got[:, 5 + K + 1:]).all()   # nothing outside the block is touched
+    r0 = 5 + (pitch & 1)
+    np.testing.assert_allclose(got[:, r0:r0 + K + 1, :len(idxs)], full[:, :, idxs], rtol=1e-12, atol=1e-14)
+    # nothing outside the block is touched; padding columns of a pitched cache are unspecified (untouched or zero)
+    assert np.isnan(got[:, :r0]).all() and np.isnan(got[:, r0 + K + 1:]).all()
+    pad = got[:, r0:r0 + K + 1, len(idxs):]
+    assert np.all(np.isnan(pad) | (pad == 0.0))

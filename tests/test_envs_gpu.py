@@ -230,3 +230,30 @@ def test_lho_vec_env_evolve_tail_interval_and_noise(native, cuda, golden_dir):
     noise = (env.Observations - env.States).flatten()
     assert 0.5e-3 < noise.std().item() < 2e-3
     env.close()
+
+
+def test_cuda_graph_replay_equals_eager(native, cuda):
+    """``use_cuda_graph=True`` (one captured graph per action interval, device-resident time index) reproduces the
+    eager env bit for bit over two episodes, including the fused ``data`` cache rows and a tail interval."""
+    from quantrl_b200.systems import AffineLinearVecEnv, affine_matrices
+    A0, Au = affine_matrices(4, 1, seed=0)
+    E, K = 300, 10
+    kw = dict(n_envs=E, n=4, A0=A0, Au=Au, noise_prefixes=0.05, x0=1.0, t_norm_max=0.455, t_norm_ssz=0.01,
+              action_interval=K, observation_stds=[0.01] * 4, seed=9, dir_prefix="/tmp/qrl_test")
+    eager, graph = AffineLinearVecEnv(**kw), AffineLinearVecEnv(use_cuda_graph=True, **kw)
+    assert eager.shape_T == (46,) and eager.action_steps == 5         # 4 full intervals + a tail of 5 sub-steps
+    o_e, o_g = eager.reset(), graph.reset()
+    assert torch.equal(o_e, o_g)
+    rng = np.random.default_rng(0)
+    for step in range(10):
+        u = torch.as_tensor(rng.uniform(-1, 1, (E, 1)), device="cuda")
+        if step == 3:
+            d_e, d_g = eager.data.copy(), graph.data.copy()
+            np.testing.assert_array_equal(d_e, d_g)
+        oe, re_, de, _ = eager.step(u)
+        og, rg, dg, _ = graph.step(u)
+        assert torch.equal(oe, og) and torch.equal(re_, rg) and de == dg
+        assert torch.equal(eager.States, graph.States) and torch.equal(eager.rewards, graph.rewards)
+        assert eager.t_idx == graph.t_idx
+    assert graph.graph_replays == 8 and graph.graph_native_launches == 1 and eager.batch_idx == graph.batch_idx == 2
+    eager.close(); graph.close()

@@ -5,15 +5,16 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import numpy as np, torch
 from quantrl_b200 import _native as N
 
-def bench(E, n, K, philox=True, traj=True, reps=50, flags=0, graph=True):
+def bench(E, n, K, philox=True, traj=True, reps=50, flags=0, graph=True, pack=0, rotate=False):
     dev = "cuda"
     rng = np.random.default_rng(0)
     A = torch.as_tensor(0.3 * rng.standard_normal((E, n, n)), device=dev)
     nz = torch.full((n,), 0.05, dtype=torch.float64, device=dev)
     std = torch.full((n,), 0.01, dtype=torch.float64, device=dev)
     x = torch.ones((E, n), dtype=torch.float64, device=dev)
-    S = torch.empty((K + 1, E, n), dtype=torch.float64, device=dev)
-    O = torch.empty((K + 1, E, n), dtype=torch.float64, device=dev)
+    nbuf = reps if rotate else 1
+    S = torch.empty((nbuf, K + 1, E, n), dtype=torch.float64, device=dev)
+    O = torch.empty((nbuf, K + 1, E, n), dtype=torch.float64, device=dev)
     R = torch.empty((K + 1, E), dtype=torch.float64, device=dev)
     rl = torch.empty((E,), dtype=torch.float64, device=dev); rc = torch.zeros((E,), dtype=torch.float64, device=dev)
     xl = torch.empty((E, n), dtype=torch.float64, device=dev); ol = torch.empty((E, n), dtype=torch.float64, device=dev)
@@ -35,6 +36,16 @@ def bench(E, n, K, philox=True, traj=True, reps=50, flags=0, graph=True):
     a.reward_kind, a.reward_w, a.reward_last, a.rewards_cum = N.REWARD_NEG_WSQ_OBS, N.ptr(w), N.ptr(rl), N.ptr(rc)
     a.obs_minmax, a.nan_flag = N.ptr(mm), N.ptr(nan)
     a.flags = flags
+    if pack:
+        S1 = reps * K + 1
+        cache = torch.zeros((E, S1, n + 4), dtype=torch.float64, device=dev)
+        Tt = torch.arange(S1, dtype=torch.float64, device=dev) * 0.01
+        acts = torch.zeros((E, 1), dtype=torch.float64, device=dev)
+        idxs = torch.arange(n + 3, dtype=torch.int32, device=dev) if pack == 1 else torch.tensor([n + 2], dtype=torch.int32, device=dev)
+        nsel = idxs.numel()
+        pitch = nsel + (nsel & 1)
+        cache = cache[:, :, :pitch].contiguous()
+        a.packed_stride_e, a.packed_row_pitch, a.actions, a.n_actions, a.sel_idxs, a.n_sel = S1 * pitch, pitch, N.ptr(acts), 1, N.ptr(idxs), nsel
     for _ in range(5):
         N.em_step(a)
     torch.cuda.synchronize()
@@ -50,6 +61,10 @@ def bench(E, n, K, philox=True, traj=True, reps=50, flags=0, graph=True):
         with torch.cuda.graph(g):
             for i in range(reps):
                 a.t_idx = i * K
+                if pack:
+                    a.packed, a.T_step = N.ptr(cache) + 8 * i * K * pitch, N.ptr(Tt) + 8 * i * K
+                if rotate and traj:
+                    a.states, a.observations = N.ptr(S) + 8 * i * (K + 1) * E * n, N.ptr(O) + 8 * i * (K + 1) * E * n
                 N.em_step(a)
         g.replay(); torch.cuda.synchronize()
         e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
@@ -57,6 +72,8 @@ def bench(E, n, K, philox=True, traj=True, reps=50, flags=0, graph=True):
         e0.record()
         for i in range(reps):
             a.t_idx = i * K
+            if pack:
+                a.packed, a.T_step = N.ptr(cache) + 8 * i * K * pitch, N.ptr(Tt) + 8 * i * K
             N.em_step(a)
         e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
