@@ -210,14 +210,14 @@ class B200Backend:
     def conj(self, tensor):
         return torch.conj(tensor)
 
-    def min(self, tensor, axis=None):
-        return torch.min(tensor) if axis is None else torch.min(tensor, axis).values
+    def min(self, tensor):
+        return torch.min(tensor)
 
-    def max(self, tensor, axis=None):
-        return torch.max(tensor) if axis is None else torch.max(tensor, axis).values
+    def max(self, tensor):
+        return torch.max(tensor)
 
-    def argmax(self, tensor, axis=None):
-        return torch.argmax(tensor) if axis is None else torch.argmax(tensor, axis)
+    def argmax(self, tensor):
+        return torch.argmax(tensor)
 
 
 _INSTANCES = {}

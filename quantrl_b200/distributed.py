@@ -1,0 +1,99 @@
+"""Environment sharding across the GPUs of one box (one process per GPU, ``torch.distributed``).
+
+Environments are independent units (no cross-env term in the reference's RHS / EM update: quantrl/envs/
+deterministic.py:653-746, quantrl/envs/stochastic.py:196-242), so the hot path shards with NO data-path collective:
+rank ``r`` owns the contiguous block ``[offset_r, offset_r + count_r)`` of the global batch and passes ``env_offset``
+to the kernels, whose Philox counters use the GLOBAL env index — results do not depend on the number of ranks.
+
+The only exchange is the learner protocol of one action step:
+
+    learner (rank ``dst``)          workers
+    scatter  actions (E, n_act)  -> local slices
+                                    env.step_device(local actions)          # fused kernel, no collective
+    gather   [obs | reward | done-flag]  <- (E_loc, n_obs + 2) per rank      # NCCL over NVLink / gloo on CPU
+
+The truncation flag rides in the same buffer (column ``n_obs + 1``): the reference ends the episode for ALL envs
+when any observation leaves the range (quantrl/envs/base.py:485-499, 1271-1293), so the learner ORs the flags.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_envs_total: int, rank: int, world_size: int):
+    """Contiguous block of rank ``rank``: (offset, count).  The first ``n % world`` ranks get one extra env."""
+    assert 0 <= rank < world_size and n_envs_total >= 0
+    base, extra = divmod(n_envs_total, world_size)
+    count = base + (1 if rank < extra else 0)
+    offset = rank * base + min(rank, extra)
+    return offset, count
+
+
+def all_shard_bounds(n_envs_total: int, world_size: int):
+    return [shard_bounds(n_envs_total, r, world_size) for r in range(world_size)]
+
+
+class LearnerLink:
+    """Scatter actions from / gather (obs, reward, truncation flag) to the learner rank, once per action step."""
+
+    def __init__(self, n_envs_total, n_observations, n_actions, device, dst=0, group=None, dtype=torch.float64):
+        assert dist.is_initialized(), "torch.distributed is not initialised"
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.dst, self.n_obs, self.n_act, self.E = dst, n_observations, n_actions, n_envs_total
+        self.bounds = all_shard_bounds(n_envs_total, self.world)
+        self.offset, self.count = self.bounds[self.rank]
+        self.device, self.dtype = torch.device(device), dtype
+        width = n_observations + 2
+        self._local = torch.zeros((self.count, width), dtype=dtype, device=self.device)
+        self._local_actions = torch.zeros((self.count, n_actions), dtype=dtype, device=self.device)
+        self.is_learner = self.rank == dst
+        # uneven shards are padded to the largest block so that one all_gather_into_tensor / gather call suffices
+        self._max = max(c for _, c in self.bounds)
+        self._send = torch.zeros((self._max, width), dtype=dtype, device=self.device)
+        self._recv = torch.zeros((self.world, self._max, width), dtype=dtype, device=self.device) if self.is_learner else None
+        self._act_pad = torch.zeros((self.world, self._max, n_actions), dtype=dtype, device=self.device) if self.is_learner else None
+        self._act_recv = torch.zeros((self._max, n_actions), dtype=dtype, device=self.device)
+
+    def scatter_actions(self, actions_global=None):
+        """Learner passes (E, n_act); every rank returns its (E_loc, n_act) slice."""
+        if self.world == 1:
+            return actions_global.to(self.device, self.dtype).reshape(self.E, self.n_act)
+        scatter_list = None
+        if self.is_learner:
+            a = actions_global.to(self.device, self.dtype).reshape(self.E, self.n_act)
+            for r, (off, cnt) in enumerate(self.bounds):
+                self._act_pad[r, :cnt] = a[off:off + cnt]
+            scatter_list = list(self._act_pad.unbind(0))
+        dist.scatter(self._act_recv, scatter_list, src=self.dst, group=self.group)
+        self._local_actions.copy_(self._act_recv[:self.count])
+        return self._local_actions
+
+    def gather_step(self, obs_local, reward_local, truncated_local=False):
+        """Every rank passes its (E_loc, n_obs) observations, (E_loc,) rewards and truncation flag.  The learner gets
+        ``(obs (E, n_obs), reward (E,), truncated: bool)`` in global env order, the other ranks get ``None``."""
+        n = self.n_obs
+        self._send[:self.count, :n] = obs_local
+        self._send[:self.count, n] = reward_local
+        self._send[:self.count, n + 1] = float(bool(truncated_local))
+        if self.world == 1:
+            return obs_local, reward_local, bool(truncated_local)
+        gather_list = list(self._recv.unbind(0)) if self.is_learner else None
+        dist.gather(self._send, gather_list, dst=self.dst, group=self.group)
+        if not self.is_learner:
+            return None
+        parts = [self._recv[r, :cnt] for r, (_, cnt) in enumerate(self.bounds)]
+        full = torch.cat(parts, dim=0)
+        return full[:, :n], full[:, n], bool((full[:, n + 1] > 0).any().item()) if full.shape[0] else False
+
+
+def make_sharded_env(env_cls, n_envs_total, rank=None, world_size=None, **env_kwargs):
+    """Build this rank's shard of a ``n_envs_total`` batch: ``n_envs`` and ``env_offset`` are filled in, per-env array
+    arguments named in ``env_kwargs['_per_env']`` are sliced to the local block."""
+    rank = dist.get_rank() if rank is None else rank
+    world_size = dist.get_world_size() if world_size is None else world_size
+    offset, count = shard_bounds(n_envs_total, rank, world_size)
+    per_env = env_kwargs.pop("_per_env", ())
+    for key in per_env:
+        if env_kwargs.get(key) is not None:
+            env_kwargs[key] = env_kwargs[key][offset:offset + count]
+    return env_cls(n_envs=count, env_offset=offset, **env_kwargs)
