@@ -97,3 +97,42 @@ def make_sharded_env(env_cls, n_envs_total, rank=None, world_size=None, **env_kw
         if env_kwargs.get(key) is not None:
             env_kwargs[key] = env_kwargs[key][offset:offset + count]
     return env_cls(n_envs=count, env_offset=offset, **env_kwargs)
+
+
+class PeerGather:
+    """Gather-to-learner WITHOUT a collective launch: every rank's integration kernel stores its slice of the step
+    result (last observations, last reward) straight into the learner rank's buffer through NVLink peer mapping
+    (torch symmetric memory), i.e. the gather is fused into the epilogue of ``qrl_em_step`` / ``qrl_ode_step``.
+    ``fence()`` is the only cross-GPU synchronisation: a device-side barrier on the current stream after which the
+    learner may read ``obs_all`` / ``reward_all``.
+
+    The NCCL path (``LearnerLink.gather_step``) stays as the fallback and as the measured comparison.
+    """
+
+    def __init__(self, n_envs_total, n_observations, device, dst=0, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        assert dist.is_initialized()
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.dst, self.E, self.n_obs = dst, n_envs_total, n_observations
+        self.offset, self.count = shard_bounds(n_envs_total, self.rank, self.world)
+        n_words = n_envs_total * (n_observations + 1)
+        self.buf = symm_mem.empty(n_words + (n_words & 1), dtype=torch.float64, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, self.group.group_name if hasattr(self.group, "group_name") else self.group)
+        base = int(self.hdl.buffer_ptrs[dst])
+        self.obs_ptr = base + 8 * self.offset * n_observations
+        self.reward_ptr = base + 8 * (n_envs_total * n_observations + self.offset)
+        self.is_learner = self.rank == dst
+        self.obs_all = self.buf[:n_envs_total * n_observations].view(n_envs_total, n_observations)
+        self.reward_all = self.buf[n_envs_total * n_observations:n_words]
+
+    def attach(self, env):
+        """Point the env's step outputs at the learner's buffer (before the first step / graph capture)."""
+        assert env.n_envs == self.count and env.n_observations == self.n_obs
+        obs_view = self.obs_all[self.offset:self.offset + self.count] if self.is_learner else None
+        rew_view = self.reward_all[self.offset:self.offset + self.count] if self.is_learner else None
+        env.attach_step_output(self.obs_ptr, self.reward_ptr, obs_view, rew_view)
+
+    def fence(self):
+        self.hdl.barrier(channel=0)

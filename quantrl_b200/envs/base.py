@@ -244,6 +244,7 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         self._packed = torch.empty((E, K1, self.n_data), dtype=f64, device=self.device) if self.cache_all_data else None
         self._reward_fused = False
         self._cum_fused = False
+        self._obs_last_ptr = self._reward_last_ptr = None
 
     # ---- hooks the interfaced environment implements (base.py:272-317) ------------------------------------------
     def _update_states(self):
@@ -444,6 +445,18 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
 
     def truncation_pending(self):
         return self.check_truncation()
+
+    def attach_step_output(self, obs_ptr, reward_ptr, obs_view=None, reward_view=None):
+        """Redirect the per-step outputs (last observations, last reward) of the integration kernel to caller-owned
+        device memory — e.g. the learner rank's buffer mapped over NVLink (``distributed.PeerGather``).  ``obs_ptr`` /
+        ``reward_ptr`` are raw device addresses; the optional views replace the local tensors returned by
+        ``step_device`` (ranks whose outputs live on another GPU keep returning their stale local buffers)."""
+        self._obs_last_ptr, self._reward_last_ptr = int(obs_ptr), int(reward_ptr)
+        if obs_view is not None:
+            self._obs_last = obs_view
+        if reward_view is not None:
+            self._reward_last = reward_view
+        self._graph = None
 
     def _out(self, t):
         return t.detach().cpu().numpy() if self.return_numpy else t

@@ -137,6 +137,22 @@ class LinearVecEnv(BaseVecEnv):
         return nz.expand(self.n_envs, -1) if nz.dim() == 1 else nz
 
     def _launch(self, K, x0, write_traj=True):
+        a, keep = self.interval_args(K, x0, write_traj)
+        ev = getattr(self, "_em_events", None)
+        if ev is not None and K > 0:  # live per-launch timing on the launch stream (bench.py roofline)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            N.em_step(a)
+            e1.record()
+            ev.append((e0, e1))
+        else:
+            N.em_step(a)
+        return keep
+
+    def interval_args(self, K, x0=None, write_traj=True):
+        """Build the ``qrl_em_args`` of one action interval (evaluates the coefficient hooks).  Returns
+        ``(args, tensors_to_keep_alive)``; ``_launch`` enqueues it, ``bench.py`` re-launches it to time the kernel."""
+        x0 = self._x_last if x0 is None else x0
         E, n = self.n_envs, self.n_observations
         a = N.EmArgs()
         a.n, a.n_envs, a.K, a.t_ssz = n, E, K, self.t_ssz
@@ -165,12 +181,13 @@ class LinearVecEnv(BaseVecEnv):
         a.x0 = N.ptr(x0)
         if write_traj and self.store_trajectory:
             a.states, a.observations = N.ptr(self._States), N.ptr(self._Observations)
-        a.x_last, a.obs_last = N.ptr(self._x_last), N.ptr(self._obs_last)
+        a.x_last = N.ptr(self._x_last)
+        a.obs_last = self._obs_last_ptr if self._obs_last_ptr is not None else N.ptr(self._obs_last)
         if self._reward_fused and K > 0:
             a.reward_kind = _REWARD_KINDS[self.reward_functor]
             a.reward_w = N.ptr(self._reward_w)
             a.reward = N.ptr(self._Reward) if self.store_trajectory else None
-            a.reward_last = N.ptr(self._reward_last)
+            a.reward_last = self._reward_last_ptr if self._reward_last_ptr is not None else N.ptr(self._reward_last)
             a.rewards_cum = N.ptr(self.rewards)
         a.obs_minmax = N.ptr(self._minmax)
         a.nan_flag = N.ptr(self._nan)
@@ -189,16 +206,7 @@ class LinearVecEnv(BaseVecEnv):
             self._packed_by_kernel = True
         if self.force_generic_kernel:
             a.flags = N.EM_FORCE_GENERIC
-        ev = getattr(self, "_em_events", None)
-        if ev is not None and K > 0:  # live per-launch timing on the launch stream (bench.py roofline)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            N.em_step(a)
-            e1.record()
-            ev.append((e0, e1))
-        else:
-            N.em_step(a)
-        return keep
+        return a, keep
 
     def _initial_observations(self, states_0):
         self._launch(0, states_0, write_traj=False)  # row 0 only: obs_0 = states_0 + noise[0]
