@@ -209,7 +209,12 @@ typedef struct qrl_ode_args {
 
     double*  obs_minmax;     /* as in qrl_em_args */
     int32_t* nan_flag;
+    int32_t  flags;          /* QRL_ODE_* bits */
+    int32_t  _pad1;
 } qrl_ode_args;
+
+#define QRL_ODE_FORCE_THREAD 1  /* flags: RK4 with one thread per env whatever the batch size (A/B testing) */
+#define QRL_ODE_FORCE_LANES  2  /* flags: RK4 with q*q lanes per env (q = 4 only) whatever the batch size */
 
 QRL_API int qrl_ode_step(const qrl_ode_args* args, void* stream);
 

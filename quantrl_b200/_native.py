@@ -14,6 +14,7 @@ REWARD_NONE, REWARD_NEG_WSQ_OBS, REWARD_NEG_WSQ_STATE = 0, 1, 2
 SYS_OPTOMECH, SYS_KERR_CHAIN, SYS_CONST_AD = 1, 2, 3
 ODE_RK4, ODE_DOPRI5 = 0, 1
 EM_FORCE_GENERIC, EM_FORCE_TILED, EM_PACK_TMA = 1, 16, 128
+ODE_FORCE_THREAD, ODE_FORCE_LANES = 1, 2
 
 _dp = C.c_void_p  # device pointers travel as integers
 
@@ -49,6 +50,7 @@ class OdeArgs(C.Structure):
         ("seed", C.c_uint64), ("episode", C.c_uint32), ("_pad0", C.c_uint32), ("t_idx", C.c_int64),
         ("env_offset", C.c_int64), ("obs_std", _dp), ("obs_std_stride_e", C.c_int64),
         ("h_state", _dp), ("n_steps", _dp), ("obs_minmax", _dp), ("nan_flag", _dp),
+        ("flags", C.c_int32), ("_pad1", C.c_int32),
     ]
 
 

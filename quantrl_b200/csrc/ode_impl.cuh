@@ -331,10 +331,129 @@ __global__ void __launch_bounds__(BLOCK) dopri5_kernel(const qrl_ode_args a) {
     if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// RK4, q*q lanes per environment (q = 4: half a warp) — for batches too small to fill the chip with one thread per
+// env (BASELINE config 2: E = 1024 is 32 warps on 592 schedulers; measured 300 us per 100-sub-step interval with the
+// thread-per-env kernel above).  Lane (i,j) owns V_ij; the classical mode amplitudes are replicated in every lane
+// (a few dozen flops); per RK stage the group publishes V and the drift matrix A in shared memory and every lane
+// accumulates its 2q products  (A V)_ij + (V A^T)_ij.  Rows of the (K+1,E,d) blocks are written directly: the lanes
+// of one env cover its d contiguous doubles.
+// ------------------------------------------------------------------------------------------------------------------
+template <class Sys, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) rk4_lanes_kernel(const qrl_ode_args a) {
+    constexpr int M = Sys::M, Q = Sys::Q, D = Dim<Sys>::D, L = Q * Q;   // L lanes per env
+    static_assert(L == 16, "rk4_lanes_kernel is written for q = 4");
+    constexpr int EPB = BLOCK / L;                                    // envs per block
+    __shared__ double sA[EPB][Q][Q], sV[EPB][Q][Q];
+    const int E = a.n_envs, K = a.K;
+    const int g = threadIdx.x / L, l = threadIdx.x % L;
+    const int i = l / Q, j = l % Q;
+    const int e = blockIdx.x * EPB + g;
+    const bool live = e < E;
+    const int el = live ? e : E - 1;
+
+    Sys s;
+    load_system(s, a, el);
+    double ym[2 * M > 0 ? 2 * M : 1];                                 // modes, replicated
+#pragma unroll
+    for (int c = 0; c < 2 * M; ++c) ym[c] = a.y0[(int64_t)el * D + c];
+    double v = a.y0[(int64_t)el * D + 2 * M + l];                     // my covariance element
+    const double dij = s.D(i, j);
+
+    double lo = INFINITY, hi = -INFINITY;
+    auto emit = [&](int row) {
+        if (!live) return;
+        const int64_t base = ((int64_t)row * E + e) * D;
+        // lane l writes V element l; lanes 0 .. 2M-1 also write the modes: one env = D contiguous doubles
+        auto put = [&](int d, double val) {
+            const double ob = val + obs_noise_at(a, row, e, d, D);
+            if (a.states) a.states[base + d] = val;
+            if (a.observations) a.observations[base + d] = ob;
+            if (row == K) {
+                if (a.y_last) a.y_last[(int64_t)e * D + d] = val;
+                if (a.obs_last) a.obs_last[(int64_t)e * D + d] = ob;
+                if (a.nan_flag && !isfinite(val)) *a.nan_flag = 1;
+            }
+            lo = fmin(lo, ob);
+            hi = fmax(hi, ob);
+        };
+        put(2 * M + l, v);
+        if (l < 2 * M) {
+            double mv = 0.0;
+#pragma unroll
+            for (int c = 0; c < 2 * M; ++c) mv = (l == c) ? ym[c] : mv;
+            put(l, mv);
+        }
+    };
+    // one RHS evaluation at (modes ymt, my element vt): returns dV_ij, fills dm
+    auto rhs_lane = [&](double t, const double* ymt, double vt, double* dm) -> double {
+        double yfull[2 * M > 0 ? 2 * M : 1];
+#pragma unroll
+        for (int c = 0; c < 2 * M; ++c) yfull[c] = ymt[c];
+        double A[Q][Q];
+        s.eval(t, yfull, dm, A);
+        __syncwarp();                     // previous stage's reads of sA / sV are done
+        if (l == 0) {
+#pragma unroll
+            for (int r = 0; r < Q; ++r)
+#pragma unroll
+                for (int c = 0; c < Q; ++c) sA[g][r][c] = A[r][c];
+        }
+        sV[g][i][j] = vt;
+        __syncwarp();
+        double av = 0.0, va = 0.0;
+#pragma unroll
+        for (int k = 0; k < Q; ++k) {
+            av = fma(sA[g][i][k], sV[g][k][j], av);   // (A V)_ij
+            va = fma(sV[g][i][k], sA[g][j][k], va);   // (V A^T)_ij
+        }
+        return (av + va) + dij;
+    };
+
+    emit(0);
+    const int nsub = a.substeps;
+    const double h = a.t_ssz / (double)nsub;
+    for (int row = 1; row <= K; ++row) {
+        const double t_row = a.t0 + (double)(row - 1) * a.t_ssz;
+        for (int sub = 0; sub < nsub; ++sub) {
+            const double t = t_row + (double)sub * h;
+            double dm[2 * M > 0 ? 2 * M : 1], ymt[2 * M > 0 ? 2 * M : 1], accm[2 * M > 0 ? 2 * M : 1];
+            double k = rhs_lane(t, ym, v, dm);
+            double accv = k, vt = fma(0.5 * h, k, v);
+#pragma unroll
+            for (int c = 0; c < 2 * M; ++c) { accm[c] = dm[c]; ymt[c] = fma(0.5 * h, dm[c], ym[c]); }
+            k = rhs_lane(t + 0.5 * h, ymt, vt, dm);
+            accv = fma(2.0, k, accv); vt = fma(0.5 * h, k, v);
+#pragma unroll
+            for (int c = 0; c < 2 * M; ++c) { accm[c] = fma(2.0, dm[c], accm[c]); ymt[c] = fma(0.5 * h, dm[c], ym[c]); }
+            k = rhs_lane(t + 0.5 * h, ymt, vt, dm);
+            accv = fma(2.0, k, accv); vt = fma(h, k, v);
+#pragma unroll
+            for (int c = 0; c < 2 * M; ++c) { accm[c] = fma(2.0, dm[c], accm[c]); ymt[c] = fma(h, dm[c], ym[c]); }
+            k = rhs_lane(t + h, ymt, vt, dm);
+            v = fma(h / 6.0, accv + k, v);
+#pragma unroll
+            for (int c = 0; c < 2 * M; ++c) ym[c] = fma(h / 6.0, accm[c] + dm[c], ym[c]);
+        }
+        emit(row);
+    }
+    if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
+}
+
 template <class Sys>
 int launch_ode(const qrl_ode_args& a, cudaStream_t st) {
     constexpr int D = Dim<Sys>::D;
     if (a.method == QRL_ODE_RK4) {
+        if constexpr (Sys::Q == 4) {
+            // small batches: 16 lanes per env (measured crossover with one thread per env at E ~ 8000 on B200:
+            // 95 vs 300 us at E = 1024, 175 vs 301 us at 4096, 317 vs 301 us at 8192; tools/quick_ode_bench.py)
+            if ((a.n_envs <= 6144 || (a.flags & QRL_ODE_FORCE_LANES)) && !(a.flags & QRL_ODE_FORCE_THREAD)) {
+                constexpr int BL = 64;
+                rk4_lanes_kernel<Sys, BL><<<(a.n_envs + BL / 16 - 1) / (BL / 16), BL, 0, st>>>(a);
+                return after_launch("rk4_lanes_kernel");
+            }
+        }
         constexpr int BLOCK = 32;
         const size_t smem = (size_t)BLOCK * (D | 1) * sizeof(double);
         const int blocks = (a.n_envs + BLOCK - 1) / BLOCK;

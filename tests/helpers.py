@@ -77,7 +77,7 @@ def em_step(x0, A, nz, t_ssz, K, W=None, obs_noise=None, philox=None, obs_std=No
 
 
 def ode_step(system, m, q, y0, K, t0, t_ssz, params=None, actions=None, A=None, D=None, method="rk4", substeps=1,
-             atol=1e-9, rtol=1e-6, obs_noise=None, h_state=None, philox=None, obs_std=None):
+             atol=1e-9, rtol=1e-6, obs_noise=None, h_state=None, philox=None, obs_std=None, flags=0):
     """Run qrl_ode_step once; returns dict of torch tensors."""
     y0 = dev(y0).double()
     E, d = y0.shape
@@ -116,6 +116,7 @@ def ode_step(system, m, q, y0, K, t0, t_ssz, params=None, actions=None, A=None, 
     a.y_last, a.obs_last = N.ptr(out["y_last"]), N.ptr(out["obs_last"])
     a.h_state, a.n_steps = N.ptr(out["h_state"]), N.ptr(out["n_steps"])
     a.obs_minmax, a.nan_flag = N.ptr(out["minmax"]), N.ptr(out["nan"])
+    a.flags = flags
     N.ode_step(a)
     torch.cuda.synchronize()
     return out

@@ -171,3 +171,31 @@ def test_ode_edge_cases_and_errors(native, cuda):
     a.method = 5
     with pytest.raises(N.NativeError, match="RK4 or DOPRI5"):
         N.ode_step(a)
+
+
+@pytest.mark.parametrize("E", [1, 3, 17, 1024])
+def test_rk4_lanes_kernel_equals_thread_kernel(native, cuda, E):
+    """q*q lanes per env (small batches) vs one thread per env: same RK4, sums associate differently only inside
+    (A V + V A^T), so agreement is to rounding; fed noise, min/max and last rows included."""
+    from quantrl_b200 import _native as N
+    rng = np.random.default_rng(E)
+    for system, m in (("optomech", 2), ("kerr_chain", 2)):
+        if system == "optomech":
+            p = sy.optomech_default_params(max(E, 2), seed=2)[:E]; y0 = sy.optomech_y0(p)
+        else:
+            p = sy.kerr_default_params(E, 2, seed=4); y0 = sy.kerr_y0(p, 2); y0[:, :2] = 0.3
+        u = rng.uniform(-1, 1, E)
+        noise = 1e-3 * rng.standard_normal((31, E, 20))
+        kw = dict(params=p, actions=u, obs_noise=noise, substeps=2)
+        a = ode_step(system, m, 4, y0, 30, 0.5, 0.01, flags=N.ODE_FORCE_LANES, **kw)
+        b = ode_step(system, m, 4, y0, 30, 0.5, 0.01, flags=N.ODE_FORCE_THREAD, **kw)
+        for key in ("states", "observations", "y_last", "obs_last"):
+            torch.testing.assert_close(a[key], b[key], rtol=1e-13, atol=1e-15)
+        torch.testing.assert_close(a["minmax"], b["minmax"], rtol=1e-13, atol=1e-15)
+    # const_AD (no modes) through the lanes kernel
+    A = -np.eye(4) * 1.5 + 0.2 * rng.standard_normal((E, 4, 4))
+    Dm = rng.standard_normal((E, 4, 4))
+    V0 = rng.standard_normal((E, 16))
+    a = ode_step("const_AD", 0, 4, V0, 12, 0.0, 0.05, A=A, D=Dm, flags=N.ODE_FORCE_LANES)
+    b = ode_step("const_AD", 0, 4, V0, 12, 0.0, 0.05, A=A, D=Dm, flags=N.ODE_FORCE_THREAD)
+    torch.testing.assert_close(a["states"], b["states"], rtol=1e-13, atol=1e-15)

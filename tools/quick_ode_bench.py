@@ -6,7 +6,7 @@ import numpy as np, torch
 import systems as sy
 from quantrl_b200 import _native as N
 
-def bench(system, E, m, q, K=100, method="rk4", reps=10, traj=True, atol=1e-9, rtol=1e-6):
+def bench(system, E, m, q, K=100, method="rk4", reps=10, traj=True, atol=1e-9, rtol=1e-6, flags=0):
     dev = "cuda"
     d = 2 * m + q * q
     if system == "optomech":
@@ -29,6 +29,7 @@ def bench(system, E, m, q, K=100, method="rk4", reps=10, traj=True, atol=1e-9, r
     if traj:
         a.states, a.observations = N.ptr(S), N.ptr(O)
     a.h_state, a.n_steps, a.obs_minmax, a.nan_flag = N.ptr(hs), N.ptr(ns), N.ptr(mm), N.ptr(nan)
+    a.flags = flags
     for _ in range(3):
         N.ode_step(a)
     torch.cuda.synchronize()
@@ -48,14 +49,10 @@ def bench(system, E, m, q, K=100, method="rk4", reps=10, traj=True, atol=1e-9, r
     sub = E * K / (ms * 1e-3)
     steps = ns.sum().item() / reps if method != "rk4" else E * K
     flops = (4 * (4 * q ** 3 + 40) + 13 * d) if method == "rk4" else 0
-    return dict(system=system, E=E, q=q, method=method, traj=traj, ms=round(ms, 4), substeps_per_s=f"{sub:.3e}",
+    return dict(system=system, E=E, q=q, method=method, traj=traj, flags=flags, ms=round(ms, 4), substeps_per_s=f"{sub:.3e}",
                 rk_steps_per_interval=steps / E, gflops=round(sub * flops / 1e9, 1), hbm_GBs=round(sub * 8 * (2 * d + 1) / 1e9, 1) if traj else 0)
 
 if __name__ == "__main__":
-    for E in (1024, 8192, 65536):
-        print(json.dumps(bench("optomech", E, 2, 4)))
-        print(json.dumps(bench("optomech", E, 2, 4, traj=False)))
-        print(json.dumps(bench("optomech", E, 2, 4, method="dopri5")))
-    print(json.dumps(bench("kerr_chain", 1024, 2, 4)))
-    print(json.dumps(bench("kerr_chain", 4096, 4, 8)))
-    print(json.dumps(bench("kerr_chain", 4096, 4, 8, method="dopri5")))
+    for E in (256, 1024, 2048, 4096, 8192):
+        for flags in (1, 2):
+            print(json.dumps(bench("optomech", E, 2, 4, flags=flags)))
