@@ -316,6 +316,12 @@ def main():
         alg_bytes = bytes_per_substep * E * K
         achieved = alg_bytes / (em_ms * 1e-3) / 1e9
         fp64_peak = N.measure_fp64_peak(8192)
+        traffic, traffic_src = None, None
+        try:   # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture (profiles/)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["capture"]
+        except Exception:  # noqa: BLE001
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -332,8 +338,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * 1 * 8, "d2h_bytes_per_step": (E * (n + 1) + 4) * 8,
                     "steps": e2e_steps, "api": "AffineLinearVecEnv.step(host actions) -> host obs, reward"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "em_step_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "em_tile_kernel<4> (qrl_em_step)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                          "algorithmic_bytes_per_substep": bytes_per_substep, "kernel_ms": em_ms,
                          "kernel_share_of_step": em_ms / (ms_max / args.steps),
                          "fp64_peak_tflops_measured": fp64_peak,

@@ -46,6 +46,7 @@ class AffineLinearVecEnv(LinearVecEnv):
         self._nz = torch.as_tensor(np.broadcast_to(np.asarray(noise_prefixes, dtype=np.float64), (n,)).copy(), device=dev)
         self._x0 = torch.as_tensor(np.broadcast_to(np.asarray(x0, dtype=np.float64), (n_envs, n)).copy(), device=dev)
         self._A = torch.empty((n_envs, n, n), dtype=torch.float64, device=dev)
+        self._A0f = self._A0.reshape(-1, n * n).expand(n_envs, n * n) if self._A0.dim() == 2 else self._A0.reshape(n_envs, n * n)
 
     def reset_states(self):
         return self._x0
@@ -55,10 +56,10 @@ class AffineLinearVecEnv(LinearVecEnv):
         # A0 + sum_a u_a A_a -> (E,n,n): small elementwise torch ops, once per action interval
         u = args[0]
         A = self._A.view(self.n_envs, n * n)
-        torch.mul(u[:, 0:1], self._Au[0:1], out=A)
+        torch.addcmul(self._A0f, u[:, 0:1], self._Au[0:1], out=A)          # A0 + u_0 A_0 in one launch
         for k in range(1, self.n_actions):
             A.addcmul_(u[:, k:k + 1], self._Au[k:k + 1])
-        return self._A.add_(self._A0)
+        return self._A
 
     def get_noise_prefixes(self, t_idx, args):
         return self._nz
