@@ -151,7 +151,7 @@ def make_env(rank, return_numpy, use_cuda_graph=True):
     return AffineLinearVecEnv(
         n_envs=E_PER_GPU, n=N_STATE, A0=A0, Au=Au, noise_prefixes=0.05, x0=1.0, t_norm_max=S_EPISODE * T_SSZ + T_SSZ / 2,
         t_norm_ssz=T_SSZ, action_interval=K_SUB, observation_stds=[0.01] * N_STATE, seed=1, rng="philox",
-        env_offset=rank * E_PER_GPU, return_numpy=return_numpy, use_cuda_graph=use_cuda_graph, data_idxs=[-1],
+        env_offset=rank * E_PER_GPU, return_numpy=return_numpy, use_cuda_graph=use_cuda_graph, fused_coefficients=True, data_idxs=[-1],
         dir_prefix="/tmp/qrl_bench")
 
 

@@ -149,6 +149,13 @@ typedef struct qrl_em_args {
      * of the WHOLE episode (time index 0): it adds t_idx rows itself.  The launch is then identical from step to step
      * and can be captured once and replayed (the caller advances dyn[0] by K on the same stream). */
     const int64_t* dyn;
+
+    /* action-affine drift functor (the shipped "affine" system family): when A_act != NULL
+     *   A_e = A[e] + sum_a (actions[e,a] * action_scale[a]) * A_act[a]        (A keeps its strides; A_stride_k must be 0)
+     * is evaluated inside the launch (no coefficient tensor, no separate scaling kernel) and the actions column of the
+     * packed rows holds the scaled action.  action_scale NULL = 1. */
+    const double* A_act;        /* (n_actions, n, n) */
+    const double* action_scale; /* (n_actions,) = action_maximums, or NULL */
 } qrl_em_args;
 
 #define QRL_EM_FORCE_GENERIC 1   /* flags: always use the generic lane-per-component kernel (A/B testing) */
@@ -240,6 +247,7 @@ typedef struct qrl_pack_args {
     int64_t  selected_row_pitch;/* doubles per row, >= n_sel (0 = n_sel) */
     const int64_t* dyn;         /* optional DEVICE pointer {int64 t_idx, ...} (CUDA-graph replay): when non-NULL, T_step,
                                  * packed and selected are the bases of the whole episode and t_idx rows are added here */
+    const double*  action_scale;/* (n_actions,) multiplied into the actions column; NULL = actions are already scaled */
 } qrl_pack_args;
 
 QRL_API int qrl_pack_rows(const qrl_pack_args* args, void* stream);

@@ -35,7 +35,7 @@ class EmArgs(C.Structure):
         ("reward_kind", C.c_int32), ("flags", C.c_int32), ("reward_w", _dp), ("reward", _dp), ("reward_last", _dp),
         ("rewards_cum", _dp), ("obs_minmax", _dp), ("nan_flag", _dp),
         ("packed", _dp), ("packed_stride_e", C.c_int64), ("packed_row_pitch", C.c_int64), ("T_step", _dp), ("actions", _dp), ("sel_idxs", _dp),
-        ("n_actions", C.c_int32), ("n_sel", C.c_int32), ("dyn", _dp),
+        ("n_actions", C.c_int32), ("n_sel", C.c_int32), ("dyn", _dp), ("A_act", _dp), ("action_scale", _dp),
     ]
 
 
@@ -60,7 +60,7 @@ class PackArgs(C.Structure):
         ("n_props", C.c_int32), ("n_sel", C.c_int32),
         ("T_step", _dp), ("actions", _dp), ("observations", _dp), ("properties", _dp), ("rewards_cum", _dp),
         ("idxs", _dp), ("packed", _dp), ("packed_stride_e", C.c_int64), ("selected", _dp),
-        ("selected_stride_e", C.c_int64), ("selected_row_pitch", C.c_int64), ("dyn", _dp),
+        ("selected_stride_e", C.c_int64), ("selected_row_pitch", C.c_int64), ("dyn", _dp), ("action_scale", _dp),
     ]
 
 

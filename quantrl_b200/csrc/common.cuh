@@ -58,6 +58,23 @@ __device__ __forceinline__ qrl_em_args resolve_dyn(const qrl_em_args& in) {
     return a;
 }
 
+// drift element (r,c) of environment e: coefficient tensor, or the action-affine functor A0 + sum_a u_a A_a
+__device__ __forceinline__ double em_drift(const qrl_em_args& a, const double* Ae, int e, int rc) {
+    double v = Ae[rc];
+    if (a.A_act) {
+        const int nn = a.n * a.n;
+        for (int k = 0; k < a.n_actions; ++k) {
+            const double u = a.actions[(int64_t)e * a.n_actions + k] * (a.action_scale ? a.action_scale[k] : 1.0);
+            v = fma(u, a.A_act[k * nn + rc], v);
+        }
+    }
+    return v;
+}
+__device__ __forceinline__ double em_action(const qrl_em_args& a, int e, int k) {
+    const double u = a.actions[(int64_t)e * a.n_actions + k];
+    return (a.A_act && a.action_scale) ? u * a.action_scale[k] : u;
+}
+
 __device__ __forceinline__ double shfl_d(double v, int src, int width = 32) {
     return __shfl_sync(0xffffffffu, v, src, width);
 }

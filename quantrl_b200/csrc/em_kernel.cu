@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(128) em_step_kernel(const qrl_em_args a_in, co
         const double* Ar = a.A + (int64_t)i * a.A_stride_k + (int64_t)el * a.A_stride_e + (int64_t)cl * n;
 #pragma unroll
         for (int j = 0; j < LPE; ++j) {
-            const double aij = (live && j < n) ? Ar[j] : 0.0;
+            const double aij = (live && j < n) ? em_drift(a, Ar - (int64_t)cl * n, el, cl * n + j) : 0.0;
             // M = I + A * t_ssz, unfused like the reference (stochastic.py:219-222)
             M[j] = __dadd_rn((j == c) ? 1.0 : 0.0, __dmul_rn(aij, dt));
         }
@@ -147,6 +147,8 @@ extern "C" int qrl_em_step(const qrl_em_args* args, void* stream) {
     QRL_REQUIRE(a.rng_mode != QRL_RNG_FED || a.K == 0 || a.W != nullptr, "qrl_em_step: fed mode needs W");
     QRL_REQUIRE(a.reward_kind == QRL_REWARD_NONE || a.reward_w != nullptr, "qrl_em_step: reward_w is NULL");
     QRL_REQUIRE(a.t_idx >= 0 && a.env_offset >= 0, "qrl_em_step: negative t_idx / env_offset");
+    QRL_REQUIRE(a.A_act == nullptr || (a.actions != nullptr && a.n_actions >= 1 && a.A_stride_k == 0),
+                "qrl_em_step: the affine drift functor needs actions, n_actions >= 1 and a time-invariant A");
     if (a.packed) {
         QRL_REQUIRE(a.reward_kind != QRL_REWARD_NONE && a.rewards_cum != nullptr,
                     "qrl_em_step: packed rows need a fused reward functor and rewards_cum");
@@ -179,5 +181,6 @@ extern "C" int qrl_em_step(const qrl_em_args* args, void* stream) {
     p.T_step = a.T_step; p.actions = a.actions; p.observations = a.observations; p.rewards_cum = a.rewards_cum;
     p.idxs = a.sel_idxs; p.selected = a.packed; p.selected_stride_e = a.packed_stride_e;
     p.selected_row_pitch = a.packed_row_pitch; p.dyn = a.dyn;
+    p.action_scale = a.A_act ? a.action_scale : nullptr;
     return qrl_pack_rows(&p, stream);
 }

@@ -125,7 +125,7 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
                 if (sel_identity) {
                     // all n_data columns in their natural order (the reference's cache_all_data layout): straight copy
                     dst[0] = a.T_step[r];
-                    for (int k = 0; k < a.n_actions; ++k) dst[1 + k] = a.actions[(int64_t)e * a.n_actions + k];
+                    for (int k = 0; k < a.n_actions; ++k) dst[1 + k] = em_action(a, e, k);
 #pragma unroll
                     for (int c = 0; c < N; ++c) dst[1 + a.n_actions + c] = orow[c];
                     dst[n_data - 1] = 0.0;   // cumulative reward: patched after the last sub-step
@@ -134,7 +134,7 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
                         const int col = selS[j];
                         double val = 0.0;  // cumulative-reward column: only known after the last sub-step, patched below
                         if (col == 0) val = a.T_step[r];
-                        else if (col <= a.n_actions) val = a.actions[(int64_t)e * a.n_actions + (col - 1)];
+                        else if (col <= a.n_actions) val = em_action(a, e, col - 1);
                         else if (col <= a.n_actions + N) val = orow[col - 1 - a.n_actions];
                         dst[j] = val;
                     }
@@ -210,7 +210,7 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
 #pragma unroll
         for (int r = 0; r < N; ++r) {
 #pragma unroll
-            for (int c = 0; c < N; ++c) M[r][c] = __dadd_rn((r == c) ? 1.0 : 0.0, __dmul_rn(Ar[r * N + c], a.t_ssz));
+            for (int c = 0; c < N; ++c) M[r][c] = __dadd_rn((r == c) ? 1.0 : 0.0, __dmul_rn(em_drift(a, Ar, e, r * N + c), a.t_ssz));
             nz[r] = a.nz[(int64_t)e * a.nz_stride_e + r];
             x[r] = x0S[el_r * N + r];
         }

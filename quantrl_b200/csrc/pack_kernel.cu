@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const qrl_pack_args a_in
 
     auto column = [&](int el, int t, int col) -> double {
         if (col == 0) return a.T_step[t0 + t];
-        if (col <= na) return a.actions[(int64_t)(e0 + el) * na + (col - 1)];
+        if (col <= na) return a.actions[(int64_t)(e0 + el) * na + (col - 1)] * (a.action_scale ? a.action_scale[col - 1] : 1.0);
         if (col <= na + n_src) return tile[(t * PACK_G + el) * n_src + (col - 1 - na)];
         return a.rewards_cum[e0 + el];
     };

@@ -236,6 +236,8 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         self._nan = torch.zeros((1,), dtype=torch.int32, device=self.device)
         self._h_out = torch.empty(self._step_out.shape, dtype=f64).pin_memory()
         self._h_actions = torch.empty((E, self.n_actions), dtype=f64).pin_memory()
+        self._h_actions_np = self._h_actions.numpy()       # NumPy views of the pinned staging buffers (cheap indexing)
+        self._h_out_np = self._h_out.numpy()
         self.rewards = None
         self.data_rewards = []
         self._data_dev = None
@@ -323,15 +325,18 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         if isinstance(actions, torch.Tensor):
             a = actions.to(device=self.device, dtype=torch.float64)
         else:
-            self._h_actions.copy_(torch.as_tensor(np.asarray(actions, dtype=np.float64)).reshape(self.n_envs, self.n_actions))
+            # host actions: one NumPy copy into pinned memory, then an asynchronous H2D on the launch stream
+            self._h_actions_np[...] = np.asarray(actions, dtype=np.float64).reshape(self.n_envs, self.n_actions)
             a = self._h_actions
         self._set_actions(a)
 
     def _set_actions(self, a):
         """``actions = float(action) * action_maximums`` (base.py:1244-1248).  With ``use_cuda_graph`` the raw actions
         land in the graph's static input buffer and the scaling is part of the captured graph."""
-        if getattr(self, "use_cuda_graph", False):
+        if getattr(self, "use_cuda_graph", False) or getattr(self, "fused_coefficients", False):
             self._actions_in.copy_(a.reshape(self.n_envs, self.n_actions), non_blocking=True)
+            if not getattr(self, "use_cuda_graph", False):
+                self.actions = self._actions_in * self.action_maximums_batch
         else:
             a = a.to(self.device, non_blocking=True) if not a.is_cuda else a
             self.actions = (a.reshape(self.n_envs, self.n_actions) * self.action_maximums_batch).contiguous()
@@ -351,14 +356,14 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         if reset_minmax:
             self._minmax.copy_(self._minmax_init, non_blocking=True)
         self.States = self._update_states()        # ONE fused launch: States, Observations (+Reward, rewards, min/max)
-        self.Observations = self._Observations[:dim]
+        self.Observations = self._Observations if dim == K + 1 else self._Observations[:dim]
         if self.n_properties > 0:
             self.Properties = self.backend.convert_to_typed(tensor=self.get_properties(), dtype="real")
         if not self._reward_fused:
             self.Reward = self.backend.convert_to_typed(tensor=self.get_reward(), dtype="real")
             self._reward_last.copy_(self.Reward[dim - 1])
         else:
-            self.Reward = self._Reward[:dim]
+            self.Reward = self._Reward if dim == K + 1 else self._Reward[:dim]
 
         self.t_idx += dim - 1
         self.t = self._T_host[self.t_idx]
@@ -406,9 +411,10 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
 
     def check_truncation(self, host=None):
         """``max(Observations) > range[1] or min(Observations) < range[0]`` over the whole block (base.py:485-499)."""
-        h = self._fetch_step_outputs() if host is None else host
+        if host is None:
+            self._fetch_step_outputs()
         E, no = self.n_envs, self.n_observations
-        lo, hi = float(h[E * (no + 1)]), float(h[E * (no + 1) + 1])
+        lo, hi = self._h_out_np[E * (no + 1)], self._h_out_np[E * (no + 1) + 1]
         return bool(hi > self.observation_space_range[1] or lo < self.observation_space_range[0])
 
     def step_wait(self):
@@ -420,8 +426,8 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
             print(f"Batch #{self.batch_idx} truncated")
         E, no = self.n_envs, self.n_observations
         if self.return_numpy:
-            reward_out = host[E * no:E * (no + 1)].numpy().copy()
-            obs_out = host[:E * no].view(E, no).numpy().copy()
+            reward_out = self._h_out_np[E * no:E * (no + 1)].copy()
+            obs_out = self._h_out_np[:E * no].reshape(E, no).copy()
         else:
             reward_out, obs_out = reward.clone(), observations.clone()
         done = bool(terminated or truncated)

@@ -47,6 +47,8 @@ class LinearVecEnv(BaseVecEnv):
         # replay one captured CUDA graph per action interval (hooks + integration launch) instead of launching eagerly;
         # requires hooks that do not depend on ``t_idx`` (``is_A_time_dependent=False``)
         self.use_cuda_graph = bool(kwargs.pop("use_cuda_graph", False))
+        # evaluate an action-affine drift inside the kernel (``_affine_drift``) instead of through the ``get_A`` hook
+        self.fused_coefficients = bool(kwargs.pop("fused_coefficients", False))
         self.reward_functor = kwargs.pop("reward_functor", None)
         reward_weights = kwargs.pop("reward_weights", None)
         assert self.reward_functor in _REWARD_KINDS, f"``reward_functor`` should be one of {list(_REWARD_KINDS)}"
@@ -115,6 +117,12 @@ class LinearVecEnv(BaseVecEnv):
             assert tuple(self.Observation_noises.shape) == (S1, E, n)
         self._fed_assigned = True
 
+    def _affine_drift(self):
+        """Optional hook for the in-kernel action-affine drift functor: return ``(A0, A_act)`` with ``A0`` ``(n,n)`` or
+        ``(n_envs,n,n)`` and ``A_act`` ``(n_actions,n,n)`` to have ``A = A0 + sum_a u_a A_act[a]`` (u = actions *
+        action_maximums) evaluated inside the integration launch instead of calling ``get_A``; ``None`` = not affine."""
+        return None
+
     def _coefficients(self, K):
         args = (self.actions, None, None)
         E, n = self.n_envs, self.n_observations
@@ -157,7 +165,17 @@ class LinearVecEnv(BaseVecEnv):
         a = N.EmArgs()
         a.n, a.n_envs, a.K, a.t_ssz = n, E, K, self.t_ssz
         keep = []
-        if K > 0:
+        affine = self._affine_drift() if (K > 0 and self.fused_coefficients) else None
+        if affine is not None:
+            # drift evaluated in-kernel from the RAW actions (scaling by action_maximums included): no hook launches
+            A0, A_act = affine
+            nz = self.backend.convert_to_typed(tensor=self.get_noise_prefixes(self.t_idx, (self.actions, None, None)), dtype="real").contiguous()
+            keep += [A0, A_act, nz]
+            a.A, a.A_stride_k, a.A_stride_e = N.ptr(A0), 0, (n * n if A0.dim() == 3 else 0)
+            a.nz, a.nz_stride_k, a.nz_stride_e = N.ptr(nz), 0, (n if nz.dim() == 2 else 0)
+            a.A_act, a.action_scale = N.ptr(A_act), N.ptr(self.action_maximums)
+            a.actions, a.n_actions = N.ptr(self._actions_in), self.n_actions
+        elif K > 0:
             A, a.A_stride_k, a.A_stride_e, nz, a.nz_stride_k, a.nz_stride_e = self._coefficients(K)
             keep += [A, nz]
             a.A, a.nz = N.ptr(A), N.ptr(nz)
@@ -201,7 +219,8 @@ class LinearVecEnv(BaseVecEnv):
             a.packed_stride_e = self.shape_T[0] * self._data_pitch
             a.packed_row_pitch = self._data_pitch
             a.T_step = N.ptr(self.T) + 8 * t_off
-            a.actions, a.n_actions = N.ptr(self.actions), self.n_actions
+            if affine is None:
+                a.actions, a.n_actions = N.ptr(self.actions), self.n_actions
             a.sel_idxs, a.n_sel = N.ptr(self._sel_idxs), n_sel
             self._packed_by_kernel = True
         if self.force_generic_kernel:
@@ -235,7 +254,8 @@ class LinearVecEnv(BaseVecEnv):
             n0 = N.launch_count()
             with torch.cuda.stream(side):
                 with torch.cuda.graph(graph, stream=side):
-                    self.actions = self._actions_in * self.action_maximums_batch
+                    if not (self.fused_coefficients and self._affine_drift() is not None):
+                        self.actions = self._actions_in * self.action_maximums_batch
                     self._graph_keep = self._launch(K, self._x_last)
                     self._dyn[0] += K
             torch.cuda.current_stream().wait_stream(side)

@@ -45,11 +45,15 @@ class AffineLinearVecEnv(LinearVecEnv):
         self._Au = torch.as_tensor(Au, device=dev).reshape(n_act, n * n).contiguous()
         self._nz = torch.as_tensor(np.broadcast_to(np.asarray(noise_prefixes, dtype=np.float64), (n,)).copy(), device=dev)
         self._x0 = torch.as_tensor(np.broadcast_to(np.asarray(x0, dtype=np.float64), (n_envs, n)).copy(), device=dev)
+        self._Au3 = self._Au.view(n_act, n, n)
         self._A = torch.empty((n_envs, n, n), dtype=torch.float64, device=dev)
         self._A0f = self._A0.reshape(-1, n * n).expand(n_envs, n * n) if self._A0.dim() == 2 else self._A0.reshape(n_envs, n * n)
 
     def reset_states(self):
         return self._x0
+
+    def _affine_drift(self):
+        return self._A0, self._Au3
 
     def get_A(self, t_idx, args):
         n = self.n_observations

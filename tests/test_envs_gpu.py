@@ -257,3 +257,33 @@ def test_cuda_graph_replay_equals_eager(native, cuda):
         assert eager.t_idx == graph.t_idx
     assert graph.graph_replays == 8 and graph.graph_native_launches == 1 and eager.batch_idx == graph.batch_idx == 2
     eager.close(); graph.close()
+
+
+def test_fused_affine_coefficients_match_hook_path(native, cuda):
+    """``fused_coefficients=True`` evaluates A = A0 + sum_a u_a A_a (u = actions * action_maximums) inside the kernel:
+    same trajectories as the ``get_A`` torch hook up to the rounding of one fused multiply-add, bit-identical between
+    eager and CUDA-graph replay, scaled actions in the cache rows."""
+    from quantrl_b200.systems import AffineLinearVecEnv, affine_matrices
+    A0, Au = affine_matrices(4, 2, seed=3)
+    E, K = 130, 10
+    kw = dict(n_envs=E, n=4, A0=A0, Au=Au, noise_prefixes=[0.05, 0.04, 0.03, 0.02], x0=1.0, t_norm_max=0.405,
+              t_norm_ssz=0.01, action_interval=K, action_maximums=[0.5, 2.0], observation_stds=[0.01] * 4, seed=2,
+              dir_prefix="/tmp/qrl_test")
+    hook, fused, fgraph = AffineLinearVecEnv(**kw), AffineLinearVecEnv(fused_coefficients=True, **kw), \
+        AffineLinearVecEnv(fused_coefficients=True, use_cuda_graph=True, **kw)
+    for e in (hook, fused, fgraph):
+        e.reset()
+    rng = np.random.default_rng(1)
+    for step in range(3):
+        u = rng.uniform(-1, 1, (E, 2))
+        oh, rh, _, _ = hook.step(u)
+        of, rf, _, _ = fused.step(u)
+        og, rg, _, _ = fgraph.step(u)
+        torch.testing.assert_close(of, oh, rtol=1e-12, atol=1e-14)
+        torch.testing.assert_close(rf, rh, rtol=1e-12, atol=1e-14)
+        assert torch.equal(of, og) and torch.equal(rf, rg) and torch.equal(fused.States, fgraph.States)
+    np.testing.assert_allclose(fused.data, hook.data, rtol=1e-12, atol=1e-14)
+    np.testing.assert_array_equal(fused.data, fgraph.data)
+    np.testing.assert_allclose(fused.data[:, 21:30, 1:3], np.broadcast_to((u * [0.5, 2.0])[:, None, :], (E, 9, 2)), rtol=1e-15)
+    for e in (hook, fused, fgraph):
+        e.close()
