@@ -58,6 +58,10 @@ extern "C" {
 #define QRL_REWARD_NONE        0  /* leave `reward` untouched: the Python `get_reward()` hook fills it */
 #define QRL_REWARD_NEG_WSQ_OBS 1  /* r = -sum_c w_c * Observations_c^2 */
 #define QRL_REWARD_NEG_WSQ_STATE 2 /* r = -sum_c w_c * States_c^2 */
+/* deterministic path (qrl_ode_step, num_quads == 4): analytic logarithmic negativity of modes (0,1), restating
+ * QCMSolver.get_entanglement_logarithmic_negativity_2 (quantrl/solvers/measure.py:401-440) */
+#define QRL_REWARD_ENTAN_LN_OBS   3 /* evaluated on the covariance block of the Observations */
+#define QRL_REWARD_ENTAN_LN_STATE 4 /* evaluated on the covariance block of the States */
 
 /* deterministic system functors (replace user hooks get_mode_rates/get_A/get_D, quantrl/envs/deterministic.py:748-818);
  * formulas in oracle/systems.py */
@@ -217,7 +221,10 @@ typedef struct qrl_ode_args {
     double*  obs_minmax;     /* as in qrl_em_args */
     int32_t* nan_flag;
     int32_t  flags;          /* QRL_ODE_* bits */
-    int32_t  _pad1;
+    int32_t  reward_kind;    /* QRL_REWARD_NONE | QRL_REWARD_ENTAN_LN_OBS | QRL_REWARD_ENTAN_LN_STATE */
+    double*  reward;         /* (K+1,E) or NULL */
+    double*  reward_last;    /* (E,) = Reward[K]; or NULL */
+    double*  rewards_cum;    /* (E,) in/out: += Reward[K]; or NULL */
 } qrl_ode_args;
 
 #define QRL_ODE_FORCE_THREAD 1  /* flags: RK4 with one thread per env whatever the batch size (A/B testing) */

@@ -221,6 +221,15 @@ def golden_lyap(system, tag_sizes, fname):
                 res["T"] = np.array(env.T)[:S + 1]
                 res["States_rk4_reffunc"] = rk4_on_reference_func(env, y0, res["T"], K, actions, 1)
                 res["States_rk4x2_reffunc"] = rk4_on_reference_func(env, y0, res["T"], K, actions, 2)
+        if q == 4:
+            # reward-functor pin: the reference's own QCMSolver on the tight trajectory (measure.py:401-440)
+            from quantrl.solvers.measure import QCMSolver
+            St = res["States_dop853_tight"]
+            Corrs = St[:, :, 2 * m:].reshape(-1, q, q)
+            Modes = (St[:, :, :m] + 1j * St[:, :, m:2 * m]).reshape(-1, m)
+            qcm = QCMSolver(Modes=Modes, Corrs=Corrs, params={"show_progress": False, "measure_codes": ["entan_ln_2"],
+                                                              "indices": (0, 1)})
+            res["entan_ln_ref"] = qcm.get_entanglement_logarithmic_negativity_2(pos_i=0, pos_j=2).reshape(St.shape[:2])
         # G4: single-env twin of env 0 (quantrl/envs/deterministic.py:18-437)
         env1 = make_vec_env(system, p[:1], m, q, y0[:1], K, S, ssz, "dop853", 1e-14, 1e-13, cls=LinearizedHOEnv)
         St1, _, _ = run_vec(env1, actions[:, :1], single=True)

@@ -10,7 +10,7 @@ from .build import LIB_PATH
 ABI_VERSION = 1
 
 RNG_FED, RNG_PHILOX = 0, 1
-REWARD_NONE, REWARD_NEG_WSQ_OBS, REWARD_NEG_WSQ_STATE = 0, 1, 2
+REWARD_NONE, REWARD_NEG_WSQ_OBS, REWARD_NEG_WSQ_STATE, REWARD_ENTAN_LN_OBS, REWARD_ENTAN_LN_STATE = 0, 1, 2, 3, 4
 SYS_OPTOMECH, SYS_KERR_CHAIN, SYS_CONST_AD = 1, 2, 3
 ODE_RK4, ODE_DOPRI5 = 0, 1
 EM_FORCE_GENERIC, EM_FORCE_TILED, EM_PACK_TMA = 1, 16, 128
@@ -50,7 +50,7 @@ class OdeArgs(C.Structure):
         ("seed", C.c_uint64), ("episode", C.c_uint32), ("_pad0", C.c_uint32), ("t_idx", C.c_int64),
         ("env_offset", C.c_int64), ("obs_std", _dp), ("obs_std_stride_e", C.c_int64),
         ("h_state", _dp), ("n_steps", _dp), ("obs_minmax", _dp), ("nan_flag", _dp),
-        ("flags", C.c_int32), ("_pad1", C.c_int32),
+        ("flags", C.c_int32), ("reward_kind", C.c_int32), ("reward", _dp), ("reward_last", _dp), ("rewards_cum", _dp),
     ]
 
 

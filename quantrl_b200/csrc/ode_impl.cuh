@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "philox.cuh"
 #include "systems.cuh"
+#include "measures.cuh"
 
 namespace qrl {
 
@@ -69,6 +70,26 @@ __device__ __forceinline__ double obs_noise_at(const qrl_ode_args& a, int row, i
     return 0.0;
 }
 
+// fused reward of (row, env e) from the env's state vector y (covariance block at y + 2M): log-negativity of the States
+// or of the Observations (= states + this row's measurement noise); updates reward / reward_last / rewards_cum
+template <int M, int Q>
+__device__ __forceinline__ void ode_reward_row(const qrl_ode_args& a, int row, int e, const double* y) {
+    if constexpr (Q == 4) {
+        if (a.reward_kind == QRL_REWARD_NONE) return;
+        constexpr int D = 2 * M + Q * Q;
+        double V[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+            V[c] = y[2 * M + c] + (a.reward_kind == QRL_REWARD_ENTAN_LN_OBS ? obs_noise_at(a, row, e, 2 * M + c, D) : 0.0);
+        const double r = log_negativity_2mode(V);
+        if (a.reward) a.reward[(int64_t)row * a.n_envs + e] = r;
+        if (row == a.K) {
+            if (a.reward_last) a.reward_last[e] = r;
+            if (a.rewards_cum) a.rewards_cum[e] += r;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // RK4
 // ------------------------------------------------------------------------------------------------------------------
@@ -99,7 +120,7 @@ __global__ void __launch_bounds__(BLOCK) rk4_kernel(const qrl_ode_args a) {
     double lo = INFINITY, hi = -INFINITY;
     const int nsub = a.substeps;
     const double h = a.t_ssz / (double)nsub;
-    const bool want_rows = a.states || a.observations || a.obs_minmax;
+    const bool want_rows = a.states || a.observations || a.obs_minmax || (a.reward_kind != QRL_REWARD_NONE && a.reward);
 
     for (int row = 0; row <= K; ++row) {
         if (row > 0) {
@@ -141,6 +162,7 @@ __global__ void __launch_bounds__(BLOCK) rk4_kernel(const qrl_ode_args a) {
                 lo = fmin(lo, ob);
                 hi = fmax(hi, ob);
             }
+            if (live) ode_reward_row<Sys::M, Sys::Q>(a, row, e, y);
             __syncthreads();
         }
     }
@@ -203,6 +225,7 @@ __global__ void __launch_bounds__(BLOCK) dopri5_kernel(const qrl_ode_args a) {
             lo = fmin(lo, ob);
             hi = fmax(hi, ob);
         }
+        ode_reward_row<Sys::M, Sys::Q>(a, row, e, v);
     };
     emit(0, y);
 
@@ -386,6 +409,22 @@ __global__ void __launch_bounds__(BLOCK) rk4_lanes_kernel(const qrl_ode_args a) 
             put(l, mv);
         }
     };
+    // fused reward: the group publishes its covariance elements, lane 0 evaluates the measure
+    auto reward_row = [&](int row) {
+        if (a.reward_kind == QRL_REWARD_NONE) return;
+        __syncwarp();
+        sV[g][i][j] = v;
+        __syncwarp();
+        if (live && l == 0) {
+            double yfull[D];
+#pragma unroll
+            for (int c = 0; c < 2 * M; ++c) yfull[c] = ym[c];
+#pragma unroll
+            for (int c = 0; c < L; ++c) yfull[2 * M + c] = (&sV[g][0][0])[c];
+            ode_reward_row<M, Q>(a, row, e, yfull);
+        }
+        __syncwarp();
+    };
     // one RHS evaluation at (modes ymt, my element vt): returns dV_ij, fills dm
     auto rhs_lane = [&](double t, const double* ymt, double vt, double* dm) -> double {
         double yfull[2 * M > 0 ? 2 * M : 1];
@@ -412,6 +451,7 @@ __global__ void __launch_bounds__(BLOCK) rk4_lanes_kernel(const qrl_ode_args a) 
     };
 
     emit(0);
+    reward_row(0);
     const int nsub = a.substeps;
     const double h = a.t_ssz / (double)nsub;
     for (int row = 1; row <= K; ++row) {
@@ -437,6 +477,7 @@ __global__ void __launch_bounds__(BLOCK) rk4_lanes_kernel(const qrl_ode_args a) 
             for (int c = 0; c < 2 * M; ++c) ym[c] = fma(h / 6.0, accm[c] + dm[c], ym[c]);
         }
         emit(row);
+        reward_row(row);
     }
     if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
 }

@@ -26,6 +26,9 @@ extern "C" int qrl_ode_step(const qrl_ode_args* args, void* stream) {
     if (a.n_envs == 0) return 0;
     QRL_REQUIRE(a.y0 != nullptr, "qrl_ode_step: y0 is NULL");
     QRL_REQUIRE(a.t_idx >= 0 && a.env_offset >= 0, "qrl_ode_step: negative t_idx / env_offset");
+    QRL_REQUIRE(a.reward_kind == QRL_REWARD_NONE ||
+                    ((a.reward_kind == QRL_REWARD_ENTAN_LN_OBS || a.reward_kind == QRL_REWARD_ENTAN_LN_STATE) && a.num_quads == 4),
+                "qrl_ode_step: reward_kind must be NONE or ENTAN_LN_* (num_quads == 4)");
     cudaStream_t st = (cudaStream_t)stream;
     const int m = a.num_modes, q = a.num_quads;
     switch (a.system) {

@@ -38,6 +38,9 @@ class LinearizedHOVecEnv(BaseVecEnv):
         for key, val in self.default_ode_solver_params.items():
             kwargs.setdefault(key, val)
         ode = {k: kwargs.pop(k) for k in list(self.default_ode_solver_params)}
+        self.reward_functor = kwargs.pop("reward_functor", None)
+        assert self.reward_functor in (None, "entan_ln_obs", "entan_ln_state"), \
+            "``reward_functor`` should be None, 'entan_ln_obs' or 'entan_ln_state'"
         system = kwargs.pop("system", None)
         system_params = kwargs.pop("system_params", None)
         assert n_observations == 2 * self.num_modes + self.num_corrs, \
@@ -67,6 +70,9 @@ class LinearizedHOVecEnv(BaseVecEnv):
                 assert tuple(P.shape) in [(npar,), (E, npar)], f"``system_params`` should have shape ({npar},) or (n_envs, {npar})"
                 sysd["params"] = P
         self.system = sysd
+        if self.reward_functor is not None:
+            assert sysd is not None and q == 4, "fused reward functors need a device functor system with num_quads == 4"
+            self._reward_fused = self._cum_fused = True
         self.solver = IVPSolver(
             func=self.func, y_0=self._States[-1], T=self.T,
             solver_params={"method": ode["ode_method"], "atol": ode["ode_atol"], "rtol": ode["ode_rtol"], "is_stiff": False,
@@ -158,6 +164,10 @@ class LinearizedHOVecEnv(BaseVecEnv):
             self.solver.epilogue = dict(
                 self._noise_epilogue(t0), observations=N.ptr(self._Observations), y_last=N.ptr(self._x_last),
                 obs_last=N.ptr(self._obs_last), obs_minmax=N.ptr(self._minmax), nan_flag=N.ptr(self._nan))
+            if self.reward_functor is not None:
+                self.solver.epilogue.update(
+                    reward_kind={"entan_ln_obs": N.REWARD_ENTAN_LN_OBS, "entan_ln_state": N.REWARD_ENTAN_LN_STATE}[self.reward_functor],
+                    reward=N.ptr(self._Reward), reward_last=N.ptr(self._reward_last), rewards_cum=N.ptr(self.rewards))
             return self.solver.integrate(T_step=self.T_step, y_0=self._x_last, params=self.actions,
                                          out=self._States[:dim])
         # stage-callback mode: integrate with torch hooks, then the (unfused) noise add / reductions

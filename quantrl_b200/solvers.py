@@ -108,6 +108,9 @@ class B200IVPSolver:
         ep = self.epilogue
         a.observations, a.y_last, a.obs_last = ep.get("observations"), ep.get("y_last"), ep.get("obs_last")
         a.obs_noise, a.obs_minmax, a.nan_flag = ep.get("obs_noise"), ep.get("obs_minmax"), ep.get("nan_flag")
+        if ep.get("reward_kind"):
+            a.reward_kind, a.reward = ep["reward_kind"], ep.get("reward")
+            a.reward_last, a.rewards_cum = ep.get("reward_last"), ep.get("rewards_cum")
         if ep.get("obs_std") is not None:
             a.obs_std, a.obs_std_stride_e = ep["obs_std"], ep["obs_std_stride_e"]
             a.seed, a.episode, a.t_idx, a.env_offset = ep["seed"], ep["episode"], ep["t_idx"], ep["env_offset"]

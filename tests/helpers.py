@@ -77,7 +77,8 @@ def em_step(x0, A, nz, t_ssz, K, W=None, obs_noise=None, philox=None, obs_std=No
 
 
 def ode_step(system, m, q, y0, K, t0, t_ssz, params=None, actions=None, A=None, D=None, method="rk4", substeps=1,
-             atol=1e-9, rtol=1e-6, obs_noise=None, h_state=None, philox=None, obs_std=None, flags=0):
+             atol=1e-9, rtol=1e-6, obs_noise=None, h_state=None, philox=None, obs_std=None, flags=0, reward_kind=0,
+             rewards_cum=None):
     """Run qrl_ode_step once; returns dict of torch tensors."""
     y0 = dev(y0).double()
     E, d = y0.shape
@@ -117,6 +118,12 @@ def ode_step(system, m, q, y0, K, t0, t_ssz, params=None, actions=None, A=None, 
     a.h_state, a.n_steps = N.ptr(out["h_state"]), N.ptr(out["n_steps"])
     a.obs_minmax, a.nan_flag = N.ptr(out["minmax"]), N.ptr(out["nan"])
     a.flags = flags
+    if reward_kind:
+        out["reward"] = torch.full((K + 1, E), float("nan"), dtype=torch.float64, device="cuda")
+        out["reward_last"] = torch.zeros((E,), dtype=torch.float64, device="cuda")
+        out["rewards_cum"] = torch.zeros((E,), dtype=torch.float64, device="cuda") if rewards_cum is None else dev(rewards_cum).double()
+        a.reward_kind, a.reward = reward_kind, N.ptr(out["reward"])
+        a.reward_last, a.rewards_cum = N.ptr(out["reward_last"]), N.ptr(out["rewards_cum"])
     N.ode_step(a)
     torch.cuda.synchronize()
     return out

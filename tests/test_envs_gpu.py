@@ -287,3 +287,33 @@ def test_fused_affine_coefficients_match_hook_path(native, cuda):
     np.testing.assert_allclose(fused.data[:, 21:30, 1:3], np.broadcast_to((u * [0.5, 2.0])[:, None, :], (E, 9, 2)), rtol=1e-15)
     for e in (hook, fused, fgraph):
         e.close()
+
+
+def test_lho_vec_env_fused_entanglement_reward(native, cuda, golden_dir):
+    """``reward_functor='entan_ln_state'``: reward rows, per-step reward and cumulative reward come out of the
+    integration launch; values == the oracle's restatement of the reference's QCMSolver on the env's own States."""
+    import measure_oracle as mo
+    from quantrl_b200.envs import LinearizedHOVecEnv
+    g = np.load(os.path.join(golden_dir, "lyap_optomech.npz"))
+    p, y0 = g["E5_p"], g["E5_y0"]
+
+    class Env(LinearizedHOVecEnv):
+        def reset_states(self):
+            return torch.as_tensor(y0, device="cuda")
+
+    env = Env(name="optomech", desc="t", params={}, num_modes=2, num_quads=4, t_norm_max=1.205, t_norm_ssz=0.01,
+              t_norm_mul=1.0, n_envs=5, n_observations=20, n_properties=0, n_actions=1, action_maximums=[1.0],
+              action_interval=10, data_idxs=[0, -1], cache_all_data=False, dir_prefix="/tmp/qrl_test", system="optomech",
+              system_params=p, ode_method="dopri5", ode_atol=1e-14, ode_rtol=1e-13, reward_functor="entan_ln_state")
+    env.reset()
+    cum = np.zeros(5)
+    for a in range(10):
+        obs, rew, done, _ = env.step(g["E5_actions"][a])
+        ref = mo.entan_ln_2(env.States.cpu().numpy()[:, :, 4:].reshape(11, 5, 4, 4))
+        np.testing.assert_allclose(env.Reward.cpu().numpy(), ref, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(rew.cpu().numpy(), ref[-1], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(rew.cpu().numpy(), g["E5_entan_ln_ref"][(a + 1) * 10], rtol=0, atol=1e-10)
+        cum += ref[-1]
+    np.testing.assert_allclose(env.rewards.cpu().numpy(), cum, rtol=0, atol=1e-11)
+    np.testing.assert_allclose(env.data[:, 100, 1], cum, rtol=0, atol=1e-11)
+    env.close()

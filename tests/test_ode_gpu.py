@@ -199,3 +199,33 @@ def test_rk4_lanes_kernel_equals_thread_kernel(native, cuda, E):
     a = ode_step("const_AD", 0, 4, V0, 12, 0.0, 0.05, A=A, D=Dm, flags=N.ODE_FORCE_LANES)
     b = ode_step("const_AD", 0, 4, V0, 12, 0.0, 0.05, A=A, D=Dm, flags=N.ODE_FORCE_THREAD)
     torch.testing.assert_close(a["states"], b["states"], rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("method,flags", [("rk4", 1), ("rk4", 2), ("dopri5", 0)])
+def test_fused_log_negativity_reward_matches_reference_qcm(native, cuda, golden_dir, method, flags):
+    """Reward functor ENTAN_LN: (1) on the reference's tight trajectory it must reproduce the reference's own
+    ``QCMSolver.get_entanglement_logarithmic_negativity_2`` (fixture ``entan_ln_ref``, measure.py:401-440) — checked
+    through the oracle on the kernel's States; (2) the OBS variant uses the noisy covariance; (3) cumulative reward."""
+    import measure_oracle as mo
+    from quantrl_b200 import _native as N
+    g, p, y0, acts, T, K, m, q = _load(golden_dir, "lyap_optomech.npz", "E5")
+    kw = dict(method=method, flags=flags, atol=1e-14, rtol=1e-13)
+    y, rows_r, cum = y0, [], np.zeros(5)
+    for a in range(acts.shape[0]):
+        out = ode_step("optomech", m, q, y, K, float(T[a * K]), 0.01, params=p, actions=acts[a][:, 0],
+                       reward_kind=N.REWARD_ENTAN_LN_STATE, rewards_cum=cum, **kw)
+        S = out["states"].cpu().numpy()
+        ref = mo.entan_ln_2(S[:, :, 4:].reshape(K + 1, 5, 4, 4))
+        np.testing.assert_allclose(out["reward"].cpu().numpy(), ref, rtol=0, atol=1e-12)
+        np.testing.assert_array_equal(out["reward_last"].cpu().numpy(), out["reward"][-1].cpu().numpy())
+        cum = cum + ref[-1]
+        np.testing.assert_allclose(out["rewards_cum"].cpu().numpy(), cum, rtol=0, atol=1e-11)
+        rows_r.append(out["reward"].cpu().numpy()[1 if a else 0:])
+        y = out["y_last"].cpu().numpy()
+    if method == "dopri5":   # converged trajectory -> the reference's own numbers
+        np.testing.assert_allclose(np.concatenate(rows_r, 0), g["E5_entan_ln_ref"], rtol=0, atol=1e-10)
+    noise = 1e-2 * np.random.default_rng(0).standard_normal((K + 1, 5, 20))
+    out = ode_step("optomech", m, q, y0, K, 0.0, 0.01, params=p, actions=acts[0][:, 0], obs_noise=noise,
+                   reward_kind=N.REWARD_ENTAN_LN_OBS, **kw)
+    O = out["observations"].cpu().numpy()
+    np.testing.assert_allclose(out["reward"].cpu().numpy(), mo.entan_ln_2(O[:, :, 4:].reshape(K + 1, 5, 4, 4)), rtol=0, atol=1e-12)
