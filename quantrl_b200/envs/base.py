@@ -246,6 +246,9 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         self._packed = torch.empty((E, K1, self.n_data), dtype=f64, device=self.device) if self.cache_all_data else None
         self._reward_fused = False
         self._cum_fused = False
+        # per-env replicas returned by step_wait (base.py:1293 builds ``[done] * n_envs, [{}] * n_envs`` every step)
+        self._dones_true, self._dones_false, self._infos = [True] * E, [False] * E, [{}] * E
+        self._host_step = False
         self._obs_last_ptr = self._reward_last_ptr = None
 
     # ---- hooks the interfaced environment implements (base.py:272-317) ------------------------------------------
@@ -327,7 +330,11 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         else:
             # host actions: one NumPy copy into pinned memory, then an asynchronous H2D on the launch stream
             self._h_actions_np[...] = np.asarray(actions, dtype=np.float64).reshape(self.n_envs, self.n_actions)
+            if getattr(self, "use_cuda_graph", False):
+                self._host_step = True      # H2D of the actions and D2H of the results are nodes of the captured graph
+                return
             a = self._h_actions
+        self._host_step = False
         self._set_actions(a)
 
     def _set_actions(self, a):
@@ -418,9 +425,15 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         return bool(hi > self.observation_space_range[1] or lo < self.observation_space_range[0])
 
     def step_wait(self):
-        observations, reward, terminated = self.update()
+        host_step = getattr(self, "_host_step", False)
+        observations, reward, terminated = self.update(reset_minmax=not host_step)
         self.update_data()
-        host = self._fetch_step_outputs()
+        if host_step and getattr(self, "_host_graph_done", False):
+            torch.cuda.current_stream().synchronize()      # the replayed graph already copied the results to pinned memory
+            host = self._h_out
+            self._host_graph_done = False
+        else:
+            host = self._fetch_step_outputs()
         truncated = self.check_truncation(host)
         if truncated:
             print(f"Batch #{self.batch_idx} truncated")
@@ -435,7 +448,7 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
             self.data_rewards.append(self.rewards.clone())
             obs_reset = self._reset()
             obs_out = self._out(obs_reset)
-        return obs_out, reward_out, [done] * self.n_envs, [{}] * self.n_envs
+        return obs_out, reward_out, (self._dones_true if done else self._dones_false), self._infos
 
     def step_device(self, actions):
         """Device-resident step for on-GPU learners: same work as ``step`` (integration, observations, reward,
@@ -462,7 +475,7 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
             self._obs_last = obs_view
         if reward_view is not None:
             self._reward_last = reward_view
-        self._graph = None
+        self._graph = self._graph_host = None
 
     def _out(self, t):
         return t.detach().cpu().numpy() if self.return_numpy else t

@@ -71,7 +71,7 @@ class LinearVecEnv(BaseVecEnv):
         self._dyn = torch.zeros((2,), dtype=torch.int64, device=self.device)      # {t_idx, episode} read by the kernel
         self._dyn_host = torch.zeros((2,), dtype=torch.int64).pin_memory()
         self._actions_in = torch.zeros((self.n_envs, self.n_actions), dtype=torch.float64, device=self.device)
-        self._graph = None
+        self._graph = self._graph_host = None
         self.graph_replays, self.graph_native_launches = 0, 0
         self._reward_w = None
         if self._reward_fused:
@@ -236,17 +236,24 @@ class LinearVecEnv(BaseVecEnv):
         if not self.use_cuda_graph:
             self._launch(dim - 1, self._x_last)
         elif dim == self.action_interval + 1:
-            self._replay_interval()
+            self._replay_interval(host_io=getattr(self, "_host_step", False))
         else:  # tail interval (fewer sub-steps): eager launch, then advance the device-side time index
+            if getattr(self, "_host_step", False):
+                self._actions_in.copy_(self._h_actions, non_blocking=True)
+                self._minmax.copy_(self._minmax_init, non_blocking=True)
             self.actions = (self._actions_in * self.action_maximums_batch)
             self._launch(dim - 1, self._x_last)
             self._dyn[0] += dim - 1
         return self._States[:dim]
 
-    def _replay_interval(self):
+    def _replay_interval(self, host_io=False):
         """One full action interval as ONE graph launch: actions scaling, the coefficient hooks (batched torch), the
-        fused integration kernel and the advance of the device-side time index are captured once and replayed."""
-        if self._graph is None:
+        fused integration kernel and the advance of the device-side time index are captured once and replayed.
+        ``host_io=True`` (the ``step(host actions)`` path) replays a second graph that additionally starts with the
+        H2D copy of the actions from pinned memory and the min/max reset and ends with the D2H copy of
+        ``[obs_last | reward_last | min,max]`` into pinned memory — the whole host round trip is one launch."""
+        key = "_graph_host" if host_io else "_graph"
+        if getattr(self, key, None) is None:
             K = self.action_interval
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
@@ -254,14 +261,21 @@ class LinearVecEnv(BaseVecEnv):
             n0 = N.launch_count()
             with torch.cuda.stream(side):
                 with torch.cuda.graph(graph, stream=side):
+                    if host_io:
+                        self._actions_in.copy_(self._h_actions, non_blocking=True)
+                        self._minmax.copy_(self._minmax_init, non_blocking=True)
                     if not (self.fused_coefficients and self._affine_drift() is not None):
                         self.actions = self._actions_in * self.action_maximums_batch
-                    self._graph_keep = self._launch(K, self._x_last)
+                    keep = self._launch(K, self._x_last)
                     self._dyn[0] += K
+                    if host_io:
+                        self._h_out.copy_(self._step_out, non_blocking=True)
             torch.cuda.current_stream().wait_stream(side)
-            self._graph = graph
+            setattr(self, key, graph)
+            setattr(self, key + "_keep", keep)
             self._graph_packs = self._packed_by_kernel
             self.graph_native_launches = N.launch_count() - n0   # kernels of libquantrl_b200.so inside one replay
         self.graph_replays += 1
         self._packed_by_kernel = self._graph_packs
-        self._graph.replay()
+        getattr(self, key).replay()
+        self._host_graph_done = host_io

@@ -241,9 +241,11 @@ def test_cuda_graph_replay_equals_eager(native, cuda):
     kw = dict(n_envs=E, n=4, A0=A0, Au=Au, noise_prefixes=0.05, x0=1.0, t_norm_max=0.455, t_norm_ssz=0.01,
               action_interval=K, observation_stds=[0.01] * 4, seed=9, dir_prefix="/tmp/qrl_test")
     eager, graph = AffineLinearVecEnv(**kw), AffineLinearVecEnv(use_cuda_graph=True, **kw)
+    # host-I/O variant: NumPy actions in, NumPy results out; H2D + kernel + D2H replayed as one graph
+    hostg = AffineLinearVecEnv(use_cuda_graph=True, return_numpy=True, **kw)
     assert eager.shape_T == (46,) and eager.action_steps == 5         # 4 full intervals + a tail of 5 sub-steps
-    o_e, o_g = eager.reset(), graph.reset()
-    assert torch.equal(o_e, o_g)
+    o_e, o_g, o_h = eager.reset(), graph.reset(), hostg.reset()
+    assert torch.equal(o_e, o_g) and np.array_equal(o_e.cpu().numpy(), o_h)
     rng = np.random.default_rng(0)
     for step in range(10):
         u = torch.as_tensor(rng.uniform(-1, 1, (E, 1)), device="cuda")
@@ -252,11 +254,16 @@ def test_cuda_graph_replay_equals_eager(native, cuda):
             np.testing.assert_array_equal(d_e, d_g)
         oe, re_, de, _ = eager.step(u)
         og, rg, dg, _ = graph.step(u)
+        oh, rh, dh, ih = hostg.step(u.cpu().numpy())
         assert torch.equal(oe, og) and torch.equal(re_, rg) and de == dg
+        assert isinstance(oh, np.ndarray) and np.array_equal(oe.cpu().numpy(), oh) and np.array_equal(re_.cpu().numpy(), rh)
+        assert dh == de and len(ih) == E and hostg.t_idx == eager.t_idx
         assert torch.equal(eager.States, graph.States) and torch.equal(eager.rewards, graph.rewards)
         assert eager.t_idx == graph.t_idx
     assert graph.graph_replays == 8 and graph.graph_native_launches == 1 and eager.batch_idx == graph.batch_idx == 2
-    eager.close(); graph.close()
+    assert hostg.graph_replays == 8 and hostg.batch_idx == 2
+    np.testing.assert_array_equal(hostg.data, eager.data)
+    eager.close(); graph.close(); hostg.close()
 
 
 def test_fused_affine_coefficients_match_hook_path(native, cuda):
