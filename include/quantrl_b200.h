@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define QRL_ABI_VERSION 1
+#define QRL_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define QRL_API __attribute__((visibility("default")))
@@ -160,12 +160,25 @@ typedef struct qrl_em_args {
      * packed rows holds the scaled action.  action_scale NULL = 1. */
     const double* A_act;        /* (n_actions, n, n) */
     const double* action_scale; /* (n_actions,) = action_maximums, or NULL */
+
+    /* per-launch bookkeeping done by the LAST thread block to finish (ABI 2) — lets a captured step consist of this one
+     * kernel, without a reset copy for the min/max pair and without a second kernel that advances dyn[0]:
+     *   finish_counter  DEVICE scratch, one uint32 that is 0 before the launch; every block increments it when it is
+     *                   done, the last one runs the two actions below and leaves it 0 again.  NULL = off.
+     *   minmax_out      when non-NULL: [min, max] accumulated in obs_minmax by THIS launch is copied to minmax_out[0..1]
+     *                   and obs_minmax is re-initialised to [+inf, -inf] (so obs_minmax is private scratch that the
+     *                   caller initialises once, and minmax_out needs no initialisation at all).
+     *   dyn_advance     when != 0 and dyn != NULL: added to dyn[0] after every block has read it. */
+    uint32_t* finish_counter;
+    double*   minmax_out;
+    int64_t   dyn_advance;
 } qrl_em_args;
 
 #define QRL_EM_FORCE_GENERIC 1   /* flags: always use the generic lane-per-component kernel (A/B testing) */
 #define QRL_EM_FORCE_TILED   16  /* flags: use the tiled kernel whenever it supports the case, whatever the batch size */
-#define QRL_EM_PACK_TMA     128 /* flags: tiled kernel stages the packed rows in shared memory and writes each env's run
-                                 * with one TMA bulk store (needs an even packed_row_pitch / packed_stride_e) */
+#define QRL_EM_ITEM_OUTPUT  32  /* flags: tiled kernel uses its one-(row, env)-item-per-lane output pass even when the
+                                 * 16-byte-piece pass applies (A/B testing; n not in {2,4,8} always takes it) */
+#define QRL_EM_PACK_TMA     128 /* flags: reserved (accepted and ignored; the cache rows are written from registers) */
 /* flag bits 2, 4, 8 are diagnostics of the tiled kernel (skip produce / recurrence / output stage); results invalid */
 
 QRL_API int qrl_em_step(const qrl_em_args* args, void* stream);

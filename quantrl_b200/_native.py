@@ -7,13 +7,13 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 RNG_FED, RNG_PHILOX = 0, 1
 REWARD_NONE, REWARD_NEG_WSQ_OBS, REWARD_NEG_WSQ_STATE, REWARD_ENTAN_LN_OBS, REWARD_ENTAN_LN_STATE = 0, 1, 2, 3, 4
 SYS_OPTOMECH, SYS_KERR_CHAIN, SYS_CONST_AD = 1, 2, 3
 ODE_RK4, ODE_DOPRI5 = 0, 1
-EM_FORCE_GENERIC, EM_FORCE_TILED, EM_PACK_TMA = 1, 16, 128
+EM_FORCE_GENERIC, EM_FORCE_TILED, EM_ITEM_OUTPUT, EM_PACK_TMA = 1, 16, 32, 128
 ODE_FORCE_THREAD, ODE_FORCE_LANES = 1, 2
 
 _dp = C.c_void_p  # device pointers travel as integers
@@ -36,6 +36,7 @@ class EmArgs(C.Structure):
         ("rewards_cum", _dp), ("obs_minmax", _dp), ("nan_flag", _dp),
         ("packed", _dp), ("packed_stride_e", C.c_int64), ("packed_row_pitch", C.c_int64), ("T_step", _dp), ("actions", _dp), ("sel_idxs", _dp),
         ("n_actions", C.c_int32), ("n_sel", C.c_int32), ("dyn", _dp), ("A_act", _dp), ("action_scale", _dp),
+        ("finish_counter", _dp), ("minmax_out", _dp), ("dyn_advance", C.c_int64),
     ]
 
 

@@ -82,23 +82,18 @@ __device__ __forceinline__ double shfl_xor_d(double v, int mask, int width = 32)
     return __shfl_xor_sync(0xffffffffu, v, mask, width);
 }
 
+// Atomic min / max on doubles without a CAS loop: for IEEE-754 bit patterns, non-negative values order like signed
+// integers and negative values order inversely like unsigned integers, so one integer atomic (a fire-and-forget RED)
+// per call is enough whatever the signs of the stored and the new value.  NaN is never passed in (fmin/fmax drop it).
 __device__ __forceinline__ void atomic_min_d(double* addr, double v) {
-    unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
-    unsigned long long old = *a;
-    while (v < __longlong_as_double((long long)old)) {
-        unsigned long long assumed = old;
-        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
-        if (old == assumed) break;
-    }
+    const long long b = __double_as_longlong(v);
+    if (b >= 0) atomicMin(reinterpret_cast<long long*>(addr), b);
+    else atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)b);
 }
 __device__ __forceinline__ void atomic_max_d(double* addr, double v) {
-    unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
-    unsigned long long old = *a;
-    while (v > __longlong_as_double((long long)old)) {
-        unsigned long long assumed = old;
-        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
-        if (old == assumed) break;
-    }
+    const long long b = __double_as_longlong(v);
+    if (b >= 0) atomicMax(reinterpret_cast<long long*>(addr), b);
+    else atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)b);
 }
 
 // Block-wide min/max of per-thread running extrema followed by one atomic pair per block.
@@ -119,6 +114,27 @@ __device__ __forceinline__ void block_minmax_commit(double lo, double hi, double
         atomic_min_d(obs_minmax + 0, lo);
         atomic_max_d(obs_minmax + 1, hi);
     }
+}
+
+// Last-block-done bookkeeping of qrl_em_args (finish_counter / minmax_out / dyn_advance); call once per block, by all
+// threads, after block_minmax_commit (whose atomics are issued by thread 0, like the counter increment below).
+__device__ __forceinline__ void em_finish_launch(const qrl_em_args& a) {
+    if (a.finish_counter == nullptr) return;
+    __syncthreads();                                    // every thread of the block has read dyn and is done
+    if (threadIdx.x != 0) return;
+    __threadfence();                                    // this block's min/max atomics and dyn reads come first
+    const unsigned prev = atomicAdd(a.finish_counter, 1u);
+    if (prev != gridDim.x - 1) return;
+    __threadfence();
+    if (a.minmax_out && a.obs_minmax) {
+        volatile double* acc = a.obs_minmax;
+        a.minmax_out[0] = acc[0];
+        a.minmax_out[1] = acc[1];
+        acc[0] = INFINITY;
+        acc[1] = -INFINITY;
+    }
+    if (a.dyn && a.dyn_advance != 0) const_cast<int64_t*>(a.dyn)[0] += a.dyn_advance;
+    *a.finish_counter = 0u;
 }
 
 }  // namespace qrl

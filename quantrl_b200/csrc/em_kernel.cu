@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(128) em_step_kernel(const qrl_em_args a_in, co
         if (a.nan_flag && !isfinite(x)) *a.nan_flag = 1;
     }
     if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
+    em_finish_launch(a);
 }
 
 template <int LPE>
@@ -149,6 +150,9 @@ extern "C" int qrl_em_step(const qrl_em_args* args, void* stream) {
     QRL_REQUIRE(a.t_idx >= 0 && a.env_offset >= 0, "qrl_em_step: negative t_idx / env_offset");
     QRL_REQUIRE(a.A_act == nullptr || (a.actions != nullptr && a.n_actions >= 1 && a.A_stride_k == 0),
                 "qrl_em_step: the affine drift functor needs actions, n_actions >= 1 and a time-invariant A");
+    QRL_REQUIRE(a.finish_counter != nullptr || (a.minmax_out == nullptr && a.dyn_advance == 0),
+                "qrl_em_step: minmax_out / dyn_advance need finish_counter");
+    QRL_REQUIRE(a.minmax_out == nullptr || a.obs_minmax != nullptr, "qrl_em_step: minmax_out needs obs_minmax");
     if (a.packed) {
         QRL_REQUIRE(a.reward_kind != QRL_REWARD_NONE && a.rewards_cum != nullptr,
                     "qrl_em_step: packed rows need a fused reward functor and rewards_cum");

@@ -2,22 +2,33 @@
 //
 // Why: with one lane per state component (em_kernel.cu) config 3 (E = 4096) puts a single warp on each SM
 // sub-partition and the kernel is latency bound (ncu r1a: IPC 0.25, FP64 pipe 12 %).  The noise generation
-// (Philox4x32-10 + FP64 Box–Muller, ~95 % of the instructions) does not depend on the state, so it is spread over
-// 15 "worker" warps per CTA, while ONE warp runs the short sequential recurrence for all environments of the CTA.
+// (Philox4x32-10 + FP64 Box–Muller, > 80 % of the necessary instructions) does not depend on the state, so it is
+// spread over 15 "worker" warps per CTA, while ONE warp runs the short sequential recurrence for all environments
+// of the CTA.
 //
 // One CTA owns G <= 32 environments for the whole interval; time is cut into chunks of C sub-steps that flow through
-// double-buffered shared-memory tiles in a 3-stage pipeline, one __syncthreads per chunk:
-//   iteration it:  workers   produce noise(chunk it)      -> Wt/Vt[it & 1]          (Philox, or fed loads)
-//                  warp 0    recurrence(chunk it-1)        Wt[(it-1) & 1] -> Xt[(it-1) & 1]   (x-update only: the warp
-//                                                          is the sequential critical path, ncu r1b)
-//                  workers   output(chunk it-2)            Ot = Xt[it & 1] + Vt[it & 1], then -> global:
-//                              * Observations rows: lane-contiguous (fully coalesced) 8-byte stores;
-//                              * States rows: each tile row is one contiguous run of the (K+1,E,n) block and
-//                                leaves through the TMA engine (cp.async.bulk shared -> global), no LSU work;
-//                              * Reward rows: one coalesced 8-byte store per (row, env);
-//                              * packed cache rows [t, actions, obs, cum. reward] (env-major): element-wise,
-//                                lane-contiguous 8-byte stores;
-//                              * min/max of the observations (truncation check).
+// shared-memory tiles in a 3-stage pipeline with ONE __syncthreads per chunk and no other barrier:
+//   iteration it:  workers   output(chunk it-2)           Xt[it & 1] + Vt[(it-2) % 3] -> global
+//                  workers   produce noise(chunk it)      -> Wt[it & 1], Vt[it % 3]     (Philox, or fed loads)
+//                  warp 0    recurrence(chunk it-1)       Wt[(it-1) & 1] -> Xt[(it-1) & 1]
+// The measurement-noise tiles are triple buffered so that the output stage (which reads chunk it-2) and the producers
+// (which write chunk it) never touch the same buffer inside an iteration.
+//
+// The kernel is issue bound (one instruction per clock per scheduler; ncu r1d: the r1 version executed 411
+// instructions per pair of normals, only 165 of them in the generator), so the work distribution is chosen for
+// instruction economy:
+//   * production: a worker owns ONE (environment, component) column for the whole launch and walks the sub-steps
+//     with a fixed stride — counter words, noise scale and shared-memory column are loop invariants, the only
+//     per-pair integer work is `tau += stride`.  Two pairs per trip (ILP) and the Philox rounds of the NEXT trip are
+//     issued in the same basic block as the Box–Muller polynomials of the current one, so the integer, IMAD and FP64
+//     pipes overlap inside a warp (4 independent dependency chains per warp, ~15 per scheduler);
+//   * output (n = 2, 4, 8): a worker owns a 16-byte piece (two components) of a tile row, which is also a 16-byte
+//     piece of the global row: 128-bit shared loads of states and noise, two adds, 128-bit stores into the States /
+//     Observations blocks (a warp writes 512 contiguous bytes), min/max, and the reward as ONE chain of FMAs that
+//     hops over the n/2 adjacent lanes of an environment with a shuffle (same order of operations as a sequential
+//     sum over the components).  No staging tile, no barrier; ~90 instructions per 32 (row, env) items (ncu r1e:
+//     the one-item-per-lane version needed 200, a third of them for NaN-aware fmin/fmax);
+//   * output (other n, unaligned blocks, and the cache rows): one (row, environment) item per worker.
 // Replaces the same reference code as em_kernel.cu (quantrl/envs/stochastic.py:178-242, envs/base.py:408-426,462,
 // 471-473,485-499) plus the packed rows of BaseSB3Env.update_data (envs/base.py:1314-1372).
 #include <stdlib.h>
@@ -26,63 +37,52 @@
 
 namespace qrl {
 
-#ifndef QRL_EM_TILE_THREADS
-#define QRL_EM_TILE_THREADS 512
-#endif
-#ifndef QRL_EM_TILE_ILP
-#define QRL_EM_TILE_ILP 1
-#endif
-constexpr int EM_TILE_THREADS = QRL_EM_TILE_THREADS;
+constexpr int EM_TILE_THREADS = 512;
 constexpr int EM_TILE_WORKERS = EM_TILE_THREADS - 32;
-constexpr int EM_TILE_ILP = QRL_EM_TILE_ILP;
-
-__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-// make generic-proxy shared-memory writes visible to the async proxy (TMA) before the barrier that precedes the copy
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+constexpr int EM_TILE_CMAX = 32;
 
 __device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, %0;" :: "n"(EM_TILE_WORKERS) : "memory"); }
 
-template <int N>
+// NaN-ignoring running extrema (lo / hi are never NaN): 3 instructions each instead of the ~8 of fmin / fmax
+__device__ __forceinline__ void track_minmax(double v, double& lo, double& hi) {
+    lo = (v < lo) ? v : lo;
+    hi = (v > hi) ? v : hi;
+}
+
+template <int N, int ILP>
 __global__ void __launch_bounds__(EM_TILE_THREADS, 1)
-em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const int C) {
+em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const int C, const int nphase) {
     const qrl_em_args a = resolve_dyn(a_in);
     extern __shared__ __align__(128) double sm[];
     const int E = a.n_envs, K = a.K;
     const int e0 = blockIdx.x * G;
     const int Gl = min(G, E - e0);             // live environments of this CTA
-    const int RP = Gl * N;                     // doubles per tile row
-    const int tile = C * G * N;                // doubles per tile buffer (even: G is even, see plan_tiles)
-    double* NB = sm;                           // [2][2][tile] noise buffers {W, V}[b]: Wiener increments and measurement
-                                               // noise (scaled) of one chunk sit next to each other, so that the pair
-                                               // doubles as the staging area of the packed cache rows once consumed
-    double* Xt = NB + 4 * tile;                // [2][tile] states, written by the recurrence warp
-    double* Ot = Xt + 2 * tile;                // [tile]    observations = states + noise, written by the workers
-    double* Pt = Ot + tile;                    // [G][C][pitch] packed cache rows of one chunk, in each env's global layout
-    const int pitch = a.packed ? (int)(a.packed_row_pitch > 0 ? a.packed_row_pitch : a.n_sel) : 0;
-    double* x0S = Pt + (size_t)C * G * pitch;  // [G*N] initial state (row 0)
-    double* stdS = x0S + G * N;                // [G*N] measurement-noise std per (env, comp)
-    double* cumS = stdS + G * N;               // [G]   cumulative reward after this interval
-    double* wS = cumS + G;                     // [N]   reward weights
+    const int RP = G * N;                      // doubles per tile row (same for every CTA: the column map is static)
+    const int tile = C * RP;                   // doubles per tile buffer
+    double* Wt = sm;                           // [2][tile] Wiener increments, already scaled by sqrt(dt)
+    double* Vt = Wt + 2 * tile;                // [3][tile] measurement noise, already scaled by obs_std
+    double* Xt = Vt + 3 * tile;                // [2][tile] states, written by the recurrence warp
+    double* x0S = Xt + 2 * tile;               // [RP] initial state (row 0)
+    double* v0S = x0S + RP;                    // [RP] measurement noise of row 0
+    double* stdS = v0S + RP;                   // [RP] measurement-noise std per (env, comp)
+    double* cumS = stdS + RP;                  // [G]  cumulative reward after this interval
+    double* wS = cumS + G;                     // [N]  reward weights
     int* selS = reinterpret_cast<int*>(wS + N);  // [n_sel]
 
     const int tid = threadIdx.x;
     const bool is_rec = tid < 32;
-    const int wt = tid - 32;                   // worker lane id (0..EM_TILE_WORKERS-1)
+    const int wt = tid - 32;                   // worker id (0..EM_TILE_WORKERS-1)
     const bool philox = a.rng_mode == QRL_RNG_PHILOX;
     const bool has_reward = a.reward_kind != QRL_REWARD_NONE;
+    const bool reward_on_obs = a.reward_kind == QRL_REWARD_NEG_WSQ_OBS;
     const double sqrt_dt = sqrt(a.t_ssz);
     const int NC = (K + C - 1) / C;
     const int64_t row = (int64_t)E * N;
     const int n_data = 1 + a.n_actions + N + 1;
     const int n_sel = a.n_sel;
+    const int pitch = a.packed ? (int)(a.packed_row_pitch > 0 ? a.packed_row_pitch : a.n_sel) : 0;
 
-    for (int i = tid; i < RP; i += EM_TILE_THREADS) {
+    for (int i = tid; i < Gl * N; i += EM_TILE_THREADS) {
         const int el = i / N, c = i - el * N;
         stdS[i] = (philox && a.obs_std) ? a.obs_std[(int64_t)(e0 + el) * a.obs_std_stride_e + c] : 0.0;
         x0S[i] = a.x0[(int64_t)e0 * N + i];
@@ -94,92 +94,79 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
             selS[i] = s < 0 ? s + n_data : s;
         }
     __syncthreads();
-    bool sel_identity = a.packed != nullptr && n_sel == n_data;
-    if (sel_identity)
-        for (int j = 0; j < n_sel; ++j) sel_identity &= (selS[j] == j);
-
-    // TMA eligibility of the packed rows: every env's run of this CTA starts 16-byte aligned and has a 16-byte size
-    const bool tma_p = a.packed != nullptr && (pitch % 2 == 0) && (a.packed_stride_e % 2 == 0) &&
-                       ((uintptr_t)a.packed % 16 == 0);
+    // does any selected cache column have to be written row by row?  (the cumulative-reward column is only known
+    // after the last sub-step and is written for all K+1 rows at the end)
+    bool pack_rows = false;
+    if (a.packed)
+        for (int j = 0; j < n_sel; ++j) pack_rows |= (selS[j] != n_data - 1);
+    // 128-bit accesses need even N (tile rows and every env's N-run are then 16-byte aligned) and aligned bases
+    const bool vec_g = (N % 2 == 0) && ((((uintptr_t)a.states) | ((uintptr_t)a.observations)) % 16 == 0);
+    // piece pass: n/2 adjacent lanes per environment
+    constexpr bool PIECE_N = (N == 2 || N == 4 || N == 8);
+    constexpr int L = PIECE_N ? N / 2 : 1;
+    const bool piece_out = PIECE_N && vec_g && !(a.flags & QRL_EM_ITEM_OUTPUT);
 
     double lo = INFINITY, hi = -INFINITY;
 
-    // ---- worker helpers: everything derived from a finished observation row block in Ot ------------------------
-    // reward rows, last-row outputs and packed cache rows for rows r_first .. r_first+ns-1 whose states/observations
-    // sit in Xb/Ob (row-major [slot][env][comp])
-    auto emit_derived = [&](const double* Xb, const double* Ob, int r_first, int ns, double* stage) {
-        if (a.packed) {
-            // Rows are built in shared memory as [env][slot][pitch] = the global layout of each env's run, then leave
-            // as ONE TMA bulk store per env (ns * pitch * 8 contiguous bytes) when the 16-byte rules hold, else through
-            // lane-contiguous 8-byte stores.  (Direct per-row stores from the lanes cost +12 us per launch at config 3:
-            // ~300 instructions per row of address arithmetic and 8-byte pieces of 7 different sectors.)
-            const int per_env = ns * pitch;
-            const bool staged = stage != nullptr;
-            int el = wt / ns, sl = wt - el * ns;
-            const int d_el = EM_TILE_WORKERS / ns, d_sl = EM_TILE_WORKERS - d_el * ns;
-            while (el < Gl) {
-                const int r = r_first + sl, e = e0 + el;
-                const double* orow = Ob + sl * RP + el * N;
-                double* dst = staged ? stage + (el * ns + sl) * pitch
-                                     : a.packed + (int64_t)e * a.packed_stride_e + (int64_t)r * pitch;
-                if (sel_identity) {
-                    // all n_data columns in their natural order (the reference's cache_all_data layout): straight copy
-                    dst[0] = a.T_step[r];
-                    for (int k = 0; k < a.n_actions; ++k) dst[1 + k] = em_action(a, e, k);
+    // ---- output stage, item pass: one (row, env) item per worker and trip ------------------------------------------
+    // rows r_first .. r_first+ns-1 whose states / noises sit in Xb / Vb (row-major [slot][env][comp], row pitch RP).
+    // full: the item does everything (adds, States / Observations rows, min/max, reward, last-row outputs, cache row);
+    // otherwise the piece pass has done all that and only the cache row is left.
+    const int o_dsl = EM_TILE_WORKERS / Gl, o_del = EM_TILE_WORKERS - o_dsl * Gl;
+    const int o_sl0 = wt / Gl, o_el0 = wt - o_sl0 * Gl;
+    auto item_pass = [&](const double* Xb, const double* Vb, int r_first, int ns, const bool full) {
+        int sl = o_sl0, el = o_el0;
+        while (sl < ns) {
+            const int r = r_first + sl, e = e0 + el;
+            const int off = sl * RP + el * N;
+            double xv[N], ov[N];
+            if constexpr (N % 2 == 0) {
+                const double2* xp = reinterpret_cast<const double2*>(Xb + off);
+                const double2* vp = reinterpret_cast<const double2*>(Vb + off);
 #pragma unroll
-                    for (int c = 0; c < N; ++c) dst[1 + a.n_actions + c] = orow[c];
-                    dst[n_data - 1] = 0.0;   // cumulative reward: patched after the last sub-step
-                } else {
-                    for (int j = 0; j < n_sel; ++j) {
-                        const int col = selS[j];
-                        double val = 0.0;  // cumulative-reward column: only known after the last sub-step, patched below
-                        if (col == 0) val = a.T_step[r];
-                        else if (col <= a.n_actions) val = em_action(a, e, col - 1);
-                        else if (col <= a.n_actions + N) val = orow[col - 1 - a.n_actions];
-                        dst[j] = val;
-                    }
+                for (int c = 0; c < N / 2; ++c) {
+                    const double2 x2 = xp[c], v2 = vp[c];
+                    xv[2 * c] = x2.x; xv[2 * c + 1] = x2.y;
+                    ov[2 * c] = __dadd_rn(x2.x, v2.x); ov[2 * c + 1] = __dadd_rn(x2.y, v2.y);
                 }
-                if (staged)
-                    for (int j = n_sel; j < pitch; ++j) dst[j] = 0.0;   // padding columns travel with the bulk store
-                el += d_el;
-                sl += d_sl;
-                if (sl >= ns) { sl -= ns; ++el; }
+            } else {
+#pragma unroll
+                for (int c = 0; c < N; ++c) { xv[c] = Xb[off + c]; ov[c] = __dadd_rn(xv[c], Vb[off + c]); }
             }
-            if (staged) {
-                const bool tma_now = tma_p && (((int64_t)r_first * pitch) % 2 == 0) && (per_env % 2 == 0);
-                if (tma_now) fence_async_smem();
-                worker_barrier();
-                if (tma_now) {
-                    if (wt < 32) {
-                        for (int e2 = wt; e2 < Gl; e2 += 32)
-                            bulk_store(a.packed + (int64_t)(e0 + e2) * a.packed_stride_e + (int64_t)r_first * pitch,
-                                       stage + e2 * per_env, per_env * 8);
-                        bulk_commit();
+            if (full) {
+                const int64_t g = (int64_t)r * row + (int64_t)e * N;
+                if (vec_g) {
+                    if constexpr (N % 2 == 0) {
+                        if (a.states) {
+                            double2* sp = reinterpret_cast<double2*>(a.states + g);
+#pragma unroll
+                            for (int c = 0; c < N / 2; ++c) sp[c] = make_double2(xv[2 * c], xv[2 * c + 1]);
+                        }
+                        if (a.observations) {
+                            double2* op = reinterpret_cast<double2*>(a.observations + g);
+#pragma unroll
+                            for (int c = 0; c < N / 2; ++c) op[c] = make_double2(ov[2 * c], ov[2 * c + 1]);
+                        }
                     }
                 } else {
-                    int e2 = wt / per_env, off = wt - e2 * per_env;
-                    const int d_e2 = EM_TILE_WORKERS / per_env, d_off = EM_TILE_WORKERS - d_e2 * per_env;
-                    while (e2 < Gl) {
-                        a.packed[(int64_t)(e0 + e2) * a.packed_stride_e + (int64_t)r_first * pitch + off] = stage[e2 * per_env + off];
-                        e2 += d_e2;
-                        off += d_off;
-                        if (off >= per_env) { off -= per_env; ++e2; }
+#pragma unroll
+                    for (int c = 0; c < N; ++c) {
+                        if (a.states) a.states[g + c] = xv[c];
+                        if (a.observations) a.observations[g + c] = ov[c];
                     }
                 }
-            }
-        }
-        if (has_reward || a.x_last || a.obs_last) {
-            for (int item = wt; item < ns * Gl; item += EM_TILE_WORKERS) {
-                const int sl = item / Gl, el = item - sl * Gl;
-                const int r = r_first + sl, e = e0 + el;
-                const double* xr = Xb + sl * RP + el * N;
-                const double* orow = Ob + sl * RP + el * N;
+#pragma unroll
+                for (int c = 0; c < N; ++c) track_minmax(ov[c], lo, hi);
                 double rv = 0.0;
                 if (has_reward) {
-                    const double* s = (a.reward_kind == QRL_REWARD_NEG_WSQ_OBS) ? orow : xr;
                     double acc = 0.0;
+                    if (reward_on_obs) {
 #pragma unroll
-                    for (int c = 0; c < N; ++c) acc = fma(wS[c] * s[c], s[c], acc);
+                        for (int c = 0; c < N; ++c) acc = fma(wS[c] * ov[c], ov[c], acc);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < N; ++c) acc = fma(wS[c] * xv[c], xv[c], acc);
+                    }
                     rv = -acc;
                     if (a.reward) a.reward[(int64_t)r * E + e] = rv;
                 }
@@ -192,11 +179,105 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
                     }
 #pragma unroll
                     for (int c = 0; c < N; ++c) {
-                        if (a.x_last) a.x_last[(int64_t)e * N + c] = xr[c];
-                        if (a.obs_last) a.obs_last[(int64_t)e * N + c] = orow[c];
+                        if (a.x_last) a.x_last[(int64_t)e * N + c] = xv[c];
+                        if (a.obs_last) a.obs_last[(int64_t)e * N + c] = ov[c];
                     }
                 }
             }
+            if (pack_rows) {
+                // cache row [T_step[r], actions[e,:], Obs[r,e,:], cum. reward] restricted to the selected columns,
+                // straight from registers into the env-major cache (envs/base.py:1314-1372)
+                double* dst = a.packed + (int64_t)e * a.packed_stride_e + (int64_t)r * pitch;
+                for (int j = 0; j < n_sel; ++j) {
+                    const int col = selS[j];
+                    if (col == n_data - 1) continue;   // cumulative reward: written for all rows after the last sub-step
+                    double val;
+                    if (col == 0) val = a.T_step[r];
+                    else if (col <= a.n_actions) val = em_action(a, e, col - 1);
+                    else {
+                        const int c = col - 1 - a.n_actions;
+                        val = ov[0];
+#pragma unroll
+                        for (int cc = 1; cc < N; ++cc) val = (c == cc) ? ov[cc] : val;
+                    }
+                    dst[j] = val;
+                }
+            }
+            sl += o_dsl;
+            el += o_del;
+            if (el >= Gl) { el -= Gl; ++sl; }
+        }
+    };
+
+    // ---- output stage, piece pass: one 16-byte piece (two components) of a row per worker and trip ----------------
+    const int PR = Gl * L;                     // pieces per live row
+    const int q_dsl = EM_TILE_WORKERS / PR, q_dpc = EM_TILE_WORKERS - q_dsl * PR;
+    const int q_sl0 = wt / PR, q_pc0 = wt - q_sl0 * PR;
+    const int q_h = wt & (L - 1);              // which piece of its environment this lane holds (pieces of an env sit
+                                               // in adjacent lanes: EM_TILE_WORKERS and PR are multiples of L)
+    double q_w0 = 0.0, q_w1 = 0.0;             // reward weights of this lane's two components
+    if constexpr (PIECE_N) { q_w0 = wS[2 * q_h]; q_w1 = wS[2 * q_h + 1]; }
+    auto piece_pass = [&](const double* Xb, const double* Vb, int r_first, int ns) {
+        if constexpr (PIECE_N) {
+            int sl = q_sl0, pc = q_pc0;
+            // warp-uniform trip count (the shuffles below need all 32 lanes): lane 0 holds the smallest piece index
+            int sl_lead = __shfl_sync(0xffffffffu, sl, 0);
+            while (sl_lead < ns) {
+                const bool live = sl < ns;
+                const int off = live ? sl * RP + 2 * pc : 0;
+                const double2 x2 = *reinterpret_cast<const double2*>(Xb + off);
+                const double2 v2 = *reinterpret_cast<const double2*>(Vb + off);
+                const double2 o2 = make_double2(__dadd_rn(x2.x, v2.x), __dadd_rn(x2.y, v2.y));
+                const int r = r_first + sl;
+                const int64_t g = (int64_t)r * row + (int64_t)e0 * N + 2 * pc;
+                if (live) {
+                    if (a.states) *reinterpret_cast<double2*>(a.states + g) = x2;
+                    if (a.observations) *reinterpret_cast<double2*>(a.observations + g) = o2;
+                    track_minmax(o2.x, lo, hi);
+                    track_minmax(o2.y, lo, hi);
+                }
+                double rv = 0.0;
+                if (has_reward) {
+                    // -sum_c w_c s_c^2 as one chain of FMAs in component order, hopping over the L lanes of the env
+                    const double s0 = reward_on_obs ? o2.x : x2.x, s1 = reward_on_obs ? o2.y : x2.y;
+                    const double ws0 = q_w0 * s0, ws1 = q_w1 * s1;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < L; ++j) {
+                        const double t = fma(ws1, s1, fma(ws0, s0, acc));
+                        if (j == L - 1) { rv = -t; break; }
+                        const double up = __shfl_up_sync(0xffffffffu, t, 1);
+                        if (q_h == j + 1) acc = up;
+                    }
+                }
+                if (live) {
+                    const int el = pc / L, e = e0 + el;
+                    if (has_reward && q_h == L - 1 && a.reward) a.reward[(int64_t)r * E + e] = rv;
+                    if (r == K) {
+                        if (has_reward && q_h == L - 1) {
+                            if (a.reward_last) a.reward_last[e] = rv;
+                            double cum = rv;
+                            if (a.rewards_cum) { cum += a.rewards_cum[e]; a.rewards_cum[e] = cum; }
+                            cumS[el] = cum;
+                        }
+                        const int64_t gl = (int64_t)e0 * N + 2 * pc;
+                        if (a.x_last) { a.x_last[gl] = x2.x; a.x_last[gl + 1] = x2.y; }
+                        if (a.obs_last) { a.obs_last[gl] = o2.x; a.obs_last[gl + 1] = o2.y; }
+                    }
+                }
+                sl += q_dsl;
+                pc += q_dpc;
+                if (pc >= PR) { pc -= PR; ++sl; }
+                sl_lead = __shfl_sync(0xffffffffu, sl, 0);
+            }
+        }
+    };
+    auto output_rows = [&](const double* Xb, const double* Vb, int r_first, int ns) {
+        if (piece_out) {
+            piece_pass(Xb, Vb, r_first, ns);
+            if (pack_rows) item_pass(Xb, Vb, r_first, ns, false);
+        } else {
+            item_pass(Xb, Vb, r_first, ns, true);
         }
     };
 
@@ -204,19 +285,45 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
     double M[N][N], nz[N], x[N];
     const int el_r = tid;                      // env handled by this recurrence lane
     const bool rec_live = is_rec && el_r < Gl;
+    // ---- producer: the (env, comp) column of this worker and its position in the sub-step walk ------------------
+    const int p_phase = wt / RP, p_col = wt - p_phase * RP;
+    const int p_el = p_col / N, p_c = p_col - p_el * N;
+    const bool p_live = !is_rec && p_phase < nphase && p_el < Gl;
+    const uint32_t p_env = (uint32_t)(a.env_offset + e0 + p_el);
+    const uint32_t tau_base = (uint32_t)a.t_idx;
+    double p_sd = 0.0;
+    int pj = p_phase;                          // next sub-step (within the interval) this worker generates
+    uint4 nxt[ILP];
+
     if (rec_live) {
         const int e = e0 + el_r;
         const double* Ar = a.A + (int64_t)e * a.A_stride_e;
 #pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+            for (int c = 0; c < N; ++c) M[r][c] = Ar[r * N + c];
+        if (a.A_act) {
+            // action-affine drift functor, same accumulation order as em_drift(): A += u_k * A_k for k = 0, 1, ...
+#pragma unroll 1
+            for (int k = 0; k < a.n_actions; ++k) {
+                const double u = a.actions[(int64_t)e * a.n_actions + k] * (a.action_scale ? a.action_scale[k] : 1.0);
+                const double* Ak = a.A_act + (int64_t)k * N * N;
+#pragma unroll
+                for (int r = 0; r < N; ++r)
+#pragma unroll
+                    for (int c = 0; c < N; ++c) M[r][c] = fma(u, Ak[r * N + c], M[r][c]);
+            }
+        }
+#pragma unroll
         for (int r = 0; r < N; ++r) {
 #pragma unroll
-            for (int c = 0; c < N; ++c) M[r][c] = __dadd_rn((r == c) ? 1.0 : 0.0, __dmul_rn(em_drift(a, Ar, e, r * N + c), a.t_ssz));
+            for (int c = 0; c < N; ++c) M[r][c] = __dadd_rn((r == c) ? 1.0 : 0.0, __dmul_rn(M[r][c], a.t_ssz));
             nz[r] = a.nz[(int64_t)e * a.nz_stride_e + r];
             x[r] = x0S[el_r * N + r];
         }
     } else if (!is_rec) {
         // ---- workers: row 0, Observations[0] = States[0] + noise[t_idx]  (envs/base.py:462) ----
-        for (int i = wt; i < RP; i += EM_TILE_WORKERS) {
+        for (int i = wt; i < Gl * N; i += EM_TILE_WORKERS) {
             const int el = i / N, c = i - el * N;
             double v = 0.0;
             if (philox) {
@@ -229,140 +336,86 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
             } else if (a.obs_noise) {
                 v = a.obs_noise[(int64_t)e0 * N + i];
             }
-            const double xv = x0S[i], o = __dadd_rn(xv, v);
-            Ot[i] = o;
-            if (a.states) a.states[(int64_t)e0 * N + i] = xv;
-            if (a.observations) a.observations[(int64_t)e0 * N + i] = o;
-            lo = fmin(lo, o);
-            hi = fmax(hi, o);
+            v0S[i] = v;
+        }
+        if (philox && p_live) {
+            p_sd = stdS[p_col];
+#pragma unroll
+            for (int u = 0; u < ILP; ++u)
+                nxt[u] = philox4x32_10(make_uint4(tau_base + (uint32_t)(pj + u * nphase), a.episode, p_env, (uint32_t)p_c), keys);
         }
         worker_barrier();
-        emit_derived(x0S, Ot, 0, 1, nullptr);
+        output_rows(x0S, v0S, 0, 1);
     }
 
-    // incremental (slot, rem) walkers avoid runtime integer divisions in the hot loops
-    const int p_dslot = EM_TILE_WORKERS / RP, p_drem = EM_TILE_WORKERS - p_dslot * RP;
     const bool dbg_no_prod = a.flags & 2, dbg_no_rec = a.flags & 4, dbg_no_out = a.flags & 8;  // diagnostics only
 
     for (int it = 0; it < NC + 2; ++it) {
         if (!is_rec) {
-            const bool out_now = it >= 2;
-            const int co = it - 2;
-            // ---------------- output chunk `it - 2`, part A: observations = states + noise ----------------
-            if (out_now) {
-                const int ns = min(C, K - co * C);
-                const double* Xb = Xt + (co & 1) * tile;
-                const double* Vb = NB + (co & 1) * 2 * tile + tile;
-                const int r0 = co * C;
-                if (wt < 32) bulk_wait_read();   // the bulk stores of the previous chunk have read Pt by now (long ago)
-                if (!dbg_no_out) {
-                    // states and observations leave through the LSU right here: lane-contiguous 8-byte stores = fully
-                    // coalesced runs of the (K+1,E,n) blocks.  (TMA bulk stores of the state rows were tried: the
-                    // recurrence warp may not overwrite its tile before the engine has read it, and waiting for that
-                    // at the end of every iteration cost more barrier time than the stores cost issue slots.)
-                    int s2 = wt / RP, rem = wt - s2 * RP;
-                    const int64_t gbase = (int64_t)(r0 + 1) * row + (int64_t)e0 * N;
-                    while (s2 < ns) {
-                        const int idx = s2 * RP + rem;
-                        const double o = __dadd_rn(Xb[idx], Vb[idx]);
-                        Ot[idx] = o;
-                        if (a.observations) a.observations[gbase + (int64_t)s2 * row + rem] = o;
-                        if (a.states) a.states[gbase + (int64_t)s2 * row + rem] = Xb[idx];
-                        lo = fmin(lo, o);
-                        hi = fmax(hi, o);
-                        s2 += p_dslot;
-                        rem += p_drem;
-                        if (rem >= RP) { rem -= RP; ++s2; }
-                    }
-                }
-                worker_barrier();   // Ot complete; every read of Vt[it & 1] is done before it is refilled below
-                // ---------------- part B: reward rows, last-row outputs, packed rows ----------------
-                if (!dbg_no_out) {
-                    // Packed rows: direct per-row stores by default.  The shared-memory-staged variant (one TMA bulk
-                    // store per env run, flag QRL_EM_PACK_TMA) moves the bytes for free but needs a proxy fence and a
-                    // second worker barrier per chunk and measured slower on B200 (49.7 vs 43.3 us at config 3).
-                    emit_derived(Xb, Ot, r0 + 1, ns, (a.flags & QRL_EM_PACK_TMA) ? Pt : nullptr);
-                }
+            // ---------------- output chunk `it - 2` ----------------
+            if (it >= 2 && !dbg_no_out) {
+                const int co = it - 2;
+                output_rows(Xt + (co & 1) * tile, Vt + (co % 3) * tile, co * C + 1, min(C, K - co * C));
             }
             // ---------------- produce noise of chunk `it` ----------------
             if (it < NC && !dbg_no_prod) {
                 const int j0 = it * C;
-                const int ns = min(C, K - j0);
-                double* Wb = NB + (it & 1) * 2 * tile;
-                double* Vb = NB + (it & 1) * 2 * tile + tile;
-                int slot = wt / RP, rem = wt - slot * RP;
+                const int j_end = min(j0 + C, K);
+                double* Wb = Wt + (it & 1) * tile;
+                double* Vb = Vt + (it % 3) * tile;
                 if (philox) {
-                    // Software pipeline: the Philox rounds (integer ALU / IMAD pipes) of the NEXT pair are issued inside
-                    // the same straight-line block as the Box-Muller polynomials (FP64 pipe) of the CURRENT pair, so the
-                    // half-rate pipes overlap instead of all warps sitting in the same phase (ncu r1c: issue slots 50 %
-                    // busy with ALU 31 %, FMA-heavy 29 %, FP64 20 % when the phases ran back to back).
-                    // EM_TILE_ILP pairs per trip give that many independent DFMA chains (DFMA latency 8.4 cycles, measured).
-                    const uint32_t envg0 = (uint32_t)(a.env_offset + e0);
-                    const uint32_t tau0 = (uint32_t)(a.t_idx + j0);
-                    int sl[EM_TILE_ILP], rm[EM_TILE_ILP];
-                    uint4 bits[EM_TILE_ILP];
+                    if (p_live) {
+                        // C is a multiple of ILP * nphase (plan_tiles), so a trip never straddles a chunk boundary and
+                        // the prefetched counters of the next trip stay valid across chunks.
+                        double* wp = Wb + (pj - j0) * RP + p_col;
+                        double* vp = Vb + (pj - j0) * RP + p_col;
+                        const int step = ILP * nphase;
+                        for (; pj < j_end; pj += step, wp += step * RP, vp += step * RP) {
+                            uint4 cur[ILP];
 #pragma unroll
-                    for (int u = 0; u < EM_TILE_ILP; ++u) {
-                        sl[u] = slot;
-                        rm[u] = rem;
-                        bits[u] = philox4x32_10(make_uint4(tau0 + slot, a.episode, envg0 + rem / N, (uint32_t)(rem % N)), keys);
-                        slot += p_dslot;
-                        rem += p_drem;
-                        if (rem >= RP) { rem -= RP; ++slot; }
-                    }
-                    while (sl[0] < ns) {
-                        uint4 cur[EM_TILE_ILP];
-                        int idx[EM_TILE_ILP];
-                        double sd[EM_TILE_ILP];
-                        bool ok[EM_TILE_ILP];
+                            for (int u = 0; u < ILP; ++u) {
+                                cur[u] = nxt[u];
+                                // next trip of this chain: unconditional (a pair past the end of the interval is
+                                // computed and dropped), so the whole trip is one basic block
+                                nxt[u] = philox4x32_10(make_uint4(tau_base + (uint32_t)(pj + step + u * nphase), a.episode, p_env, (uint32_t)p_c), keys);
+                            }
+                            double z0[ILP], z1[ILP];
 #pragma unroll
-                        for (int u = 0; u < EM_TILE_ILP; ++u) {
-                            cur[u] = bits[u];
-                            ok[u] = sl[u] < ns;
-                            idx[u] = sl[u] * RP + rm[u];
-                            sd[u] = stdS[rm[u]];
-                            // next pair of this chain: unconditional (a pair past the end of the chunk is computed and
-                            // dropped), so the whole trip is one basic block the scheduler can interleave freely
-                            sl[u] = slot;
-                            rm[u] = rem;
-                            bits[u] = philox4x32_10(make_uint4(tau0 + slot, a.episode, envg0 + rem / N, (uint32_t)(rem % N)), keys);
-                            slot += p_dslot;
-                            rem += p_drem;
-                            if (rem >= RP) { rem -= RP; ++slot; }
-                        }
-                        double z0[EM_TILE_ILP], z1[EM_TILE_ILP];
+                            for (int u = 0; u < ILP; ++u) normal_pair(cur[u], z0[u], z1[u]);
 #pragma unroll
-                        for (int u = 0; u < EM_TILE_ILP; ++u) normal_pair(cur[u], z0[u], z1[u]);
-#pragma unroll
-                        for (int u = 0; u < EM_TILE_ILP; ++u) {
-                            if (ok[u]) {
-                                Wb[idx[u]] = __dmul_rn(sqrt_dt, z0[u]);
-                                Vb[idx[u]] = __dmul_rn(sd[u], z1[u]);
+                            for (int u = 0; u < ILP; ++u) {
+                                if (u == 0 || pj + u * nphase < j_end) {
+                                    wp[u * nphase * RP] = __dmul_rn(sqrt_dt, z0[u]);
+                                    vp[u * nphase * RP] = __dmul_rn(p_sd, z1[u]);
+                                }
                             }
                         }
                     }
                 } else {
                     // fed noise: 4 independent loads in flight per lane (the loop is global-latency bound otherwise)
-                    const int total = ns * RP;
+                    const int ns = j_end - j0;
+                    const int RL = Gl * N;
+                    const int total = ns * RL;
                     const int64_t g0 = (int64_t)j0 * row + (int64_t)e0 * N;
                     for (int base = wt; base < total; base += 4 * EM_TILE_WORKERS) {
                         double wv[4], vv[4];
+                        int sidx[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const int idx = base + u * EM_TILE_WORKERS;
                             wv[u] = vv[u] = 0.0;
+                            sidx[u] = -1;
                             if (idx < total) {
-                                const int s2 = idx / RP;
-                                const int64_t g = g0 + (int64_t)s2 * row + (idx - s2 * RP);
+                                const int s2 = idx / RL, rem = idx - s2 * RL;
+                                const int64_t g = g0 + (int64_t)s2 * row + rem;
+                                sidx[u] = s2 * RP + rem;
                                 wv[u] = a.W[g];
                                 if (a.obs_noise) vv[u] = a.obs_noise[g + row];
                             }
                         }
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int idx = base + u * EM_TILE_WORKERS;
-                            if (idx < total) { Wb[idx] = wv[u]; Vb[idx] = vv[u]; }
-                        }
+                        for (int u = 0; u < 4; ++u)
+                            if (sidx[u] >= 0) { Wb[sidx[u]] = wv[u]; Vb[sidx[u]] = vv[u]; }
                     }
                 }
             }
@@ -370,10 +423,10 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
             // ---------------- recurrence of chunk `it - 1` (the only sequential part) ----------------
             const int cr = it - 1;
             const int ns = min(C, K - cr * C);
-            const double* Wb = NB + (cr & 1) * 2 * tile + el_r * N;
+            const double* Wb = Wt + (cr & 1) * tile + el_r * N;
             double* Xb = Xt + (cr & 1) * tile + el_r * N;
-            for (int slot = 0; slot < ns; ++slot) {
-                double w[N], xn[N];
+            double w[N];
+            auto load_w = [&](int slot) {
                 if constexpr (N % 2 == 0) {   // RP even and 16-byte aligned tiles: 128-bit shared-memory accesses
                     const double2* wp = reinterpret_cast<const double2*>(Wb + slot * RP);
 #pragma unroll
@@ -382,6 +435,11 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
 #pragma unroll
                     for (int c = 0; c < N; ++c) w[c] = Wb[slot * RP + c];
                 }
+            };
+            load_w(0);
+#pragma unroll 2
+            for (int slot = 0; slot < ns; ++slot) {
+                double xn[N];
 #pragma unroll
                 for (int r = 0; r < N; ++r) {
                     double acc = __dmul_rn(M[r][0], x[0]);
@@ -389,6 +447,7 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
                     for (int c = 1; c < N; ++c) acc = fma(M[r][c], x[c], acc);
                     xn[r] = fma(nz[r], w[r], acc);
                 }
+                if (slot + 1 < ns) load_w(slot + 1);   // the next increments arrive while this sub-step's chain drains
 #pragma unroll
                 for (int c = 0; c < N; ++c) x[c] = xn[c];
                 if constexpr (N % 2 == 0) {
@@ -410,55 +469,73 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
         for (int c = 0; c < N; ++c) bad |= !isfinite(x[c]);
         if (bad) *a.nan_flag = 1;
     }
-    // cumulative-reward column of every packed row of this interval (envs/base.py:1311, 1342-1349)
+    // cumulative-reward column of every cache row of this interval (envs/base.py:1311, 1342-1349): one warp per env,
+    // lanes along the rows of that env's contiguous run
     if (a.packed) {
+        const int warp = tid >> 5, lane = tid & 31;
         for (int j = 0; j < n_sel; ++j) {
             if (selS[j] != n_data - 1) continue;
-            for (int item = tid; item < Gl * (K + 1); item += EM_TILE_THREADS) {
-                const int el = item / (K + 1), r = item - el * (K + 1);
-                a.packed[(int64_t)(e0 + el) * a.packed_stride_e + (int64_t)r * pitch + j] = cumS[el];
+            for (int el = warp; el < Gl; el += EM_TILE_THREADS / 32) {
+                double* dst = a.packed + (int64_t)(e0 + el) * a.packed_stride_e + j;
+                const double cum = cumS[el];
+                for (int r = lane; r <= K; r += 32) dst[(int64_t)r * pitch] = cum;
             }
         }
     }
-    if (!is_rec && wt < 32) bulk_wait_all();   // the bulk stores have reached global memory
     if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
+    em_finish_launch(a);
 }
 
-struct TilePlan { int G, C, grid; size_t smem; };
+struct TilePlan { int G, C, nphase, ilp, grid; size_t smem; };
 
-static TilePlan plan_tiles(int E, int N, int K, int n_sel, int pitch, int sms) {
+static TilePlan plan_tiles(int E, int N, int K, int n_sel, int sms) {
     TilePlan p;
     p.G = E <= 32 * sms ? (E + sms - 1) / sms : 32;
-    if (p.G & 1) ++p.G;                        // even G keeps every tile row 16-byte aligned for the bulk stores
+    if (p.G & 1) ++p.G;                        // even G keeps every tile row 16-byte aligned whatever N
     if (p.G > 32) p.G = 32;
     if (p.G < 2) p.G = 2;
     p.grid = (E + p.G - 1) / p.G;
-    const size_t budget = 200 * 1024;
-    const size_t fixed = (size_t)(2 * p.G * N + p.G + N) * sizeof(double) + (size_t)n_sel * sizeof(int) + 256;
-    const size_t per_c = (size_t)(7 * p.G * N + p.G * pitch) * sizeof(double);
-    int C = (int)((budget - fixed) / per_c);
-    if (C > K) C = K;
-    if (C > 32) C = 32;
-    if (C < 1) C = 1;
-    // balance the chunks (K = 100, C = 27 -> 4 chunks of 25)
-    const int nc = (K + C - 1) / C;
-    C = (K + nc - 1) / nc;
-    p.C = C;
-    p.smem = per_c * C + fixed;
-    if (const char* pad = getenv("QRL_DEBUG_SMEM_PAD")) p.smem += (size_t)atoi(pad);
+    const int RP = p.G * N;
+    const size_t budget = 210 * 1024;
+    const size_t fixed = (size_t)(3 * RP + p.G + N) * sizeof(double) + (size_t)n_sel * sizeof(int) + 256;
+    const size_t per_c = (size_t)(7 * RP) * sizeof(double);
+    int cmax = (int)((budget - fixed) / per_c);
+    if (cmax > K) cmax = K;
+    if (cmax > EM_TILE_CMAX) cmax = EM_TILE_CMAX;
+    if (cmax < 1) cmax = 1;
+    // producers: nphase workers share one (env, comp) column and interleave its sub-steps; the chunk length is a
+    // multiple of ILP * nphase so that every worker generates the same number of pairs per chunk
+    p.nphase = EM_TILE_WORKERS / RP;
+    if (p.nphase < 1) p.nphase = 1;
+    if (p.nphase > cmax) p.nphase = cmax;
+    // Pairs per trip: measured on B200 at config 3, two pairs per trip (ILP 2) are no faster than one (25.6 vs 28.8 us:
+    // the loop is bound by issue slots and pipe contention between warps, not by dependency latency, and the second
+    // pair costs registers), so 1 is the default; QRL_EM_TILE_ILP=2 keeps the variant reachable for tuning.
+    p.ilp = 1;
+    static const char* ilp_env = getenv("QRL_EM_TILE_ILP");
+    if (ilp_env && atoi(ilp_env) >= 2 && cmax >= 2 * p.nphase) p.ilp = 2;
+    p.C = cmax / (p.ilp * p.nphase) * (p.ilp * p.nphase);
+    static const char* c_env = getenv("QRL_EM_TILE_C");
+    if (c_env) {   // tuning knob: a smaller multiple of ilp * nphase
+        const int want = atoi(c_env) / (p.ilp * p.nphase) * (p.ilp * p.nphase);
+        if (want >= p.ilp * p.nphase && want <= p.C) p.C = want;
+    }
+    p.smem = per_c * p.C + fixed;
     return p;
 }
 
 template <int N>
 static int launch_tile(const qrl_em_args& a, cudaStream_t st, int sms) {
-    const int pitch = a.packed ? (int)(a.packed_row_pitch > 0 ? a.packed_row_pitch : a.n_sel) : 0;
-    const TilePlan p = plan_tiles(a.n_envs, N, a.K, a.packed ? a.n_sel : 0, pitch, sms);
+    const TilePlan p = plan_tiles(a.n_envs, N, a.K, a.packed ? a.n_sel : 0, sms);
     static bool attr_set = false;
     if (!attr_set) {
-        QRL_CUDA(cudaFuncSetAttribute(em_tile_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        QRL_CUDA(cudaFuncSetAttribute(em_tile_kernel<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        QRL_CUDA(cudaFuncSetAttribute(em_tile_kernel<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_set = true;
     }
-    em_tile_kernel<N><<<p.grid, EM_TILE_THREADS, p.smem, st>>>(a, make_philox_keys(a.seed), p.G, p.C);
+    const PhiloxKeys keys = make_philox_keys(a.seed);
+    if (p.ilp == 2) em_tile_kernel<N, 2><<<p.grid, EM_TILE_THREADS, p.smem, st>>>(a, keys, p.G, p.C, p.nphase);
+    else em_tile_kernel<N, 1><<<p.grid, EM_TILE_THREADS, p.smem, st>>>(a, keys, p.G, p.C, p.nphase);
     return after_launch("em_tile_kernel");
 }
 

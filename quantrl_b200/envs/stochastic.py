@@ -73,6 +73,9 @@ class LinearVecEnv(BaseVecEnv):
         self._actions_in = torch.zeros((self.n_envs, self.n_actions), dtype=torch.float64, device=self.device)
         self._graph = self._graph_host = None
         self.graph_replays, self.graph_native_launches = 0, 0
+        # last-block bookkeeping of the captured step (qrl_em_args.finish_counter / minmax_out / dyn_advance)
+        self._finish = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        self._minmax_acc = torch.tensor([float("inf"), float("-inf")], dtype=torch.float64, device=self.device)
         self._reward_w = None
         if self._reward_fused:
             w = np.ones(n) if reward_weights is None else np.asarray(reward_weights, dtype=np.float64)
@@ -144,8 +147,8 @@ class LinearVecEnv(BaseVecEnv):
         nz = self.backend.convert_to_typed(tensor=nz, dtype="real")
         return nz.expand(self.n_envs, -1) if nz.dim() == 1 else nz
 
-    def _launch(self, K, x0, write_traj=True):
-        a, keep = self.interval_args(K, x0, write_traj)
+    def _launch(self, K, x0, write_traj=True, graph_mode=None):
+        a, keep = self.interval_args(K, x0, write_traj, graph_mode)
         ev = getattr(self, "_em_events", None)
         if ev is not None and K > 0:  # live per-launch timing on the launch stream (bench.py roofline)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -157,9 +160,12 @@ class LinearVecEnv(BaseVecEnv):
             N.em_step(a)
         return keep
 
-    def interval_args(self, K, x0=None, write_traj=True):
+    def interval_args(self, K, x0=None, write_traj=True, graph_mode=None):
         """Build the ``qrl_em_args`` of one action interval (evaluates the coefficient hooks).  Returns
-        ``(args, tensors_to_keep_alive)``; ``_launch`` enqueues it, ``bench.py`` re-launches it to time the kernel."""
+        ``(args, tensors_to_keep_alive)``; ``_launch`` enqueues it, ``bench.py`` re-launches it to time the kernel.
+        ``graph_mode`` (``"device"`` / ``"host"``) is set while a step is captured into a CUDA graph: the kernel's last
+        block then advances the device-side time index itself and, for the host round trip, delivers this step's
+        [min, max] without a reset copy."""
         x0 = self._x_last if x0 is None else x0
         E, n = self.n_envs, self.n_observations
         a = N.EmArgs()
@@ -209,6 +215,10 @@ class LinearVecEnv(BaseVecEnv):
             a.rewards_cum = N.ptr(self.rewards)
         a.obs_minmax = N.ptr(self._minmax)
         a.nan_flag = N.ptr(self._nan)
+        if graph_mode is not None:
+            a.finish_counter, a.dyn_advance = N.ptr(self._finish), K
+            if graph_mode == "host":
+                a.obs_minmax, a.minmax_out = N.ptr(self._minmax_acc), N.ptr(self._minmax)
         self._packed_by_kernel = False
         if (self._reward_fused and K > 0 and self.n_properties == 0 and self.store_trajectory
                 and not self.cache_all_data and self.fuse_cache_rows):
@@ -247,10 +257,10 @@ class LinearVecEnv(BaseVecEnv):
         return self._States[:dim]
 
     def _replay_interval(self, host_io=False):
-        """One full action interval as ONE graph launch: actions scaling, the coefficient hooks (batched torch), the
-        fused integration kernel and the advance of the device-side time index are captured once and replayed.
+        """One full action interval as ONE graph launch: actions scaling, the coefficient hooks (batched torch) and the
+        fused integration kernel (which also advances the device-side time index) are captured once and replayed.
         ``host_io=True`` (the ``step(host actions)`` path) replays a second graph that additionally starts with the
-        H2D copy of the actions from pinned memory and the min/max reset and ends with the D2H copy of
+        H2D copy of the actions from pinned memory and ends with the D2H copy of
         ``[obs_last | reward_last | min,max]`` into pinned memory — the whole host round trip is one launch."""
         key = "_graph_host" if host_io else "_graph"
         if getattr(self, key, None) is None:
@@ -263,11 +273,11 @@ class LinearVecEnv(BaseVecEnv):
                 with torch.cuda.graph(graph, stream=side):
                     if host_io:
                         self._actions_in.copy_(self._h_actions, non_blocking=True)
-                        self._minmax.copy_(self._minmax_init, non_blocking=True)
                     if not (self.fused_coefficients and self._affine_drift() is not None):
                         self.actions = self._actions_in * self.action_maximums_batch
-                    keep = self._launch(K, self._x_last)
-                    self._dyn[0] += K
+                    # the kernel's last block advances dyn[0] by K and (host round trip) hands over this step's
+                    # [min, max]: no reset copy, no second kernel
+                    keep = self._launch(K, self._x_last, graph_mode="host" if host_io else "device")
                     if host_io:
                         self._h_out.copy_(self._step_out, non_blocking=True)
             torch.cuda.current_stream().wait_stream(side)

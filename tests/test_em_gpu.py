@@ -260,3 +260,47 @@ def test_fused_cache_rows_match_oracle_pack_rows(native, cuda, flags, idxs, pitc
     assert np.isnan(got[:, :r0]).all() and np.isnan(got[:, r0 + K + 1:]).all()
     pad = got[:, r0:r0 + K + 1, len(idxs):]
     assert np.all(np.isnan(pad) | (pad == 0.0))
+
+
+@pytest.mark.parametrize("flags", [N.EM_FORCE_TILED, N.EM_FORCE_GENERIC, N.EM_FORCE_TILED | N.EM_ITEM_OUTPUT])
+def test_last_block_bookkeeping_advances_dyn_and_delivers_minmax(native, cuda, flags):
+    """ABI 2 ``finish_counter`` protocol: the last block of the launch adds ``dyn_advance`` to dyn[0], copies this
+    launch's [min, max] to ``minmax_out``, re-arms the accumulator and leaves the counter at zero — three launches in
+    a row (as a replayed CUDA graph issues them) equal three launches with host-side bookkeeping, bit for bit."""
+    rng = np.random.default_rng(5)
+    E, n, K = 300, 4, 40
+    A = torch.as_tensor(0.4 * rng.standard_normal((E, n, n)), device="cuda")
+    nz = torch.as_tensor(rng.uniform(0.01, 0.1, (E, n)), device="cuda")
+    std = torch.as_tensor(rng.uniform(0.01, 0.02, (E, n)), device="cuda")
+    x = torch.as_tensor(rng.standard_normal((E, n)), device="cuda")
+    x_ref = x.clone()
+    dyn = torch.tensor([7, 3], dtype=torch.int64, device="cuda")
+    counter = torch.zeros((1,), dtype=torch.int32, device="cuda")
+    acc = torch.tensor([float("inf"), float("-inf")], dtype=torch.float64, device="cuda")
+    mm_out = torch.full((2,), float("nan"), dtype=torch.float64, device="cuda")
+    obs = torch.empty((K + 1, E, n), dtype=torch.float64, device="cuda")
+    obs_ref = torch.empty_like(obs)
+
+    def args(x0, obs_buf):
+        a = N.EmArgs()
+        a.n, a.n_envs, a.K, a.t_ssz = n, E, K, 0.01
+        a.A, a.A_stride_e, a.nz, a.nz_stride_e = N.ptr(A), n * n, N.ptr(nz), n
+        a.rng_mode, a.seed, a.obs_std, a.obs_std_stride_e = N.RNG_PHILOX, 11, N.ptr(std), n
+        a.x0, a.x_last, a.observations = N.ptr(x0), N.ptr(x0), N.ptr(obs_buf)
+        a.flags = flags
+        return a
+
+    for step in range(3):
+        a = args(x, obs)
+        a.dyn, a.finish_counter, a.dyn_advance = N.ptr(dyn), N.ptr(counter), K
+        a.obs_minmax, a.minmax_out = N.ptr(acc), N.ptr(mm_out)
+        N.em_step(a)
+        b = args(x_ref, obs_ref)
+        mm_ref = torch.tensor([float("inf"), float("-inf")], dtype=torch.float64, device="cuda")
+        b.t_idx, b.episode, b.obs_minmax = 7 + step * K, 3, N.ptr(mm_ref)
+        N.em_step(b)
+        torch.cuda.synchronize()
+        assert torch.equal(obs, obs_ref) and torch.equal(x, x_ref)
+        assert dyn.tolist() == [7 + (step + 1) * K, 3] and counter.item() == 0
+        assert torch.equal(mm_out, mm_ref) and mm_out[0].item() == obs.min().item() and mm_out[1].item() == obs.max().item()
+        assert acc.tolist() == [float("inf"), float("-inf")]
