@@ -80,6 +80,12 @@ QRL_API int         qrl_device_count(void);
 QRL_API int         qrl_release(void);
 /* number of kernel launches this library has enqueued in this process (all entry points) */
 QRL_API uint64_t    qrl_launch_count(void);
+/* Device-side address of page-locked HOST memory (cudaHostAlloc / cudaHostRegister, e.g. a torch pinned tensor) so that
+ * it can be passed where this header asks for a device pointer: qrl_em_step then reads the actions from, and writes
+ * obs_last / reward_last / minmax_out to, host memory directly over PCIe (no staging copies in the step, replaces
+ * the H2D of BaseSB3Env.step_async and the D2H of step_wait, quantrl/envs/base.py:1245,1357).
+ * Returns QRL_E_INVALID if the memory is pageable or not mapped for the current device. */
+QRL_API int         qrl_host_device_pointer(const void* h_ptr, void** device_ptr);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Euler–Maruyama action interval for E independent linear SDE environments.

@@ -72,6 +72,7 @@ SYMBOLS = {
     "qrl_device_count": (C.c_int, []),
     "qrl_release": (C.c_int, []),
     "qrl_launch_count": (C.c_uint64, []),
+    "qrl_host_device_pointer": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "qrl_em_step": (C.c_int, [C.POINTER(EmArgs), C.c_void_p]),
     "qrl_ode_step": (C.c_int, [C.POINTER(OdeArgs), C.c_void_p]),
     "qrl_pack_rows": (C.c_int, [C.POINTER(PackArgs), C.c_void_p]),
@@ -134,6 +135,13 @@ def ode_step(args: OdeArgs, stream=None):
 
 def pack_rows(args: PackArgs, stream=None):
     check(lib().qrl_pack_rows(C.byref(args), stream if stream is not None else current_stream()), "qrl_pack_rows")
+
+
+def host_device_pointer(t) -> int:
+    """Device-side address of a pinned host tensor (raises NativeError if it is pageable / not mapped)."""
+    out = C.c_void_p(0)
+    check(lib().qrl_host_device_pointer(C.c_void_p(t.data_ptr()), C.byref(out)), "qrl_host_device_pointer")
+    return int(out.value)
 
 
 def launch_count() -> int:

@@ -41,6 +41,16 @@ extern "C" int qrl_device_count(void) {
     return n;
 }
 extern "C" int qrl_release(void) { return 0; }
+extern "C" int qrl_host_device_pointer(const void* h_ptr, void** device_ptr) {
+    using namespace qrl;
+    QRL_REQUIRE(h_ptr != nullptr && device_ptr != nullptr, "qrl_host_device_pointer: NULL argument");
+    cudaPointerAttributes at;
+    QRL_CUDA(cudaPointerGetAttributes(&at, h_ptr));
+    QRL_REQUIRE(at.type == cudaMemoryTypeHost && at.devicePointer != nullptr,
+                "qrl_host_device_pointer: not page-locked host memory mapped for the current device");
+    *device_ptr = at.devicePointer;
+    return 0;
+}
 
 extern "C" int qrl_measure_fp64_latency(double* cycles_per_dfma) {
     using namespace qrl;

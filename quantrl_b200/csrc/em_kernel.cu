@@ -166,7 +166,10 @@ extern "C" int qrl_em_step(const qrl_em_args* args, void* stream) {
     // Tiled kernel: one CTA per SM, noise generation spread over 15 warps -> best while the batch cannot fill the chip
     // with one lane per component (measured crossover on B200: E*n ~ 32k, tools/size_sweep.py).  Beyond that the
     // generic kernel has enough warps per scheduler and no shared-memory round trip.
-    const bool small_batch = (int64_t)a.n_envs * a.n <= 32768 || (a.flags & QRL_EM_FORCE_TILED);
+    // n > 4: the recurrence lane cannot hold M = I + A dt (n*n doubles) in registers next to the producers' working set
+    // (spills under the 128-register cap of a 512-thread CTA) and the generic kernel wins from E = 4096 on
+    // (tools/variants_em.py: n = 8, E = 4096: 72 vs 108 us), so the tiled kernel is the default only up to n = 4.
+    const bool small_batch = ((int64_t)a.n_envs * a.n <= 32768 && a.n <= 4) || (a.flags & QRL_EM_FORCE_TILED);
     const bool tiled = a.K >= 1 && a.n <= 8 && a.A_stride_k == 0 && a.nz_stride_k == 0 && small_batch &&
                        !(a.flags & QRL_EM_FORCE_GENERIC);
     if (tiled) return em_tile_launch(a, st);

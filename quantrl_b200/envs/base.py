@@ -219,7 +219,7 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         self.t_idx, self.t, self.action_idx, self._idx_s = 0, self.numpy_real(0.0), 0, 0
         self.batch_idx = -1
         self.actions = None
-        self.T_step = None
+        self._t_range = None
         self._States = torch.empty((K1, E, no), dtype=f64, device=self.device)
         self._Observations = torch.empty((K1, E, no), dtype=f64, device=self.device)
         self._Reward = torch.zeros((K1, E), dtype=f64, device=self.device)
@@ -357,8 +357,7 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         K = self.action_interval
         dim = K + 1 if self.t_idx + K < S1 else S1 - self.t_idx
         self._dim = dim
-        self._T_step_host = self._T_host[self.t_idx:self.t_idx + dim]
-        self.T_step = self.T[self.t_idx:self.t_idx + dim]
+        self._t_range = (self.t_idx, self.t_idx + dim)     # T_step / _T_step_host are views built on demand
 
         if reset_minmax:
             self._minmax.copy_(self._minmax_init, non_blocking=True)
@@ -377,6 +376,17 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         self.action_idx += 1
         terminated = not self.t_idx + 1 < S1
         return self._obs_last, self._reward_last, terminated
+
+    @property
+    def T_step(self):
+        """``T[t_idx : t_idx+K+1]`` of the current action interval (base.py:454-458), device tensor."""
+        r = self._t_range
+        return None if r is None else self.T[r[0]:r[1]]
+
+    @property
+    def _T_step_host(self):
+        r = self._t_range
+        return None if r is None else self._T_host[r[0]:r[1]]
 
     def update_data(self):
         """Packed rows ``[t, actions, obs, props, cumulative reward]`` (base.py:1295-1380) — one pack-kernel launch."""
@@ -429,7 +439,7 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         observations, reward, terminated = self.update(reset_minmax=not host_step)
         self.update_data()
         if host_step and getattr(self, "_host_graph_done", False):
-            torch.cuda.current_stream().synchronize()      # the replayed graph already copied the results to pinned memory
+            self._replay_stream.synchronize()     # the replayed graph already delivered the results to pinned memory
             host = self._h_out
             self._host_graph_done = False
         else:

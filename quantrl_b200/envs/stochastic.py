@@ -49,6 +49,10 @@ class LinearVecEnv(BaseVecEnv):
         self.use_cuda_graph = bool(kwargs.pop("use_cuda_graph", False))
         # evaluate an action-affine drift inside the kernel (``_affine_drift``) instead of through the ``get_A`` hook
         self.fused_coefficients = bool(kwargs.pop("fused_coefficients", False))
+        # host round trip of ``step(host actions)`` under ``use_cuda_graph`` + ``return_numpy``: the kernel reads the
+        # actions from, and writes obs_last / reward_last / [min,max] to, pinned host memory directly (no copy nodes)
+        self.host_zero_copy = bool(kwargs.pop("host_zero_copy", True))
+        self._zc = None
         self.reward_functor = kwargs.pop("reward_functor", None)
         reward_weights = kwargs.pop("reward_weights", None)
         assert self.reward_functor in _REWARD_KINDS, f"``reward_functor`` should be one of {list(_REWARD_KINDS)}"
@@ -219,6 +223,13 @@ class LinearVecEnv(BaseVecEnv):
             a.finish_counter, a.dyn_advance = N.ptr(self._finish), K
             if graph_mode == "host":
                 a.obs_minmax, a.minmax_out = N.ptr(self._minmax_acc), N.ptr(self._minmax)
+                zc = self._zero_copy()
+                if zc is not None:
+                    a.obs_last, a.minmax_out = zc["out"], zc["out"] + 8 * E * (n + 1)
+                    if a.reward_kind != N.REWARD_NONE:
+                        a.reward_last = zc["out"] + 8 * E * n
+                    if affine is not None:
+                        a.actions = zc["actions"]
         self._packed_by_kernel = False
         if (self._reward_fused and K > 0 and self.n_properties == 0 and self.store_trajectory
                 and not self.cache_all_data and self.fuse_cache_rows):
@@ -236,6 +247,18 @@ class LinearVecEnv(BaseVecEnv):
         if self.force_generic_kernel:
             a.flags = N.EM_FORCE_GENERIC
         return a, keep
+
+    def _zero_copy(self):
+        """Device-side addresses of the pinned step buffers (``_h_out``, ``_h_actions``) when the zero-copy host round
+        trip applies, else ``None``."""
+        if not (self.host_zero_copy and self.return_numpy and self._obs_last_ptr is None and self._reward_fused):
+            return None
+        if self._zc is None:
+            try:
+                self._zc = {"out": N.host_device_pointer(self._h_out), "actions": N.host_device_pointer(self._h_actions)}
+            except N.NativeError:
+                self._zc = False    # pinned memory not mapped on this platform: keep the copy nodes
+        return self._zc or None
 
     def _initial_observations(self, states_0):
         self._launch(0, states_0, write_traj=False)  # row 0 only: obs_0 = states_0 + noise[0]
@@ -259,9 +282,10 @@ class LinearVecEnv(BaseVecEnv):
     def _replay_interval(self, host_io=False):
         """One full action interval as ONE graph launch: actions scaling, the coefficient hooks (batched torch) and the
         fused integration kernel (which also advances the device-side time index) are captured once and replayed.
-        ``host_io=True`` (the ``step(host actions)`` path) replays a second graph that additionally starts with the
-        H2D copy of the actions from pinned memory and ends with the D2H copy of
-        ``[obs_last | reward_last | min,max]`` into pinned memory — the whole host round trip is one launch."""
+        ``host_io=True`` (the ``step(host actions)`` path) replays a second graph that also covers the host round trip:
+        with ``host_zero_copy`` (default, ``return_numpy`` envs) the kernel itself reads the actions from and writes
+        ``[obs_last | reward_last | min,max]`` to pinned host memory over PCIe, so the graph is still one kernel;
+        otherwise it starts with the H2D copy of the actions and ends with the D2H copy of the results."""
         key = "_graph_host" if host_io else "_graph"
         if getattr(self, key, None) is None:
             K = self.action_interval
@@ -271,16 +295,19 @@ class LinearVecEnv(BaseVecEnv):
             n0 = N.launch_count()
             with torch.cuda.stream(side):
                 with torch.cuda.graph(graph, stream=side):
-                    if host_io:
+                    affine = self.fused_coefficients and self._affine_drift() is not None
+                    zc = self._zero_copy() if host_io else None
+                    if host_io and not (zc is not None and affine):
                         self._actions_in.copy_(self._h_actions, non_blocking=True)
-                    if not (self.fused_coefficients and self._affine_drift() is not None):
+                    if not affine:
                         self.actions = self._actions_in * self.action_maximums_batch
                     # the kernel's last block advances dyn[0] by K and (host round trip) hands over this step's
                     # [min, max]: no reset copy, no second kernel
                     keep = self._launch(K, self._x_last, graph_mode="host" if host_io else "device")
-                    if host_io:
+                    if host_io and zc is None:
                         self._h_out.copy_(self._step_out, non_blocking=True)
             torch.cuda.current_stream().wait_stream(side)
+            self._replay_stream = torch.cuda.current_stream()   # looked up once: the call costs ~10 us per step otherwise
             setattr(self, key, graph)
             setattr(self, key + "_keep", keep)
             self._graph_packs = self._packed_by_kernel
