@@ -20,6 +20,12 @@ import sys
 import threading
 import time
 
+# The contract is ONE JSON line on stdout.  Native libraries write banners to fd 1 (e.g. "NCCL version ..." when the
+# box exports NCCL_DEBUG=VERSION), so fd 1 is pointed at stderr for the whole run and the JSON line goes to a private
+# duplicate of the original stdout.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -91,7 +97,7 @@ def reference_arm(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -353,7 +359,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             v, cores, sample, _ = run_cpu_port(steps=20, warmup=2, budget_s=15.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
