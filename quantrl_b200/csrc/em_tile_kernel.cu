@@ -110,11 +110,10 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
 
     // ---- output stage, item pass: one (row, env) item per worker and trip ------------------------------------------
     // rows r_first .. r_first+ns-1 whose states / noises sit in Xb / Vb (row-major [slot][env][comp], row pitch RP).
-    // full: the item does everything (adds, States / Observations rows, min/max, reward, last-row outputs, cache row);
-    // otherwise the piece pass has done all that and only the cache row is left.
+    // the item does everything but the cache rows: adds, States / Observations rows, min/max, reward, last-row outputs.
     const int o_dsl = EM_TILE_WORKERS / Gl, o_del = EM_TILE_WORKERS - o_dsl * Gl;
     const int o_sl0 = wt / Gl, o_el0 = wt - o_sl0 * Gl;
-    auto item_pass = [&](const double* Xb, const double* Vb, int r_first, int ns, const bool full) {
+    auto item_pass = [&](const double* Xb, const double* Vb, int r_first, int ns) {
         int sl = o_sl0, el = o_el0;
         while (sl < ns) {
             const int r = r_first + sl, e = e0 + el;
@@ -133,7 +132,7 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
 #pragma unroll
                 for (int c = 0; c < N; ++c) { xv[c] = Xb[off + c]; ov[c] = __dadd_rn(xv[c], Vb[off + c]); }
             }
-            if (full) {
+            {
                 const int64_t g = (int64_t)r * row + (int64_t)e * N;
                 if (vec_g) {
                     if constexpr (N % 2 == 0) {
@@ -182,25 +181,6 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
                         if (a.x_last) a.x_last[(int64_t)e * N + c] = xv[c];
                         if (a.obs_last) a.obs_last[(int64_t)e * N + c] = ov[c];
                     }
-                }
-            }
-            if (pack_rows) {
-                // cache row [T_step[r], actions[e,:], Obs[r,e,:], cum. reward] restricted to the selected columns,
-                // straight from registers into the env-major cache (envs/base.py:1314-1372)
-                double* dst = a.packed + (int64_t)e * a.packed_stride_e + (int64_t)r * pitch;
-                for (int j = 0; j < n_sel; ++j) {
-                    const int col = selS[j];
-                    if (col == n_data - 1) continue;   // cumulative reward: written for all rows after the last sub-step
-                    double val;
-                    if (col == 0) val = a.T_step[r];
-                    else if (col <= a.n_actions) val = em_action(a, e, col - 1);
-                    else {
-                        const int c = col - 1 - a.n_actions;
-                        val = ov[0];
-#pragma unroll
-                        for (int cc = 1; cc < N; ++cc) val = (c == cc) ? ov[cc] : val;
-                    }
-                    dst[j] = val;
                 }
             }
             sl += o_dsl;
@@ -272,13 +252,45 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
             }
         }
     };
-    auto output_rows = [&](const double* Xb, const double* Vb, int r_first, int ns) {
-        if (piece_out) {
-            piece_pass(Xb, Vb, r_first, ns);
-            if (pack_rows) item_pass(Xb, Vb, r_first, ns, false);
-        } else {
-            item_pass(Xb, Vb, r_first, ns, true);
+    // ---- output stage, cache rows: packed[e, r, j] = column sel[j] of [T_step[r], actions[e,:], Obs[r,e,:], cum. reward]
+    // (envs/base.py:1314-1372).  The rows r_first .. r_first+ns-1 of ONE environment are a contiguous run of ns * pitch
+    // doubles of the env-major cache, so a warp walks such a run 32 elements at a time (lane-contiguous 8-byte stores =
+    // 256-byte segments) and gathers each element from the tiles; (env, trip) pairs are dealt round-robin to the 15
+    // worker warps.  The cumulative-reward column is skipped here and written for all rows after the last sub-step.
+    const uint32_t pk_magic = pitch > 0 ? 0xFFFFFFFFu / (uint32_t)pitch + 1u : 0u;   // idx / pitch for idx < 2^16
+    auto pack_pass = [&](const double* Xb, const double* Vb, int r_first, int ns) {
+        const int run = ns * pitch;                       // doubles per environment
+        const int trips = (run + 31) >> 5;
+        const int lane = wt & 31;
+        int t = wt >> 5;                                  // worker warp 0..14
+        int el = t / trips, trip = t - el * trips;
+        const int d_el = (EM_TILE_WORKERS / 32) / trips, d_trip = (EM_TILE_WORKERS / 32) - d_el * trips;
+        while (el < Gl) {
+            const int idx = (trip << 5) + lane;
+            if (idx < run) {
+                const int sl = pitch == 1 ? idx : (int)__umulhi((uint32_t)idx, pk_magic), j = idx - sl * pitch;
+                const int col = j < n_sel ? selS[j] : n_data - 1;
+                if (col != n_data - 1) {
+                    const int r = r_first + sl, e = e0 + el;
+                    double val;
+                    if (col == 0) val = a.T_step[r];
+                    else if (col <= a.n_actions) val = em_action(a, e, col - 1);
+                    else {
+                        const int off = sl * RP + el * N + (col - 1 - a.n_actions);
+                        val = __dadd_rn(Xb[off], Vb[off]);
+                    }
+                    a.packed[(int64_t)e * a.packed_stride_e + (int64_t)r_first * pitch + idx] = val;
+                }
+            }
+            el += d_el;
+            trip += d_trip;
+            if (trip >= trips) { trip -= trips; ++el; }
         }
+    };
+    auto output_rows = [&](const double* Xb, const double* Vb, int r_first, int ns) {
+        if (piece_out) piece_pass(Xb, Vb, r_first, ns);
+        else item_pass(Xb, Vb, r_first, ns);
+        if (pack_rows) pack_pass(Xb, Vb, r_first, ns);
     };
 
     // ---- recurrence warp: coefficients and state in registers ----------------------------------------------------
