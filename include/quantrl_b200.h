@@ -62,6 +62,13 @@ extern "C" {
  * QCMSolver.get_entanglement_logarithmic_negativity_2 (quantrl/solvers/measure.py:401-440) */
 #define QRL_REWARD_ENTAN_LN_OBS   3 /* evaluated on the covariance block of the Observations */
 #define QRL_REWARD_ENTAN_LN_STATE 4 /* evaluated on the covariance block of the States */
+/* complete quantum synchronization of modes (0,1), QCMSolver.get_synchronization_complete (measure.py:442-468) */
+#define QRL_REWARD_SYNC_C_OBS     5
+#define QRL_REWARD_SYNC_C_STATE   6
+/* quantum phase synchronization of modes (0,1), QCMSolver.get_synchronization_phase (measure.py:470-514); uses the
+ * mode amplitudes too (num_modes >= 2) */
+#define QRL_REWARD_SYNC_P_OBS     7
+#define QRL_REWARD_SYNC_P_STATE   8
 
 /* deterministic system functors (replace user hooks get_mode_rates/get_A/get_D, quantrl/envs/deterministic.py:748-818);
  * formulas in oracle/systems.py */
@@ -240,7 +247,7 @@ typedef struct qrl_ode_args {
     double*  obs_minmax;     /* as in qrl_em_args */
     int32_t* nan_flag;
     int32_t  flags;          /* QRL_ODE_* bits */
-    int32_t  reward_kind;    /* QRL_REWARD_NONE | QRL_REWARD_ENTAN_LN_OBS | QRL_REWARD_ENTAN_LN_STATE */
+    int32_t  reward_kind;    /* QRL_REWARD_NONE | QRL_REWARD_ENTAN_LN_* | QRL_REWARD_SYNC_C_* | QRL_REWARD_SYNC_P_* */
     double*  reward;         /* (K+1,E) or NULL */
     double*  reward_last;    /* (E,) = Reward[K]; or NULL */
     double*  rewards_cum;    /* (E,) in/out: += Reward[K]; or NULL */

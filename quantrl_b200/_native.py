@@ -11,6 +11,7 @@ ABI_VERSION = 2
 
 RNG_FED, RNG_PHILOX = 0, 1
 REWARD_NONE, REWARD_NEG_WSQ_OBS, REWARD_NEG_WSQ_STATE, REWARD_ENTAN_LN_OBS, REWARD_ENTAN_LN_STATE = 0, 1, 2, 3, 4
+REWARD_SYNC_C_OBS, REWARD_SYNC_C_STATE, REWARD_SYNC_P_OBS, REWARD_SYNC_P_STATE = 5, 6, 7, 8
 SYS_OPTOMECH, SYS_KERR_CHAIN, SYS_CONST_AD = 1, 2, 3
 ODE_RK4, ODE_DOPRI5 = 0, 1
 EM_FORCE_GENERIC, EM_FORCE_TILED, EM_ITEM_OUTPUT, EM_PACK_TMA = 1, 16, 32, 128

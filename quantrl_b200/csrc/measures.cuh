@@ -1,6 +1,7 @@
 // Fused reward functors of the deterministic path: quantum-correlation measures evaluated in the kernel epilogue instead
 // of a (K+1, E, q, q) round trip through Python.  Restates QCMSolver.get_entanglement_logarithmic_negativity_2 and its
-// helpers (quantrl/solvers/measure.py:184-254, 401-440); CPU twin: oracle/measure_oracle.py.
+// helpers (quantrl/solvers/measure.py:184-254, 401-440), get_synchronization_complete (:442-468) and
+// get_synchronization_phase (:470-514); CPU twin: oracle/measure_oracle.py, pinned by tests/golden/measures_optomech.npz.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -30,6 +31,27 @@ __device__ __forceinline__ double log_negativity_2mode(const double* V) {
     if (!(disc >= 0.0) || !(I4 >= 0.0)) return 0.0;
     const double en = -log(1.4142135623730951 * sqrt(sigma - sqrt(disc)));
     return (en > 0.0 && isfinite(en)) ? en : 0.0;
+}
+
+// Complete quantum synchronization of modes (0,1), QCMSolver.get_synchronization_complete (measure.py:442-468):
+//   S_c = 1 / (<q_-^2> + <p_-^2>),  <q_-^2> = (V00 + V22 - 2 V02) / 2,  <p_-^2> = (V11 + V33 - 2 V13) / 2
+__device__ __forceinline__ double sync_complete_2mode(const double* V) {
+    const double q2 = 0.5 * (V[0] + V[10] - 2.0 * V[2]);
+    const double p2 = 0.5 * (V[5] + V[15] - 2.0 * V[7]);
+    return 1.0 / (q2 + p2);
+}
+
+// Quantum phase synchronization of modes (0,1), QCMSolver.get_synchronization_phase (measure.py:470-514): the momentum
+// quadratures are rotated by the phases of the mode amplitudes a_i = re_i + i im_i (cos/sin of np.angle = re/|a|, im/|a|;
+// np.angle(0) = 0), S_p = 1 / (2 <p'_-^2>).
+__device__ __forceinline__ double sync_phase_2mode(double re_i, double im_i, double re_j, double im_j, const double* V) {
+    const double ri = hypot(re_i, im_i), rj = hypot(re_j, im_j);
+    const double ci = ri > 0.0 ? re_i / ri : 1.0, si = ri > 0.0 ? im_i / ri : 0.0;
+    const double cj = rj > 0.0 ? re_j / rj : 1.0, sj = rj > 0.0 ? im_j / rj : 0.0;
+    const double pi2 = si * si * V[0] - si * ci * V[1] - ci * si * V[4] + ci * ci * V[5];
+    const double pj2 = sj * sj * V[10] - sj * cj * V[11] - cj * sj * V[14] + cj * cj * V[15];
+    const double pij = si * sj * V[2] - si * cj * V[3] - ci * sj * V[6] + ci * cj * V[7];
+    return 0.5 / (0.5 * (pi2 + pj2 - 2.0 * pij));
 }
 
 }  // namespace qrl

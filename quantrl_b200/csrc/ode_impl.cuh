@@ -77,11 +77,25 @@ __device__ __forceinline__ void ode_reward_row(const qrl_ode_args& a, int row, i
     if constexpr (Q == 4) {
         if (a.reward_kind == QRL_REWARD_NONE) return;
         constexpr int D = 2 * M + Q * Q;
+        // odd kinds are evaluated on the Observations (= states + this row's measurement noise), even ones on the States
+        const bool on_obs = (a.reward_kind & 1) != 0;
         double V[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c)
-            V[c] = y[2 * M + c] + (a.reward_kind == QRL_REWARD_ENTAN_LN_OBS ? obs_noise_at(a, row, e, 2 * M + c, D) : 0.0);
-        const double r = log_negativity_2mode(V);
+            V[c] = y[2 * M + c] + (on_obs ? obs_noise_at(a, row, e, 2 * M + c, D) : 0.0);
+        double r;
+        if (a.reward_kind <= QRL_REWARD_ENTAN_LN_STATE) r = log_negativity_2mode(V);
+        else if (a.reward_kind <= QRL_REWARD_SYNC_C_STATE) r = sync_complete_2mode(V);
+        else {
+            double md[4] = {1.0, 0.0, 1.0, 0.0};    // re_0, im_0, re_1, im_1
+            if constexpr (M >= 2) {
+                md[0] = y[0] + (on_obs ? obs_noise_at(a, row, e, 0, D) : 0.0);
+                md[1] = y[M] + (on_obs ? obs_noise_at(a, row, e, M, D) : 0.0);
+                md[2] = y[1] + (on_obs ? obs_noise_at(a, row, e, 1, D) : 0.0);
+                md[3] = y[M + 1] + (on_obs ? obs_noise_at(a, row, e, M + 1, D) : 0.0);
+            }
+            r = sync_phase_2mode(md[0], md[1], md[2], md[3], V);
+        }
         if (a.reward) a.reward[(int64_t)row * a.n_envs + e] = r;
         if (row == a.K) {
             if (a.reward_last) a.reward_last[e] = r;

@@ -27,8 +27,10 @@ extern "C" int qrl_ode_step(const qrl_ode_args* args, void* stream) {
     QRL_REQUIRE(a.y0 != nullptr, "qrl_ode_step: y0 is NULL");
     QRL_REQUIRE(a.t_idx >= 0 && a.env_offset >= 0, "qrl_ode_step: negative t_idx / env_offset");
     QRL_REQUIRE(a.reward_kind == QRL_REWARD_NONE ||
-                    ((a.reward_kind == QRL_REWARD_ENTAN_LN_OBS || a.reward_kind == QRL_REWARD_ENTAN_LN_STATE) && a.num_quads == 4),
-                "qrl_ode_step: reward_kind must be NONE or ENTAN_LN_* (num_quads == 4)");
+                    (a.reward_kind >= QRL_REWARD_ENTAN_LN_OBS && a.reward_kind <= QRL_REWARD_SYNC_P_STATE && a.num_quads == 4),
+                "qrl_ode_step: reward_kind must be NONE, ENTAN_LN_*, SYNC_C_* or SYNC_P_* (num_quads == 4)");
+    QRL_REQUIRE(a.reward_kind < QRL_REWARD_SYNC_P_OBS || a.num_modes >= 2,
+                "qrl_ode_step: SYNC_P_* needs the amplitudes of two modes (num_modes >= 2)");
     cudaStream_t st = (cudaStream_t)stream;
     const int m = a.num_modes, q = a.num_quads;
     switch (a.system) {

@@ -18,6 +18,12 @@ from ..solvers import SYSTEM_NPARAMS, SYSTEMS, get_IVP_solver
 from .base import BaseVecEnv, default_backend
 
 
+# fused reward functors of qrl_ode_step (csrc/measures.cuh): measure evaluated on the Observations or on the States
+_REWARD_KINDS = {"entan_ln_obs": N.REWARD_ENTAN_LN_OBS, "entan_ln_state": N.REWARD_ENTAN_LN_STATE,
+                 "sync_c_obs": N.REWARD_SYNC_C_OBS, "sync_c_state": N.REWARD_SYNC_C_STATE,
+                 "sync_p_obs": N.REWARD_SYNC_P_OBS, "sync_p_state": N.REWARD_SYNC_P_STATE}
+
+
 class LinearizedHOVecEnv(BaseVecEnv):
     default_params = {}
     default_ode_solver_params = {"ode_method": "rk4", "ode_atol": 1e-9, "ode_rtol": 1e-6, "ode_substeps": 1}
@@ -39,8 +45,8 @@ class LinearizedHOVecEnv(BaseVecEnv):
             kwargs.setdefault(key, val)
         ode = {k: kwargs.pop(k) for k in list(self.default_ode_solver_params)}
         self.reward_functor = kwargs.pop("reward_functor", None)
-        assert self.reward_functor in (None, "entan_ln_obs", "entan_ln_state"), \
-            "``reward_functor`` should be None, 'entan_ln_obs' or 'entan_ln_state'"
+        assert self.reward_functor in (None,) + tuple(_REWARD_KINDS), \
+            f"``reward_functor`` should be None or one of {list(_REWARD_KINDS)}"
         system = kwargs.pop("system", None)
         system_params = kwargs.pop("system_params", None)
         assert n_observations == 2 * self.num_modes + self.num_corrs, \
@@ -166,7 +172,7 @@ class LinearizedHOVecEnv(BaseVecEnv):
                 obs_last=N.ptr(self._obs_last), obs_minmax=N.ptr(self._minmax), nan_flag=N.ptr(self._nan))
             if self.reward_functor is not None:
                 self.solver.epilogue.update(
-                    reward_kind={"entan_ln_obs": N.REWARD_ENTAN_LN_OBS, "entan_ln_state": N.REWARD_ENTAN_LN_STATE}[self.reward_functor],
+                    reward_kind=_REWARD_KINDS[self.reward_functor],
                     reward=N.ptr(self._Reward), reward_last=N.ptr(self._reward_last), rewards_cum=N.ptr(self.rewards))
             return self.solver.integrate(T_step=self.T_step, y_0=self._x_last, params=self.actions,
                                          out=self._States[:dim])

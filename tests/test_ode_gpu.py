@@ -229,3 +229,33 @@ def test_fused_log_negativity_reward_matches_reference_qcm(native, cuda, golden_
                    reward_kind=N.REWARD_ENTAN_LN_OBS, **kw)
     O = out["observations"].cpu().numpy()
     np.testing.assert_allclose(out["reward"].cpu().numpy(), mo.entan_ln_2(O[:, :, 4:].reshape(K + 1, 5, 4, 4)), rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("method,flags", [("rk4", 1), ("rk4", 2), ("dopri5", 0)])
+@pytest.mark.parametrize("measure", ["sync_c", "sync_p", "entan_ln"])
+def test_fused_synchronization_and_entanglement_rewards_match_reference(native, cuda, golden_dir, method, flags, measure):
+    """Reward functors SYNC_C / SYNC_P / ENTAN_LN of all three ODE kernels vs the reference's ``QCMSolver`` numbers
+    (fixture measures_optomech.npz): STATE kinds on the integrated trajectory (tight dopri5 -> the reference's own
+    values), OBS kinds on states + fed measurement noise (oracle restatement, itself bit-exact on the fixture)."""
+    import measure_oracle as mo
+    from quantrl_b200 import _native as N
+    kinds = {"sync_c": (N.REWARD_SYNC_C_OBS, N.REWARD_SYNC_C_STATE), "sync_p": (N.REWARD_SYNC_P_OBS, N.REWARD_SYNC_P_STATE),
+             "entan_ln": (N.REWARD_ENTAN_LN_OBS, N.REWARD_ENTAN_LN_STATE)}[measure]
+    g, p, y0, acts, T, K, m, q = _load(golden_dir, "lyap_optomech.npz", "E5")
+    gm = np.load(os.path.join(golden_dir, "measures_optomech.npz"))
+    kw = dict(method=method, flags=flags, atol=1e-14, rtol=1e-13)
+    y, rows = y0, []
+    for a in range(acts.shape[0]):
+        out = ode_step("optomech", m, q, y, K, float(T[a * K]), 0.01, params=p, actions=acts[a][:, 0],
+                       reward_kind=kinds[1], **kw)
+        ref = mo.measures_of_states(out["states"].cpu().numpy())[measure]
+        np.testing.assert_allclose(out["reward"].cpu().numpy(), ref, rtol=1e-12, atol=1e-13)
+        rows.append(out["reward"].cpu().numpy()[1 if a else 0:])
+        y = out["y_last"].cpu().numpy()
+    if method == "dopri5":
+        np.testing.assert_allclose(np.concatenate(rows, 0), gm[measure + "_ref"], rtol=1e-8, atol=1e-10)
+    noise = 1e-2 * np.random.default_rng(0).standard_normal((K + 1, 5, 20))
+    out = ode_step("optomech", m, q, y0, K, 0.0, 0.01, params=p, actions=acts[0][:, 0], obs_noise=noise,
+                   reward_kind=kinds[0], **kw)
+    ref = mo.measures_of_states(out["observations"].cpu().numpy())[measure]
+    np.testing.assert_allclose(out["reward"].cpu().numpy(), ref, rtol=1e-12, atol=1e-13)
