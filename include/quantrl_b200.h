@@ -76,8 +76,19 @@ extern "C" {
 #define QRL_SYS_KERR_CHAIN  2  /* m=N, q=2N (N = 1..4), 5+N params/env, 1 action */
 #define QRL_SYS_CONST_AD    3  /* m=0; A (E,q,q), D (E,q,q) constant over the interval (is_A_constant/is_D_constant) */
 
-#define QRL_ODE_RK4    0
-#define QRL_ODE_DOPRI5 1
+#define QRL_ODE_RK4    0     /* classic RK4, fixed step t_ssz / substeps */
+#define QRL_ODE_DOPRI5 1     /* Dormand–Prince 5(4), free-running steps + dense output on the grid */
+/* generic explicit Runge–Kutta engine (csrc/ode_erk.cuh): steps are clipped to the grid points; one step-size
+ * controller per environment for the adaptive pairs; EULER / MIDPOINT use the fixed step t_ssz / substeps.  These are the
+ * explicit-RK method names of the reference's solver plugins (torchdiffeq: quantrl/solvers/torch.py:28, diffrax:
+ * quantrl/solvers/jax.py:29, SciPy: quantrl/solvers/numpy.py:31) */
+#define QRL_ODE_BOSH3     2  /* Bogacki–Shampine 3(2)   ('bosh3', SciPy 'RK23') */
+#define QRL_ODE_TSIT5     3  /* Tsitouras 5(4)          ('tsit5') */
+#define QRL_ODE_HEUN21    4  /* Heun 2(1)               ('adaptive_heun', 'heun') */
+#define QRL_ODE_FEHLBERG2 5  /* Fehlberg 2(1)           ('fehlberg2') */
+#define QRL_ODE_DOP853    6  /* Dormand–Prince 8(5,3)   ('dop853' / 'DOP853'; stands in for 'dopri8'); d <= 64 */
+#define QRL_ODE_EULER     7  /* explicit Euler          ('euler') */
+#define QRL_ODE_MIDPOINT  8  /* explicit midpoint rule  ('midpoint') */
 
 QRL_API int         qrl_abi_version(void);
 QRL_API const char* qrl_last_error(void);
@@ -212,11 +223,11 @@ typedef struct qrl_ode_args {
     int32_t  n_envs;         /* E */
     int32_t  K;              /* grid intervals = len(T_step) - 1 */
     int32_t  method;         /* QRL_ODE_* */
-    int32_t  substeps;       /* RK4 steps per grid interval (>= 1) */
+    int32_t  substeps;       /* fixed-step methods (RK4, EULER, MIDPOINT): steps per grid interval (>= 1) */
     int32_t  n_actions;
     double   t0;             /* T_step[0] */
     double   t_ssz;          /* grid spacing */
-    double   atol, rtol;     /* DOPRI5 */
+    double   atol, rtol;     /* adaptive methods */
 
     const double* params;    /* (E, n_params) system parameters, row stride params_stride_e (0 = shared) */
     int64_t  params_stride_e;
@@ -241,8 +252,8 @@ typedef struct qrl_ode_args {
     int64_t  env_offset;
     const double* obs_std;   /* element [e,d] at obs_std[e*obs_std_stride_e + d]; or NULL */
     int64_t  obs_std_stride_e;
-    double*  h_state;        /* DOPRI5: (E,) in/out carried step size (<= 0: start from t_ssz); or NULL */
-    int32_t* n_steps;        /* DOPRI5: (E,2) accepted, rejected counters (accumulated); or NULL */
+    double*  h_state;        /* adaptive methods: (E,) in/out carried step size (<= 0: start from t_ssz); or NULL */
+    int32_t* n_steps;        /* adaptive methods: (E,2) accepted, rejected counters (accumulated); or NULL */
 
     double*  obs_minmax;     /* as in qrl_em_args */
     int32_t* nan_flag;

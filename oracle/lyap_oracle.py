@@ -188,3 +188,129 @@ def dopri5_dense_interval(func_single, t0, t_ssz, K, y0, args_per_env, atol, rto
                 n_rej[e] += 1
         h_last[e] = h
     return Y, n_acc, n_rej, h_last
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Generic explicit Runge–Kutta engine (CPU twin of csrc/ode_erk.cuh): the explicit-RK method names of the reference's
+# solver plugins (torchdiffeq quantrl/solvers/torch.py:28, diffrax quantrl/solvers/jax.py:29, SciPy
+# quantrl/solvers/numpy.py:31).  Tableaus are the published ones, written here independently of the CUDA header
+# (``tests/test_oracle_golden.py`` checks their order conditions); DOP853's come from SciPy's coefficient module.
+# Form: S stages, y_new = y + h sum B_j k_j, k_S = f(t + h, y_new) closes the error estimate and starts the next step.
+# ---------------------------------------------------------------------------------------------------------------------
+def _tableau(name):
+    name = {"RK23": "bosh3", "heun": "adaptive_heun", "DOP853": "dop853", "dopri8": "dop853"}.get(name, name)
+    if name == "bosh3":
+        A = [[0, 0, 0], [1 / 2, 0, 0], [0, 3 / 4, 0]]
+        B = [2 / 9, 1 / 3, 4 / 9]
+        Ev = [2 / 9 - 7 / 24, 1 / 3 - 1 / 4, 4 / 9 - 1 / 3, -1 / 8]
+        return dict(A=A, B=B, E=Ev, order=3, err_order=2, adaptive=True)
+    if name == "tsit5":
+        A = np.zeros((6, 6))
+        A[1, 0] = 0.161
+        A[2, :2] = [-0.008480655492356989, 0.335480655492357]
+        A[3, :3] = [2.8971530571054935, -6.359448489975075, 4.3622954328695815]
+        A[4, :4] = [5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525]
+        A[5, :5] = [5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383]
+        B = [0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774]
+        Ev = [-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629,
+              0.5823571654525552, -0.45808210592918697, 1 / 66]
+        return dict(A=A, B=B, E=Ev, order=5, err_order=4, adaptive=True)
+    if name == "adaptive_heun":
+        return dict(A=[[0, 0], [1.0, 0]], B=[0.5, 0.5], E=[-0.5, 0.5, 0.0], order=2, err_order=1, adaptive=True)
+    if name == "fehlberg2":
+        return dict(A=[[0, 0, 0], [1 / 2, 0, 0], [1 / 256, 255 / 256, 0]], B=[1 / 512, 255 / 256, 1 / 512],
+                    E=[-1 / 512, 0.0, 1 / 512, 0.0], order=2, err_order=1, adaptive=True)
+    if name == "euler":
+        return dict(A=[[0]], B=[1.0], E=None, order=1, adaptive=False)
+    if name == "midpoint":
+        return dict(A=[[0, 0], [0.5, 0]], B=[0.0, 1.0], E=None, order=2, adaptive=False)
+    if name == "dop853":
+        from scipy.integrate._ivp import dop853_coefficients as dc
+        S = dc.N_STAGES
+        return dict(A=np.asarray(dc.A[:S, :S]), B=np.asarray(dc.B), E=np.asarray(dc.E5), E3=np.asarray(dc.E3), order=8,
+                    err_order=7, adaptive=True)
+    raise ValueError(name)
+
+
+def erk_tableau(name):
+    """(A (S,S), B (S,), C (S,), E (S+1,) or None, meta) of an explicit RK method of the generic engine."""
+    tb = _tableau(name)
+    A = np.asarray(tb["A"], dtype=np.float64)
+    tb = dict(tb, A=A, B=np.asarray(tb["B"], dtype=np.float64), C=A.sum(axis=1))
+    return tb
+
+
+def erk_interval(method, func_single, t0, t_ssz, K, y0, args_per_env, atol=1e-9, rtol=1e-6, h0=None, substeps=1):
+    """One action interval with the generic explicit RK engine, one controller per env, steps clipped to the grid points
+    ``t0 + i * t_ssz`` (rows are step results, no interpolation).  Same controller as ``dopri5_dense_interval`` with the
+    exponent ``-1 / (err_order + 1)``; DOP853 combines its two estimators as in SciPy (``|h| e5^2 / sqrt((e5^2 + 0.01
+    e3^2) d)``).  Fixed-step methods take ``substeps`` equal steps per grid interval.
+    Returns Y (K+1,E,d), n_accepted (E,), n_rejected (E,), h_last (E,)."""
+    tb = erk_tableau(method)
+    A, B, C, Ev = tb["A"], tb["B"], tb["C"], tb["E"]
+    S = len(B)
+    E_, d = y0.shape
+    Y = np.empty((K + 1, E_, d))
+    Y[0] = y0
+    n_acc, n_rej, h_last = np.zeros(E_, dtype=np.int64), np.zeros(E_, dtype=np.int64), np.zeros(E_)
+    t_end = t0 + K * t_ssz
+    expo = -1.0 / (tb["err_order"] + 1) if tb["adaptive"] else 0.0
+    for e in range(E_):
+        y = y0[e].copy()
+        args = args_per_env(e)
+        t = t0
+        h = (float(h0[e]) if (h0 is not None and h0[e] > 0.0) else t_ssz) if tb["adaptive"] else t_ssz / substeps
+        k = [None] * (S + 1)
+        k[0] = func_single(t, y, args, e)
+        rejected = False
+        for row in range(1, K + 1):
+            t_row = t_end if row == K else t0 + row * t_ssz
+            sub = 0
+            while True:
+                remaining = t_row - t
+                if tb["adaptive"]:
+                    last = h >= remaining * (1.0 - 1e-12)
+                    ht = remaining if last else h
+                else:
+                    sub += 1
+                    last = sub >= substeps
+                    ht = remaining if last else t_ssz / substeps
+                for s in range(1, S):
+                    ys = y + ht * sum(A[s, j] * k[j] for j in range(s) if A[s, j] != 0.0)
+                    k[s] = func_single(t + C[s] * ht, ys, args, e)
+                y_new = y + ht * sum(B[j] * k[j] for j in range(S) if B[j] != 0.0)
+                t_new = t_row if last else t + ht
+                k[S] = func_single(t_new, y_new, args, e)
+                accept, fac = True, 1.0
+                if tb["adaptive"]:
+                    sc = atol + rtol * np.maximum(np.abs(y), np.abs(y_new))
+                    if method in ("dop853", "DOP853", "dopri8"):
+                        e5 = sum(Ev[j] * k[j] for j in range(S + 1)) / sc
+                        e3 = sum(tb["E3"][j] * k[j] for j in range(S + 1)) / sc
+                        s5, s3 = float(e5 @ e5), float(e3 @ e3)
+                        den = s5 + 0.01 * s3
+                        err = abs(ht) * s5 / np.sqrt(den * d) if den > 0.0 else 0.0
+                    else:
+                        err = float(np.sqrt(np.mean((ht * sum(Ev[j] * k[j] for j in range(S + 1)) / sc) ** 2)))
+                    accept = err <= 1.0
+                    if accept:
+                        fac = DOPRI5_MAX_FACTOR if err == 0.0 else min(DOPRI5_MAX_FACTOR, max(DOPRI5_MIN_FACTOR, DOPRI5_SAFETY * err ** expo))
+                        if rejected:
+                            fac = min(1.0, fac)
+                    else:
+                        fac = max(DOPRI5_MIN_FACTOR, DOPRI5_SAFETY * err ** expo)
+                if accept:
+                    rejected = False
+                    n_acc[e] += 1
+                    t, y, k[0] = t_new, y_new, k[S]
+                    if tb["adaptive"]:
+                        h = max(h, ht * fac) if (last and fac >= 1.0) else ht * fac
+                    if last:
+                        break
+                else:
+                    h = ht * fac
+                    rejected = True
+                    n_rej[e] += 1
+            Y[row, e] = y
+        h_last[e] = h
+    return Y, n_acc, n_rej, h_last

@@ -13,7 +13,12 @@ RNG_FED, RNG_PHILOX = 0, 1
 REWARD_NONE, REWARD_NEG_WSQ_OBS, REWARD_NEG_WSQ_STATE, REWARD_ENTAN_LN_OBS, REWARD_ENTAN_LN_STATE = 0, 1, 2, 3, 4
 REWARD_SYNC_C_OBS, REWARD_SYNC_C_STATE, REWARD_SYNC_P_OBS, REWARD_SYNC_P_STATE = 5, 6, 7, 8
 SYS_OPTOMECH, SYS_KERR_CHAIN, SYS_CONST_AD = 1, 2, 3
-ODE_RK4, ODE_DOPRI5 = 0, 1
+ODE_RK4, ODE_DOPRI5, ODE_BOSH3, ODE_TSIT5, ODE_HEUN21, ODE_FEHLBERG2, ODE_DOP853, ODE_EULER, ODE_MIDPOINT = range(9)
+# method names of the solver plugin -> (id, adaptive); aliases follow the reference's torchdiffeq / diffrax / SciPy names
+ODE_METHODS = {"rk4": (ODE_RK4, False), "dopri5": (ODE_DOPRI5, True), "bosh3": (ODE_BOSH3, True), "RK23": (ODE_BOSH3, True),
+               "tsit5": (ODE_TSIT5, True), "adaptive_heun": (ODE_HEUN21, True), "heun": (ODE_HEUN21, True),
+               "fehlberg2": (ODE_FEHLBERG2, True), "dop853": (ODE_DOP853, True), "DOP853": (ODE_DOP853, True),
+               "dopri8": (ODE_DOP853, True), "euler": (ODE_EULER, False), "midpoint": (ODE_MIDPOINT, False)}
 EM_FORCE_GENERIC, EM_FORCE_TILED, EM_ITEM_OUTPUT, EM_PACK_TMA = 1, 16, 32, 128
 ODE_FORCE_THREAD, ODE_FORCE_LANES = 1, 2
 

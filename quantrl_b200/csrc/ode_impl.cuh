@@ -496,6 +496,10 @@ __global__ void __launch_bounds__(BLOCK) rk4_lanes_kernel(const qrl_ode_args a) 
     if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
 }
 
+}  // namespace qrl
+#include "ode_erk.cuh"
+namespace qrl {
+
 template <class Sys>
 int launch_ode(const qrl_ode_args& a, cudaStream_t st) {
     constexpr int D = Dim<Sys>::D;
@@ -514,6 +518,22 @@ int launch_ode(const qrl_ode_args& a, cudaStream_t st) {
         const int blocks = (a.n_envs + BLOCK - 1) / BLOCK;
         rk4_kernel<Sys, BLOCK><<<blocks, BLOCK, smem, st>>>(a);
         return after_launch("rk4_kernel");
+    }
+    if (a.method > QRL_ODE_DOPRI5) {
+        // the generic explicit Runge–Kutta engine (ode_erk.cuh) is instantiated for num_quads <= 4 (the BASELINE configs);
+        // larger systems have RK4 and DOPRI5 (seven more kernels per system at q = 8 triple the build time)
+        if constexpr (Sys::Q > 4)
+            return fail(QRL_E_UNSUPPORTED, "%s", "qrl_ode_step: this method is built for num_quads <= 4 (use RK4 or DOPRI5)");
+    }
+    if constexpr (Sys::Q <= 4) switch (a.method) {
+        case QRL_ODE_BOSH3: return launch_erk<Sys, erk::Bosh3>(a, st, "erk_kernel<bosh3>");
+        case QRL_ODE_TSIT5: return launch_erk<Sys, erk::Tsit5>(a, st, "erk_kernel<tsit5>");
+        case QRL_ODE_HEUN21: return launch_erk<Sys, erk::Heun21>(a, st, "erk_kernel<heun21>");
+        case QRL_ODE_FEHLBERG2: return launch_erk<Sys, erk::Fehlberg2>(a, st, "erk_kernel<fehlberg2>");
+        case QRL_ODE_DOP853: return launch_erk<Sys, erk::Dop853>(a, st, "erk_kernel<dop853>");
+        case QRL_ODE_EULER: return launch_erk<Sys, erk::Euler>(a, st, "erk_kernel<euler>");
+        case QRL_ODE_MIDPOINT: return launch_erk<Sys, erk::Midpoint>(a, st, "erk_kernel<midpoint>");
+        default: break;
     }
     constexpr int BLOCK = 32;
     const size_t smem = (size_t)7 * D * BLOCK * sizeof(double);

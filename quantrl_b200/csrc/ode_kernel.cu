@@ -19,9 +19,10 @@ extern "C" int qrl_ode_step(const qrl_ode_args* args, void* stream) {
     QRL_REQUIRE(args != nullptr, "qrl_ode_step: args is NULL");
     const qrl_ode_args& a = *args;
     QRL_REQUIRE(a.n_envs >= 0 && a.K >= 0, "qrl_ode_step: n_envs and K must be non-negative");
-    QRL_REQUIRE(a.method == QRL_ODE_RK4 || a.method == QRL_ODE_DOPRI5, "qrl_ode_step: method must be RK4 or DOPRI5");
-    QRL_REQUIRE(a.method != QRL_ODE_RK4 || a.substeps >= 1, "qrl_ode_step: substeps must be >= 1");
-    QRL_REQUIRE(a.method != QRL_ODE_DOPRI5 || (a.atol > 0.0 && a.rtol > 0.0), "qrl_ode_step: atol and rtol must be positive");
+    QRL_REQUIRE(a.method >= QRL_ODE_RK4 && a.method <= QRL_ODE_MIDPOINT, "qrl_ode_step: unknown method");
+    const bool fixed_step = a.method == QRL_ODE_RK4 || a.method == QRL_ODE_EULER || a.method == QRL_ODE_MIDPOINT;
+    QRL_REQUIRE(!fixed_step || a.substeps >= 1, "qrl_ode_step: substeps must be >= 1");
+    QRL_REQUIRE(fixed_step || (a.atol > 0.0 && a.rtol > 0.0), "qrl_ode_step: atol and rtol must be positive");
     QRL_REQUIRE(a.t_ssz > 0.0, "qrl_ode_step: t_ssz must be positive");
     if (a.n_envs == 0) return 0;
     QRL_REQUIRE(a.y0 != nullptr, "qrl_ode_step: y0 is NULL");

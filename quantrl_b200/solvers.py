@@ -9,7 +9,9 @@ Two execution modes:
 
 * **fused** (the product path): the env that owns ``func`` declares a device functor (``system=...``); the whole
   interval — all grid points, all RK stages, the RHS and its hooks — is ONE launch of ``qrl_ode_step``
-  (methods ``'rk4'`` fixed step and ``'dopri5'`` per-env adaptive with dense output).
+  (``'rk4'`` fixed step, ``'dopri5'`` per-env adaptive with dense output, and the generic explicit Runge–Kutta engine
+  for the other explicit method names of the reference's plugins: ``'bosh3'/'RK23'``, ``'tsit5'``,
+  ``'adaptive_heun'/'heun'``, ``'fehlberg2'``, ``'dop853'/'DOP853'/'dopri8'``, ``'euler'``, ``'midpoint'``).
 * **stage-callback**: no functor, arbitrary user hooks written in torch; classic RK4 whose four stage evaluations
   call ``func`` (batched torch on the device).  This keeps every reference env runnable on the backend; it is not
   the accelerated path.
@@ -26,7 +28,7 @@ SYSTEM_NPARAMS = {"optomech": lambda m: 7, "kerr_chain": lambda m: 5 + m, "const
 class B200IVPSolver:
     default_solver_params = {"method": "rk4", "atol": 1e-12, "rtol": 1e-9, "is_stiff": False, "step_interval": 10,
                              "complex": False, "substeps": 1}
-    solver_methods = ["rk4", "dopri5"]
+    solver_methods = list(N.ODE_METHODS)   # fused mode; the stage-callback mode implements "rk4" only
 
     def __init__(self, func, y_0, T, solver_params: dict, func_controls=None, has_delay: bool = False, func_delay=None,
                  delay_interval: int = 0, backend=None, system=None):
@@ -81,7 +83,7 @@ class B200IVPSolver:
         Y = out if out is not None else torch.empty((dim, E, d), dtype=torch.float64, device=y_0.device)
         a = N.OdeArgs()
         a.system, a.num_modes, a.num_quads, a.n_envs, a.K = SYSTEMS[sysd["system"]], m, q, E, K
-        a.method = N.ODE_RK4 if self.solver_params["method"] == "rk4" else N.ODE_DOPRI5
+        a.method, adaptive = N.ODE_METHODS[self.solver_params["method"]]
         a.substeps = int(self.solver_params["substeps"])
         t_host = sysd.get("T_host")
         if t_host is not None:
@@ -114,7 +116,7 @@ class B200IVPSolver:
         if ep.get("obs_std") is not None:
             a.obs_std, a.obs_std_stride_e = ep["obs_std"], ep["obs_std_stride_e"]
             a.seed, a.episode, a.t_idx, a.env_offset = ep["seed"], ep["episode"], ep["t_idx"], ep["env_offset"]
-        if a.method == N.ODE_DOPRI5:
+        if adaptive:
             if self.h_state is None or self.h_state.shape[0] != E:
                 self.h_state = torch.zeros((E,), dtype=torch.float64, device=y_0.device)
                 self.n_steps = torch.zeros((E, 2), dtype=torch.int32, device=y_0.device)

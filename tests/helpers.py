@@ -85,7 +85,7 @@ def ode_step(system, m, q, y0, K, t0, t_ssz, params=None, actions=None, A=None, 
     a = N.OdeArgs()
     a.system = {"optomech": N.SYS_OPTOMECH, "kerr_chain": N.SYS_KERR_CHAIN, "const_AD": N.SYS_CONST_AD}[system]
     a.num_modes, a.num_quads, a.n_envs, a.K = m, q, E, K
-    a.method = N.ODE_RK4 if method == "rk4" else N.ODE_DOPRI5
+    a.method = N.ODE_METHODS[method][0]
     a.substeps, a.t0, a.t_ssz, a.atol, a.rtol = substeps, t0, t_ssz, atol, rtol
     keep = [y0]
     if params is not None:

@@ -185,6 +185,23 @@ def test_lho_vec_env_matches_reference_vec_env(native, cuda, golden_dir):
     env.close()
 
 
+@pytest.mark.parametrize("method", ["tsit5", "DOP853", "dopri8"])
+def test_lho_vec_env_accepts_the_reference_plugins_method_names(native, cuda, golden_dir, method):
+    """``ode_method`` takes the explicit-RK names of the reference's torchdiffeq / diffrax / SciPy plugins (generic
+    engine); at tight tolerance the env reproduces the reference's LinearizedHOVecEnv + SciPy trajectory (fixture G1)."""
+    g = np.load(os.path.join(golden_dir, "lyap_optomech.npz"))
+    tag = "E5"
+    env = _optomech_env(g, tag, method, atol=1e-14, rtol=1e-13)
+    K = int(g[f"{tag}_K"])
+    env.reset()
+    ref = g[f"{tag}_States_dop853_tight"]
+    scale = np.abs(ref).max(axis=(0, 1)) + 1e-300
+    for a in range(4):
+        env.step(g[f"{tag}_actions"][a])
+        assert np.max(np.abs(env.States.cpu().numpy() - ref[a * K:(a + 1) * K + 1]) / scale) < 1e-9
+    env.close()
+
+
 def test_lho_vec_env_stage_callback_equals_fused(native, cuda, golden_dir):
     """The same env with torch hooks (no device functor; RK4 stages call ``func``) == the fused kernel == fixture G2."""
     g = np.load(os.path.join(golden_dir, "lyap_optomech.npz"))
@@ -312,6 +329,11 @@ def test_lho_vec_env_fused_entanglement_reward(native, cuda, golden_dir):
               t_norm_mul=1.0, n_envs=5, n_observations=20, n_properties=0, n_actions=1, action_maximums=[1.0],
               action_interval=10, data_idxs=[0, -1], cache_all_data=False, dir_prefix="/tmp/qrl_test", system="optomech",
               system_params=p, ode_method="dopri5", ode_atol=1e-14, ode_rtol=1e-13, reward_functor="entan_ln_state")
+    with pytest.raises(AssertionError, match="reward_functor"):
+        Env(name="optomech", desc="t", params={}, num_modes=2, num_quads=4, t_norm_max=1.205, t_norm_ssz=0.01,
+            t_norm_mul=1.0, n_envs=5, n_observations=20, n_properties=0, n_actions=1, action_maximums=[1.0],
+            action_interval=10, data_idxs=[0, -1], cache_all_data=False, dir_prefix="/tmp/qrl_test", system="optomech",
+            system_params=p, reward_functor="no_such_measure")
     env.reset()
     cum = np.zeros(5)
     for a in range(10):

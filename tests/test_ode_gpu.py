@@ -168,8 +168,11 @@ def test_ode_edge_cases_and_errors(native, cuda):
     a.params = a.actions = N.ptr(yk); a.n_actions = 1
     with pytest.raises(N.NativeError, match="num_modes 1..4"):
         N.ode_step(a)
-    a.method = 5
-    with pytest.raises(N.NativeError, match="RK4 or DOPRI5"):
+    a.method = 99
+    with pytest.raises(N.NativeError, match="unknown method"):
+        N.ode_step(a)
+    a.method = N.ODE_TSIT5     # adaptive methods need tolerances
+    with pytest.raises(N.NativeError, match="atol and rtol must be positive"):
         N.ode_step(a)
 
 
@@ -259,3 +262,63 @@ def test_fused_synchronization_and_entanglement_rewards_match_reference(native, 
                    reward_kind=kinds[0], **kw)
     ref = mo.measures_of_states(out["observations"].cpu().numpy())[measure]
     np.testing.assert_allclose(out["reward"].cpu().numpy(), ref, rtol=1e-12, atol=1e-13)
+
+
+ERK_ADAPTIVE = ["bosh3", "tsit5", "adaptive_heun", "fehlberg2", "dop853"]
+
+
+@pytest.mark.parametrize("method", ERK_ADAPTIVE)
+@pytest.mark.parametrize("fname,tag,osys,system", CASES[:2])
+def test_generic_erk_engine_follows_oracle_controller(native, cuda, golden_dir, fname, tag, osys, system, method):
+    """Generic explicit RK engine (csrc/ode_erk.cuh) == oracle/lyap_oracle.py:erk_interval for every adaptive tableau:
+    same states, the same accept/reject counts and the same carried step size over consecutive intervals."""
+    g, p, y0, acts, T, K, m, q = _load(golden_dir, fname, tag)
+    f = _single_rhs(osys, p, m, q)
+    atol, rtol = (1e-9, 1e-6) if method != "dop853" else (1e-12, 1e-10)
+    y, h, yk, hk = y0, None, y0, None
+    for a in range(3):
+        Y, nacc, nrej, h = lo.erk_interval(method, f, float(T[a * K]), 0.01, K, y, lambda e: acts[a][e, 0], atol, rtol, h)
+        out = ode_step(system, m, q, yk, K, float(T[a * K]), 0.01, params=p, actions=acts[a][:, 0], method=method,
+                       atol=atol, rtol=rtol, h_state=hk)
+        np.testing.assert_allclose(out["states"].cpu().numpy(), Y, rtol=1e-9, atol=1e-11)
+        np.testing.assert_array_equal(out["n_steps"].cpu().numpy(), np.stack([nacc, nrej], 1))
+        # (DOP853 at 1e-12: the two error estimates are differences at rounding level, the next step size follows them)
+        np.testing.assert_allclose(out["h_state"].cpu().numpy(), h, rtol=1e-6 if method != "dop853" else 1e-3)
+        assert int(out["nan"].item()) == 0
+        y, yk, hk = Y[-1], out["y_last"].cpu().numpy(), out["h_state"]
+
+
+@pytest.mark.parametrize("method,substeps,order", [("euler", 4, 1), ("midpoint", 2, 2)])
+def test_generic_erk_fixed_step_methods(native, cuda, golden_dir, method, substeps, order):
+    """Fixed-step Euler / midpoint: kernel == oracle, and halving the step reduces the error vs the reference's tight
+    trajectory by ~2^order."""
+    g, p, y0, acts, T, K, m, q = _load(golden_dir, "lyap_optomech.npz", "E5")
+    f = _single_rhs("optomech", p, m, q)
+    Y, _, _, _ = lo.erk_interval(method, f, 0.0, 0.01, K, y0, lambda e: acts[0][e, 0], substeps=substeps)
+    out = ode_step("optomech", m, q, y0, K, 0.0, 0.01, params=p, actions=acts[0][:, 0], method=method, substeps=substeps)
+    np.testing.assert_allclose(out["states"].cpu().numpy(), Y, rtol=1e-11, atol=1e-13)
+    ref = g["E5_States_dop853_tight"][:K + 1]
+    errs = []
+    for ss in (substeps, 2 * substeps):
+        o = ode_step("optomech", m, q, y0, K, 0.0, 0.01, params=p, actions=acts[0][:, 0], method=method, substeps=ss)
+        errs.append(np.max(np.abs(o["states"].cpu().numpy() - ref)))
+    assert 0.7 * 2 ** order < errs[0] / errs[1] < 1.4 * 2 ** order
+
+
+@pytest.mark.parametrize("method,tol", [("tsit5", 1e-9), ("dop853", 1e-10), ("bosh3", 1e-6)])
+def test_generic_erk_tight_tolerance_matches_reference_scipy(native, cuda, golden_dir, method, tol):
+    """Converged runs of the new methods reproduce the reference's own tight SciPy trajectory (fixture G1) over the
+    whole episode, and the env-level plugin accepts the reference's method names."""
+    g, p, y0, acts, T, K, m, q = _load(golden_dir, "lyap_optomech.npz", "E5")
+    atol, rtol = (1e-14, 1e-13) if method != "bosh3" else (1e-11, 1e-10)
+    got, _ = _run_episode("optomech", m, q, p, y0, acts, T, K, method=method, atol=atol, rtol=rtol)
+    ref = g["E5_States_dop853_tight"]
+    assert np.max(np.abs(got - ref) / (1.0 + np.abs(ref))) < tol
+
+
+def test_generic_erk_rejects_unsupported_sizes(native, cuda):
+    from quantrl_b200._native import NativeError
+    V0 = np.broadcast_to(np.eye(8).reshape(1, -1), (3, 64)).copy()
+    A = -np.broadcast_to(np.eye(8), (3, 8, 8)).copy()
+    with pytest.raises(NativeError, match="num_quads <= 4"):
+        ode_step("const_AD", 0, 8, V0, 4, 0.0, 0.05, A=A, D=-A, method="tsit5")
