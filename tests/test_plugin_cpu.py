@@ -23,7 +23,8 @@ def test_register_into_reference_registries():
         assert backend is None and "b200" not in bcm.BACKEND_INSTANCES
     assert solver is B200IVPSolver and scm.get_IVP_solver("b200") is B200IVPSolver
     # the solver honours the reference's BaseIVPSolver contract (solvers/base.py:60-67, 115-116)
-    assert set(B200IVPSolver.solver_methods) == {"rk4", "dopri5"}
+    assert {"rk4", "dopri5", "bosh3", "RK23", "tsit5", "adaptive_heun", "heun", "fehlberg2", "dop853", "DOP853", "dopri8",
+            "euler", "midpoint"} == set(B200IVPSolver.solver_methods)
     for key in ("method", "atol", "rtol", "is_stiff", "step_interval", "complex"):
         assert key in B200IVPSolver.default_solver_params
 
