@@ -340,7 +340,8 @@ def main():
                              "every step and stay L2-resident (126 MB L2), the episode cache (655 MB) streams to HBM", "parallelism": f"env-sharded dp{world}",
                        "collective": {"none": "none", "nccl": "all_gather(obs|reward) per step (NCCL, async)",
                                       "p2p": "obs|reward stored into the learner rank's buffer over NVLink by the kernel "
-                                             "epilogue + one device-side barrier per step (no collective launch)"}[gather_mode]},
+                                             "epilogue; the per-step cross-GPU barrier is fused into the same kernel's last block "
+                                             "(no collective or barrier launch)"}[gather_mode]},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * 1 * 8, "d2h_bytes_per_step": (E * (n + 1) + 4) * 8,
                     "steps": e2e_steps, "api": "AffineLinearVecEnv.step(host actions) -> host obs, reward",

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define QRL_ABI_VERSION 2
+#define QRL_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define QRL_API __attribute__((visibility("default")))
@@ -196,6 +196,20 @@ typedef struct qrl_em_args {
     uint32_t* finish_counter;
     double*   minmax_out;
     int64_t   dyn_advance;
+
+    /* cross-GPU barrier fused into the end of the launch (ABI 3; needs finish_counter) — the only exchange step of the
+     * sharded path: after every block of this rank has stored its slice of obs_last / reward_last into the learner
+     * rank's peer-mapped buffer (NVLink), the last block publishes a new epoch number in every rank's flag array and
+     * waits until all ranks have published theirs, so that kernel completion == "every rank's step result is visible
+     * on every rank".  Replaces a separate barrier launch per step.
+     *   peer_flags   DEVICE array of peer_world pointers; peer_flags[p] = rank p's flag array (peer_world uint64,
+     *                zero-initialised, peer-mapped symmetric memory); NULL = off
+     *   peer_epoch   DEVICE uint64 of this rank, zero-initialised; incremented once per launch
+     * A rank that waits longer than ~2 s raises nan_flag (if given) and returns instead of hanging the device. */
+    uint64_t* const* peer_flags;
+    uint64_t* peer_epoch;
+    int32_t   peer_rank;
+    int32_t   peer_world;
 } qrl_em_args;
 
 #define QRL_EM_FORCE_GENERIC 1   /* flags: always use the generic lane-per-component kernel (A/B testing) */
@@ -203,7 +217,8 @@ typedef struct qrl_em_args {
 #define QRL_EM_ITEM_OUTPUT  32  /* flags: tiled kernel uses its one-(row, env)-item-per-lane output pass even when the
                                  * 16-byte-piece pass applies (A/B testing; n not in {2,4,8} always takes it) */
 #define QRL_EM_PACK_TMA     128 /* flags: reserved (accepted and ignored; the cache rows are written from registers) */
-/* flag bits 2, 4, 8 are diagnostics of the tiled kernel (skip produce / recurrence / output stage); results invalid */
+/* flag bits 2, 4, 8 are diagnostics of the tiled kernel (skip produce / recurrence / output stage) and bits 512, 1024 of
+ * the peer barrier (gpu-scope fences only / signal without waiting); results invalid */
 
 QRL_API int qrl_em_step(const qrl_em_args* args, void* stream);
 

@@ -7,7 +7,7 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 RNG_FED, RNG_PHILOX = 0, 1
 REWARD_NONE, REWARD_NEG_WSQ_OBS, REWARD_NEG_WSQ_STATE, REWARD_ENTAN_LN_OBS, REWARD_ENTAN_LN_STATE = 0, 1, 2, 3, 4
@@ -43,6 +43,7 @@ class EmArgs(C.Structure):
         ("packed", _dp), ("packed_stride_e", C.c_int64), ("packed_row_pitch", C.c_int64), ("T_step", _dp), ("actions", _dp), ("sel_idxs", _dp),
         ("n_actions", C.c_int32), ("n_sel", C.c_int32), ("dyn", _dp), ("A_act", _dp), ("action_scale", _dp),
         ("finish_counter", _dp), ("minmax_out", _dp), ("dyn_advance", C.c_int64),
+        ("peer_flags", _dp), ("peer_epoch", _dp), ("peer_rank", C.c_int32), ("peer_world", C.c_int32),
     ]
 
 

@@ -116,13 +116,20 @@ __device__ __forceinline__ void block_minmax_commit(double lo, double hi, double
     }
 }
 
-// Last-block-done bookkeeping of qrl_em_args (finish_counter / minmax_out / dyn_advance); call once per block, by all
-// threads, after block_minmax_commit (whose atomics are issued by thread 0, like the counter increment below).
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Last-block-done bookkeeping of qrl_em_args (finish_counter / minmax_out / dyn_advance / peer barrier); call once per
+// block, by all threads, after block_minmax_commit (whose atomics are issued by thread 0, like the counter increment).
 __device__ __forceinline__ void em_finish_launch(const qrl_em_args& a) {
     if (a.finish_counter == nullptr) return;
     __syncthreads();                                    // every thread of the block has read dyn and is done
     if (threadIdx.x != 0) return;
-    __threadfence();                                    // this block's min/max atomics and dyn reads come first
+    // this block's min/max atomics, dyn reads and (peer barrier) its stores into the learner's buffer come first
+    if (a.peer_flags && !(a.flags & 512)) __threadfence_system(); else __threadfence();
     const unsigned prev = atomicAdd(a.finish_counter, 1u);
     if (prev != gridDim.x - 1) return;
     __threadfence();
@@ -135,6 +142,27 @@ __device__ __forceinline__ void em_finish_launch(const qrl_em_args& a) {
     }
     if (a.dyn && a.dyn_advance != 0) const_cast<int64_t*>(a.dyn)[0] += a.dyn_advance;
     *a.finish_counter = 0u;
+    if (a.peer_flags) {
+        // cross-GPU barrier: publish this rank's new epoch everywhere, then wait for everybody's
+        const unsigned long long epoch = *a.peer_epoch + 1ull;
+        *a.peer_epoch = epoch;
+        __threadfence_system();
+        for (int p = 0; p < a.peer_world; ++p)
+            reinterpret_cast<volatile unsigned long long*>(a.peer_flags[p])[a.peer_rank] = epoch;
+        __threadfence_system();
+        volatile unsigned long long* mine = reinterpret_cast<volatile unsigned long long*>(a.peer_flags[a.peer_rank]);
+        const unsigned long long t0 = global_timer_ns();
+        for (int q = 0; q < a.peer_world && !(a.flags & 1024); ++q) {
+            while (mine[q] < epoch) {
+                if (global_timer_ns() - t0 > 2000000000ull) {   // a peer never arrived: fail loudly, do not hang
+                    if (a.nan_flag) *a.nan_flag = 1;
+                    q = a.peer_world;
+                    break;
+                }
+            }
+        }
+        __threadfence_system();
+    }
 }
 
 }  // namespace qrl

@@ -153,6 +153,9 @@ extern "C" int qrl_em_step(const qrl_em_args* args, void* stream) {
     QRL_REQUIRE(a.finish_counter != nullptr || (a.minmax_out == nullptr && a.dyn_advance == 0),
                 "qrl_em_step: minmax_out / dyn_advance need finish_counter");
     QRL_REQUIRE(a.minmax_out == nullptr || a.obs_minmax != nullptr, "qrl_em_step: minmax_out needs obs_minmax");
+    QRL_REQUIRE(a.peer_flags == nullptr || (a.finish_counter != nullptr && a.peer_epoch != nullptr && a.peer_world >= 1 &&
+                                            a.peer_rank >= 0 && a.peer_rank < a.peer_world),
+                "qrl_em_step: the peer barrier needs finish_counter, peer_epoch and 0 <= peer_rank < peer_world");
     if (a.packed) {
         QRL_REQUIRE(a.reward_kind != QRL_REWARD_NONE && a.rewards_cum != nullptr,
                     "qrl_em_step: packed rows need a fused reward functor and rewards_cum");

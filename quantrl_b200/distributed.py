@@ -126,6 +126,14 @@ class PeerGather:
         self.is_learner = self.rank == dst
         self.obs_all = self.buf[:n_envs_total * n_observations].view(n_envs_total, n_observations)
         self.reward_all = self.buf[n_envs_total * n_observations:n_words]
+        # in-kernel barrier (qrl_em_args.peer_flags): one uint64 epoch flag per rank in every rank's symmetric buffer
+        self.flags = symm_mem.empty(max(self.world, 2), dtype=torch.int64, device=device)
+        self.flags.zero_()
+        self.flags_hdl = symm_mem.rendezvous(self.flags, self.group.group_name if hasattr(self.group, "group_name") else self.group)
+        self.flag_ptrs = torch.tensor([int(p) for p in self.flags_hdl.buffer_ptrs], dtype=torch.int64, device=device)
+        self.epoch = torch.zeros((1,), dtype=torch.int64, device=device)
+        self.hdl.barrier(channel=0)      # everybody's flags are zeroed before the first fused barrier
+        self._env = None
 
     def attach(self, env):
         """Point the env's step outputs at the learner's buffer (before the first step / graph capture)."""
@@ -133,6 +141,13 @@ class PeerGather:
         obs_view = self.obs_all[self.offset:self.offset + self.count] if self.is_learner else None
         rew_view = self.reward_all[self.offset:self.offset + self.count] if self.is_learner else None
         env.attach_step_output(self.obs_ptr, self.reward_ptr, obs_view, rew_view)
+        if hasattr(env, "attach_peer_barrier"):
+            env.attach_peer_barrier(self.flag_ptrs, self.epoch, self.rank, self.world)
+            self._env = env
 
     def fence(self):
+        """Cross-GPU barrier after a step.  Steps that went through a captured graph already ended with the barrier
+        fused into the kernel (``qrl_em_args.peer_flags``): nothing to launch then."""
+        if self._env is not None and getattr(self._env, "last_step_peer_fenced", False):
+            return
         self.hdl.barrier(channel=0)

@@ -20,6 +20,8 @@ once per action interval (``is_A_time_dependent=False``) or once per sub-step of
 ``rng='fed'``: ``Ws`` ``(shape_T-1, E, n)`` and ``Observation_noises`` ``(shape_T, E, n)`` are drawn at ``reset`` exactly
 like the reference (or assigned by the caller) and fed to the kernel — used for pathwise parity with the reference.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -53,6 +55,8 @@ class LinearVecEnv(BaseVecEnv):
         # actions from, and writes obs_last / reward_last / [min,max] to, pinned host memory directly (no copy nodes)
         self.host_zero_copy = bool(kwargs.pop("host_zero_copy", True))
         self._zc = None
+        self._peer_barrier = None           # (flag pointer table, epoch, rank, world) of distributed.PeerGather
+        self.last_step_peer_fenced = False
         self.reward_functor = kwargs.pop("reward_functor", None)
         reward_weights = kwargs.pop("reward_weights", None)
         assert self.reward_functor in _REWARD_KINDS, f"``reward_functor`` should be one of {list(_REWARD_KINDS)}"
@@ -221,6 +225,9 @@ class LinearVecEnv(BaseVecEnv):
         a.nan_flag = N.ptr(self._nan)
         if graph_mode is not None:
             a.finish_counter, a.dyn_advance = N.ptr(self._finish), K
+            if self._peer_barrier is not None:
+                flag_ptrs, epoch, prank, pworld = self._peer_barrier
+                a.peer_flags, a.peer_epoch, a.peer_rank, a.peer_world = N.ptr(flag_ptrs), N.ptr(epoch), prank, pworld
             if graph_mode == "host":
                 a.obs_minmax, a.minmax_out = N.ptr(self._minmax_acc), N.ptr(self._minmax)
                 zc = self._zero_copy()
@@ -246,7 +253,13 @@ class LinearVecEnv(BaseVecEnv):
             self._packed_by_kernel = True
         if self.force_generic_kernel:
             a.flags = N.EM_FORCE_GENERIC
+        a.flags |= int(os.environ.get("QRL_EM_DEBUG_FLAGS", "0"))    # development knob (kernel diagnostics bits)
         return a, keep
+
+    def attach_peer_barrier(self, flag_ptrs, epoch, rank, world):
+        """Fuse the per-step cross-GPU barrier of the sharded path into the captured step kernel (ABI 3)."""
+        self._peer_barrier = (flag_ptrs, epoch, int(rank), int(world))
+        self._graph = self._graph_host = None
 
     def _zero_copy(self):
         """Device-side addresses of the pinned step buffers (``_h_out``, ``_h_actions``) when the zero-copy host round
@@ -266,10 +279,12 @@ class LinearVecEnv(BaseVecEnv):
 
     def _update_states(self):
         dim = self._dim
+        self.last_step_peer_fenced = False
         if not self.use_cuda_graph:
             self._launch(dim - 1, self._x_last)
         elif dim == self.action_interval + 1:
             self._replay_interval(host_io=getattr(self, "_host_step", False))
+            self.last_step_peer_fenced = self._peer_barrier is not None
         else:  # tail interval (fewer sub-steps): eager launch, then advance the device-side time index
             if getattr(self, "_host_step", False):
                 self._actions_in.copy_(self._h_actions, non_blocking=True)

@@ -40,16 +40,30 @@ def _worker(rank, world, port, out):
         full = AffineLinearVecEnv(n_envs=E, **kw) if rank == 0 else None   # the unsharded twin on the learner
         if full is not None:
             full.reset()
-        for step in range(3):
+        # the same shard once more with the step captured in a CUDA graph: the cross-GPU barrier is then fused into the
+        # kernel's last block (qrl_em_args.peer_flags) and peer.fence() launches nothing
+        env_g = make_sharded_env(AffineLinearVecEnv, E, use_cuda_graph=True, fused_coefficients=True, **kw)
+        peer_g = PeerGather(E, n, dev, dst=0)
+        peer_g.attach(env_g)
+        env_g.reset()
+        for step in range(4):
             a_loc = link.scatter_actions(actions if rank == 0 else None)
             env.step_device(a_loc)
             peer.fence()
+            env_g.step_device(a_loc)
+            assert env_g.last_step_peer_fenced
+            peer_g.fence()
             res = link.gather_step(env.Observations[-1], env.Reward[-1])
             if rank == 0:
                 o_full, r_full, _ = full.step_device(actions)
                 torch.cuda.synchronize()
                 assert torch.equal(peer.obs_all, res[0]) and torch.equal(peer.reward_all, res[1])
                 assert torch.equal(peer.obs_all, o_full) and torch.equal(peer.reward_all, r_full)
+                torch.testing.assert_close(peer_g.obs_all, o_full, rtol=1e-12, atol=1e-14)   # in-kernel affine drift
+                torch.testing.assert_close(peer_g.reward_all, r_full, rtol=1e-12, atol=1e-14)
+            assert int(env_g._nan.item()) == 0      # no barrier time-out
+        torch.cuda.synchronize()
+        assert peer_g.flags.tolist()[:world] == [4] * world and int(peer_g.epoch.item()) == 4
         out.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         out.put((rank, repr(e)))
