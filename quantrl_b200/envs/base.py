@@ -341,12 +341,18 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         """``actions = float(action) * action_maximums`` (base.py:1244-1248).  With ``use_cuda_graph`` the raw actions
         land in the graph's static input buffer and the scaling is part of the captured graph."""
         if getattr(self, "use_cuda_graph", False) or getattr(self, "fused_coefficients", False):
+            if self._direct_actions(a):
+                return      # single-kernel step: the launch reads the caller's tensor in place (no staging copy)
             self._actions_in.copy_(a.reshape(self.n_envs, self.n_actions), non_blocking=True)
             if not getattr(self, "use_cuda_graph", False):
                 self.actions = self._actions_in * self.action_maximums_batch
         else:
             a = a.to(self.device, non_blocking=True) if not a.is_cuda else a
             self.actions = (a.reshape(self.n_envs, self.n_actions) * self.action_maximums_batch).contiguous()
+
+    def _direct_actions(self, a):
+        """Hook: environments whose captured step is a single native kernel may consume the actions tensor in place."""
+        return False
 
     def step(self, actions):
         self.step_async(actions)
@@ -486,6 +492,8 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         if reward_view is not None:
             self._reward_last = reward_view
         self._graph = self._graph_host = None
+        if hasattr(self, "_static"):
+            self._static = {}
 
     def _out(self, t):
         return t.detach().cpu().numpy() if self.return_numpy else t
