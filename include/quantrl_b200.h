@@ -216,6 +216,10 @@ typedef struct qrl_em_args {
 #define QRL_EM_FORCE_TILED   16  /* flags: use the tiled kernel whenever it supports the case, whatever the batch size */
 #define QRL_EM_ITEM_OUTPUT  32  /* flags: tiled kernel uses its one-(row, env)-item-per-lane output pass even when the
                                  * 16-byte-piece pass applies (A/B testing; n not in {2,4,8} always takes it) */
+#define QRL_EM_PDL          256 /* flags: launch the tiled kernel with programmatic stream serialization: it may be
+                                 * scheduled while the previous kernel of the stream drains (it waits for that kernel's
+                                 * completion before reading anything), which hides the launch latency between the
+                                 * back-to-back step kernels of a device-resident loop */
 #define QRL_EM_PACK_TMA     128 /* flags: reserved (accepted and ignored; the cache rows are written from registers) */
 /* flag bits 2, 4, 8 are diagnostics of the tiled kernel (skip produce / recurrence / output stage) and bits 512, 1024 of
  * the peer barrier (gpu-scope fences only / signal without waiting); results invalid */

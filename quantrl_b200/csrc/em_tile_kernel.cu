@@ -52,6 +52,12 @@ __device__ __forceinline__ void track_minmax(double v, double& lo, double& hi) {
 template <int N, int ILP>
 __global__ void __launch_bounds__(EM_TILE_THREADS, 1)
 em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const int C, const int nphase) {
+    // Programmatic dependent launch (QRL_EM_PDL): this grid may be scheduled while the previous kernel of the stream is
+    // still draining; everything it reads (dyn, x0, cumulative rewards) is only valid after the wait.  Its own
+    // dependents are released at once — they block on the same wait and, at 200 KB of shared memory per CTA, cannot
+    // become resident before this grid's CTAs have exited anyway; what overlaps is the launch latency.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const qrl_em_args a = resolve_dyn(a_in);
     extern __shared__ __align__(128) double sm[];
     const int E = a.n_envs, K = a.K;
@@ -546,8 +552,19 @@ static int launch_tile(const qrl_em_args& a, cudaStream_t st, int sms) {
         attr_set = true;
     }
     const PhiloxKeys keys = make_philox_keys(a.seed);
-    if (p.ilp == 2) em_tile_kernel<N, 2><<<p.grid, EM_TILE_THREADS, p.smem, st>>>(a, keys, p.G, p.C, p.nphase);
-    else em_tile_kernel<N, 1><<<p.grid, EM_TILE_THREADS, p.smem, st>>>(a, keys, p.G, p.C, p.nphase);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(p.grid);
+    cfg.blockDim = dim3(EM_TILE_THREADS);
+    cfg.dynamicSmemBytes = p.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (a.flags & QRL_EM_PDL) ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (p.ilp == 2) QRL_CUDA(cudaLaunchKernelEx(&cfg, em_tile_kernel<N, 2>, a, keys, p.G, p.C, p.nphase));
+    else QRL_CUDA(cudaLaunchKernelEx(&cfg, em_tile_kernel<N, 1>, a, keys, p.G, p.C, p.nphase));
     return after_launch("em_tile_kernel");
 }
 
