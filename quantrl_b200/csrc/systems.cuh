@@ -7,6 +7,8 @@
 //     void load(const double* params_row, const double* actions_row)
 //     void eval(double t, const double* y, double* dmodes /*2M*/, double (&A)[Q][Q]) const     // mode rates + drift
 //     double D(int i, int j) const                                                              // diffusion matrix
+//     static constexpr bool nz(int i, int k) / d_nz(int i, int j)   // false = A_ik / D_ij is a structural zero: the
+//                                                                   // right-hand side skips that product / addition
 // y = [Re a (M) | Im a (M) | vec(V) (Q*Q)]  (deterministic.py:667).
 #pragma once
 #include <cuda_runtime.h>
@@ -38,6 +40,10 @@ struct SysOptomech {
         A[3][0] = GR;   A[3][1] = GI;     A[3][2] = -om;  A[3][3] = -hg;
     }
     __device__ __forceinline__ double D(int i, int j) const { return i != j ? 0.0 : (i < 2 ? hk : dth); }
+    __host__ __device__ static constexpr bool nz(int i, int k) {
+        return !((i < 2 && k == 3) || (i == 2 && k < 2));
+    }
+    __host__ __device__ static constexpr bool d_nz(int i, int j) { return i == j; }
 };
 
 // kerr_chain: m=N, q=2N.  p = [kappa, chi, J, n_th, eps, Delta_0..Delta_{N-1}]
@@ -76,6 +82,11 @@ struct SysKerrChain {
         }
     }
     __device__ __forceinline__ double D(int i, int j) const { return i == j ? dd : 0.0; }
+    // 2x2 blocks on the diagonal, and the two hopping entries (different parity) of the neighbouring blocks
+    __host__ __device__ static constexpr bool nz(int i, int k) {
+        return (i / 2 == k / 2) || (((i / 2 - k / 2) == 1 || (k / 2 - i / 2) == 1) && (i % 2 != k % 2));
+    }
+    __host__ __device__ static constexpr bool d_nz(int i, int j) { return i == j; }
 };
 
 // const_AD: no modes; A, D given per env and constant over the interval (is_A_constant / is_D_constant,
@@ -98,6 +109,8 @@ struct SysConstAD {
             for (int j = 0; j < Q_; ++j) A[i][j] = Ac[i][j];
     }
     __device__ __forceinline__ double D(int i, int j) const { return Dc[i][j]; }
+    __host__ __device__ static constexpr bool nz(int, int) { return true; }
+    __host__ __device__ static constexpr bool d_nz(int, int) { return true; }
 };
 
 template <class S> struct is_const_ad { static constexpr bool value = false; };
