@@ -95,9 +95,9 @@ constexpr int MAX_STEPS = 4000000;
 }  // namespace erk
 
 template <class Sys, class TB, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) erk_kernel(const qrl_ode_args a) {
+__global__ void __launch_bounds__(BLOCK) erk_kernel(const __grid_constant__ qrl_ode_args a) {
     constexpr int D = Dim<Sys>::D, S = TB::S;
-    extern __shared__ double ks[];  // [S + 1][D][BLOCK]: stage derivatives, one column per thread (conflict-free)
+    extern __shared__ double ks[];  // [S + 2][D][BLOCK]: stage derivatives + the row being written, one column per thread
     const int E = a.n_envs, K = a.K;
     const int e = blockIdx.x * BLOCK + threadIdx.x;
     const bool live = e < E;
@@ -111,19 +111,14 @@ __global__ void __launch_bounds__(BLOCK) erk_kernel(const qrl_ode_args a) {
     for (int d = 0; d < D; ++d) y[d] = a.y0[(int64_t)el * D + d];
 
     double lo = INFINITY, hi = -INFINITY;
+    // rows go out through the shared, non-inlined emitter (ode_impl.cuh:emit_row_thread) from a scratch column
     auto emit = [&](int row, const double* v) {
         if (!live) return;
-        const int64_t base = ((int64_t)row * E + e) * D;
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            const double ob = v[d] + obs_noise_at(a, row, e, d, D);
-            if (a.states) a.states[base + d] = v[d];
-            if (a.observations) a.observations[base + d] = ob;
-            if (row == K && a.obs_last) a.obs_last[(int64_t)e * D + d] = ob;
-            lo = fmin(lo, ob);
-            hi = fmax(hi, ob);
-        }
-        ode_reward_row<Sys::M, Sys::Q>(a, row, e, v);
+        for (int d = 0; d < D; ++d) KS(S + 1, d) = v[d];
+        const double2 mm = emit_row_thread<Sys::M, Sys::Q>(a, row, e, &KS(S + 1, 0), BLOCK, lo, hi);
+        lo = mm.x;
+        hi = mm.y;
     };
     emit(0, y);
 
@@ -264,7 +259,7 @@ __global__ void __launch_bounds__(BLOCK) erk_kernel(const qrl_ode_args a) {
 template <class Sys, class TB>
 int launch_erk(const qrl_ode_args& a, cudaStream_t st, const char* name) {
     constexpr int D = Dim<Sys>::D, BLOCK = 32;
-    constexpr size_t smem = (size_t)(TB::S + 1) * D * BLOCK * sizeof(double);
+    constexpr size_t smem = (size_t)(TB::S + 2) * D * BLOCK * sizeof(double);
     if constexpr (smem > 220 * 1024) {
         return fail(QRL_E_UNSUPPORTED, "%s", "qrl_ode_step: this method's stage storage does not fit for this state size");
     } else {

@@ -73,8 +73,28 @@ __device__ __forceinline__ double obs_noise_at(const qrl_ode_args& a, int row, i
     return 0.0;
 }
 
-// fused reward of (row, env e) from the env's state vector y (covariance block at y + 2M): log-negativity of the States
-// or of the Observations (= states + this row's measurement noise); updates reward / reward_last / rewards_cum
+// fused reward of one row of one env from the vector yv the measure is defined on (the States row, or the Observations
+// row = states + measurement noise, for the odd reward kinds); covariance block at yv + 2M
+template <int M, int Q>
+__device__ __forceinline__ double ode_reward_value(int reward_kind, const double* yv) {
+    if constexpr (Q == 4) {
+        const double* V = yv + 2 * M;
+        if (reward_kind <= QRL_REWARD_ENTAN_LN_STATE) return log_negativity_2mode(V);
+        if (reward_kind <= QRL_REWARD_SYNC_C_STATE) return sync_complete_2mode(V);
+        if constexpr (M >= 2) return sync_phase_2mode(yv[0], yv[M], yv[1], yv[M + 1], V);   // re_0, im_0, re_1, im_1
+        else return sync_phase_2mode(1.0, 0.0, 1.0, 0.0, V);
+    } else {
+        return 0.0;
+    }
+}
+__device__ __forceinline__ void ode_reward_store(const qrl_ode_args& a, int row, int e, double r) {
+    if (a.reward) a.reward[(int64_t)row * a.n_envs + e] = r;
+    if (row == a.K) {
+        if (a.reward_last) a.reward_last[e] = r;
+        if (a.rewards_cum) a.rewards_cum[e] += r;
+    }
+}
+// from the env's state vector y in registers (RK4 kernels)
 template <int M, int Q>
 __device__ __forceinline__ void ode_reward_row(const qrl_ode_args& a, int row, int e, const double* y) {
     if constexpr (Q == 4) {
@@ -82,29 +102,79 @@ __device__ __forceinline__ void ode_reward_row(const qrl_ode_args& a, int row, i
         constexpr int D = 2 * M + Q * Q;
         // odd kinds are evaluated on the Observations (= states + this row's measurement noise), even ones on the States
         const bool on_obs = (a.reward_kind & 1) != 0;
-        double V[16];
+        double yv[D];
 #pragma unroll
-        for (int c = 0; c < 16; ++c)
-            V[c] = y[2 * M + c] + (on_obs ? obs_noise_at(a, row, e, 2 * M + c, D) : 0.0);
-        double r;
-        if (a.reward_kind <= QRL_REWARD_ENTAN_LN_STATE) r = log_negativity_2mode(V);
-        else if (a.reward_kind <= QRL_REWARD_SYNC_C_STATE) r = sync_complete_2mode(V);
-        else {
-            double md[4] = {1.0, 0.0, 1.0, 0.0};    // re_0, im_0, re_1, im_1
-            if constexpr (M >= 2) {
-                md[0] = y[0] + (on_obs ? obs_noise_at(a, row, e, 0, D) : 0.0);
-                md[1] = y[M] + (on_obs ? obs_noise_at(a, row, e, M, D) : 0.0);
-                md[2] = y[1] + (on_obs ? obs_noise_at(a, row, e, 1, D) : 0.0);
-                md[3] = y[M + 1] + (on_obs ? obs_noise_at(a, row, e, M + 1, D) : 0.0);
+        for (int c = 0; c < D; ++c) yv[c] = y[c];
+        if (on_obs && (a.obs_noise || a.obs_std)) {
+            // the measures read the covariance block and (phase synchronization) the amplitudes of modes 0 and 1
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                const bool is_amp = M >= 2 && (c == 0 || c == 1 || c == M || c == M + 1);
+                if (c >= 2 * M || (is_amp && a.reward_kind > QRL_REWARD_SYNC_C_STATE))
+                    yv[c] = y[c] + obs_noise_at(a, row, e, c, D);
             }
-            r = sync_phase_2mode(md[0], md[1], md[2], md[3], V);
         }
-        if (a.reward) a.reward[(int64_t)row * a.n_envs + e] = r;
-        if (row == a.K) {
-            if (a.reward_last) a.reward_last[e] = r;
-            if (a.rewards_cum) a.rewards_cum[e] += r;
+        ode_reward_store(a, row, e, ode_reward_value<M, Q>(a.reward_kind, yv));
+    }
+}
+
+// the same from a row in memory (shared-memory staging tile), kept out of line: the RK4 kernel's hot loop stays compact
+template <int M, int Q>
+__device__ __noinline__ void ode_reward_row_mem(const qrl_ode_args& a, int row, int e, const double* yrow) {
+    constexpr int D = 2 * M + Q * Q;
+    double y[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) y[c] = yrow[c];
+    ode_reward_row<M, Q>(a, row, e, y);
+}
+
+// One grid row of ONE environment, written by its own thread — the adaptive kernels, where the lanes of a warp reach
+// a row at different times.  The row sits in a shared-memory column (element d at col[d * stride]).  Deliberately NOT
+// inlined and not unrolled: inlined at every call site with the Philox measurement noise unrolled over the D
+// components, the adaptive kernels were 18k-28k instructions each and stalled on instruction fetch (ncu r1m, dopri5:
+// 6.9 no-instruction stall cycles per issued instruction).  Components move in pairs: one Philox call, one 16-byte
+// store per tensor.  Returns the updated (min, max) of the observations.
+template <int M, int Q>
+__device__ __noinline__ double2 emit_row_thread(const qrl_ode_args& a, int row, int e, const double* col, int stride,
+                                                double lo, double hi) {
+    constexpr int D = 2 * M + Q * Q, D2 = D / 2;
+    static_assert(D % 2 == 0, "even state size");
+    const int64_t base2 = ((int64_t)row * a.n_envs + e) * D2;
+    double2* st = a.states ? reinterpret_cast<double2*>(a.states) + base2 : nullptr;
+    double2* ob = a.observations ? reinterpret_cast<double2*>(a.observations) + base2 : nullptr;
+    double2* ol = (row == a.K && a.obs_last) ? reinterpret_cast<double2*>(a.obs_last) + (int64_t)e * D2 : nullptr;
+    const double2* fed = a.obs_noise ? reinterpret_cast<const double2*>(a.obs_noise) + base2 : nullptr;
+    const double* sd = (!fed && a.obs_std) ? a.obs_std + (int64_t)e * a.obs_std_stride_e : nullptr;
+    const bool want_reward = Q == 4 && a.reward_kind != QRL_REWARD_NONE;
+    const bool on_obs = (a.reward_kind & 1) != 0;
+    double yv[D];   // the vector the reward is defined on (local memory: indexed by the loop counter)
+#pragma unroll 1
+    for (int c = 0; c < D2; ++c) {
+        const double2 v = make_double2(col[(2 * c) * stride], col[(2 * c + 1) * stride]);
+        double2 o = v;
+        if (fed) {
+            const double2 z = fed[c];
+            o.x = v.x + z.x;
+            o.y = v.y + z.y;
+        } else if (sd) {
+            double z0, z1;
+            philox_normal2(a.seed, (uint32_t)(a.t_idx + row), a.episode, (uint32_t)(a.env_offset + e), 0x10000u + (uint32_t)c,
+                           z0, z1);
+            o.x = v.x + sd[2 * c] * z0;
+            o.y = v.y + sd[2 * c + 1] * z1;
+        }
+        if (st) st[c] = v;
+        if (ob) ob[c] = o;
+        if (ol) ol[c] = o;
+        lo = fmin(lo, fmin(o.x, o.y));
+        hi = fmax(hi, fmax(o.x, o.y));
+        if (want_reward) {
+            yv[2 * c] = on_obs ? o.x : v.x;
+            yv[2 * c + 1] = on_obs ? o.y : v.y;
         }
     }
+    if (want_reward) ode_reward_store(a, row, e, ode_reward_value<M, Q>(a.reward_kind, yv));
+    return make_double2(lo, hi);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -156,7 +226,7 @@ __device__ __forceinline__ void rk4_row_out(const qrl_ode_args& a, const double2
 }
 
 template <class Sys, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) rk4_kernel(const qrl_ode_args a) {
+__global__ void __launch_bounds__(BLOCK) rk4_kernel(const __grid_constant__ qrl_ode_args a) {
     constexpr int D = Dim<Sys>::D;
     static_assert(D % 2 == 0, "the state vector [Re a | Im a | vec(V)] has an even number of components");
     constexpr int D2 = D / 2, P2 = D2 | 1;
@@ -222,7 +292,8 @@ __global__ void __launch_bounds__(BLOCK) rk4_kernel(const qrl_ode_args a) {
             if (noise == 0) rk4_row_out<D, BLOCK, 0>(a, stage2, row, e0, n_live, lo, hi);
             else if (noise == 1) rk4_row_out<D, BLOCK, 1>(a, stage2, row, e0, n_live, lo, hi);
             else rk4_row_out<D, BLOCK, 2>(a, stage2, row, e0, n_live, lo, hi);
-            if (live) ode_reward_row<Sys::M, Sys::Q>(a, row, e, y);
+            if (Sys::Q == 4 && a.reward_kind != QRL_REWARD_NONE && live)
+                ode_reward_row_mem<Sys::M, Sys::Q>(a, row, e, reinterpret_cast<const double*>(stage2 + threadIdx.x * P2));
             __syncthreads();
         }
     }
@@ -257,9 +328,9 @@ constexpr int MAX_STEPS = 1000000;
 }  // namespace dp
 
 template <class Sys, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) dopri5_kernel(const qrl_ode_args a) {
+__global__ void __launch_bounds__(BLOCK) dopri5_kernel(const __grid_constant__ qrl_ode_args a) {
     constexpr int D = Dim<Sys>::D;
-    extern __shared__ double ks[];  // [7][D][BLOCK]: stage derivatives, one column per thread (conflict-free)
+    extern __shared__ double ks[];  // [7 + 1][D][BLOCK]: stage derivatives + the row being written, one column per thread
     const int E = a.n_envs, K = a.K;
     const int e = blockIdx.x * BLOCK + threadIdx.x;
     const bool live = e < E;
@@ -273,19 +344,17 @@ __global__ void __launch_bounds__(BLOCK) dopri5_kernel(const qrl_ode_args a) {
     for (int d = 0; d < D; ++d) y[d] = a.y0[(int64_t)el * D + d];
 
     double lo = INFINITY, hi = -INFINITY;
+    // the row staged in this thread's scratch column goes out through the shared (non-inlined) emitter
+    auto emit_staged = [&](int row) {
+        const double2 mm = emit_row_thread<Sys::M, Sys::Q>(a, row, e, &KS(7, 0), BLOCK, lo, hi);
+        lo = mm.x;
+        hi = mm.y;
+    };
     auto emit = [&](int row, const double* v) {
         if (!live) return;
-        const int64_t base = ((int64_t)row * E + e) * D;
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            const double ob = v[d] + obs_noise_at(a, row, e, d, D);
-            if (a.states) a.states[base + d] = v[d];
-            if (a.observations) a.observations[base + d] = ob;
-            if (row == K && a.obs_last) a.obs_last[(int64_t)e * D + d] = ob;
-            lo = fmin(lo, ob);
-            hi = fmax(hi, ob);
-        }
-        ode_reward_row<Sys::M, Sys::Q>(a, row, e, v);
+        for (int d = 0; d < D; ++d) KS(7, d) = v[d];
+        emit_staged(row);
     };
     emit(0, y);
 
@@ -372,19 +441,21 @@ __global__ void __launch_bounds__(BLOCK) dopri5_kernel(const qrl_ode_args a) {
                     emit(next_row, yt);
                 } else {
                     const double x = (tg - t) / ht;
-                    double yo[D];
+                    double pw[7];
+#pragma unroll
+                    for (int st = 0; st < 7; ++st)
+                        pw[st] = fma(fma(fma(dp::P[st][3], x, dp::P[st][2]), x, dp::P[st][1]), x, dp::P[st][0]);
 #pragma unroll
                     for (int d = 0; d < D; ++d) {
                         double q = 0.0;
 #pragma unroll
                         for (int st = 0; st < 7; ++st) {
                             if (st == 1) continue;
-                            const double p = fma(fma(fma(dp::P[st][3], x, dp::P[st][2]), x, dp::P[st][1]), x, dp::P[st][0]);
-                            q = fma(KS(st, d), p, q);
+                            q = fma(KS(st, d), pw[st], q);
                         }
-                        yo[d] = fma(ht * x, q, y[d]);
+                        KS(7, d) = fma(ht * x, q, y[d]);
                     }
-                    emit(next_row, yo);
+                    emit_staged(next_row);
                 }
                 ++next_row;
             }
@@ -576,6 +647,11 @@ namespace qrl {
 template <class Sys>
 int launch_ode(const qrl_ode_args& a, cudaStream_t st) {
     constexpr int D = Dim<Sys>::D;
+    // rows move as 16-byte pieces (LDG/STG.128): torch allocations are 256-byte aligned, slices at odd offsets are not
+    const uintptr_t align = (uintptr_t)a.y0 | (uintptr_t)a.states | (uintptr_t)a.observations | (uintptr_t)a.y_last |
+                            (uintptr_t)a.obs_last | (uintptr_t)a.obs_noise;
+    if (align & 15)
+        return fail(QRL_E_INVALID, "%s", "qrl_ode_step: y0, states, observations, y_last, obs_last and obs_noise must be 16-byte aligned");
     if (a.method == QRL_ODE_RK4) {
         if constexpr (Sys::Q == 4) {
             // small batches: 16 lanes per env (measured crossover with one thread per env at E ~ 8000 on B200:
@@ -589,10 +665,6 @@ int launch_ode(const qrl_ode_args& a, cudaStream_t st) {
         constexpr int BLOCK = 32;
         const size_t smem = (size_t)BLOCK * ((D / 2) | 1) * sizeof(double2);
         const int blocks = (a.n_envs + BLOCK - 1) / BLOCK;
-        // rows move as 16-byte pieces (LDG/STG.128): torch allocations are 256-byte aligned, slices of odd offset are not
-        const uintptr_t align = (uintptr_t)a.y0 | (uintptr_t)a.states | (uintptr_t)a.observations | (uintptr_t)a.y_last |
-                                (uintptr_t)a.obs_last | (uintptr_t)a.obs_noise;
-        if (align & 15) return fail(QRL_E_INVALID, "%s", "qrl_ode_step: y0, states, observations, y_last, obs_last and obs_noise must be 16-byte aligned");
         // 204 registers at q = 4 = 2 warps per scheduler; capping at 168 (3 warps, 4 bytes of spill) measured slower at
         // every batch size (0.67 vs 0.58 ms at E = 65536)
         rk4_kernel<Sys, BLOCK><<<blocks, BLOCK, smem, st>>>(a);
@@ -615,7 +687,7 @@ int launch_ode(const qrl_ode_args& a, cudaStream_t st) {
         default: break;
     }
     constexpr int BLOCK = 32;
-    const size_t smem = (size_t)7 * D * BLOCK * sizeof(double);
+    const size_t smem = (size_t)8 * D * BLOCK * sizeof(double);
     static bool attr_set = false;
     if (smem > 48 * 1024 && !attr_set) {
         QRL_CUDA(cudaFuncSetAttribute(dopri5_kernel<Sys, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
