@@ -284,7 +284,9 @@ typedef struct qrl_ode_args {
 } qrl_ode_args;
 
 #define QRL_ODE_FORCE_THREAD 1  /* flags: RK4 with one thread per env whatever the batch size (A/B testing) */
-#define QRL_ODE_FORCE_LANES  2  /* flags: RK4 with q*q lanes per env (q = 4 only) whatever the batch size */
+#define QRL_ODE_FORCE_LANES  2  /* flags: RK4 with q*q lanes per env (q = 4 only) whatever the batch size: the
+                                * warp-specialised split kernel (mode producer / covariance lanes / row writers) */
+#define QRL_ODE_LANES_SINGLE 4 /* flags: with FORCE_LANES (or a small batch), the single-role lanes kernel (A/B testing) */
 
 QRL_API int qrl_ode_step(const qrl_ode_args* args, void* stream);
 

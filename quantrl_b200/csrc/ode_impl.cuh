@@ -14,6 +14,7 @@
 //           grid, the interval end is hit exactly (actions change there).  Stage vectors live in shared memory.
 //           Controller = oracle/lyap_oracle.py:dopri5_dense_interval.
 #pragma once
+#include <stdlib.h>
 #include "common.cuh"
 #include "philox.cuh"
 #include "systems.cuh"
@@ -60,15 +61,24 @@ __device__ __forceinline__ void load_system(Sys& s, const qrl_ode_args& a, int e
     }
 }
 
+// The measurement noise of the deterministic path is a cold path (observation_stds is None by default in the reference,
+// envs/base.py:417-424) that costs ~150 instructions per pair of normals: one out-of-line copy per kernel instead of one
+// inlined copy per call site (the adaptive kernels were 18k-28k instructions and stalled on instruction fetch, ncu r1m).
+// Arguments by value: a by-reference qrl_ode_args would turn every field access into a generic load.
+static __device__ __noinline__ double2 philox_normal2_call(uint64_t seed, uint32_t tau, uint32_t episode, uint32_t env, uint32_t comp) {
+    double z0, z1;
+    philox_normal2(seed, tau, episode, env, comp, z0, z1);
+    return make_double2(z0, z1);
+}
+
 // measurement noise of one element (row tau, env, component d): fed tensor or the Philox stream
 // counter = (tau, episode, env_global, 0x10000 + d/2), z[d & 1]  (include/quantrl_b200.h)
 __device__ __forceinline__ double obs_noise_at(const qrl_ode_args& a, int row, int e, int d, int Dd) {
     if (a.obs_noise) return a.obs_noise[((int64_t)row * a.n_envs + e) * Dd + d];
     if (a.obs_std) {
-        double z0, z1;
-        philox_normal2(a.seed, (uint32_t)(a.t_idx + row), a.episode, (uint32_t)(a.env_offset + e),
-                       0x10000u + (uint32_t)(d >> 1), z0, z1);
-        return a.obs_std[(int64_t)e * a.obs_std_stride_e + d] * ((d & 1) ? z1 : z0);
+        const double2 z = philox_normal2_call(a.seed, (uint32_t)(a.t_idx + row), a.episode, (uint32_t)(a.env_offset + e),
+                                              0x10000u + (uint32_t)(d >> 1));
+        return a.obs_std[(int64_t)e * a.obs_std_stride_e + d] * ((d & 1) ? z.y : z.x);
     }
     return 0.0;
 }
@@ -118,7 +128,8 @@ __device__ __forceinline__ void ode_reward_row(const qrl_ode_args& a, int row, i
     }
 }
 
-// the same from a row in memory (shared-memory staging tile), kept out of line: the RK4 kernel's hot loop stays compact
+// the same from a row in memory, OUT OF LINE (a cold path: the hot loops of the callers stay compact; the by-reference
+// argument block costs generic loads here, which is why the hot row writers do not go through such a call)
 template <int M, int Q>
 __device__ __noinline__ void ode_reward_row_mem(const qrl_ode_args& a, int row, int e, const double* yrow) {
     constexpr int D = 2 * M + Q * Q;
@@ -129,14 +140,14 @@ __device__ __noinline__ void ode_reward_row_mem(const qrl_ode_args& a, int row, 
 }
 
 // One grid row of ONE environment, written by its own thread — the adaptive kernels, where the lanes of a warp reach
-// a row at different times.  The row sits in a shared-memory column (element d at col[d * stride]).  Deliberately NOT
-// inlined and not unrolled: inlined at every call site with the Philox measurement noise unrolled over the D
-// components, the adaptive kernels were 18k-28k instructions each and stalled on instruction fetch (ncu r1m, dopri5:
-// 6.9 no-instruction stall cycles per issued instruction).  Components move in pairs: one Philox call, one 16-byte
-// store per tensor.  Returns the updated (min, max) of the observations.
+// a row at different times.  The row sits in a shared-memory column (element d at col[d * stride]).  A compact loop
+// (not unrolled) over PAIRS of components: one Philox call (out of line), one 16-byte store per tensor.  Unrolled over
+// the D components with the Philox code inlined at every call site, the adaptive kernels were 18k-28k instructions each
+// and stalled on instruction fetch (ncu r1m, dopri5: 6.9 no-instruction stall cycles per issued instruction).
+// Returns the updated (min, max) of the observations.
 template <int M, int Q>
-__device__ __noinline__ double2 emit_row_thread(const qrl_ode_args& a, int row, int e, const double* col, int stride,
-                                                double lo, double hi) {
+__device__ __forceinline__ double2 emit_row_thread(const qrl_ode_args& a, int row, int e, const double* col, int stride,
+                                                   double lo, double hi) {
     constexpr int D = 2 * M + Q * Q, D2 = D / 2;
     static_assert(D % 2 == 0, "even state size");
     const int64_t base2 = ((int64_t)row * a.n_envs + e) * D2;
@@ -146,8 +157,7 @@ __device__ __noinline__ double2 emit_row_thread(const qrl_ode_args& a, int row, 
     const double2* fed = a.obs_noise ? reinterpret_cast<const double2*>(a.obs_noise) + base2 : nullptr;
     const double* sd = (!fed && a.obs_std) ? a.obs_std + (int64_t)e * a.obs_std_stride_e : nullptr;
     const bool want_reward = Q == 4 && a.reward_kind != QRL_REWARD_NONE;
-    const bool on_obs = (a.reward_kind & 1) != 0;
-    double yv[D];   // the vector the reward is defined on (local memory: indexed by the loop counter)
+    double yv[D];   // the States row for the fused reward (local memory: indexed by the loop counter)
 #pragma unroll 1
     for (int c = 0; c < D2; ++c) {
         const double2 v = make_double2(col[(2 * c) * stride], col[(2 * c + 1) * stride]);
@@ -157,11 +167,10 @@ __device__ __noinline__ double2 emit_row_thread(const qrl_ode_args& a, int row, 
             o.x = v.x + z.x;
             o.y = v.y + z.y;
         } else if (sd) {
-            double z0, z1;
-            philox_normal2(a.seed, (uint32_t)(a.t_idx + row), a.episode, (uint32_t)(a.env_offset + e), 0x10000u + (uint32_t)c,
-                           z0, z1);
-            o.x = v.x + sd[2 * c] * z0;
-            o.y = v.y + sd[2 * c + 1] * z1;
+            const double2 z = philox_normal2_call(a.seed, (uint32_t)(a.t_idx + row), a.episode, (uint32_t)(a.env_offset + e),
+                                                  0x10000u + (uint32_t)c);
+            o.x = v.x + sd[2 * c] * z.x;
+            o.y = v.y + sd[2 * c + 1] * z.y;
         }
         if (st) st[c] = v;
         if (ob) ob[c] = o;
@@ -169,11 +178,11 @@ __device__ __noinline__ double2 emit_row_thread(const qrl_ode_args& a, int row, 
         lo = fmin(lo, fmin(o.x, o.y));
         hi = fmax(hi, fmax(o.x, o.y));
         if (want_reward) {
-            yv[2 * c] = on_obs ? o.x : v.x;
-            yv[2 * c + 1] = on_obs ? o.y : v.y;
+            yv[2 * c] = v.x;
+            yv[2 * c + 1] = v.y;
         }
     }
-    if (want_reward) ode_reward_store(a, row, e, ode_reward_value<M, Q>(a.reward_kind, yv));
+    if (want_reward) ode_reward_row_mem<M, Q>(a, row, e, yv);
     return make_double2(lo, hi);
 }
 
@@ -206,12 +215,11 @@ __device__ __forceinline__ void rk4_row_out(const qrl_ode_args& a, const double2
             o.x = v.x + z.x;
             o.y = v.y + z.y;
         } else if constexpr (NOISE == 2) {
-            double z0, z1;
-            philox_normal2(a.seed, (uint32_t)(a.t_idx + row), a.episode, (uint32_t)(a.env_offset + e0 + elx),
-                           0x10000u + (uint32_t)c, z0, z1);
+            const double2 z = philox_normal2_call(a.seed, (uint32_t)(a.t_idx + row), a.episode,
+                                                  (uint32_t)(a.env_offset + e0 + elx), 0x10000u + (uint32_t)c);
             const double* sd = a.obs_std + (int64_t)(e0 + elx) * a.obs_std_stride_e + 2 * c;
-            o.x = v.x + sd[0] * z0;
-            o.y = v.y + sd[1] * z1;
+            o.x = v.x + sd[0] * z.x;
+            o.y = v.y + sd[1] * z.y;
         }
         if (st) st[idx2] = v;
         if (ob) ob[idx2] = o;
@@ -495,7 +503,7 @@ __global__ void __launch_bounds__(BLOCK) dopri5_kernel(const __grid_constant__ q
 // of one env cover its d contiguous doubles.
 // ------------------------------------------------------------------------------------------------------------------
 template <class Sys, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) rk4_lanes_kernel(const qrl_ode_args a) {
+__global__ void __launch_bounds__(BLOCK) rk4_lanes_kernel(const __grid_constant__ qrl_ode_args a) {
     constexpr int M = Sys::M, Q = Sys::Q, D = Dim<Sys>::D, L = Q * Q;   // L lanes per env
     constexpr int M2 = 2 * M > 0 ? 2 * M : 1;
     static_assert(L == 16, "rk4_lanes_kernel is written for q = 4");
@@ -564,7 +572,7 @@ __global__ void __launch_bounds__(BLOCK) rk4_lanes_kernel(const qrl_ode_args a) 
             for (int c = 0; c < 2 * M; ++c) yfull[c] = ym[c];
 #pragma unroll
             for (int c = 0; c < L; ++c) yfull[2 * M + c] = sV[0][g][c];
-            ode_reward_row<M, Q>(a, row, e, yfull);
+            ode_reward_row_mem<M, Q>(a, row, e, yfull);
         }
         __syncwarp();
     };
@@ -640,6 +648,225 @@ __global__ void __launch_bounds__(BLOCK) rk4_lanes_kernel(const qrl_ode_args a) 
     if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// RK4, warp-specialised small-batch kernel (q = 4).  With E = 1024 there is at most one warp per scheduler, so every
+// instruction of a lane's loop is on the critical path.  The classical mode amplitudes do not depend on the
+// covariance, and writing a row does not feed back into the integration, so both are taken OUT of the covariance
+// lanes' dependency chain.  Per CTA of EPB environments, time cut into chunks of C sub-steps, three roles in a 3-stage
+// pipeline with one __syncthreads per chunk (like the tiled EM kernel):
+//   iteration it:  producer warp   chunk it      one lane per env integrates the modes with RK4 and publishes, per RK
+//                                                stage, the drift matrix A (8 pieces of 16 bytes), and per sub-step the
+//                                                new amplitudes (into the row ring)
+//                  consumer warps  chunk it-1    EPB/2 warps, q*q = 16 lanes per env: lane (i,j) owns V_ij; a stage is
+//                                                STS V_ij -> __syncwarp -> LDS row i / column j -> two 4-FMA chains ->
+//                                                RK update (the A rows are loaded before the warp barrier); after a
+//                                                sub-step the lane drops V_ij into the row ring: ONE store
+//                  4 writer warps  chunk it-2    rows [modes | V] of the CTA's envs leave the ring as contiguous runs of
+//                                                16-byte pieces (+ measurement noise, min/max, fused reward, carry-over)
+// Same operations in the same order as rk4_lanes_kernel / rk4_kernel: results are bit-identical.
+// ------------------------------------------------------------------------------------------------------------------
+template <class Sys, int EPB>
+__global__ void __launch_bounds__(EPB * 16 + 32 + 128) rk4_split_kernel(const __grid_constant__ qrl_ode_args a, const int C) {
+    constexpr int M = Sys::M, Q = Sys::Q, D = Dim<Sys>::D, L = Q * Q, D2 = D / 2;
+    constexpr int M2 = 2 * M > 0 ? 2 * M : 1;
+    static_assert(L == 16 && EPB % 2 == 0 && EPB <= 32 && D % 2 == 0, "q = 4, an even number of envs per CTA");
+    constexpr int NV = EPB * L;              // consumer threads
+    constexpr int PP = EPB + 1;              // piece pitch of the A ring in 16-byte units: conflict-free writes and reads
+    constexpr int RW = EPB * D;              // doubles per ring row: the CTA's envs, [modes | V] each
+    extern __shared__ double2 ring2[];
+    // A ring: [2 buffers][C sub-steps * 4 stages][8 pieces][PP]   (producer -> consumers)
+    // row ring: [3 buffers][C sub-steps][EPB][D]                   (producer: modes, consumers: V  -> writer)
+    double2* Ar = ring2;
+    double* Rr = reinterpret_cast<double*>(ring2 + (size_t)2 * C * 4 * 8 * PP);
+    __shared__ __align__(16) double sV[2][EPB][L];   // covariance exchange, double buffered over the stages
+    const int E = a.n_envs, K = a.K;
+    const int tid = threadIdx.x;
+    const int role = tid < NV ? 0 : (tid < NV + 32 ? 1 : 2);   // 0 consumer, 1 producer, 2 writer
+    const int e0 = blockIdx.x * EPB;
+    const int n_live = min(EPB, E - e0);
+    const int nsub = a.substeps;
+    const int NS = K * nsub;                 // sub-steps of the interval
+    const int NCH = (NS + C - 1) / C;
+    const double h = a.t_ssz / (double)nsub, hh = 0.5 * h, h6 = h / 6.0;
+    double lo = INFINITY, hi = -INFINITY;
+
+    // ---- producer state: one lane per env ----
+    const int pg = tid - NV;
+    const bool p_on = role == 1 && pg < EPB;
+    Sys s;
+    double ym[M2];
+    if (p_on) {
+        const int el = min(e0 + pg, E - 1);
+        load_system(s, a, el);
+#pragma unroll
+        for (int c = 0; c < 2 * M; ++c) ym[c] = a.y0[(int64_t)el * D + c];
+    }
+    int p_row = 1, p_sub = 0;                // row being integrated towards, sub-step inside it
+    // ---- consumer state: lane (i, j) of env g ----
+    const int g = tid / L, l = tid % L;
+    const int i = l / Q, j = l % Q;
+    double v = 0.0, dij = 0.0;               // my covariance element, my D_ij
+    if (role == 0) {
+        const int el = min(e0 + g, E - 1);
+        Sys sc;
+        load_system(sc, a, el);
+        dij = sc.D(i, j);
+        v = a.y0[(int64_t)el * D + 2 * M + l];
+    }
+    const int oi0 = (2 * i) * PP + g, oi1 = (2 * i + 1) * PP + g, oj0 = (2 * j) * PP + g, oj1 = (2 * j + 1) * PP + g;
+    int par = 0;                             // exchange-buffer parity of the next stage
+    auto stage = [&](const double2* A2, double vt) -> double {
+        sV[par][g][l] = vt;
+        const double2 ai0 = A2[oi0], ai1 = A2[oi1], aj0 = A2[oj0], aj1 = A2[oj1];   // independent of the exchange
+        __syncwarp();
+        const double2* Vi = reinterpret_cast<const double2*>(sV[par][g] + i * Q);
+        const double2 vi0 = Vi[0], vi1 = Vi[1];
+        const double* Vc = sV[par][g] + j;
+        const double v0 = Vc[0], v1 = Vc[Q], v2 = Vc[2 * Q], v3 = Vc[3 * Q];
+        par ^= 1;
+        // same order of operations as rhs(): (A V)_ij and (V A^T)_ij as two chains over k, then (av + va) + D_ij
+        const double av = fma(ai1.y, v3, fma(ai1.x, v2, fma(ai0.y, v1, fma(ai0.x, v0, 0.0))));
+        const double va = fma(vi1.y, aj1.y, fma(vi1.x, aj1.x, fma(vi0.y, aj0.y, fma(vi0.x, aj0.x, 0.0))));
+        return (av + va) + dij;
+    };
+    // ---- writer: n_rows grid rows (first one = row_first, in ring slot slot_first, then every nsub-th slot) --------
+    // One flat walk over the 16-byte pieces of all rows of a chunk (a row = n_live * D2 contiguous pieces in the ring
+    // and in the (K+1, E, D) blocks), one piece per lane and trip; NaN-ignoring min/max by compare+select.
+    constexpr int NW = 128;                  // writer threads (4 warps: one warp needs ~210 cycles per trip of this walk)
+    const int lane = tid - NV - 32;          // writer thread index
+    const int RL2 = n_live * D2;             // live 16-byte pieces per row
+    const int noise = a.obs_noise ? 1 : (a.obs_std ? 2 : 0);
+    const int64_t row_pitch2 = (int64_t)E * D2;
+    auto write_rows = [&](const double* Rslot, int row_first, int n_rows) {
+        const double2* R2 = reinterpret_cast<const double2*>(Rslot);
+        const int ring_pitch2 = nsub * (RW / 2);                 // ring pieces between two rows
+        int r = 0, p = lane;                                     // row within the call, piece within the row
+        while (p >= RL2) { p -= RL2; ++r; }
+        int64_t g2 = ((int64_t)row_first * E + e0) * D2 + (int64_t)r * row_pitch2 + p;   // piece index in the global blocks
+        int s2 = r * ring_pitch2 + p;                            // piece index in the ring
+        while (r < n_rows) {
+            const double2 x = R2[s2];
+            const int row = row_first + r;
+            double2 o = x;
+            if (noise == 1) {
+                const double2 z = reinterpret_cast<const double2*>(a.obs_noise)[g2];
+                o.x = x.x + z.x;
+                o.y = x.y + z.y;
+            } else if (noise == 2) {
+                const int elx = p / D2, c = p - elx * D2;
+                const double2 z = philox_normal2_call(a.seed, (uint32_t)(a.t_idx + row), a.episode,
+                                                      (uint32_t)(a.env_offset + e0 + elx), 0x10000u + (uint32_t)c);
+                const double* sd = a.obs_std + (int64_t)(e0 + elx) * a.obs_std_stride_e + 2 * c;
+                o.x = x.x + sd[0] * z.x;
+                o.y = x.y + sd[1] * z.y;
+            }
+            if (a.states) reinterpret_cast<double2*>(a.states)[g2] = x;
+            if (a.observations) reinterpret_cast<double2*>(a.observations)[g2] = o;
+            if (row == K) {
+                const int64_t c2 = (int64_t)e0 * D2 + p;
+                if (a.y_last) reinterpret_cast<double2*>(a.y_last)[c2] = x;
+                if (a.obs_last) reinterpret_cast<double2*>(a.obs_last)[c2] = o;
+                if (a.nan_flag && !(isfinite(x.x) && isfinite(x.y))) *a.nan_flag = 1;
+            }
+            lo = (o.x < lo) ? o.x : lo;
+            lo = (o.y < lo) ? o.y : lo;
+            hi = (o.x > hi) ? o.x : hi;
+            hi = (o.y > hi) ? o.y : hi;
+            p += NW; g2 += NW; s2 += NW;
+            while (p >= RL2 && r < n_rows) { p -= RL2; ++r; g2 += row_pitch2 - RL2; s2 += ring_pitch2 - RL2; }
+        }
+        if (a.reward_kind != QRL_REWARD_NONE && lane < n_live)
+            for (int rr = 0; rr < n_rows; ++rr)
+                ode_reward_row_mem<M, Q>(a, row_first + rr, e0 + lane, Rslot + (size_t)rr * nsub * RW + lane * D);
+    };
+
+    // ---- row 0: the initial state goes through slot 0 of row buffer 2 (free until iteration 2) ----
+    {
+        double* R0 = Rr + (size_t)2 * C * RW;
+        for (int idx = tid; idx < n_live * D; idx += EPB * 16 + 32 + NW) R0[idx] = a.y0[(int64_t)e0 * D + idx];
+        __syncthreads();
+        if (role == 2) write_rows(R0, 0, 1);
+        __syncthreads();
+    }
+    int w_row = 0, w_until = nsub;           // writer: last row written, sub-steps until the next one
+    for (int it = 0; it < NCH + 2; ++it) {
+        if (role == 1) {
+            if (p_on && it < NCH && !(a.flags & 8)) {
+                // ---------------- producer: chunk `it` -> A buffer it & 1, modes into row buffer it % 3 ----------------
+                const int gs0 = it * C, gs1 = min(gs0 + C, NS);
+                double2* Ab = Ar + (size_t)(it & 1) * C * 4 * 8 * PP;
+                double* Rb = Rr + (size_t)(it % 3) * C * RW + pg * D;
+                auto publish = [&](int slot, const double (&A)[Q][Q]) {
+                    double2* dst = Ab + (size_t)slot * 8 * PP + pg;
+#pragma unroll
+                    for (int r = 0; r < Q; ++r)
+#pragma unroll
+                        for (int c = 0; c < Q; c += 2) dst[((r * Q + c) / 2) * PP] = make_double2(A[r][c], A[r][c + 1]);
+                };
+                for (int gs = gs0; gs < gs1; ++gs) {
+                    const double t = (a.t0 + (double)(p_row - 1) * a.t_ssz) + (double)p_sub * h;
+                    if (++p_sub == nsub) { p_sub = 0; ++p_row; }
+                    const int slot = (gs - gs0) * 4;
+                    double A[Q][Q], dm[M2], ymt[M2], accm[M2];
+                    s.eval(t, ym, dm, A);
+                    publish(slot, A);
+#pragma unroll
+                    for (int c = 0; c < 2 * M; ++c) { accm[c] = dm[c]; ymt[c] = fma(hh, dm[c], ym[c]); }
+                    s.eval(t + hh, ymt, dm, A);
+                    publish(slot + 1, A);
+#pragma unroll
+                    for (int c = 0; c < 2 * M; ++c) { accm[c] = fma(2.0, dm[c], accm[c]); ymt[c] = fma(hh, dm[c], ym[c]); }
+                    s.eval(t + hh, ymt, dm, A);
+                    publish(slot + 2, A);
+#pragma unroll
+                    for (int c = 0; c < 2 * M; ++c) { accm[c] = fma(2.0, dm[c], accm[c]); ymt[c] = fma(h, dm[c], ym[c]); }
+                    s.eval(t + h, ymt, dm, A);
+                    publish(slot + 3, A);
+#pragma unroll
+                    for (int c = 0; c < 2 * M; ++c) {
+                        ym[c] = fma(h6, accm[c] + dm[c], ym[c]);
+                        Rb[(gs - gs0) * RW + c] = ym[c];
+                    }
+                }
+            }
+        } else if (role == 0) {
+            if (it >= 1 && it <= NCH && !(a.flags & 16)) {
+                // ---------------- consumers: chunk `it - 1` ----------------
+                const int cc = it - 1;
+                const int ns = min(C, NS - cc * C);
+                const double2* A2 = Ar + (size_t)(cc & 1) * C * 4 * 8 * PP;
+                double* Rv = Rr + (size_t)(cc % 3) * C * RW + g * D + 2 * M + l;
+                for (int ss = 0; ss < ns; ++ss, A2 += 32 * PP, Rv += RW) {
+                    double k = stage(A2, v);
+                    double accv = k;
+                    k = stage(A2 + 8 * PP, fma(hh, k, v));
+                    accv = fma(2.0, k, accv);
+                    k = stage(A2 + 16 * PP, fma(hh, k, v));
+                    accv = fma(2.0, k, accv);
+                    k = stage(A2 + 24 * PP, fma(h, k, v));
+                    v = fma(h6, accv + k, v);
+                    *Rv = v;
+                }
+            }
+        } else if (it >= 2 && !(a.flags & 32)) {
+            // ---------------- writer: chunk `it - 2` ----------------
+            const int cw = it - 2;
+            const int ns = min(C, NS - cw * C);
+            const double* Rb = Rr + (size_t)(cw % 3) * C * RW;
+            // rows of this chunk: the sub-steps ss with (cw * C + ss + 1) % nsub == 0
+            if (w_until <= ns) {
+                const int n_rows = (ns - w_until) / nsub + 1;
+                write_rows(Rb + (size_t)(w_until - 1) * RW, w_row + 1, n_rows);
+                w_row += n_rows;
+                w_until += n_rows * nsub;
+            }
+            w_until -= ns;
+        }
+        __syncthreads();
+    }
+    if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
+}
+
 }  // namespace qrl
 #include "ode_erk.cuh"
 namespace qrl {
@@ -654,12 +881,33 @@ int launch_ode(const qrl_ode_args& a, cudaStream_t st) {
         return fail(QRL_E_INVALID, "%s", "qrl_ode_step: y0, states, observations, y_last, obs_last and obs_noise must be 16-byte aligned");
     if (a.method == QRL_ODE_RK4) {
         if constexpr (Sys::Q == 4) {
-            // small batches: 16 lanes per env (measured crossover with one thread per env at E ~ 8000 on B200:
-            // 95 vs 300 us at E = 1024, 175 vs 301 us at 4096, 317 vs 301 us at 8192; tools/quick_ode_bench.py)
-            if ((a.n_envs <= 6144 || (a.flags & QRL_ODE_FORCE_LANES)) && !(a.flags & QRL_ODE_FORCE_THREAD)) {
-                constexpr int BL = 64;
-                rk4_lanes_kernel<Sys, BL><<<(a.n_envs + BL / 16 - 1) / (BL / 16), BL, 0, st>>>(a);
-                return after_launch("rk4_lanes_kernel");
+            // small batches, 16 lanes per env (B200, 100 sub-steps, tools/quick_ode_bench.py):
+            //   E      split (3 roles)   lanes (1 role)   thread per env
+            //   1024   54 us             74 us            195 us
+            //   2048   107 us            98 us            164 us        (two split CTAs per SM: shared-memory bound)
+            //   4096   206 us            171 us           165 us
+            // FORCE_LANES picks the split kernel, FORCE_LANES | QRL_ODE_LANES_SINGLE the single-role lanes kernel
+            const bool force_lanes = (a.flags & QRL_ODE_FORCE_LANES) != 0;
+            if ((a.n_envs <= 3072 || force_lanes) && !(a.flags & QRL_ODE_FORCE_THREAD)) {
+                if ((a.flags & QRL_ODE_LANES_SINGLE) || (a.n_envs > 1536 && !force_lanes)) {   // functor inside the lanes' chain
+                    constexpr int BL = 64;
+                    rk4_lanes_kernel<Sys, BL><<<(a.n_envs + BL / 16 - 1) / (BL / 16), BL, 0, st>>>(a);
+                    return after_launch("rk4_lanes_kernel");
+                }
+                constexpr int EPB = 8;
+                const int NS = a.K * a.substeps;
+                static const char* c_env = getenv("QRL_ODE_SPLIT_C");   // tuning knob: sub-steps per chunk
+                const int c_want = c_env ? atoi(c_env) : 8;
+                const int c_max = c_want >= 1 && c_want <= 16 ? c_want : 8;
+                const int C = NS < c_max ? (NS > 0 ? NS : 1) : c_max;
+                const size_t smem = (size_t)2 * C * 4 * 8 * (EPB + 1) * sizeof(double2) + (size_t)3 * C * EPB * D * sizeof(double);
+                static bool attr_set = false;
+                if (!attr_set) {
+                    QRL_CUDA(cudaFuncSetAttribute(rk4_split_kernel<Sys, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                    attr_set = true;
+                }
+                rk4_split_kernel<Sys, EPB><<<(a.n_envs + EPB - 1) / EPB, EPB * 16 + 32 + 128, smem, st>>>(a, C);
+                return after_launch("rk4_split_kernel");
             }
         }
         constexpr int BLOCK = 32;

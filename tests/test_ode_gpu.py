@@ -176,10 +176,12 @@ def test_ode_edge_cases_and_errors(native, cuda):
         N.ode_step(a)
 
 
+@pytest.mark.parametrize("lanes_flags", [2, 6])   # 2: warp-specialised split kernel, 6: single-role lanes kernel
 @pytest.mark.parametrize("E", [1, 3, 17, 1024])
-def test_rk4_lanes_kernel_equals_thread_kernel(native, cuda, E):
-    """q*q lanes per env (small batches) vs one thread per env: same RK4, sums associate differently only inside
-    (A V + V A^T), so agreement is to rounding; fed noise, min/max and last rows included."""
+def test_rk4_lanes_kernel_equals_thread_kernel(native, cuda, E, lanes_flags):
+    """q*q lanes per env (small batches; split = mode producer / covariance lanes / row writers, or single-role) vs
+    one thread per env: same RK4, same order of operations; fed noise, min/max, last rows, sub-steps that are not
+    rows, ragged last block and an interval shorter than one chunk included."""
     from quantrl_b200 import _native as N
     rng = np.random.default_rng(E)
     for system, m in (("optomech", 2), ("kerr_chain", 2)):
@@ -190,16 +192,23 @@ def test_rk4_lanes_kernel_equals_thread_kernel(native, cuda, E):
         u = rng.uniform(-1, 1, E)
         noise = 1e-3 * rng.standard_normal((31, E, 20))
         kw = dict(params=p, actions=u, obs_noise=noise, substeps=2)
-        a = ode_step(system, m, 4, y0, 30, 0.5, 0.01, flags=N.ODE_FORCE_LANES, **kw)
+        a = ode_step(system, m, 4, y0, 30, 0.5, 0.01, flags=lanes_flags, **kw)
         b = ode_step(system, m, 4, y0, 30, 0.5, 0.01, flags=N.ODE_FORCE_THREAD, **kw)
         for key in ("states", "observations", "y_last", "obs_last"):
             torch.testing.assert_close(a[key], b[key], rtol=1e-13, atol=1e-15)
         torch.testing.assert_close(a["minmax"], b["minmax"], rtol=1e-13, atol=1e-15)
+        # Philox measurement noise (same stream in every kernel), 3 sub-steps per row, 2 rows (< one chunk)
+        kw = dict(params=p, actions=u, substeps=3, philox=dict(seed=11, episode=2, t_idx=40, env_offset=5),
+                  obs_std=np.full((E, 20), 1e-3))
+        a = ode_step(system, m, 4, y0, 2, 0.5, 0.01, flags=lanes_flags, **kw)
+        b = ode_step(system, m, 4, y0, 2, 0.5, 0.01, flags=N.ODE_FORCE_THREAD, **kw)
+        for key in ("states", "observations", "y_last", "obs_last", "minmax"):
+            torch.testing.assert_close(a[key], b[key], rtol=1e-13, atol=1e-15)
     # const_AD (no modes) through the lanes kernel
     A = -np.eye(4) * 1.5 + 0.2 * rng.standard_normal((E, 4, 4))
     Dm = rng.standard_normal((E, 4, 4))
     V0 = rng.standard_normal((E, 16))
-    a = ode_step("const_AD", 0, 4, V0, 12, 0.0, 0.05, A=A, D=Dm, flags=N.ODE_FORCE_LANES)
+    a = ode_step("const_AD", 0, 4, V0, 12, 0.0, 0.05, A=A, D=Dm, flags=lanes_flags)
     b = ode_step("const_AD", 0, 4, V0, 12, 0.0, 0.05, A=A, D=Dm, flags=N.ODE_FORCE_THREAD)
     torch.testing.assert_close(a["states"], b["states"], rtol=1e-13, atol=1e-15)
 
