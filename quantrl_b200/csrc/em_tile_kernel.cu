@@ -110,7 +110,8 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
     // piece pass: n/2 adjacent lanes per environment
     constexpr bool PIECE_N = (N == 2 || N == 4 || N == 8);
     constexpr int L = PIECE_N ? N / 2 : 1;
-    const bool piece_out = PIECE_N && vec_g && !(a.flags & QRL_EM_ITEM_OUTPUT);
+    // (the piece pass walks the blocks with 32-bit element offsets)
+    const bool piece_out = PIECE_N && vec_g && !(a.flags & QRL_EM_ITEM_OUTPUT) && (int64_t)(K + 1) * row < (1ll << 31);
 
     double lo = INFINITY, hi = -INFINITY;
 
@@ -206,6 +207,11 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
     auto piece_pass = [&](const double* Xb, const double* Vb, int r_first, int ns) {
         if constexpr (PIECE_N) {
             int sl = q_sl0, pc = q_pc0;
+            // running element offset of this lane's piece in the (K+1, E, N) blocks: one 32-bit add per trip instead
+            // of a 64-bit multiply-add chain per tensor (the pass is issue bound: ncu r1k, 136 instructions per trip)
+            const uint32_t row32 = (uint32_t)row;
+            uint32_t g = (uint32_t)(r_first + sl) * row32 + (uint32_t)(e0 * N + 2 * pc);
+            const uint32_t g_step = (uint32_t)q_dsl * row32 + (uint32_t)(2 * q_dpc), g_wrap = row32 - (uint32_t)(2 * PR);
             // warp-uniform trip count (the shuffles below need all 32 lanes): lane 0 holds the smallest piece index
             int sl_lead = __shfl_sync(0xffffffffu, sl, 0);
             while (sl_lead < ns) {
@@ -215,7 +221,6 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
                 const double2 v2 = *reinterpret_cast<const double2*>(Vb + off);
                 const double2 o2 = make_double2(__dadd_rn(x2.x, v2.x), __dadd_rn(x2.y, v2.y));
                 const int r = r_first + sl;
-                const int64_t g = (int64_t)r * row + (int64_t)e0 * N + 2 * pc;
                 if (live) {
                     if (a.states) *reinterpret_cast<double2*>(a.states + g) = x2;
                     if (a.observations) *reinterpret_cast<double2*>(a.observations + g) = o2;
@@ -238,7 +243,7 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
                 }
                 if (live) {
                     const int el = pc / L, e = e0 + el;
-                    if (has_reward && q_h == L - 1 && a.reward) a.reward[(int64_t)r * E + e] = rv;
+                    if (has_reward && q_h == L - 1 && a.reward) a.reward[(uint32_t)r * (uint32_t)E + (uint32_t)e] = rv;
                     if (r == K) {
                         if (has_reward && q_h == L - 1) {
                             if (a.reward_last) a.reward_last[e] = rv;
@@ -253,7 +258,8 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
                 }
                 sl += q_dsl;
                 pc += q_dpc;
-                if (pc >= PR) { pc -= PR; ++sl; }
+                g += g_step;
+                if (pc >= PR) { pc -= PR; ++sl; g += g_wrap; }
                 sl_lead = __shfl_sync(0xffffffffu, sl, 0);
             }
         }

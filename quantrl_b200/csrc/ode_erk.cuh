@@ -97,7 +97,8 @@ constexpr int MAX_STEPS = 4000000;
 template <class Sys, class TB, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) erk_kernel(const __grid_constant__ qrl_ode_args a) {
     constexpr int D = Dim<Sys>::D, S = TB::S;
-    extern __shared__ double ks[];  // [S + 2][D][BLOCK]: stage derivatives + the row being written, one column per thread
+    extern __shared__ double ks[];  // [S + 1][D][BLOCK]: stage derivatives k_0..k_{S-1}, one column per thread; column S
+                                    // stages the row being written (k_S = f(t + h, y_new) stays in registers)
     const int E = a.n_envs, K = a.K;
     const int e = blockIdx.x * BLOCK + threadIdx.x;
     const bool live = e < E;
@@ -115,8 +116,8 @@ __global__ void __launch_bounds__(BLOCK) erk_kernel(const __grid_constant__ qrl_
     auto emit = [&](int row, const double* v) {
         if (!live) return;
 #pragma unroll
-        for (int d = 0; d < D; ++d) KS(S + 1, d) = v[d];
-        const double2 mm = emit_row_thread<Sys::M, Sys::Q>(a, row, e, &KS(S + 1, 0), BLOCK, lo, hi);
+        for (int d = 0; d < D; ++d) KS(S, d) = v[d];
+        const double2 mm = emit_row_thread<Sys::M, Sys::Q>(a, row, e, &KS(S, 0), BLOCK, lo, hi);
         lo = mm.x;
         hi = mm.y;
     };
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(BLOCK) erk_kernel(const __grid_constant__ qrl_
 template <class Sys, class TB>
 int launch_erk(const qrl_ode_args& a, cudaStream_t st, const char* name) {
     constexpr int D = Dim<Sys>::D, BLOCK = 32;
-    constexpr size_t smem = (size_t)(TB::S + 2) * D * BLOCK * sizeof(double);
+    constexpr size_t smem = (size_t)(TB::S + 1) * D * BLOCK * sizeof(double);
     if constexpr (smem > 220 * 1024) {
         return fail(QRL_E_UNSUPPORTED, "%s", "qrl_ode_step: this method's stage storage does not fit for this state size");
     } else {

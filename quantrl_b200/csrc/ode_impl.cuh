@@ -338,7 +338,9 @@ constexpr int MAX_STEPS = 1000000;
 template <class Sys, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) dopri5_kernel(const __grid_constant__ qrl_ode_args a) {
     constexpr int D = Dim<Sys>::D;
-    extern __shared__ double ks[];  // [7 + 1][D][BLOCK]: stage derivatives + the row being written, one column per thread
+    extern __shared__ double ks[];  // [7][D][BLOCK]: stage derivatives, one column per thread.  Column 1 (k2: zero weight in
+                                    // the solution, the error estimate and the interpolant) doubles as the staging column of
+                                    // the row being written: k2 is dead once stage 6 is done
     const int E = a.n_envs, K = a.K;
     const int e = blockIdx.x * BLOCK + threadIdx.x;
     const bool live = e < E;
@@ -354,14 +356,14 @@ __global__ void __launch_bounds__(BLOCK) dopri5_kernel(const __grid_constant__ q
     double lo = INFINITY, hi = -INFINITY;
     // the row staged in this thread's scratch column goes out through the shared (non-inlined) emitter
     auto emit_staged = [&](int row) {
-        const double2 mm = emit_row_thread<Sys::M, Sys::Q>(a, row, e, &KS(7, 0), BLOCK, lo, hi);
+        const double2 mm = emit_row_thread<Sys::M, Sys::Q>(a, row, e, &KS(1, 0), BLOCK, lo, hi);
         lo = mm.x;
         hi = mm.y;
     };
     auto emit = [&](int row, const double* v) {
         if (!live) return;
 #pragma unroll
-        for (int d = 0; d < D; ++d) KS(7, d) = v[d];
+        for (int d = 0; d < D; ++d) KS(1, d) = v[d];
         emit_staged(row);
     };
     emit(0, y);
@@ -461,7 +463,7 @@ __global__ void __launch_bounds__(BLOCK) dopri5_kernel(const __grid_constant__ q
                             if (st == 1) continue;
                             q = fma(KS(st, d), pw[st], q);
                         }
-                        KS(7, d) = fma(ht * x, q, y[d]);
+                        KS(1, d) = fma(ht * x, q, y[d]);
                     }
                     emit_staged(next_row);
                 }
@@ -867,6 +869,232 @@ __global__ void __launch_bounds__(EPB * 16 + 32 + 128) rk4_split_kernel(const __
     if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// DOPRI5, q*q lanes per environment (q = 4).  Same method, controller, dense output and order of operations as
+// dopri5_kernel, in the layout of rk4_lanes_kernel: lane (i,j) owns V_ij (and the classical modes, replicated), so the
+// seven stage derivatives of a step are 7 + 7*2M REGISTERS per lane instead of 7*d shared-memory columns per env (41 KB
+// per warp = 5 warps per SM in dopri5_kernel), a row is d contiguous doubles written by the env's own lanes, and the
+// per-env controller is uniform over a half-warp: the two envs of a warp diverge only against each other.  The error
+// norm is the one reduction across the env's lanes (4 xor-shuffle steps; the thread kernel sums sequentially over d, so
+// the two agree to rounding, not bit for bit).  Every warp-level primitive carries the env's 16-lane mask.
+// ------------------------------------------------------------------------------------------------------------------
+template <class Sys, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) dopri5_lanes_kernel(const __grid_constant__ qrl_ode_args a) {
+    constexpr int M = Sys::M, Q = Sys::Q, D = Dim<Sys>::D, L = Q * Q;
+    constexpr int M2 = 2 * M > 0 ? 2 * M : 1;
+    static_assert(L == 16, "dopri5_lanes_kernel is written for q = 4");
+    constexpr int EPB = BLOCK / L;
+    __shared__ __align__(16) double sA[2][EPB][L], sV[2][EPB][L];
+    __shared__ __align__(16) double sRow[EPB][D];
+    const int E = a.n_envs, K = a.K;
+    const int g = threadIdx.x / L, l = threadIdx.x % L;
+    const int i = l / Q, j = l % Q;
+    const int e = blockIdx.x * EPB + g;
+    const bool live = e < E;
+    const int el = live ? e : E - 1;
+    const unsigned gmask = 0xFFFFu << (threadIdx.x & 16);     // the 16 lanes of this env
+    const bool mode_lane = l < 2 * M;
+
+    Sys s;
+    load_system(s, a, el);
+    double ym[M2];
+#pragma unroll
+    for (int c = 0; c < 2 * M; ++c) ym[c] = a.y0[(int64_t)el * D + c];
+    double v = a.y0[(int64_t)el * D + 2 * M + l];
+    const double dij = s.D(i, j);
+    const int noise = a.obs_noise ? 1 : (a.obs_std ? 2 : 0);
+    const int64_t col_v = (int64_t)el * D + 2 * M + l, row_pitch = (int64_t)E * D;
+
+    double lo = INFINITY, hi = -INFINITY;
+    auto pick_mode = [&](const double* m) {
+        double mv = 0.0;
+#pragma unroll
+        for (int c = 0; c < 2 * M; ++c) mv = (l == c) ? m[c] : mv;
+        return mv;
+    };
+    // row `row` of this env: my covariance element vv and (mode lanes) my mode amplitude mv
+    auto emit = [&](int row, double vv, double mv) {
+        double ov = vv, om = mv;
+        if (noise) {
+            ov = vv + obs_noise_at(a, row, el, 2 * M + l, D);
+            if (mode_lane) om = mv + obs_noise_at(a, row, el, l, D);
+        }
+        const int64_t r0 = (int64_t)row * row_pitch + col_v;
+        if (a.states) {
+            a.states[r0] = vv;
+            if (mode_lane) a.states[r0 - 2 * M] = mv;
+        }
+        if (a.observations) {
+            a.observations[r0] = ov;
+            if (mode_lane) a.observations[r0 - 2 * M] = om;
+        }
+        if (row == K && a.obs_last) {
+            a.obs_last[col_v] = ov;
+            if (mode_lane) a.obs_last[col_v - 2 * M] = om;
+        }
+        lo = fmin(lo, ov);
+        hi = fmax(hi, ov);
+        if (mode_lane) { lo = fmin(lo, om); hi = fmax(hi, om); }
+        if (a.reward_kind != QRL_REWARD_NONE) {
+            __syncwarp(gmask);
+            sRow[g][2 * M + l] = vv;
+            if (mode_lane) sRow[g][l] = mv;
+            __syncwarp(gmask);
+            if (l == 0) ode_reward_row_mem<M, Q>(a, row, e, sRow[g]);
+            __syncwarp(gmask);
+        }
+    };
+    int par = 0;
+    // one RHS evaluation at (modes ymt, my element vt): returns dV_ij, fills dm  (cf. rk4_lanes_kernel)
+    auto rhs_lane = [&](double t, const double* ymt, double vt, double* dm) -> double {
+        double A[Q][Q];
+        s.eval(t, ymt, dm, A);
+        sV[par][g][l] = vt;
+        if (l == 0) {
+            double2* dst = reinterpret_cast<double2*>(sA[par][g]);
+#pragma unroll
+            for (int r = 0; r < Q; ++r)
+#pragma unroll
+                for (int c = 0; c < Q; c += 2) dst[(r * Q + c) / 2] = make_double2(A[r][c], A[r][c + 1]);
+        }
+        __syncwarp(gmask);
+        const double2* Ai = reinterpret_cast<const double2*>(sA[par][g] + i * Q);
+        const double2* Aj = reinterpret_cast<const double2*>(sA[par][g] + j * Q);
+        const double2* Vi = reinterpret_cast<const double2*>(sV[par][g] + i * Q);
+        const double2 ai0 = Ai[0], ai1 = Ai[1], aj0 = Aj[0], aj1 = Aj[1], vi0 = Vi[0], vi1 = Vi[1];
+        const double* Vc = sV[par][g] + j;
+        const double v0 = Vc[0], v1 = Vc[Q], v2 = Vc[2 * Q], v3 = Vc[3 * Q];
+        par ^= 1;
+        const double av = fma(ai1.y, v3, fma(ai1.x, v2, fma(ai0.y, v1, fma(ai0.x, v0, 0.0))));
+        const double va = fma(vi1.y, aj1.y, fma(vi1.x, aj1.x, fma(vi0.y, aj0.y, fma(vi0.x, aj0.x, 0.0))));
+        return (av + va) + dij;
+    };
+
+    if (live) {
+        emit(0, v, pick_mode(ym));
+        const double t_end = a.t0 + (double)K * a.t_ssz;
+        double t = a.t0;
+        double h = (a.h_state && a.h_state[el] > 0.0) ? a.h_state[el] : a.t_ssz;
+        int next_row = 1, n_acc = 0, n_rej = 0, guard = 0;
+        bool rejected = false;
+        double kv[7], km[7][M2];        // stage derivatives of my element and of the modes
+        kv[0] = rhs_lane(t, ym, v, km[0]);
+        while (next_row <= K && guard++ < dp::MAX_STEPS) {
+            const double remaining = t_end - t;
+            const bool last = h >= remaining * (1.0 - 1e-12);
+            const double ht = last ? remaining : h;
+            double ymt[M2], vt;
+            // the stage arguments, element by element exactly as in dopri5_kernel
+#define QRL_DP_ARG(EXPR_V, EXPR_M)                                       \
+            vt = EXPR_V;                                                 \
+            _Pragma("unroll") for (int c = 0; c < 2 * M; ++c) ymt[c] = EXPR_M;
+            QRL_DP_ARG(fma(ht * dp::A21, kv[0], v), fma(ht * dp::A21, km[0][c], ym[c]))
+            kv[1] = rhs_lane(t + dp::C2 * ht, ymt, vt, km[1]);
+            QRL_DP_ARG(fma(ht, fma(dp::A32, kv[1], dp::A31 * kv[0]), v),
+                       fma(ht, fma(dp::A32, km[1][c], dp::A31 * km[0][c]), ym[c]))
+            kv[2] = rhs_lane(t + dp::C3 * ht, ymt, vt, km[2]);
+            QRL_DP_ARG(fma(ht, fma(dp::A43, kv[2], fma(dp::A42, kv[1], dp::A41 * kv[0])), v),
+                       fma(ht, fma(dp::A43, km[2][c], fma(dp::A42, km[1][c], dp::A41 * km[0][c])), ym[c]))
+            kv[3] = rhs_lane(t + dp::C4 * ht, ymt, vt, km[3]);
+            QRL_DP_ARG(fma(ht, fma(dp::A54, kv[3], fma(dp::A53, kv[2], fma(dp::A52, kv[1], dp::A51 * kv[0]))), v),
+                       fma(ht, fma(dp::A54, km[3][c], fma(dp::A53, km[2][c], fma(dp::A52, km[1][c], dp::A51 * km[0][c]))), ym[c]))
+            kv[4] = rhs_lane(t + dp::C5 * ht, ymt, vt, km[4]);
+            QRL_DP_ARG(fma(ht, fma(dp::A65, kv[4], fma(dp::A64, kv[3], fma(dp::A63, kv[2], fma(dp::A62, kv[1], dp::A61 * kv[0])))), v),
+                       fma(ht, fma(dp::A65, km[4][c], fma(dp::A64, km[3][c], fma(dp::A63, km[2][c],
+                                   fma(dp::A62, km[1][c], dp::A61 * km[0][c])))), ym[c]))
+            kv[5] = rhs_lane(t + ht, ymt, vt, km[5]);
+            // 5th-order solution (= stage-7 argument, FSAL)
+            QRL_DP_ARG(fma(ht, fma(dp::B6, kv[5], fma(dp::B5, kv[4], fma(dp::B4, kv[3], fma(dp::B3, kv[2], dp::B1 * kv[0])))), v),
+                       fma(ht, fma(dp::B6, km[5][c], fma(dp::B5, km[4][c], fma(dp::B4, km[3][c],
+                                   fma(dp::B3, km[2][c], dp::B1 * km[0][c])))), ym[c]))
+#undef QRL_DP_ARG
+            kv[6] = rhs_lane(t + ht, ymt, vt, km[6]);
+            // error estimate: my element (+ my mode amplitude), then the sum over the env's lanes
+            auto err_term = [&](double k1, double k3, double k4, double k5, double k6, double k7, double yo, double yn) {
+                const double ev = ht * fma(dp::E7, k7, fma(dp::E6, k6, fma(dp::E5, k5, fma(dp::E4, k4, fma(dp::E3, k3, dp::E1 * k1)))));
+                const double sc = fma(a.rtol, fmax(fabs(yo), fabs(yn)), a.atol);
+                const double r = ev / sc;
+                return r * r;
+            };
+            double sq = err_term(kv[0], kv[2], kv[3], kv[4], kv[5], kv[6], v, vt);
+            if (mode_lane) {
+                double k1 = 0, k3 = 0, k4 = 0, k5 = 0, k6 = 0, k7 = 0;
+#pragma unroll
+                for (int c = 0; c < 2 * M; ++c)
+                    if (l == c) { k1 = km[0][c]; k3 = km[2][c]; k4 = km[3][c]; k5 = km[4][c]; k6 = km[5][c]; k7 = km[6][c]; }
+                sq += err_term(k1, k3, k4, k5, k6, k7, pick_mode(ym), pick_mode(ymt));
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) sq += __shfl_xor_sync(gmask, sq, o, 16);
+            sq = __shfl_sync(gmask, sq, 0, 16);   // one value for the whole env: the controller must not diverge inside it
+            const double err = sqrt(sq / (double)D);
+            if (err <= 1.0) {
+                double fac = (err == 0.0) ? dp::MAX_FACTOR : fmin(dp::MAX_FACTOR, fmax(dp::MIN_FACTOR, dp::SAFETY * pow(err, -0.2)));
+                if (rejected) fac = fmin(1.0, fac);
+                rejected = false;
+                ++n_acc;
+                const double t_new = last ? t_end : t + ht;
+                // dense output on every grid point inside (t, t_new]
+                while (next_row <= K) {
+                    const double tg = (next_row == K) ? t_end : a.t0 + (double)next_row * a.t_ssz;
+                    if (tg > t_new) break;
+                    if (tg == t_new) {
+                        emit(next_row, vt, pick_mode(ymt));
+                    } else {
+                        const double x = (tg - t) / ht;
+                        double pw[7];
+#pragma unroll
+                        for (int st = 0; st < 7; ++st)
+                            pw[st] = fma(fma(fma(dp::P[st][3], x, dp::P[st][2]), x, dp::P[st][1]), x, dp::P[st][0]);
+                        double q = 0.0;
+#pragma unroll
+                        for (int st = 0; st < 7; ++st) {
+                            if (st == 1) continue;
+                            q = fma(kv[st], pw[st], q);
+                        }
+                        const double vo = fma(ht * x, q, v);
+                        double mo = 0.0;
+                        if (mode_lane) {
+                            double qm = 0.0;
+#pragma unroll
+                            for (int st = 0; st < 7; ++st) {
+                                if (st == 1) continue;
+                                qm = fma(pick_mode(km[st]), pw[st], qm);
+                            }
+                            mo = fma(ht * x, qm, pick_mode(ym));
+                        }
+                        emit(next_row, vo, mo);
+                    }
+                    ++next_row;
+                }
+                t = t_new;
+                v = vt;
+                kv[0] = kv[6];
+#pragma unroll
+                for (int c = 0; c < 2 * M; ++c) { ym[c] = ymt[c]; km[0][c] = km[6][c]; }
+                // a step that was clipped to the interval end does not shrink the carried step size
+                h = (last && fac >= 1.0) ? fmax(h, ht * fac) : ht * fac;
+            } else {
+                h = ht * fmax(dp::MIN_FACTOR, dp::SAFETY * pow(err, -0.2));
+                rejected = true;
+                ++n_rej;
+            }
+        }
+        const double mv = pick_mode(ym);
+        if (a.y_last) {
+            a.y_last[col_v] = v;
+            if (mode_lane) a.y_last[col_v - 2 * M] = mv;
+        }
+        if (l == 0) {
+            if (a.h_state) a.h_state[e] = h;
+            if (a.n_steps) { a.n_steps[2 * e] += n_acc; a.n_steps[2 * e + 1] += n_rej; }
+        }
+        const bool bad = next_row <= K || !isfinite(v) || !isfinite(mv);   // step budget exhausted, or NaN / Inf
+        if (a.nan_flag && bad) *a.nan_flag = 1;
+    }
+    if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
+}
+
 }  // namespace qrl
 #include "ode_erk.cuh"
 namespace qrl {
@@ -934,8 +1162,19 @@ int launch_ode(const qrl_ode_args& a, cudaStream_t st) {
         case QRL_ODE_MIDPOINT: return launch_erk<Sys, erk::Midpoint>(a, st, "erk_kernel<midpoint>");
         default: break;
     }
+    if constexpr (Sys::Q == 4) {
+        // q = 4: 16 lanes per env, stage derivatives in registers.  B200, 100 grid rows, default tolerances (8.5 steps per
+        // interval), lanes vs thread per env: E = 64: 89 vs 477 us, 1024: 98 vs 534 us, 8192: 377 vs 583 us,
+        // 65536: 2.57 vs 2.12 ms (tools/quick_ode_bench.py)
+        const bool lanes = (a.n_envs <= 32768 || (a.flags & QRL_ODE_FORCE_LANES)) && !(a.flags & QRL_ODE_FORCE_THREAD);
+        if (lanes) {
+            constexpr int BL = 64;
+            dopri5_lanes_kernel<Sys, BL><<<(a.n_envs + BL / 16 - 1) / (BL / 16), BL, 0, st>>>(a);
+            return after_launch("dopri5_lanes_kernel");
+        }
+    }
     constexpr int BLOCK = 32;
-    const size_t smem = (size_t)8 * D * BLOCK * sizeof(double);
+    const size_t smem = (size_t)7 * D * BLOCK * sizeof(double);
     static bool attr_set = false;
     if (smem > 48 * 1024 && !attr_set) {
         QRL_CUDA(cudaFuncSetAttribute(dopri5_kernel<Sys, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

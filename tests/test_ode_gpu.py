@@ -174,6 +174,14 @@ def test_ode_edge_cases_and_errors(native, cuda):
     a.method = N.ODE_TSIT5     # adaptive methods need tolerances
     with pytest.raises(N.NativeError, match="atol and rtol must be positive"):
         N.ode_step(a)
+    # rows move as 16-byte pieces: a state tensor at an odd 8-byte offset is refused, not mis-written
+    a.system, a.num_modes, a.num_quads, a.method = N.SYS_OPTOMECH, 2, 4, N.ODE_RK4
+    pp = dev(sy.optomech_default_params(2, seed=2)); uu = dev(np.zeros((2, 1)))
+    a.params, a.params_stride_e, a.actions, a.n_actions = N.ptr(pp), pp.shape[1], N.ptr(uu), 1
+    buf = torch.zeros(2 * 20 + 1, dtype=torch.float64, device="cuda")
+    a.n_envs, a.y0 = 2, N.ptr(buf[1:])
+    with pytest.raises(N.NativeError, match="16-byte aligned"):
+        N.ode_step(a)
 
 
 @pytest.mark.parametrize("lanes_flags", [2, 6])   # 2: warp-specialised split kernel, 6: single-role lanes kernel
@@ -213,7 +221,33 @@ def test_rk4_lanes_kernel_equals_thread_kernel(native, cuda, E, lanes_flags):
     torch.testing.assert_close(a["states"], b["states"], rtol=1e-13, atol=1e-15)
 
 
-@pytest.mark.parametrize("method,flags", [("rk4", 1), ("rk4", 2), ("dopri5", 0)])
+@pytest.mark.parametrize("E", [1, 5, 64])
+def test_dopri5_lanes_kernel_equals_thread_kernel(native, cuda, E):
+    """dopri5 with q*q lanes per env (stage derivatives in registers, error norm reduced across the env's lanes) vs the
+    thread-per-env kernel: same controller decisions (step counts), trajectories equal to rounding; carried step
+    sizes, fed noise, min/max and last rows included; default and tight tolerances."""
+    from quantrl_b200 import _native as N
+    rng = np.random.default_rng(100 + E)
+    p = sy.optomech_default_params(max(E, 2), seed=2)[:E]; y0 = sy.optomech_y0(p)
+    u = rng.uniform(-1, 1, E)
+    noise = 1e-3 * rng.standard_normal((41, E, 20))
+    for atol, rtol in ((1e-9, 1e-6), (1e-13, 1e-11)):
+        kw = dict(params=p, actions=u, obs_noise=noise, method="dopri5", atol=atol, rtol=rtol)
+        a = ode_step("optomech", 2, 4, y0, 40, 0.5, 0.01, flags=0, **kw)
+        b = ode_step("optomech", 2, 4, y0, 40, 0.5, 0.01, flags=N.ODE_FORCE_THREAD, **kw)
+        np.testing.assert_array_equal(a["n_steps"].cpu().numpy(), b["n_steps"].cpu().numpy())
+        for key in ("states", "observations", "y_last", "obs_last", "minmax"):
+            torch.testing.assert_close(a[key], b[key], rtol=1e-11, atol=1e-14)
+        # the error estimate is a difference of O(1) stage derivatives: rounding-level differences are amplified by
+        # 1 / atol in err and hence in the carried step size
+        torch.testing.assert_close(a["h_state"], b["h_state"], rtol=1e-4, atol=0)
+        # second interval: carried step sizes
+        a2 = ode_step("optomech", 2, 4, a["y_last"].cpu().numpy(), 40, 0.9, 0.01, flags=0, h_state=a["h_state"].cpu().numpy(), **kw)
+        b2 = ode_step("optomech", 2, 4, b["y_last"].cpu().numpy(), 40, 0.9, 0.01, flags=N.ODE_FORCE_THREAD, h_state=b["h_state"].cpu().numpy(), **kw)
+        torch.testing.assert_close(a2["states"], b2["states"], rtol=1e-10, atol=1e-13)
+
+
+@pytest.mark.parametrize("method,flags", [("rk4", 1), ("rk4", 2), ("dopri5", 0), ("dopri5", 1)])
 def test_fused_log_negativity_reward_matches_reference_qcm(native, cuda, golden_dir, method, flags):
     """Reward functor ENTAN_LN: (1) on the reference's tight trajectory it must reproduce the reference's own
     ``QCMSolver.get_entanglement_logarithmic_negativity_2`` (fixture ``entan_ln_ref``, measure.py:401-440) — checked
