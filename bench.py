@@ -245,10 +245,14 @@ def main():
     with ClockSampler(local) as clocks:
         barrier()
         e0.record()
+        t_host0 = time.perf_counter()
         run_device(args.steps)
+        host_enqueue_us = (time.perf_counter() - t_host0) * 1e6 / args.steps   # host time to ENQUEUE one step (no sync)
         e1.record()
         barrier()
     ms = e0.elapsed_time(e1)
+    print(f"[bench] rank {rank}: host enqueue {host_enqueue_us:.1f} us/step, device {ms * 1e3 / args.steps:.1f} us/step",
+          file=sys.stderr)
     if peer is not None:
         # not timed: the learner's peer-written buffer must equal an NCCL all_gather of every rank's local last rows
         ref = torch.empty((world, E, n), dtype=torch.float64, device=dev)

@@ -283,8 +283,11 @@ typedef struct qrl_ode_args {
     double*  rewards_cum;    /* (E,) in/out: += Reward[K]; or NULL */
 } qrl_ode_args;
 
-#define QRL_ODE_FORCE_THREAD 1  /* flags: RK4 with one thread per env whatever the batch size (A/B testing) */
-#define QRL_ODE_FORCE_LANES  2  /* flags: RK4 with q*q lanes per env (q = 4 only) whatever the batch size: the
+/* Kernel selection of qrl_ode_step at num_quads = 4 (all variants perform the same operations; measured crossovers on
+ * B200 in DESIGN.md 4.2):  RK4: n_envs <= 1536 split kernel, <= 3072 single-role lanes kernel, else one thread per env;
+ * DOPRI5: n_envs <= 32768 lanes kernel, else one thread per env.  Other num_quads: one thread per env. */
+#define QRL_ODE_FORCE_THREAD 1  /* flags: RK4 / DOPRI5 with one thread per env whatever the batch size (A/B testing) */
+#define QRL_ODE_FORCE_LANES  2  /* flags: RK4 / DOPRI5 with q*q lanes per env (q = 4 only) whatever the batch size; RK4: the
                                 * warp-specialised split kernel (mode producer / covariance lanes / row writers) */
 #define QRL_ODE_LANES_SINGLE 4 /* flags: with FORCE_LANES (or a small batch), the single-role lanes kernel (A/B testing) */
 

@@ -150,7 +150,8 @@ __device__ __forceinline__ void em_finish_launch(const qrl_em_args& a) {
         for (int p = 0; p < a.peer_world; ++p)
             reinterpret_cast<volatile unsigned long long*>(a.peer_flags[p])[a.peer_rank] = epoch;
         // no fence here: the flag stores need not be acknowledged before this rank starts polling its own flags
-        // (they were ordered after the data by the release fence above; the round trip of a fence costs ~2 us)
+        // (they were ordered after the data by the release fence above); diagnostic flag 2048 restores it for A/B runs
+        if (a.flags & 2048) __threadfence_system();
         volatile unsigned long long* mine = reinterpret_cast<volatile unsigned long long*>(a.peer_flags[a.peer_rank]);
         const unsigned long long t0 = global_timer_ns();
         for (int q = 0; q < a.peer_world && !(a.flags & 1024); ++q) {

@@ -107,6 +107,7 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
         for (int j = 0; j < n_sel; ++j) pack_rows |= (selS[j] != n_data - 1);
     // 128-bit accesses need even N (tile rows and every env's N-run are then 16-byte aligned) and aligned bases
     const bool vec_g = (N % 2 == 0) && ((((uintptr_t)a.states) | ((uintptr_t)a.observations)) % 16 == 0);
+    const bool vec_l = (N % 2 == 0) && ((((uintptr_t)a.x_last) | ((uintptr_t)a.obs_last)) % 16 == 0);
     // piece pass: n/2 adjacent lanes per environment
     constexpr bool PIECE_N = (N == 2 || N == 4 || N == 8);
     constexpr int L = PIECE_N ? N / 2 : 1;
@@ -251,9 +252,16 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
                             if (a.rewards_cum) { cum += a.rewards_cum[e]; a.rewards_cum[e] = cum; }
                             cumS[el] = cum;
                         }
+                        // last rows: one 16-byte store per piece (obs_last may be the learner's peer-mapped buffer:
+                        // 8-byte stores would double the NVLink write packets)
                         const int64_t gl = (int64_t)e0 * N + 2 * pc;
-                        if (a.x_last) { a.x_last[gl] = x2.x; a.x_last[gl + 1] = x2.y; }
-                        if (a.obs_last) { a.obs_last[gl] = o2.x; a.obs_last[gl + 1] = o2.y; }
+                        if (vec_l) {
+                            if (a.x_last) *reinterpret_cast<double2*>(a.x_last + gl) = x2;
+                            if (a.obs_last) *reinterpret_cast<double2*>(a.obs_last + gl) = o2;
+                        } else {
+                            if (a.x_last) { a.x_last[gl] = x2.x; a.x_last[gl + 1] = x2.y; }
+                            if (a.obs_last) { a.obs_last[gl] = o2.x; a.obs_last[gl + 1] = o2.y; }
+                        }
                     }
                 }
                 sl += q_dsl;
