@@ -151,14 +151,14 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------------
-def make_env(rank, return_numpy, use_cuda_graph=True, host_zero_copy=True):
+def make_env(rank, return_numpy, use_cuda_graph=True, host_zero_copy=True, host_output_views=False):
     from quantrl_b200.systems import AffineLinearVecEnv, affine_matrices
     A0, Au = affine_matrices(N_STATE, 1, seed=0)
     return AffineLinearVecEnv(
         n_envs=E_PER_GPU, n=N_STATE, A0=A0, Au=Au, noise_prefixes=0.05, x0=1.0, t_norm_max=S_EPISODE * T_SSZ + T_SSZ / 2,
         t_norm_ssz=T_SSZ, action_interval=K_SUB, observation_stds=[0.01] * N_STATE, seed=1, rng="philox",
         env_offset=rank * E_PER_GPU, return_numpy=return_numpy, use_cuda_graph=use_cuda_graph, fused_coefficients=True, data_idxs=[-1],
-        host_zero_copy=host_zero_copy, dir_prefix="/tmp/qrl_bench")
+        host_zero_copy=host_zero_copy, host_output_views=host_output_views, dir_prefix="/tmp/qrl_bench")
 
 
 def main():
@@ -292,7 +292,7 @@ def main():
 
     # ---- e2e: public VecEnv API, host actions in, host obs/reward out, every step ----
     # (multi-GPU: the learner gather below reads the device-side last rows, so the results take the copy-node route)
-    env2 = make_env(rank, return_numpy=True, host_zero_copy=(world == 1))
+    env2 = make_env(rank, return_numpy=True, host_zero_copy=(world == 1), host_output_views=True)
     host_actions = [np.random.default_rng(5 + rank).uniform(-1, 1, (E, 1)) for _ in range(8)]
     env2.reset()
     e2e_steps = max(10, min(args.steps, 300))
@@ -350,7 +350,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * 1 * 8, "d2h_bytes_per_step": (E * (n + 1) + 4) * 8,
                     "steps": e2e_steps, "api": "AffineLinearVecEnv.step(host actions) -> host obs, reward",
                     "transport": ("zero-copy: the step kernel reads the actions from and writes obs|reward|min,max to pinned host "
-                                  "memory over PCIe inside the launch" if getattr(env2, "_zc", None) else
+                                  "memory over PCIe inside the launch; step() returns NumPy views of that (double buffered) "
+                                  "pinned memory, valid until the end of the next step" if getattr(env2, "_zc", None) else
                                   "H2D / D2H copy nodes from / to pinned host memory around the step kernel")},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "em_tile_kernel<4> (qrl_em_step)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

@@ -132,7 +132,20 @@ __device__ __forceinline__ void em_finish_launch(const qrl_em_args& a) {
     if (a.peer_flags && !(a.flags & 512)) __threadfence_system(); else __threadfence();
     const unsigned prev = atomicAdd(a.finish_counter, 1u);
     if (prev != gridDim.x - 1) return;
-    __threadfence();
+    // last block.  Cross-GPU barrier, part 1: publish this rank's new epoch in every rank's flag array FIRST — the
+    // release fence then has nothing of this thread's own bookkeeping to wait for, and the flags travel over NVLink
+    // while the local bookkeeping below is done.  (The other blocks' stores were fenced at system scope before their
+    // counter increments, which this thread has observed.)
+    unsigned long long epoch = 0ull;
+    if (a.peer_flags) {
+        epoch = *a.peer_epoch + 1ull;
+        __threadfence_system();
+        for (int p = 0; p < a.peer_world; ++p)
+            reinterpret_cast<volatile unsigned long long*>(a.peer_flags[p])[a.peer_rank] = epoch;
+        if (a.flags & 2048) __threadfence_system();   // diagnostic (A/B): wait for the flag stores before polling
+    } else {
+        __threadfence();
+    }
     if (a.minmax_out && a.obs_minmax) {
         volatile double* acc = a.obs_minmax;
         a.minmax_out[0] = acc[0];
@@ -143,19 +156,18 @@ __device__ __forceinline__ void em_finish_launch(const qrl_em_args& a) {
     if (a.dyn && a.dyn_advance != 0) const_cast<int64_t*>(a.dyn)[0] += a.dyn_advance;
     *a.finish_counter = 0u;
     if (a.peer_flags) {
-        // cross-GPU barrier: publish this rank's new epoch everywhere, then wait for everybody's
-        const unsigned long long epoch = *a.peer_epoch + 1ull;
         *a.peer_epoch = epoch;
-        __threadfence_system();
-        for (int p = 0; p < a.peer_world; ++p)
-            reinterpret_cast<volatile unsigned long long*>(a.peer_flags[p])[a.peer_rank] = epoch;
-        // no fence here: the flag stores need not be acknowledged before this rank starts polling its own flags
-        // (they were ordered after the data by the release fence above); diagnostic flag 2048 restores it for A/B runs
-        if (a.flags & 2048) __threadfence_system();
-        volatile unsigned long long* mine = reinterpret_cast<volatile unsigned long long*>(a.peer_flags[a.peer_rank]);
+        // part 2: wait for everybody's epoch.  Acquire loads at system scope (what the peers' data stores were released
+        // to), so no separate acquire fence after the loop; diagnostic flag 4096 = plain volatile polling + a system fence
+        const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(a.peer_flags[a.peer_rank]);
+        const bool acq = !(a.flags & 4096);
         const unsigned long long t0 = global_timer_ns();
         for (int q = 0; q < a.peer_world && !(a.flags & 1024); ++q) {
-            while (mine[q] < epoch) {
+            while (true) {
+                unsigned long long seen;
+                if (acq) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine + q) : "memory");
+                else seen = *reinterpret_cast<const volatile unsigned long long*>(mine + q);
+                if (seen >= epoch) break;
                 if (global_timer_ns() - t0 > 2000000000ull) {   // a peer never arrived: fail loudly, do not hang
                     if (a.nan_flag) *a.nan_flag = 1;
                     q = a.peer_world;
@@ -163,7 +175,7 @@ __device__ __forceinline__ void em_finish_launch(const qrl_em_args& a) {
                 }
             }
         }
-        __threadfence_system();
+        if (!acq) __threadfence_system();
     }
 }
 

@@ -257,8 +257,179 @@ __global__ void __launch_bounds__(BLOCK) erk_kernel(const __grid_constant__ qrl_
     if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
 }
 
+// The same engine with q*q lanes per environment (q = 4, LaneEnv in ode_impl.cuh): stage derivatives in registers
+// (S + 1 for the lane's covariance element, (S + 1) * 2M for the replicated modes), rows written by the env's own lanes,
+// per-env controller uniform over a half-warp, error norm reduced across the env's lanes.  Same tableaus, controller
+// and order of operations per element as erk_kernel.
+template <class Sys, class TB, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) erk_lanes_kernel(const __grid_constant__ qrl_ode_args a) {
+    using Env = LaneEnv<Sys, BLOCK / 16>;
+    constexpr int M = Env::M, M2 = Env::M2, D = Env::D, S = TB::S;
+    __shared__ typename Env::Smem smem;
+    Env env(a, smem);
+    const int K = a.K, el = env.el;
+    double ym[M2];
+#pragma unroll
+    for (int c = 0; c < 2 * M; ++c) ym[c] = a.y0[(int64_t)el * D + c];
+    double v = a.y0[env.col_v];
+    if (env.live) {
+        env.emit(0, v, env.pick_mode(ym));
+        const double t_end = a.t0 + (double)K * a.t_ssz;
+        const double h_fixed = a.t_ssz / (double)(a.substeps > 0 ? a.substeps : 1);
+        double t = a.t0;
+        double h = TB::ADAPTIVE ? ((a.h_state && a.h_state[el] > 0.0) ? a.h_state[el] : a.t_ssz) : h_fixed;
+        int n_acc = 0, n_rej = 0, guard = 0;
+        bool rejected = false, failed = false;
+        double kv[S + 1], km[S + 1][M2];
+        kv[0] = env.rhs(t, ym, v, km[0]);
+        for (int row = 1; row <= K; ++row) {
+            const double t_row = (row == K) ? t_end : a.t0 + (double)row * a.t_ssz;
+            int sub = 0;
+            while (true) {
+                if (guard++ >= erk::MAX_STEPS) { failed = true; break; }
+                // ---- step size: never across the grid point ----
+                const double remaining = t_row - t;
+                bool last;
+                double ht;
+                if (TB::ADAPTIVE) {
+                    last = h >= remaining * (1.0 - 1e-12);
+                    ht = last ? remaining : h;
+                } else {
+                    last = (++sub >= a.substeps);
+                    ht = last ? remaining : h_fixed;
+                }
+                double ymt[M2], vt;
+                // ---- stages 1 .. S-1 ----
+#pragma unroll
+                for (int st = 1; st < S; ++st) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < st; ++j)
+                        if (TB::A(st, j) != 0.0) acc = fma(TB::A(st, j), kv[j], acc);
+                    vt = fma(ht, acc, v);
+#pragma unroll
+                    for (int c = 0; c < 2 * M; ++c) {
+                        double am = 0.0;
+#pragma unroll
+                        for (int j = 0; j < st; ++j)
+                            if (TB::A(st, j) != 0.0) am = fma(TB::A(st, j), km[j][c], am);
+                        ymt[c] = fma(ht, am, ym[c]);
+                    }
+                    kv[st] = env.rhs(t + TB::C(st) * ht, ymt, vt, km[st]);
+                }
+                // ---- new solution and its derivative ----
+                {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < S; ++j)
+                        if (TB::B(j) != 0.0) acc = fma(TB::B(j), kv[j], acc);
+                    vt = fma(ht, acc, v);
+#pragma unroll
+                    for (int c = 0; c < 2 * M; ++c) {
+                        double am = 0.0;
+#pragma unroll
+                        for (int j = 0; j < S; ++j)
+                            if (TB::B(j) != 0.0) am = fma(TB::B(j), km[j][c], am);
+                        ymt[c] = fma(ht, am, ym[c]);
+                    }
+                }
+                const double t_new = last ? t_row : t + ht;
+                kv[S] = env.rhs(t_new, ymt, vt, km[S]);
+                bool accept = true;
+                double fac = 1.0;
+                if (TB::ADAPTIVE) {
+                    // my covariance element, plus (mode lanes) my mode amplitude
+                    double kme[S + 1];
+#pragma unroll
+                    for (int j = 0; j <= S; ++j) kme[j] = env.pick_mode(km[j]);
+                    const double ymo = env.pick_mode(ym), ymn = env.pick_mode(ymt);
+                    double err;
+                    if constexpr (TB::DOP853) {
+                        auto terms = [&](const double* k, double yo, double yn, double& t5, double& t3) {
+                            double e5 = TB::E(S) * k[S], e3 = TB::E3(S) * k[S];
+#pragma unroll
+                            for (int j = 0; j < S; ++j) {
+                                if (TB::E(j) != 0.0) e5 = fma(TB::E(j), k[j], e5);
+                                if (TB::E3(j) != 0.0) e3 = fma(TB::E3(j), k[j], e3);
+                            }
+                            const double sc = fma(a.rtol, fmax(fabs(yo), fabs(yn)), a.atol);
+                            e5 /= sc;
+                            e3 /= sc;
+                            t5 = e5 * e5;
+                            t3 = e3 * e3;
+                        };
+                        double s5, s3;
+                        terms(kv, v, vt, s5, s3);
+                        if (env.mode_lane) {
+                            double m5, m3;
+                            terms(kme, ymo, ymn, m5, m3);
+                            s5 += m5;
+                            s3 += m3;
+                        }
+                        s5 = env.env_sum(s5);
+                        s3 = env.env_sum(s3);
+                        const double den = s5 + 0.01 * s3;
+                        err = (den > 0.0) ? fabs(ht) * s5 / sqrt(den * (double)D) : 0.0;
+                    } else {
+                        auto term = [&](const double* k, double yo, double yn) {
+                            double ev = TB::E(S) * k[S];
+#pragma unroll
+                            for (int j = 0; j < S; ++j)
+                                if (TB::E(j) != 0.0) ev = fma(TB::E(j), k[j], ev);
+                            const double sc = fma(a.rtol, fmax(fabs(yo), fabs(yn)), a.atol);
+                            const double r = ht * ev / sc;
+                            return r * r;
+                        };
+                        double sq = term(kv, v, vt);
+                        if (env.mode_lane) sq += term(kme, ymo, ymn);
+                        err = sqrt(env.env_sum(sq) / (double)D);
+                    }
+                    accept = err <= 1.0;
+                    if (accept) {
+                        fac = (err == 0.0) ? erk::MAX_FACTOR
+                                           : fmin(erk::MAX_FACTOR, fmax(erk::MIN_FACTOR, erk::SAFETY * pow(err, TB::ERR_EXP)));
+                        if (rejected) fac = fmin(1.0, fac);
+                    } else {
+                        fac = fmax(erk::MIN_FACTOR, erk::SAFETY * pow(err, TB::ERR_EXP));
+                    }
+                    if (!(err == err)) { failed = true; break; }   // NaN: give up, the flag is raised below
+                }
+                if (accept) {
+                    rejected = false;
+                    ++n_acc;
+                    t = t_new;
+                    v = vt;
+                    kv[0] = kv[S];
+#pragma unroll
+                    for (int c = 0; c < 2 * M; ++c) { ym[c] = ymt[c]; km[0][c] = km[S][c]; }
+                    // a step that was clipped to the grid point does not shrink the carried step size
+                    if (TB::ADAPTIVE) h = (last && fac >= 1.0) ? fmax(h, ht * fac) : ht * fac;
+                    if (last) break;
+                } else {
+                    h = ht * fac;
+                    rejected = true;
+                    ++n_rej;
+                }
+            }
+            if (failed) break;
+            env.emit(row, v, env.pick_mode(ym));
+        }
+        env.finish(v, ym, h, TB::ADAPTIVE, n_acc, n_rej, failed);
+    }
+    if (a.obs_minmax) block_minmax_commit(env.lo, env.hi, a.obs_minmax);
+}
+
 template <class Sys, class TB>
 int launch_erk(const qrl_ode_args& a, cudaStream_t st, const char* name) {
+    if constexpr (Sys::Q == 4) {
+        // q = 4: 16 lanes per env for the same batch sizes as dopri5_lanes_kernel (ode_impl.cuh:launch_ode)
+        const bool lanes = (a.n_envs <= 32768 || (a.flags & QRL_ODE_FORCE_LANES)) && !(a.flags & QRL_ODE_FORCE_THREAD);
+        if (lanes) {
+            constexpr int BL = 64;
+            erk_lanes_kernel<Sys, TB, BL><<<(a.n_envs + BL / 16 - 1) / (BL / 16), BL, 0, st>>>(a);
+            return after_launch(name);
+        }
+    }
     constexpr int D = Dim<Sys>::D, BLOCK = 32;
     constexpr size_t smem = (size_t)(TB::S + 1) * D * BLOCK * sizeof(double);
     if constexpr (smem > 220 * 1024) {

@@ -870,50 +870,50 @@ __global__ void __launch_bounds__(EPB * 16 + 32 + 128) rk4_split_kernel(const __
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// DOPRI5, q*q lanes per environment (q = 4).  Same method, controller, dense output and order of operations as
-// dopri5_kernel, in the layout of rk4_lanes_kernel: lane (i,j) owns V_ij (and the classical modes, replicated), so the
-// seven stage derivatives of a step are 7 + 7*2M REGISTERS per lane instead of 7*d shared-memory columns per env (41 KB
-// per warp = 5 warps per SM in dopri5_kernel), a row is d contiguous doubles written by the env's own lanes, and the
-// per-env controller is uniform over a half-warp: the two envs of a warp diverge only against each other.  The error
-// norm is the one reduction across the env's lanes (4 xor-shuffle steps; the thread kernel sums sequentially over d, so
-// the two agree to rounding, not bit for bit).  Every warp-level primitive carries the env's 16-lane mask.
+// The 16 lanes of one environment (q = 4): shared plumbing of the adaptive lanes kernels (dopri5_lanes_kernel below,
+// erk_lanes_kernel in ode_erk.cuh).  Lane (i,j) owns V_ij and a replica of the classical modes.  Every warp-level
+// primitive carries the env's 16-lane mask: the two envs of a warp run their own controllers and may diverge.
 // ------------------------------------------------------------------------------------------------------------------
-template <class Sys, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) dopri5_lanes_kernel(const __grid_constant__ qrl_ode_args a) {
-    constexpr int M = Sys::M, Q = Sys::Q, D = Dim<Sys>::D, L = Q * Q;
-    constexpr int M2 = 2 * M > 0 ? 2 * M : 1;
-    static_assert(L == 16, "dopri5_lanes_kernel is written for q = 4");
-    constexpr int EPB = BLOCK / L;
-    __shared__ __align__(16) double sA[2][EPB][L], sV[2][EPB][L];
-    __shared__ __align__(16) double sRow[EPB][D];
-    const int E = a.n_envs, K = a.K;
-    const int g = threadIdx.x / L, l = threadIdx.x % L;
-    const int i = l / Q, j = l % Q;
-    const int e = blockIdx.x * EPB + g;
-    const bool live = e < E;
-    const int el = live ? e : E - 1;
-    const unsigned gmask = 0xFFFFu << (threadIdx.x & 16);     // the 16 lanes of this env
-    const bool mode_lane = l < 2 * M;
-
+template <class Sys, int EPB>
+struct LaneEnv {
+    static constexpr int M = Sys::M, Q = Sys::Q, D = 2 * Sys::M + Sys::Q * Sys::Q, L = Sys::Q * Sys::Q;
+    static constexpr int M2 = 2 * M > 0 ? 2 * M : 1;
+    static_assert(L == 16, "the lanes kernels are written for q = 4");
+    struct Smem {
+        alignas(16) double A[2][EPB][L], V[2][EPB][L];   // exchange tiles, double buffered over the RHS evaluations
+        alignas(16) double row[EPB][D];                  // one env's row [modes | V] for the fused reward
+    };
+    const qrl_ode_args& a;
+    Smem& sm;
     Sys s;
-    load_system(s, a, el);
-    double ym[M2];
-#pragma unroll
-    for (int c = 0; c < 2 * M; ++c) ym[c] = a.y0[(int64_t)el * D + c];
-    double v = a.y0[(int64_t)el * D + 2 * M + l];
-    const double dij = s.D(i, j);
-    const int noise = a.obs_noise ? 1 : (a.obs_std ? 2 : 0);
-    const int64_t col_v = (int64_t)el * D + 2 * M + l, row_pitch = (int64_t)E * D;
+    int g, l, i, j, e, el, par = 0, noise;
+    unsigned gmask;
+    bool live, mode_lane;
+    int64_t col_v, row_pitch;
+    double dij, lo = INFINITY, hi = -INFINITY;
 
-    double lo = INFINITY, hi = -INFINITY;
-    auto pick_mode = [&](const double* m) {
+    __device__ __forceinline__ LaneEnv(const qrl_ode_args& args, Smem& smem) : a(args), sm(smem) {
+        g = threadIdx.x / L; l = threadIdx.x % L; i = l / Q; j = l % Q;
+        e = blockIdx.x * EPB + g;
+        live = e < a.n_envs;
+        el = live ? e : a.n_envs - 1;
+        gmask = 0xFFFFu << (threadIdx.x & 16);
+        mode_lane = l < 2 * M;
+        load_system(s, a, el);
+        dij = s.D(i, j);
+        noise = a.obs_noise ? 1 : (a.obs_std ? 2 : 0);
+        col_v = (int64_t)el * D + 2 * M + l;
+        row_pitch = (int64_t)a.n_envs * D;
+    }
+    // my own element of a replicated mode vector (lanes < 2M)
+    __device__ __forceinline__ double pick_mode(const double* m) const {
         double mv = 0.0;
 #pragma unroll
         for (int c = 0; c < 2 * M; ++c) mv = (l == c) ? m[c] : mv;
         return mv;
-    };
+    }
     // row `row` of this env: my covariance element vv and (mode lanes) my mode amplitude mv
-    auto emit = [&](int row, double vv, double mv) {
+    __device__ __forceinline__ void emit(int row, double vv, double mv) {
         double ov = vv, om = mv;
         if (noise) {
             ov = vv + obs_noise_at(a, row, el, 2 * M + l, D);
@@ -928,7 +928,7 @@ __global__ void __launch_bounds__(BLOCK) dopri5_lanes_kernel(const __grid_consta
             a.observations[r0] = ov;
             if (mode_lane) a.observations[r0 - 2 * M] = om;
         }
-        if (row == K && a.obs_last) {
+        if (row == a.K && a.obs_last) {
             a.obs_last[col_v] = ov;
             if (mode_lane) a.obs_last[col_v - 2 * M] = om;
         }
@@ -937,38 +937,83 @@ __global__ void __launch_bounds__(BLOCK) dopri5_lanes_kernel(const __grid_consta
         if (mode_lane) { lo = fmin(lo, om); hi = fmax(hi, om); }
         if (a.reward_kind != QRL_REWARD_NONE) {
             __syncwarp(gmask);
-            sRow[g][2 * M + l] = vv;
-            if (mode_lane) sRow[g][l] = mv;
+            sm.row[g][2 * M + l] = vv;
+            if (mode_lane) sm.row[g][l] = mv;
             __syncwarp(gmask);
-            if (l == 0) ode_reward_row_mem<M, Q>(a, row, e, sRow[g]);
+            if (l == 0) ode_reward_row_mem<M, Q>(a, row, e, sm.row[g]);
             __syncwarp(gmask);
         }
-    };
-    int par = 0;
-    // one RHS evaluation at (modes ymt, my element vt): returns dV_ij, fills dm  (cf. rk4_lanes_kernel)
-    auto rhs_lane = [&](double t, const double* ymt, double vt, double* dm) -> double {
+    }
+    // one RHS evaluation at (modes ymt, my element vt): returns dV_ij, fills dm  (cf. rk4_lanes_kernel; same order of
+    // operations as rhs())
+    __device__ __forceinline__ double rhs(double t, const double* ymt, double vt, double* dm) {
         double A[Q][Q];
         s.eval(t, ymt, dm, A);
-        sV[par][g][l] = vt;
+        sm.V[par][g][l] = vt;
         if (l == 0) {
-            double2* dst = reinterpret_cast<double2*>(sA[par][g]);
+            double2* dst = reinterpret_cast<double2*>(sm.A[par][g]);
 #pragma unroll
             for (int r = 0; r < Q; ++r)
 #pragma unroll
                 for (int c = 0; c < Q; c += 2) dst[(r * Q + c) / 2] = make_double2(A[r][c], A[r][c + 1]);
         }
         __syncwarp(gmask);
-        const double2* Ai = reinterpret_cast<const double2*>(sA[par][g] + i * Q);
-        const double2* Aj = reinterpret_cast<const double2*>(sA[par][g] + j * Q);
-        const double2* Vi = reinterpret_cast<const double2*>(sV[par][g] + i * Q);
+        const double2* Ai = reinterpret_cast<const double2*>(sm.A[par][g] + i * Q);
+        const double2* Aj = reinterpret_cast<const double2*>(sm.A[par][g] + j * Q);
+        const double2* Vi = reinterpret_cast<const double2*>(sm.V[par][g] + i * Q);
         const double2 ai0 = Ai[0], ai1 = Ai[1], aj0 = Aj[0], aj1 = Aj[1], vi0 = Vi[0], vi1 = Vi[1];
-        const double* Vc = sV[par][g] + j;
+        const double* Vc = sm.V[par][g] + j;
         const double v0 = Vc[0], v1 = Vc[Q], v2 = Vc[2 * Q], v3 = Vc[3 * Q];
         par ^= 1;
         const double av = fma(ai1.y, v3, fma(ai1.x, v2, fma(ai0.y, v1, fma(ai0.x, v0, 0.0))));
         const double va = fma(vi1.y, aj1.y, fma(vi1.x, aj1.x, fma(vi0.y, aj0.y, fma(vi0.x, aj0.x, 0.0))));
         return (av + va) + dij;
-    };
+    }
+    // sum over the env's lanes, the same value in every lane (the controller must not diverge inside an env)
+    __device__ __forceinline__ double env_sum(double x) const {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) x += __shfl_xor_sync(gmask, x, o, 16);
+        return __shfl_sync(gmask, x, 0, 16);
+    }
+    // end of the launch: carry-over of the last state, controller state, failure flag
+    __device__ __forceinline__ void finish(double v, const double* ym, double h, bool has_h, int n_acc, int n_rej, bool failed) {
+        const double mv = pick_mode(ym);
+        if (a.y_last) {
+            a.y_last[col_v] = v;
+            if (mode_lane) a.y_last[col_v - 2 * M] = mv;
+        }
+        if (l == 0) {
+            if (has_h && a.h_state) a.h_state[e] = h;
+            if (a.n_steps) { a.n_steps[2 * e] += n_acc; a.n_steps[2 * e + 1] += n_rej; }
+        }
+        if (a.nan_flag && (failed || !isfinite(v) || !isfinite(mv))) *a.nan_flag = 1;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// DOPRI5, q*q lanes per environment (q = 4).  Same method, controller, dense output and order of operations as
+// dopri5_kernel, in the layout of rk4_lanes_kernel: lane (i,j) owns V_ij (and the classical modes, replicated), so the
+// seven stage derivatives of a step are 7 + 7*2M REGISTERS per lane instead of 7*d shared-memory columns per env (41 KB
+// per warp = 5 warps per SM in dopri5_kernel), a row is d contiguous doubles written by the env's own lanes, and the
+// per-env controller is uniform over a half-warp: the two envs of a warp diverge only against each other.  The error
+// norm is the one reduction across the env's lanes (4 xor-shuffle steps; the thread kernel sums sequentially over d, so
+// the two agree to rounding, not bit for bit).  Every warp-level primitive carries the env's 16-lane mask.
+// ------------------------------------------------------------------------------------------------------------------
+template <class Sys, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) dopri5_lanes_kernel(const __grid_constant__ qrl_ode_args a) {
+    using Env = LaneEnv<Sys, BLOCK / 16>;
+    constexpr int M = Env::M, M2 = Env::M2, D = Env::D;
+    __shared__ typename Env::Smem smem;
+    Env env(a, smem);
+    const int K = a.K, l = env.l, el = env.el;
+    const bool live = env.live, mode_lane = env.mode_lane;
+    double ym[M2];
+#pragma unroll
+    for (int c = 0; c < 2 * M; ++c) ym[c] = a.y0[(int64_t)el * D + c];
+    double v = a.y0[env.col_v];
+    auto pick_mode = [&](const double* m) { return env.pick_mode(m); };
+    auto emit = [&](int row, double vv, double mv) { env.emit(row, vv, mv); };
+    auto rhs_lane = [&](double t, const double* ymt, double vt, double* dm) { return env.rhs(t, ymt, vt, dm); };
 
     if (live) {
         emit(0, v, pick_mode(ym));
@@ -1024,9 +1069,7 @@ __global__ void __launch_bounds__(BLOCK) dopri5_lanes_kernel(const __grid_consta
                     if (l == c) { k1 = km[0][c]; k3 = km[2][c]; k4 = km[3][c]; k5 = km[4][c]; k6 = km[5][c]; k7 = km[6][c]; }
                 sq += err_term(k1, k3, k4, k5, k6, k7, pick_mode(ym), pick_mode(ymt));
             }
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) sq += __shfl_xor_sync(gmask, sq, o, 16);
-            sq = __shfl_sync(gmask, sq, 0, 16);   // one value for the whole env: the controller must not diverge inside it
+            sq = env.env_sum(sq);
             const double err = sqrt(sq / (double)D);
             if (err <= 1.0) {
                 double fac = (err == 0.0) ? dp::MAX_FACTOR : fmin(dp::MAX_FACTOR, fmax(dp::MIN_FACTOR, dp::SAFETY * pow(err, -0.2)));
@@ -1080,19 +1123,9 @@ __global__ void __launch_bounds__(BLOCK) dopri5_lanes_kernel(const __grid_consta
                 ++n_rej;
             }
         }
-        const double mv = pick_mode(ym);
-        if (a.y_last) {
-            a.y_last[col_v] = v;
-            if (mode_lane) a.y_last[col_v - 2 * M] = mv;
-        }
-        if (l == 0) {
-            if (a.h_state) a.h_state[e] = h;
-            if (a.n_steps) { a.n_steps[2 * e] += n_acc; a.n_steps[2 * e + 1] += n_rej; }
-        }
-        const bool bad = next_row <= K || !isfinite(v) || !isfinite(mv);   // step budget exhausted, or NaN / Inf
-        if (a.nan_flag && bad) *a.nan_flag = 1;
+        env.finish(v, ym, h, true, n_acc, n_rej, next_row <= K /* step budget exhausted */);
     }
-    if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
+    if (a.obs_minmax) block_minmax_commit(env.lo, env.hi, a.obs_minmax);
 }
 
 }  // namespace qrl

@@ -115,6 +115,9 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         # ---- additions of the b200 backend ----
         "rng": "philox",            # 'philox': in-kernel Philox4x32-10 noise; 'fed': pre-drawn tensors (reference layout)
         "return_numpy": False,      # step()/reset() return NumPy (pinned D2H) instead of device tensors
+        "host_output_views": False,  # with return_numpy: step() returns VIEWS of the pinned step buffer (double buffered:
+                                     # valid until the end of the NEXT step) instead of fresh copies — the reference
+                                     # returns views of its own buffers too (base.py:1293); saves two host copies per step
         "env_offset": 0,            # global index of local env 0 (multi-GPU sharding)
         "store_trajectory": True,   # keep the (K+1,E,n) States/Observations/Reward blocks (reference semantics)
         "cache_compressed": True,
@@ -192,6 +195,7 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         self.rng = kwargs["rng"]
         self.env_offset = int(kwargs["env_offset"])
         self.return_numpy = bool(kwargs["return_numpy"])
+        self.host_output_views = bool(kwargs["host_output_views"]) and self.return_numpy
         self.store_trajectory = bool(kwargs["store_trajectory"])
 
         # data / cache constants (base.py:221-240)
@@ -234,10 +238,15 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         self._minmax = self._step_out[E * (no + 1):E * (no + 1) + 2]
         self._minmax_init = torch.tensor([float("inf"), float("-inf")], dtype=f64, device=self.device)
         self._nan = torch.zeros((1,), dtype=torch.int32, device=self.device)
-        self._h_out = torch.empty(self._step_out.shape, dtype=f64).pin_memory()
+        # pinned result buffers: two when step() hands out views (the kernel of step i+1 must not write where the caller
+        # may still read the results of step i)
+        self._h_out_bufs = [torch.empty(self._step_out.shape, dtype=f64).pin_memory()
+                            for _ in range(2 if self.host_output_views else 1)]
+        self._h_out_nps = [b.numpy() for b in self._h_out_bufs]
+        self._h_sel = 0
+        self._h_out, self._h_out_np = self._h_out_bufs[0], self._h_out_nps[0]
         self._h_actions = torch.empty((E, self.n_actions), dtype=f64).pin_memory()
         self._h_actions_np = self._h_actions.numpy()       # NumPy views of the pinned staging buffers (cheap indexing)
-        self._h_out_np = self._h_out.numpy()
         self.rewards = None
         self.data_rewards = []
         self._data_dev = None
@@ -330,6 +339,9 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         else:
             # host actions: one NumPy copy into pinned memory, then an asynchronous H2D on the launch stream
             self._h_actions_np[...] = np.asarray(actions, dtype=np.float64).reshape(self.n_envs, self.n_actions)
+            if self.host_output_views:      # this step's results go to the other pinned buffer
+                self._h_sel ^= 1
+                self._h_out, self._h_out_np = self._h_out_bufs[self._h_sel], self._h_out_nps[self._h_sel]
             if getattr(self, "use_cuda_graph", False):
                 self._host_step = True      # H2D of the actions and D2H of the results are nodes of the captured graph
                 return
@@ -454,7 +466,10 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         if truncated:
             print(f"Batch #{self.batch_idx} truncated")
         E, no = self.n_envs, self.n_observations
-        if self.return_numpy:
+        if self.host_output_views:
+            reward_out = self._h_out_np[E * no:E * (no + 1)]
+            obs_out = self._h_out_np[:E * no].reshape(E, no)
+        elif self.return_numpy:
             reward_out = self._h_out_np[E * no:E * (no + 1)].copy()
             obs_out = self._h_out_np[:E * no].reshape(E, no).copy()
         else:
@@ -491,7 +506,7 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
             self._obs_last = obs_view
         if reward_view is not None:
             self._reward_last = reward_view
-        self._graph = self._graph_host = None
+        self._graph = self._graph_host = self._graph_host1 = None
         if hasattr(self, "_static"):
             self._static = {}
 

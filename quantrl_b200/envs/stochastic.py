@@ -80,7 +80,7 @@ class LinearVecEnv(BaseVecEnv):
         self._dyn = torch.zeros((2,), dtype=torch.int64, device=self.device)      # {t_idx, episode} read by the kernel
         self._dyn_host = torch.zeros((2,), dtype=torch.int64).pin_memory()
         self._actions_in = torch.zeros((self.n_envs, self.n_actions), dtype=torch.float64, device=self.device)
-        self._graph = self._graph_host = None
+        self._graph = self._graph_host = self._graph_host1 = None
         self._static = {}                   # cached argument blocks of the single-kernel step (_relaunch_interval)
         self._actions_src = None
         self.graph_replays, self.graph_native_launches = 0, 0
@@ -262,7 +262,7 @@ class LinearVecEnv(BaseVecEnv):
     def attach_peer_barrier(self, flag_ptrs, epoch, rank, world):
         """Fuse the per-step cross-GPU barrier of the sharded path into the captured step kernel (ABI 3)."""
         self._peer_barrier = (flag_ptrs, epoch, int(rank), int(world))
-        self._graph = self._graph_host = None
+        self._graph = self._graph_host = self._graph_host1 = None
         self._static = {}
 
     def _zero_copy(self):
@@ -272,10 +272,11 @@ class LinearVecEnv(BaseVecEnv):
             return None
         if self._zc is None:
             try:
-                self._zc = {"out": N.host_device_pointer(self._h_out), "actions": N.host_device_pointer(self._h_actions)}
+                act = N.host_device_pointer(self._h_actions)
+                self._zc = [{"out": N.host_device_pointer(b), "actions": act} for b in self._h_out_bufs]
             except N.NativeError:
                 self._zc = False    # pinned memory not mapped on this platform: keep the copy nodes
-        return self._zc or None
+        return self._zc[self._h_sel] if self._zc else None
 
     def _initial_observations(self, states_0):
         self._launch(0, states_0, write_traj=False)  # row 0 only: obs_0 = states_0 + noise[0]
@@ -358,7 +359,8 @@ class LinearVecEnv(BaseVecEnv):
         with ``host_zero_copy`` (default, ``return_numpy`` envs) the kernel itself reads the actions from and writes
         ``[obs_last | reward_last | min,max]`` to pinned host memory over PCIe, so the graph is still one kernel;
         otherwise it starts with the H2D copy of the actions and ends with the D2H copy of the results."""
-        key = "_graph_host" if host_io else "_graph"
+        # the host graph is captured per pinned result buffer (two of them when step() hands out views)
+        key = ("_graph_host" if self._h_sel == 0 else "_graph_host1") if host_io else "_graph"
         if getattr(self, key, None) is None:
             K = self.action_interval
             side = torch.cuda.Stream(device=self.device)

@@ -260,10 +260,14 @@ def test_cuda_graph_replay_equals_eager(native, cuda):
     eager, graph = AffineLinearVecEnv(**kw), AffineLinearVecEnv(use_cuda_graph=True, **kw)
     # host-I/O variant: NumPy actions in, NumPy results out; H2D + kernel + D2H replayed as one graph
     hostg = AffineLinearVecEnv(use_cuda_graph=True, return_numpy=True, **kw)
+    # ... and the same handing out VIEWS of its (double buffered) pinned result buffers instead of copies
+    hostv = AffineLinearVecEnv(use_cuda_graph=True, return_numpy=True, host_output_views=True, fused_coefficients=True, **kw)
     assert eager.shape_T == (46,) and eager.action_steps == 5         # 4 full intervals + a tail of 5 sub-steps
     o_e, o_g, o_h = eager.reset(), graph.reset(), hostg.reset()
+    hostv.reset()
     assert torch.equal(o_e, o_g) and np.array_equal(o_e.cpu().numpy(), o_h)
     rng = np.random.default_rng(0)
+    prev_view = prev_copy = None
     for step in range(10):
         u = torch.as_tensor(rng.uniform(-1, 1, (E, 1)), device="cuda")
         if step == 3:
@@ -275,12 +279,20 @@ def test_cuda_graph_replay_equals_eager(native, cuda):
         assert torch.equal(oe, og) and torch.equal(re_, rg) and de == dg
         assert isinstance(oh, np.ndarray) and np.array_equal(oe.cpu().numpy(), oh) and np.array_equal(re_.cpu().numpy(), rh)
         assert dh == de and len(ih) == E and hostg.t_idx == eager.t_idx
+        ov, rv, dv, _ = hostv.step(u.cpu().numpy())
+        # in-kernel affine drift vs the torch hook: one fused multiply-add of rounding (see the test below)
+        np.testing.assert_allclose(ov, oh, rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(rv, rh, rtol=1e-12, atol=1e-14)
+        assert dv == dh and isinstance(ov, np.ndarray)
+        if prev_view is not None:     # the results of the previous step are still intact after this one
+            np.testing.assert_array_equal(prev_view, prev_copy)
+        prev_view, prev_copy = (ov, ov.copy()) if not dv[0] else (None, None)
         assert torch.equal(eager.States, graph.States) and torch.equal(eager.rewards, graph.rewards)
         assert eager.t_idx == graph.t_idx
     assert graph.graph_replays == 8 and graph.graph_native_launches == 1 and eager.batch_idx == graph.batch_idx == 2
     assert hostg.graph_replays == 8 and hostg.batch_idx == 2
     np.testing.assert_array_equal(hostg.data, eager.data)
-    eager.close(); graph.close(); hostg.close()
+    eager.close(); graph.close(); hostg.close(); hostv.close()
 
 
 def test_fused_affine_coefficients_match_hook_path(native, cuda):

@@ -72,17 +72,18 @@ def _single_rhs(osys, p, m, q):
     return f
 
 
+@pytest.mark.parametrize("flags", [0, 1])   # 0: default (q = 4, small batch: 16 lanes per env), 1: one thread per env
 @pytest.mark.parametrize("fname,tag,osys,system", CASES[:2])
-def test_dopri5_default_tolerance_follows_oracle_controller(native, cuda, golden_dir, fname, tag, osys, system):
-    """Same controller, same accept/reject sequence: kernel == oracle/lyap_oracle.py:dopri5_dense_interval at the
-    reference's default tolerances (atol 1e-9, rtol 1e-6), including the carried step size and the step counts."""
+def test_dopri5_default_tolerance_follows_oracle_controller(native, cuda, golden_dir, fname, tag, osys, system, flags):
+    """Same controller, same accept/reject sequence: both dopri5 kernels == oracle/lyap_oracle.py:dopri5_dense_interval
+    at the reference's default tolerances (atol 1e-9, rtol 1e-6), including the carried step size and the step counts."""
     g, p, y0, acts, T, K, m, q = _load(golden_dir, fname, tag)
     f = _single_rhs(osys, p, m, q)
     y, h, yk, hk = y0, None, y0, None
     for a in range(4):
         Y, nacc, nrej, h = lo.dopri5_dense_interval(f, float(T[a * K]), 0.01, K, y, lambda e: acts[a][e, 0], 1e-9, 1e-6, h)
         out = ode_step(system, m, q, yk, K, float(T[a * K]), 0.01, params=p, actions=acts[a][:, 0], method="dopri5",
-                       atol=1e-9, rtol=1e-6, h_state=hk)
+                       atol=1e-9, rtol=1e-6, h_state=hk, flags=flags)
         np.testing.assert_allclose(out["states"].cpu().numpy(), Y, rtol=1e-9, atol=1e-11)
         np.testing.assert_array_equal(out["n_steps"].cpu().numpy(), np.stack([nacc, nrej], 1))
         np.testing.assert_allclose(out["h_state"].cpu().numpy(), h, rtol=1e-6)
@@ -310,11 +311,13 @@ def test_fused_synchronization_and_entanglement_rewards_match_reference(native, 
 ERK_ADAPTIVE = ["bosh3", "tsit5", "adaptive_heun", "fehlberg2", "dop853"]
 
 
+@pytest.mark.parametrize("flags", [0, 1])   # 0: default (q = 4, small batch: 16 lanes per env), 1: one thread per env
 @pytest.mark.parametrize("method", ERK_ADAPTIVE)
 @pytest.mark.parametrize("fname,tag,osys,system", CASES[:2])
-def test_generic_erk_engine_follows_oracle_controller(native, cuda, golden_dir, fname, tag, osys, system, method):
-    """Generic explicit RK engine (csrc/ode_erk.cuh) == oracle/lyap_oracle.py:erk_interval for every adaptive tableau:
-    same states, the same accept/reject counts and the same carried step size over consecutive intervals."""
+def test_generic_erk_engine_follows_oracle_controller(native, cuda, golden_dir, fname, tag, osys, system, method, flags):
+    """Generic explicit RK engine (csrc/ode_erk.cuh), both layouts == oracle/lyap_oracle.py:erk_interval for every
+    adaptive tableau: same states, the same accept/reject counts and the same carried step size over consecutive
+    intervals."""
     g, p, y0, acts, T, K, m, q = _load(golden_dir, fname, tag)
     f = _single_rhs(osys, p, m, q)
     atol, rtol = (1e-9, 1e-6) if method != "dop853" else (1e-12, 1e-10)
@@ -322,7 +325,7 @@ def test_generic_erk_engine_follows_oracle_controller(native, cuda, golden_dir, 
     for a in range(3):
         Y, nacc, nrej, h = lo.erk_interval(method, f, float(T[a * K]), 0.01, K, y, lambda e: acts[a][e, 0], atol, rtol, h)
         out = ode_step(system, m, q, yk, K, float(T[a * K]), 0.01, params=p, actions=acts[a][:, 0], method=method,
-                       atol=atol, rtol=rtol, h_state=hk)
+                       atol=atol, rtol=rtol, h_state=hk, flags=flags)
         np.testing.assert_allclose(out["states"].cpu().numpy(), Y, rtol=1e-9, atol=1e-11)
         np.testing.assert_array_equal(out["n_steps"].cpu().numpy(), np.stack([nacc, nrej], 1))
         # (DOP853 at 1e-12: the two error estimates are differences at rounding level, the next step size follows them)
@@ -338,8 +341,10 @@ def test_generic_erk_fixed_step_methods(native, cuda, golden_dir, method, subste
     g, p, y0, acts, T, K, m, q = _load(golden_dir, "lyap_optomech.npz", "E5")
     f = _single_rhs("optomech", p, m, q)
     Y, _, _, _ = lo.erk_interval(method, f, 0.0, 0.01, K, y0, lambda e: acts[0][e, 0], substeps=substeps)
-    out = ode_step("optomech", m, q, y0, K, 0.0, 0.01, params=p, actions=acts[0][:, 0], method=method, substeps=substeps)
-    np.testing.assert_allclose(out["states"].cpu().numpy(), Y, rtol=1e-11, atol=1e-13)
+    for flags in (0, 1):   # lanes layout / one thread per env
+        out = ode_step("optomech", m, q, y0, K, 0.0, 0.01, params=p, actions=acts[0][:, 0], method=method, substeps=substeps,
+                       flags=flags)
+        np.testing.assert_allclose(out["states"].cpu().numpy(), Y, rtol=1e-11, atol=1e-13)
     ref = g["E5_States_dop853_tight"][:K + 1]
     errs = []
     for ss in (substeps, 2 * substeps):

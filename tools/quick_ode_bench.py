@@ -22,7 +22,7 @@ def bench(system, E, m, q, K=100, method="rk4", reps=10, traj=True, atol=1e-9, r
     a = N.OdeArgs()
     a.system = {"optomech": N.SYS_OPTOMECH, "kerr_chain": N.SYS_KERR_CHAIN}[system]
     a.num_modes, a.num_quads, a.n_envs, a.K = m, q, E, K
-    a.method = N.ODE_RK4 if method == "rk4" else N.ODE_DOPRI5
+    a.method = N.ODE_METHODS[method][0]
     a.substeps, a.t0, a.t_ssz, a.atol, a.rtol = 1, 0.0, 0.01, atol, rtol
     a.params, a.params_stride_e, a.actions, a.n_actions = N.ptr(P), P.shape[1], N.ptr(u), 1
     a.y0, a.y_last, a.obs_last = N.ptr(yl), N.ptr(yl), N.ptr(ol)
