@@ -15,6 +15,7 @@ The only exchange is the learner protocol of one action step:
 The truncation flag rides in the same buffer (column ``n_obs + 1``): the reference ends the episode for ALL envs
 when any observation leaves the range (quantrl/envs/base.py:485-499, 1271-1293), so the learner ORs the flags.
 """
+import os
 import torch
 import torch.distributed as dist
 
