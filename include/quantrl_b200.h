@@ -285,7 +285,8 @@ typedef struct qrl_ode_args {
 
 /* Kernel selection of qrl_ode_step at num_quads = 4 (all variants perform the same operations; measured crossovers on
  * B200 in DESIGN.md 4.2):  RK4: n_envs <= 1536 split kernel, <= 3072 single-role lanes kernel, else one thread per env;
- * DOPRI5: n_envs <= 32768 lanes kernel, else one thread per env.  Other num_quads: one thread per env. */
+ * DOPRI5 and the other explicit-RK methods: n_envs <= 12288 lanes kernel, else one thread per env.  Other num_quads:
+ * one thread per env. */
 #define QRL_ODE_FORCE_THREAD 1  /* flags: RK4 / DOPRI5 with one thread per env whatever the batch size (A/B testing) */
 #define QRL_ODE_FORCE_LANES  2  /* flags: RK4 / DOPRI5 with q*q lanes per env (q = 4 only) whatever the batch size; RK4: the
                                 * warp-specialised split kernel (mode producer / covariance lanes / row writers) */

@@ -1198,8 +1198,8 @@ int launch_ode(const qrl_ode_args& a, cudaStream_t st) {
     if constexpr (Sys::Q == 4) {
         // q = 4: 16 lanes per env, stage derivatives in registers.  B200, 100 grid rows, default tolerances (8.5 steps per
         // interval), lanes vs thread per env: E = 64: 89 vs 477 us, 1024: 98 vs 534 us, 8192: 377 vs 583 us,
-        // 65536: 2.57 vs 2.12 ms (tools/quick_ode_bench.py)
-        const bool lanes = (a.n_envs <= 32768 || (a.flags & QRL_ODE_FORCE_LANES)) && !(a.flags & QRL_ODE_FORCE_THREAD);
+        // 16384: 675 vs 629 us, 65536: 2.57 vs 2.12 ms (tools/quick_ode_bench.py)
+        const bool lanes = (a.n_envs <= 12288 || (a.flags & QRL_ODE_FORCE_LANES)) && !(a.flags & QRL_ODE_FORCE_THREAD);
         if (lanes) {
             constexpr int BL = 64;
             dopri5_lanes_kernel<Sys, BL><<<(a.n_envs + BL / 16 - 1) / (BL / 16), BL, 0, st>>>(a);
