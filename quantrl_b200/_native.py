@@ -127,9 +127,15 @@ def ptr(t):
     return t.data_ptr()
 
 
-def current_stream():
+def current_raw_stream() -> int:
+    """``cudaStream_t`` of torch's current stream on the current device.  ``torch.cuda.current_stream()`` builds a Stream
+    object and re-validates the device every call (~10 us, measured per step); the raw handle costs well under 1 us."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+
+
+def current_stream():
+    return C.c_void_p(current_raw_stream())
 
 
 def em_step(args: EmArgs, stream=None):

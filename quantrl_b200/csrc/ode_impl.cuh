@@ -777,9 +777,12 @@ __global__ void __launch_bounds__(EPB * 16 + 32 + 128) rk4_split_kernel(const __
             p += NW; g2 += NW; s2 += NW;
             while (p >= RL2 && r < n_rows) { p -= RL2; ++r; g2 += row_pitch2 - RL2; s2 += ring_pitch2 - RL2; }
         }
-        if (a.reward_kind != QRL_REWARD_NONE && lane < n_live)
-            for (int rr = 0; rr < n_rows; ++rr)
-                ode_reward_row_mem<M, Q>(a, row_first + rr, e0 + lane, Rslot + (size_t)rr * nsub * RW + lane * D);
+        // fused reward: one (row, env) evaluation per writer thread and trip
+        if (a.reward_kind != QRL_REWARD_NONE)
+            for (int idx = lane; idx < n_rows * n_live; idx += NW) {
+                const int rr = idx / n_live, elx = idx - rr * n_live;
+                ode_reward_row_mem<M, Q>(a, row_first + rr, e0 + elx, Rslot + (size_t)rr * nsub * RW + elx * D);
+            }
     };
 
     // ---- row 0: the initial state goes through slot 0 of row buffer 2 (free until iteration 2) ----

@@ -441,7 +441,10 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
     def _fetch_step_outputs(self):
         """One D2H of [obs_last | reward_last | min,max] into pinned memory, then a stream sync."""
         self._h_out.copy_(self._step_out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        raw = N.current_raw_stream()
+        if raw != getattr(self, "_sync_raw", None):     # the Stream object is looked up again only when the stream changes
+            self._sync_raw, self._sync_stream = raw, torch.cuda.current_stream()
+        self._sync_stream.synchronize()
         return self._h_out
 
     def check_truncation(self, host=None):
