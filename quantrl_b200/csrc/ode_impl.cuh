@@ -882,14 +882,16 @@ struct LaneEnv {
     static constexpr int M = Sys::M, Q = Sys::Q, D = 2 * Sys::M + Sys::Q * Sys::Q, L = Sys::Q * Sys::Q;
     static constexpr int M2 = 2 * M > 0 ? 2 * M : 1;
     static_assert(L == 16, "the lanes kernels are written for q = 4");
+    static constexpr int RB = L;                         // rows buffered per env for the fused reward
     struct Smem {
         alignas(16) double A[2][EPB][L], V[2][EPB][L];   // exchange tiles, double buffered over the RHS evaluations
-        alignas(16) double row[EPB][D];                  // one env's row [modes | V] for the fused reward
+        alignas(16) double rows[EPB][RB][D];             // rows [modes | V] waiting for their fused reward
+        int ridx[EPB][RB];                               // ... and their grid-row indices
     };
     const qrl_ode_args& a;
     Smem& sm;
     Sys s;
-    int g, l, i, j, e, el, par = 0, noise;
+    int g, l, i, j, e, el, par = 0, noise, nbuf = 0;
     unsigned gmask;
     bool live, mode_lane;
     int64_t col_v, row_pitch;
@@ -938,14 +940,20 @@ struct LaneEnv {
         lo = fmin(lo, ov);
         hi = fmax(hi, ov);
         if (mode_lane) { lo = fmin(lo, om); hi = fmax(hi, om); }
+        // fused reward: rows are collected and evaluated RB at a time, one row per lane (one lane evaluating every
+        // row as it appears put ~400 cycles of measure arithmetic per row on the env's critical path)
         if (a.reward_kind != QRL_REWARD_NONE) {
-            __syncwarp(gmask);
-            sm.row[g][2 * M + l] = vv;
-            if (mode_lane) sm.row[g][l] = mv;
-            __syncwarp(gmask);
-            if (l == 0) ode_reward_row_mem<M, Q>(a, row, e, sm.row[g]);
-            __syncwarp(gmask);
+            sm.rows[g][nbuf][2 * M + l] = vv;
+            if (mode_lane) sm.rows[g][nbuf][l] = mv;
+            if (l == 0) sm.ridx[g][nbuf] = row;
+            if (++nbuf == RB) flush_rewards();
         }
+    }
+    __device__ __forceinline__ void flush_rewards() {
+        __syncwarp(gmask);
+        if (l < nbuf) ode_reward_row_mem<M, Q>(a, sm.ridx[g][l], e, sm.rows[g][l]);
+        __syncwarp(gmask);
+        nbuf = 0;
     }
     // one RHS evaluation at (modes ymt, my element vt): returns dV_ij, fills dm  (cf. rk4_lanes_kernel; same order of
     // operations as rhs())
@@ -980,6 +988,7 @@ struct LaneEnv {
     }
     // end of the launch: carry-over of the last state, controller state, failure flag
     __device__ __forceinline__ void finish(double v, const double* ym, double h, bool has_h, int n_acc, int n_rej, bool failed) {
+        if (nbuf > 0) flush_rewards();
         const double mv = pick_mode(ym);
         if (a.y_last) {
             a.y_last[col_v] = v;
