@@ -221,8 +221,9 @@ typedef struct qrl_em_args {
                                  * completion before reading anything), which hides the launch latency between the
                                  * back-to-back step kernels of a device-resident loop */
 #define QRL_EM_PACK_TMA     128 /* flags: reserved (accepted and ignored; the cache rows are written from registers) */
-/* flag bits 2, 4, 8 are diagnostics of the tiled kernel (skip produce / recurrence / output stage) and bits 512, 1024 of
- * the peer barrier (gpu-scope fences only / signal without waiting); results invalid */
+/* flag bits 2, 4, 8 are diagnostics of the tiled kernel (skip produce / recurrence / output stage; results invalid) and
+ * bits 512, 1024, 2048, 4096 of the peer barrier (gpu-scope fences only / signal without waiting: results not
+ * synchronised; extra system fence after the flag stores / volatile polling + trailing system fence: A/B variants) */
 
 QRL_API int qrl_em_step(const qrl_em_args* args, void* stream);
 
@@ -291,6 +292,8 @@ typedef struct qrl_ode_args {
 #define QRL_ODE_FORCE_LANES  2  /* flags: RK4 / DOPRI5 with q*q lanes per env (q = 4 only) whatever the batch size; RK4: the
                                 * warp-specialised split kernel (mode producer / covariance lanes / row writers) */
 #define QRL_ODE_LANES_SINGLE 4 /* flags: with FORCE_LANES (or a small batch), the single-role lanes kernel (A/B testing) */
+/* flags bits 8 / 16 / 32: diagnostics of the split kernel only (skip the producer / consumer / writer role; results are
+ * then meaningless) — used by tools/prof_ode.py to time the roles alone */
 
 QRL_API int qrl_ode_step(const qrl_ode_args* args, void* stream);
 
