@@ -139,30 +139,6 @@ __device__ __noinline__ void ode_reward_row_mem(const qrl_ode_args& a, int row, 
     ode_reward_row<M, Q>(a, row, e, y);
 }
 
-// Fused reward of a whole (K+1, E, D) block as a second, small launch behind the thread-per-env RK4 kernel.  Inside that
-// kernel an out-of-line call per row costs a spill and reload of ~150 live registers per thread (measured: 0.53 -> 2.4 ms
-// per interval at E = 65536), and inlined the measure's arithmetic perturbs the integrator's register allocation; the
-// block just written is still largely L2-resident, so re-reading it is cheap.  One thread per (row, env); the odd reward
-// kinds read the Observations rows (the stored values, measurement noise included), the even ones the States rows.
-template <int M, int Q>
-__global__ void __launch_bounds__(256) ode_reward_rows_kernel(const __grid_constant__ qrl_ode_args a) {
-    constexpr int D = 2 * M + Q * Q;
-    const int64_t total = (int64_t)(a.K + 1) * a.n_envs;
-    const double* block = (a.reward_kind & 1) ? a.observations : a.states;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int row = (int)(idx / a.n_envs), e = (int)(idx - (int64_t)row * a.n_envs);
-        const double2* src = reinterpret_cast<const double2*>(block + idx * D);
-        double yv[D];
-#pragma unroll
-        for (int c = 0; c < D / 2; ++c) {
-            const double2 t = src[c];
-            yv[2 * c] = t.x;
-            yv[2 * c + 1] = t.y;
-        }
-        ode_reward_store(a, row, e, ode_reward_value<M, Q>(a.reward_kind, yv));
-    }
-}
-
 // One grid row of ONE environment, written by its own thread — the adaptive kernels, where the lanes of a warp reach
 // a row at different times.  The row sits in a shared-memory column (element d at col[d * stride]).  A compact loop
 // (not unrolled) over PAIRS of components: one Philox call (out of line), one 16-byte store per tensor.  Unrolled over
@@ -1212,21 +1188,8 @@ int launch_ode(const qrl_ode_args& a, cudaStream_t st) {
         const int blocks = (a.n_envs + BLOCK - 1) / BLOCK;
         // 204 registers at q = 4 = 2 warps per scheduler; capping at 168 (3 warps, 4 bytes of spill) measured slower at
         // every batch size (0.67 vs 0.58 ms at E = 65536)
-        if constexpr (Sys::Q == 4) {
-            // fused reward: a second small launch over the block just written whenever that block exists
-            const double* rows = (a.reward_kind & 1) ? a.observations : a.states;
-            if (a.reward_kind != QRL_REWARD_NONE && rows != nullptr) {
-                qrl_ode_args b = a;
-                b.reward_kind = QRL_REWARD_NONE;
-                rk4_kernel<Sys, BLOCK><<<blocks, BLOCK, smem, st>>>(b);
-                const int rc = after_launch("rk4_kernel");
-                if (rc != 0) return rc;
-                const int64_t total = (int64_t)(a.K + 1) * a.n_envs;
-                const int rblocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-                ode_reward_rows_kernel<Sys::M, Sys::Q><<<rblocks, 256, 0, st>>>(a);
-                return after_launch("ode_reward_rows_kernel");
-            }
-        }
+        // (fused reward: evaluated in the kernel, out of line, +0.18 ms per interval at E = 65536 with the log-negativity on
+        // all 101 rows; a separate launch over the block just written measured the same, 0.708 vs 0.703 ms)
         rk4_kernel<Sys, BLOCK><<<blocks, BLOCK, smem, st>>>(a);
         return after_launch("rk4_kernel");
     }

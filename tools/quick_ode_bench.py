@@ -6,7 +6,7 @@ import numpy as np, torch
 import systems as sy
 from quantrl_b200 import _native as N
 
-def bench(system, E, m, q, K=100, method="rk4", reps=10, traj=True, atol=1e-9, rtol=1e-6, flags=0):
+def bench(system, E, m, q, K=100, method="rk4", reps=10, traj=True, atol=1e-9, rtol=1e-6, flags=0, reward_kind=0):
     dev = "cuda"
     d = 2 * m + q * q
     if system == "optomech":
@@ -30,6 +30,9 @@ def bench(system, E, m, q, K=100, method="rk4", reps=10, traj=True, atol=1e-9, r
         a.states, a.observations = N.ptr(S), N.ptr(O)
     a.h_state, a.n_steps, a.obs_minmax, a.nan_flag = N.ptr(hs), N.ptr(ns), N.ptr(mm), N.ptr(nan)
     a.flags = flags
+    if reward_kind:
+        R = torch.empty((K + 1, E), dtype=torch.float64, device=dev); rl = torch.empty((E,), dtype=torch.float64, device=dev)
+        a.reward_kind, a.reward, a.reward_last = reward_kind, N.ptr(R), N.ptr(rl)
     for _ in range(3):
         N.ode_step(a)
     torch.cuda.synchronize()
@@ -49,7 +52,7 @@ def bench(system, E, m, q, K=100, method="rk4", reps=10, traj=True, atol=1e-9, r
     sub = E * K / (ms * 1e-3)
     steps = ns.sum().item() / reps if method != "rk4" else E * K
     flops = (4 * (4 * q ** 3 + 40) + 13 * d) if method == "rk4" else 0
-    return dict(system=system, E=E, q=q, method=method, traj=traj, flags=flags, ms=round(ms, 4), substeps_per_s=f"{sub:.3e}",
+    return dict(system=system, E=E, q=q, method=method, traj=traj, flags=flags, reward_kind=reward_kind, ms=round(ms, 4), substeps_per_s=f"{sub:.3e}",
                 rk_steps_per_interval=steps / E, gflops=round(sub * flops / 1e9, 1), hbm_GBs=round(sub * 8 * (2 * d + 1) / 1e9, 1) if traj else 0)
 
 if __name__ == "__main__":
