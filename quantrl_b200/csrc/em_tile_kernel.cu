@@ -56,9 +56,9 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
     // still draining; everything it reads (dyn, x0, cumulative rewards) is only valid after the wait.  Its own
     // dependents are released at once — they block on the same wait and, at 200 KB of shared memory per CTA, cannot
     // become resident before this grid's CTAs have exited anyway; what overlaps is the launch latency.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const qrl_em_args a = resolve_dyn(a_in);
+    // `a` holds the launch arguments; the device-resident {t_idx, episode} are folded in after the wait below
+    qrl_em_args a = a_in;
     extern __shared__ __align__(128) double sm[];
     const int E = a.n_envs, K = a.K;
     const int e0 = blockIdx.x * G;
@@ -88,10 +88,12 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
     const int n_sel = a.n_sel;
     const int pitch = a.packed ? (int)(a.packed_row_pitch > 0 ? a.packed_row_pitch : a.n_sel) : 0;
 
+    // constants of a step sequence first (measurement-noise stds, reward weights, cache column selection: no step kernel
+    // ever writes them), so that with programmatic dependent launch a CTA that became resident while the previous grid
+    // is still draining has its first global round trip behind it when the wait returns
     for (int i = tid; i < Gl * N; i += EM_TILE_THREADS) {
         const int el = i / N, c = i - el * N;
         stdS[i] = (philox && a.obs_std) ? a.obs_std[(int64_t)(e0 + el) * a.obs_std_stride_e + c] : 0.0;
-        x0S[i] = a.x0[(int64_t)e0 * N + i];
     }
     if (tid < N) wS[tid] = has_reward ? a.reward_w[tid] : 0.0;
     if (a.packed)
@@ -99,6 +101,32 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
             const int s = a.sel_idxs[i];
             selS[i] = s < 0 ? s + n_data : s;
         }
+    // ... and with QRL_EM_PDL (a device-resident loop of single-kernel steps: the drift base, the action-affine part and
+    // the noise prefixes are constants of the sequence) the recurrence lanes pull their coefficient lines into L1
+    if ((a.flags & QRL_EM_PDL) && is_rec && tid < Gl) {
+        const char* Ab = reinterpret_cast<const char*>(a.A + (int64_t)(e0 + tid) * a.A_stride_e);
+        for (int b = 0; b < N * N * 8; b += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(Ab + b));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.nz + (int64_t)(e0 + tid) * a.nz_stride_e));
+        if (a.A_act && tid < a.n_actions) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.A_act + (int64_t)tid * N * N));
+    }
+    // everything below reads what the previous kernel of the stream wrote (dyn, x0, cumulative rewards, actions)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // the initial states do not depend on the device-resident time index: their loads go out first, so that the two
+    // global round trips (x0, dyn) overlap
+    {
+        double x0r[(32 * N + EM_TILE_THREADS - 1) / EM_TILE_THREADS];
+#pragma unroll
+        for (int u = 0; u < (32 * N + EM_TILE_THREADS - 1) / EM_TILE_THREADS; ++u) {
+            const int i = tid + u * EM_TILE_THREADS;
+            x0r[u] = i < Gl * N ? a.x0[(int64_t)e0 * N + i] : 0.0;
+        }
+        a = resolve_dyn(a_in);
+#pragma unroll
+        for (int u = 0; u < (32 * N + EM_TILE_THREADS - 1) / EM_TILE_THREADS; ++u) {
+            const int i = tid + u * EM_TILE_THREADS;
+            if (i < Gl * N) x0S[i] = x0r[u];
+        }
+    }
     __syncthreads();
     // does any selected cache column have to be written row by row?  (the cumulative-reward column is only known
     // after the last sub-step and is written for all K+1 rows at the end)
