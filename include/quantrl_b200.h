@@ -221,6 +221,10 @@ typedef struct qrl_em_args {
                                  * completion before reading anything), which hides the launch latency between the
                                  * back-to-back step kernels of a device-resident loop */
 #define QRL_EM_PACK_TMA     128 /* flags: reserved (accepted and ignored; the cache rows are written from registers) */
+#define QRL_EM_HOST_TIDX    64  /* flags: `dyn` is only ADVANCED by this launch (dyn_advance), not read: t_idx, episode and the
+                                 * pointers that depend on t_idx (W, obs_noise, T_step, packed) were set by the host for
+                                 * this launch — a host that re-enqueues every step anyway saves the kernel one global round
+                                 * trip before its first Philox counter */
 /* flag bits 2, 4, 8 are diagnostics of the tiled kernel (skip produce / recurrence / output stage; results invalid) and
  * bits 512, 1024, 2048, 4096 of the peer barrier (gpu-scope fences only / signal without waiting: results not
  * synchronised; extra system fence after the flag stores / volatile polling + trailing system fence: A/B variants) */

@@ -19,7 +19,7 @@ ODE_METHODS = {"rk4": (ODE_RK4, False), "dopri5": (ODE_DOPRI5, True), "bosh3": (
                "tsit5": (ODE_TSIT5, True), "adaptive_heun": (ODE_HEUN21, True), "heun": (ODE_HEUN21, True),
                "fehlberg2": (ODE_FEHLBERG2, True), "dop853": (ODE_DOP853, True), "DOP853": (ODE_DOP853, True),
                "dopri8": (ODE_DOP853, True), "euler": (ODE_EULER, False), "midpoint": (ODE_MIDPOINT, False)}
-EM_FORCE_GENERIC, EM_FORCE_TILED, EM_ITEM_OUTPUT, EM_PACK_TMA, EM_PDL = 1, 16, 32, 128, 256
+EM_FORCE_GENERIC, EM_FORCE_TILED, EM_ITEM_OUTPUT, EM_PACK_TMA, EM_PDL, EM_HOST_TIDX = 1, 16, 32, 128, 256, 64
 ODE_FORCE_THREAD, ODE_FORCE_LANES, ODE_LANES_SINGLE = 1, 2, 4
 
 _dp = C.c_void_p  # device pointers travel as integers

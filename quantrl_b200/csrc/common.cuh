@@ -45,7 +45,7 @@ inline int after_launch(const char* name) {
 // CUDA-graph replay support: fold the device-resident {t_idx, episode} into a private copy of the arguments
 __device__ __forceinline__ qrl_em_args resolve_dyn(const qrl_em_args& in) {
     qrl_em_args a = in;
-    if (in.dyn) {
+    if (in.dyn && !(in.flags & QRL_EM_HOST_TIDX)) {
         const int64_t t = in.dyn[0];
         const int64_t rows = t * (int64_t)in.n_envs * in.n;
         a.t_idx = t;

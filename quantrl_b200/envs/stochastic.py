@@ -334,18 +334,33 @@ class LinearVecEnv(BaseVecEnv):
             a, keep = self.interval_args(self.action_interval, self._x_last, True, graph_mode=key)
             if not host_io:
                 # back-to-back step kernels of a device-resident loop: programmatic dependent launch hides the launch
-                # latency between them (measured 32.2 -> 30.3 us per step at config 3)
-                a.flags |= N.EM_PDL
+                # latency between them (measured 32.2 -> 30.3 us per step at config 3); the host re-enqueues the block
+                # every step anyway, so it also supplies the time index (the kernel still advances the device-side copy
+                # for the graph paths) and the kernel does not wait for a global load before its first Philox counter
+                a.flags |= N.EM_PDL | N.EM_HOST_TIDX
             stream = torch.cuda.current_stream()
             self._replay_stream = stream       # looked up once: the call costs ~10 us per step otherwise
             st = self._static[key] = {"a": a, "keep": keep, "zc": zc, "packs": self._packed_by_kernel,
-                                      "stream": C.c_void_p(stream.cuda_stream), "default_actions": a.actions}
+                                      "stream": C.c_void_p(stream.cuda_stream), "default_actions": a.actions,
+                                      # bases of the t_idx-dependent pointers (interval_args leaves them at row 0 in graph mode)
+                                      "W": a.W, "obs_noise": a.obs_noise, "T_step": a.T_step, "packed": a.packed}
             self.graph_native_launches = 1
         a = st["a"]
         if host_io and st["zc"] is None:
             self._actions_in.copy_(self._h_actions, non_blocking=True)
         if not host_io:
             a.actions = actions_src.data_ptr() if actions_src is not None else st["default_actions"]
+            t = self.t_idx                      # EM_HOST_TIDX: what resolve_dyn() would derive from the device-side index
+            a.t_idx, a.episode = t, self.batch_idx & 0xFFFFFFFF
+            rows = 8 * t * self.n_envs * self.n_observations
+            if st["W"]:
+                a.W = st["W"] + rows
+            if st["obs_noise"]:
+                a.obs_noise = st["obs_noise"] + rows
+            if st["T_step"]:
+                a.T_step = st["T_step"] + 8 * t
+            if st["packed"]:
+                a.packed = st["packed"] + 8 * t * (a.packed_row_pitch if a.packed_row_pitch > 0 else a.n_sel)
         self._packed_by_kernel = st["packs"]
         N.em_step(a, st["stream"])
         if host_io and st["zc"] is None:

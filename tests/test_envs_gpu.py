@@ -307,7 +307,10 @@ def test_fused_affine_coefficients_match_hook_path(native, cuda):
               dir_prefix="/tmp/qrl_test")
     hook, fused, fgraph = AffineLinearVecEnv(**kw), AffineLinearVecEnv(fused_coefficients=True, **kw), \
         AffineLinearVecEnv(fused_coefficients=True, use_cuda_graph=True, **kw)
-    for e in (hook, fused, fgraph):
+    # device-resident loop: CUDA-tensor actions, the cached single-kernel argument block re-enqueued every step with
+    # the host-supplied time index (QRL_EM_HOST_TIDX) and programmatic dependent launch
+    fdev = AffineLinearVecEnv(fused_coefficients=True, use_cuda_graph=True, **kw)
+    for e in (hook, fused, fgraph, fdev):
         e.reset()
     rng = np.random.default_rng(1)
     for step in range(3):
@@ -315,13 +318,24 @@ def test_fused_affine_coefficients_match_hook_path(native, cuda):
         oh, rh, _, _ = hook.step(u)
         of, rf, _, _ = fused.step(u)
         og, rg, _, _ = fgraph.step(u)
+        od, rd, _, _ = fdev.step(torch.as_tensor(u, device="cuda"))
         torch.testing.assert_close(of, oh, rtol=1e-12, atol=1e-14)
         torch.testing.assert_close(rf, rh, rtol=1e-12, atol=1e-14)
         assert torch.equal(of, og) and torch.equal(rf, rg) and torch.equal(fused.States, fgraph.States)
+        assert torch.equal(of, od) and torch.equal(rf, rd) and torch.equal(fused.States, fdev.States)
     np.testing.assert_allclose(fused.data, hook.data, rtol=1e-12, atol=1e-14)
     np.testing.assert_array_equal(fused.data, fgraph.data)
+    np.testing.assert_array_equal(fused.data, fdev.data)
     np.testing.assert_allclose(fused.data[:, 21:30, 1:3], np.broadcast_to((u * [0.5, 2.0])[:, None, :], (E, 9, 2)), rtol=1e-15)
-    for e in (hook, fused, fgraph):
+    # across the episode boundary (4 action steps per episode) and into the second episode
+    for step in range(4):
+        u = rng.uniform(-1, 1, (E, 2))
+        of, rf, df, _ = fused.step(u)
+        od, rd, dd, _ = fdev.step(torch.as_tensor(u, device="cuda"))
+        assert torch.equal(of, od) and torch.equal(rf, rd) and df == dd and fused.t_idx == fdev.t_idx
+    assert fused.batch_idx == fdev.batch_idx == 1
+    np.testing.assert_array_equal(fused.data, fdev.data)
+    for e in (hook, fused, fgraph, fdev):
         e.close()
 
 
