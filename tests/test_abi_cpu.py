@@ -40,3 +40,19 @@ def test_missing_library_fails_loudly(native, monkeypatch):
     monkeypatch.setattr(N, "LIB_PATH", "/nonexistent/libquantrl_b200.so")
     with pytest.raises(N.NativeError, match="no CPU or PyTorch fallback"):
         N.lib()
+
+
+def test_flag_and_enum_constants_match_header(native):
+    """Every ``QRL_*`` integer constant of the header that the Python binding mirrors (flags, methods, systems, reward
+    and RNG kinds) has the same value on both sides."""
+    header = open(os.path.join(ROOT, "include", "quantrl_b200.h")).read()
+    defines = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"#define\s+QRL_(\w+)\s+(-?(?:0x[0-9a-fA-F]+|\d+))\b", header)}
+    # enumerators written as `QRL_NAME = value`
+    defines.update({m.group(1): int(m.group(2), 0) for m in re.finditer(r"\bQRL_(\w+)\s*=\s*(-?(?:0x[0-9a-fA-F]+|\d+))", header)})
+    mirrored = {name: getattr(native, name) for name in dir(native)
+                if name.isupper() and isinstance(getattr(native, name), int) and name in defines}
+    assert len(mirrored) >= 12, sorted(mirrored)
+    for name, value in mirrored.items():
+        assert value == defines[name], f"{name}: binding {value} != header {defines[name]}"
+    for flag in ("EM_PDL", "EM_HOST_TIDX", "EM_FORCE_GENERIC", "ODE_FORCE_THREAD", "ODE_FORCE_LANES", "ODE_LANES_SINGLE"):
+        assert flag in mirrored, f"{flag} is not mirrored in the binding"
