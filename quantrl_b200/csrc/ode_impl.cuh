@@ -5,14 +5,20 @@
 // (quantrl/envs/deterministic.py:646-651, quantrl/solvers/base.py:168-204, quantrl/solvers/numpy.py:87-178) and the RHS
 // `func` with its hooks (deterministic.py:653-746, 820-867):
 //     y = [Re a | Im a | vec(V)],   d a/dt = mode_rates(t, a, u),   dV/dt = A V + V A^T + D
-// One thread integrates one environment and keeps its state, the RK stage vectors and the drift matrix in registers;
-// the system hooks are device functors (systems.cuh).
-//   RK4   : fixed step h = t_ssz / substeps; every grid row is staged in shared memory and written by the whole block
-//           as one contiguous, coalesced run of the (K+1, E, d) block (+ observation noise, + min/max).
-//   DOPRI5: Dormand–Prince 5(4), one step-size controller PER ENVIRONMENT (the reference shares one controller across
-//           the flattened batch), free-running steps with the 4th-order dense output evaluated on the
-//           grid, the interval end is hit exactly (actions change there).  Stage vectors live in shared memory.
-//           Controller = oracle/lyap_oracle.py:dopri5_dense_interval.
+// The system hooks are device functors (systems.cuh).  Two layouts, chosen by batch size (launch_ode at the end of this
+// file; measured crossovers in DESIGN.md 4.2), all performing the same operations in the same order:
+//   * one THREAD per environment (large batches; any num_quads): state, RK stage vectors and drift matrix in registers
+//       rk4_kernel     fixed step h = t_ssz / substeps; every grid row leaves through a shared-memory tile of 16-byte
+//                      pieces as one contiguous run of the (K+1, E, d) block (+ observation noise, + min/max)
+//       dopri5_kernel  Dormand–Prince 5(4), one step-size controller PER ENVIRONMENT (the reference shares one controller
+//                      across the flattened batch), free-running steps with the 4th-order dense output
+//                      evaluated on the grid, the interval end hit exactly (actions change there); stage vectors in
+//                      shared-memory columns.  Controller = oracle/lyap_oracle.py:dopri5_dense_interval.
+//   * q*q = 16 LANES per environment (small batches, num_quads = 4): lane (i,j) owns V_ij
+//       rk4_split_kernel      warp-specialised: mode producer / covariance lanes / row writers over shared-memory rings
+//       rk4_lanes_kernel      single role, functor replicated in the lanes
+//       dopri5_lanes_kernel   stage derivatives in registers, per-env controller uniform over a half-warp (LaneEnv)
+//   The other explicit Runge–Kutta methods (ode_erk.cuh, included below) exist in both layouts as well.
 #pragma once
 #include <stdlib.h>
 #include "common.cuh"
