@@ -87,15 +87,39 @@ class PartCacheWriter:
     def dump_part_async(self, data, batch_idx, part_idx):
         if self._thread is None:
             self._start()
-        name = "_".join([str(batch_idx * self.cache_dump_interval),
-                         str((batch_idx + 1) * self.cache_dump_interval - 1), str(part_idx)])
-        self._q.put((os.path.join(self.disk_cache_dir, name + ".npz"), data))
+        self._q.put((self.part_path(batch_idx, part_idx), data))
 
-    def close(self, dump_cache=True):
+    def flush(self):
+        """Block until every queued part file is on disk (the writer thread restarts with the next dump)."""
         if self._thread is not None:
             self._q.put(None)
             self._thread.join()
             self._thread = None
+
+    def part_path(self, batch_idx, part_idx):
+        return os.path.join(self.disk_cache_dir, "_".join([
+            str(batch_idx * self.cache_dump_interval), str((batch_idx + 1) * self.cache_dump_interval - 1),
+            str(part_idx)]) + ".npz")
+
+    def load_parts(self, batch_idx, idxs=None):
+        """Read the part files of one batch back as ONE ``(E, rows, n_data)`` block (the reader the reference leaves
+        as a TODO, io.py:20; its ``get_disk_cache`` only understands the un-parted ``{start}_{end}.npz`` names).  Part
+        ``p`` holds rows ``t_idx .. t_idx+dim-1`` of action step ``p``; its row 0 repeats the last row of part ``p-1``
+        (with that step's cumulative reward — the host cache keeps the LATER one, base.py:1370-1372), so the stitched
+        block drops the last row of every part but the final one."""
+        self.flush()
+        parts, p = [], 0
+        while os.path.exists(self.part_path(batch_idx, p)):
+            with np.load(self.part_path(batch_idx, p)) as f:
+                a = f["arr_0"]
+            parts.append(a if idxs is None else a[:, :, idxs])
+            p += 1
+        if not parts:
+            raise FileNotFoundError(self.part_path(batch_idx, 0))
+        return np.concatenate([a[:, :-1] for a in parts[:-1]] + [parts[-1]], axis=1)
+
+    def close(self, dump_cache=True):
+        self.flush()
 
 
 class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
