@@ -56,3 +56,20 @@ def test_flag_and_enum_constants_match_header(native):
         assert value == defines[name], f"{name}: binding {value} != header {defines[name]}"
     for flag in ("EM_PDL", "EM_HOST_TIDX", "EM_FORCE_GENERIC", "ODE_FORCE_THREAD", "ODE_FORCE_LANES", "ODE_LANES_SINGLE"):
         assert flag in mirrored, f"{flag} is not mirrored in the binding"
+
+
+def test_integration_md_stub_matches_the_binding(native):
+    """The ctypes stub INTEGRATION.md shows a reference maintainer declares the same ``qrl_em_args`` layout as the
+    binding in use (same field names, types, offsets) and names the current ABI version."""
+    import ctypes as C
+    import os
+    import re
+    text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(import ctypes as C\n.*?)\nlib = C\.CDLL", text, re.S).group(1)
+    ns = {}
+    exec(block, ns)   # noqa: S102  (our own documentation snippet: the struct declaration only)
+    doc, ours = ns["EmArgs"], native.EmArgs
+    assert C.sizeof(doc) == C.sizeof(ours)
+    assert [(n, getattr(doc, n).offset, getattr(doc, n).size) for n, _ in doc._fields_] == \
+           [(n, getattr(ours, n).offset, getattr(ours, n).size) for n, _ in ours._fields_]
+    assert f"qrl_abi_version() == {native.ABI_VERSION}" in text
