@@ -9,6 +9,7 @@ Fixtures
   em_linear_env.npz   G3: ``LinearEnv`` (quantrl/envs/stochastic.py) for 6 envs, n=4, S=200, K=20 and 3 envs, n=8:
                       the exact ``Ws`` and ``Observation_noises`` it drew, States/Observations per sub-step,
                       rewards, plus ``env.data`` rows.
+  em_linear_env_tdep.npz  G3b: the same env with hooks that depend on the time index.
   lyap_optomech.npz   G1/G2/G4: ``LinearizedHOVecEnv`` + SciPy at tight tolerance (dop853 and vode), default-tolerance
                       vode, RK4 driven by the reference's own ``env.func``, the single-env twin, and the packed
                       ``env.data`` cache of ``BaseSB3Env.update_data``.
@@ -104,6 +105,59 @@ def golden_em():
                     f"{tag}_Observations": np.array(Ob), f"{tag}_Reward": np.array(Rw), f"{tag}_data": np.array(data)})
     np.savez_compressed(os.path.join(GOLDEN, "em_linear_env.npz"), **out)
     print("em_linear_env.npz", {k: np.shape(v) for k, v in out.items()})
+
+
+def tdep_hooks(A0, Au, B, nz):
+    """Time-INDEX dependent hooks of the G3b fixture (``get_A(t_idx, args)``, ``get_noise_prefixes(t_idx, args)`` receive the
+    integer index, stochastic.py:218-242); shared by the generator and the tests."""
+    def get_A(t_idx, args):
+        return A0 + np.einsum("a,aij->ij", np.asarray(args[0]), Au) + 0.2 * np.sin(0.3 * t_idx) * B
+
+    def get_nz(t_idx, args):
+        return nz * (1.0 + 0.5 * np.cos(0.1 * t_idx))
+    return get_A, get_nz
+
+
+def golden_em_time_dependent():
+    """G3b: ``LinearEnv`` with hooks that depend on the time index.  (No ragged last interval: with
+    ``(shape_T - 1) % action_interval != 0`` the reference's ``LinearEnv`` raises in ``BaseEnv.update`` — its States block
+    keeps K+1 rows while the noise slice has ``dim`` rows, base.py:462 — so there is nothing to pin for that case.)"""
+    n, n_env, n_act, K, S, ssz = 4, 4, 1, 20, 200, 0.01
+    A0, Au = systems.affine_matrices(n, n_act, seed=0)
+    rng = np.random.default_rng(77)
+    B = rng.standard_normal((n, n))
+    nz = np.full(n, 0.05) * (1.0 + 0.1 * np.arange(n))
+    stds = 0.01 * (1.0 + np.arange(n))
+    weights = 1.0 / (1.0 + np.arange(n))
+    get_A, get_nz = tdep_hooks(A0, Au, B, nz)
+    n_steps = -(-S // K)
+    actions = rng.uniform(-1, 1, (n_env, n_steps, n_act))
+    x0 = 1.0 + 0.1 * rng.standard_normal((n_env, n))
+    res = {k: [] for k in ("Ws", "obs_noises", "States", "Observations", "Reward", "data", "dims")}
+    for e in range(n_env):
+        env = make_linear_env(n, A0, Au, nz, x0[e], weights, seed=300 + e, K=K, S=S, ssz=ssz, stds=stds)
+        env.get_A, env.get_noise_prefixes = get_A, get_nz
+        assert env.shape_T[0] == S + 1 and env.action_steps == n_steps, (env.shape_T, env.action_steps)
+        env.reset()
+        States, Obs, Rew, dims = [env.States[-1].copy()], [env.Observations[-1].copy()], [0.0], []
+        done = False
+        for a in range(n_steps):
+            assert not done
+            _, _, done, _, _ = env.step(actions[e, a])
+            dim = S + 1 - len(States) + 1 if a == n_steps - 1 else K + 1
+            dims.append(dim)
+            States.extend(env.States[1:dim].copy())
+            Obs.extend(env.Observations[1:dim].copy())
+            Rew.extend(np.asarray(env.Reward)[1:dim].copy())
+        assert done and len(States) == S + 1
+        for k, v in (("Ws", env.Ws), ("obs_noises", env.Observation_noises), ("States", States), ("Observations", Obs),
+                     ("Reward", Rew), ("data", env.data), ("dims", dims)):
+            res[k].append(np.array(v))
+    out = {"A0": A0, "Au": Au, "B": B, "nz": nz, "stds": stds, "weights": weights, "actions": actions, "x0": x0,
+           "K": K, "S": S, "ssz": ssz}
+    out.update({k: np.array(v) for k, v in res.items()})
+    np.savez_compressed(os.path.join(GOLDEN, "em_linear_env_tdep.npz"), **out)
+    print("em_linear_env_tdep.npz", {k: np.shape(v) for k, v in out.items()})
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -241,6 +295,10 @@ def golden_lyap(system, tag_sizes, fname):
 
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
+    if "--tdep-only" in sys.argv:          # add the G3b fixture without regenerating the others
+        golden_em_time_dependent()
+        sys.exit(0)
     golden_em()
+    golden_em_time_dependent()
     golden_lyap("optomech", [("E5", 5, 0)], "lyap_optomech.npz")
     golden_lyap("kerr", [("N2", 3, 2), ("N4", 2, 4)], "lyap_kerr.npz")

@@ -71,7 +71,8 @@ class LinearVecEnv(BaseVecEnv):
             file_prefix="lin_vec_env", **kwargs)
         n = self.n_observations
         assert 1 <= n <= 16, "qrl_em_step supports 1 <= n_observations <= 16"
-        assert (self.shape_T[0] - 1) % self.action_interval == 0 or True  # tails are supported (dim < K+1)
+        # (shape_T - 1) % action_interval != 0 is supported: the last interval is shorter (dim < K+1, base.py:454-458);
+        # the reference's own LinearEnv raises there (its States block keeps K+1 rows, base.py:462)
         self.I = torch.eye(n, dtype=torch.float64, device=self.device)
         self._reward_fused = self.reward_functor is not None
         self._cum_fused = self._reward_fused

@@ -56,6 +56,46 @@ def test_linear_vec_env_fed_matches_reference_linear_env(native, cuda, golden_di
     env.close()
 
 
+def test_linear_vec_env_time_index_dependent_hooks_match_reference(native, cuda, golden_dir):
+    """Fixture G3b: user hooks that depend on the integer time index (``is_A_time_dependent=True``: evaluated for every
+    sub-step ``t_idx + i`` of the interval and stacked, stochastic.py:218-233) — each row of the vectorized env == the
+    reference's single LinearEnv with the same hooks, fed the same draws."""
+    import math
+    from quantrl_b200.envs import LinearVecEnv
+    g = np.load(os.path.join(golden_dir, "em_linear_env_tdep.npz"))
+    K, S, ssz = int(g["K"]), int(g["S"]), float(g["ssz"])
+    E, n = g["x0"].shape
+    A0, Au, B, nz, x0 = (torch.as_tensor(g[k], device="cuda") for k in ("A0", "Au", "B", "nz", "x0"))
+
+    class Env(LinearVecEnv):
+        def reset_states(self):
+            return x0
+
+        def get_A(self, t_idx, args):
+            return A0 + torch.einsum("ea,aij->eij", args[0], Au) + 0.2 * math.sin(0.3 * t_idx) * B
+
+        def get_noise_prefixes(self, t_idx, args):
+            return nz * (1.0 + 0.5 * math.cos(0.1 * t_idx))
+
+    env = Env(name="tdep", desc="golden", params={}, t_norm_max=S * ssz + ssz / 2, t_norm_ssz=ssz, t_norm_mul=1.0,
+              n_envs=E, n_observations=n, n_properties=0, n_actions=1, action_maximums=[1.0], action_interval=K,
+              data_idxs=list(range(1 + 1 + n + 1)), rng="fed", is_A_time_dependent=True,
+              observation_stds=list(g["stds"]), reward_functor="neg_wsq_obs", reward_weights=g["weights"],
+              cache_all_data=False, dir_prefix="/tmp/qrl_test")
+    env.set_fed_noise(np.transpose(g["Ws"], (1, 0, 2)), np.transpose(g["obs_noises"], (1, 0, 2)))
+    obs0 = env.reset()
+    np.testing.assert_allclose(obs0.cpu().numpy(), g["Observations"][:, 0], rtol=1e-13, atol=1e-15)
+    for a in range(S // K - 1):      # stop before the terminating step (auto-reset)
+        obs, rew, done, _ = env.step(g["actions"][:, a])
+        t1 = (a + 1) * K
+        assert done == [False] * E and env.t_idx == t1
+        np.testing.assert_allclose(env.States.cpu().numpy(), np.transpose(g["States"][:, t1 - K:t1 + 1], (1, 0, 2)),
+                                   rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(obs.cpu().numpy(), g["Observations"][:, t1], rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(rew.cpu().numpy(), g["Reward"][:, t1], rtol=1e-12, atol=1e-14)
+    env.close()
+
+
 def test_linear_vec_env_data_cache_rows(native, cuda, golden_dir):
     """env.data == BaseSB3Env.update_data's rows [t, actions, obs, cumulative reward] incl. the overlap rule
     (row 0 of a block overwrites the last row of the previous block, base.py:1370-1372), via the oracle's pack_rows."""
