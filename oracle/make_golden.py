@@ -13,6 +13,7 @@ Fixtures
   lyap_optomech.npz   G1/G2/G4: ``LinearizedHOVecEnv`` + SciPy at tight tolerance (dop853 and vode), default-tolerance
                       vode, RK4 driven by the reference's own ``env.func``, the single-env twin, and the packed
                       ``env.data`` cache of ``BaseSB3Env.update_data``.
+  dde_scipy.npz       G6: a delay system through ``SciPyIVPSolver.solve_ivp`` with ``has_delay=True`` (vode, tight).
   lyap_kerr.npz       same for the kerr_chain system (N=2 -> q=4, N=4 -> q=8).
 """
 import os
@@ -293,8 +294,39 @@ def golden_lyap(system, tag_sizes, fname):
     print(fname, {k: np.shape(v) for k, v in out.items()})
 
 
+# ---------------------------------------------------------------------------------------------------------
+# G6: delay system through the reference's solver plugin (has_delay: step = integrate + interpolate)
+# ---------------------------------------------------------------------------------------------------------
+def golden_dde():
+    """``SciPyIVPSolver.solve_ivp`` with ``has_delay=True`` (quantrl/solvers/base.py:96-112,198-256; numpy.py:180-188) on
+    ``y' = -a * y(t - tau) + b * sin(t)``, ``tau`` = one step window, constant history ``y(t <= 0) = y_0``."""
+    from quantrl.solvers.numpy import SciPyIVPSolver
+    from quantrl.backends.context_manager import get_backend_instance
+    fresh_backend()
+    backend = get_backend_instance(library="numpy", precision="double", device="cpu")
+    K, S, dt = 10, 120, 0.05
+    tau = K * dt
+    a, b = np.array([0.5, 1.0, 2.0]), np.array([0.0, 0.3, 1.0])
+    y0 = np.array([1.0, -0.5, 0.25])
+    T = np.arange(S + 1) * dt
+
+    def func(t, y, args):
+        return -a * np.asarray(args[2](t - tau), dtype=np.float64) + b * np.sin(t) * args[0]
+
+    solver = SciPyIVPSolver(func=func, y_0=y0, T=T, solver_params={"method": "vode", "atol": 1e-13, "rtol": 1e-12,
+                                                                    "step_interval": 3}, func_controls=None,
+                            has_delay=True, func_delay=lambda t: y0, delay_interval=K, backend=backend)
+    assert solver.step_interval == K       # delay_interval overrides step_interval (base.py:108-109)
+    Y = solver.solve_ivp(y_0=y0, params=1.5, show_progress=False)
+    np.savez_compressed(os.path.join(GOLDEN, "dde_scipy.npz"), Y=Y, T=T, a=a, b=b, y0=y0, K=K, tau=tau, params=1.5)
+    print("dde_scipy.npz", Y.shape, Y[-1])
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
+    if "--dde-only" in sys.argv:
+        golden_dde()
+        sys.exit(0)
     if "--tdep-only" in sys.argv:          # add the G3b fixture without regenerating the others
         golden_em_time_dependent()
         sys.exit(0)
@@ -302,3 +334,4 @@ if __name__ == "__main__":
     golden_em_time_dependent()
     golden_lyap("optomech", [("E5", 5, 0)], "lyap_optomech.npz")
     golden_lyap("kerr", [("N2", 3, 2), ("N4", 2, 4)], "lyap_kerr.npz")
+    golden_dde()

@@ -163,7 +163,8 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         assert len(kwargs["observation_space_range"]) == 2 and len(kwargs["action_space_range"]) == 2
         assert kwargs["action_space_type"] in ["binary", "box"], "parameter ``action_space_type`` can be either ``'binary'`` or ``'box'``"
         assert kwargs["rng"] in ["philox", "fed"], "parameter ``rng`` can be either ``'philox'`` or ``'fed'``"
-        assert not kwargs["has_delay"], "delay (DDE) support is out of scope of the b200 backend (SURVEY.md §2 #19)"
+        assert not kwargs["has_delay"], \
+            "delay (DDE) systems are supported at the solver level only (B200IVPSolver, stage-callback mode), not by the vectorized envs"
 
         N.lib()  # fail loudly, now, if the CUDA extension is missing
         self.backend = backend

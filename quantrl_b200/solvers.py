@@ -13,8 +13,9 @@ Two execution modes:
   for the other explicit method names of the reference's plugins: ``'bosh3'/'RK23'``, ``'tsit5'``,
   ``'adaptive_heun'/'heun'``, ``'fehlberg2'``, ``'dop853'/'DOP853'/'dopri8'``, ``'euler'``, ``'midpoint'``).
 * **stage-callback**: no functor, arbitrary user hooks written in torch; classic RK4 whose four stage evaluations
-  call ``func`` (batched torch on the device).  This keeps every reference env runnable on the backend; it is not
-  the accelerated path.
+  call ``func`` (batched torch on the device).  This keeps every reference env runnable on the backend — including
+  delay systems (``has_delay``: ``step`` refits ``func_delay`` to the rows of the last window, as
+  quantrl/solvers/base.py:198-202 does) — it is not the accelerated path.
 """
 import numpy as np
 import torch
@@ -35,10 +36,16 @@ class B200IVPSolver:
         self.func, self.y_0, self.T = func, y_0, T
         self.func_controls, self.has_delay, self.func_delay, self.delay_interval = func_controls, has_delay, func_delay, delay_interval
         self.backend = backend
-        assert not has_delay, "delay (DDE) support is out of scope of the b200 backend (SURVEY.md §2 #19)"
+        # same validation as quantrl/solvers/base.py:96-112
+        assert self.func_delay is not None if self.has_delay else True, \
+            "delay function cannot be ``None`` if parameter ``has_delay`` is ``True``"
+        assert not (has_delay and system is not None), \
+            "delay (DDE) systems run in the stage-callback mode: the device functors have no history argument"
         self.shape_y = tuple(y_0.shape)
         self.shape_T = tuple(T.shape)
         self.solver_params = {k: solver_params.get(k, v) for k, v in self.default_solver_params.items()}
+        if self.has_delay and self.delay_interval != 0:   # the history is refitted once per step: step == delay window
+            self.solver_params["step_interval"] = self.delay_interval
         assert self.solver_params["method"] in self.solver_methods, \
             f"parameter ``method`` should be one of ``{self.solver_methods}``"
         assert isinstance(self.solver_params["step_interval"], int) and self.solver_params["step_interval"] < self.shape_T[0], \
@@ -52,10 +59,30 @@ class B200IVPSolver:
 
     # ---- reference surface ---------------------------------------------------------------------------------
     def step(self, T_step, y_0, params):
-        return self.integrate(T_step=T_step, y_0=y_0, params=params)
+        """Integrate, then refit the delay function to this step's rows (quantrl/solvers/base.py:168-204)."""
+        Y = self.integrate(T_step=T_step, y_0=y_0, params=params)
+        if self.has_delay:
+            self.func_delay = self.interpolate(T_step=T_step, Y=Y)
+        return Y
 
     def interpolate(self, T_step, Y):
-        raise NotImplementedError("delay interpolation is not implemented by the b200 solver")
+        """History function of a delay system: ``t -> y(t)`` on (and, like ``splev``, extrapolated beyond) the window
+        ``T_step``.  Same interpolant as the reference's ``splrep``/``splev`` per component (quantrl/solvers/numpy.py:180-188:
+        the cubic spline through the ``len(T_step)`` rows with not-a-knot ends), but evaluated for the whole batch at
+        once: a spline through the rows is linear in them, ``y(t) = sum_i w_i(t) Y[i]``, so the weights ``w(t)`` come
+        from one B-spline basis on the host and the combination is ONE ``tensordot`` on the device.  Returns a callable
+        whose result has the shape of ``y_0`` (the reference's returns a list over components)."""
+        from scipy.interpolate import make_interp_spline
+        Th = T_step.detach().cpu().numpy() if isinstance(T_step, torch.Tensor) else np.asarray(T_step, dtype=np.float64)
+        dim = Th.shape[0]
+        assert dim >= 2 and Y.shape[0] == dim, "``interpolate`` needs at least two rows, one per element of ``T_step``"
+        basis = make_interp_spline(Th, np.eye(dim), k=min(3, dim - 1))
+        rows = Y.detach().clone()       # the env reuses its (K+1, E, d) block for the next interval
+
+        def func_delay(t):
+            w = torch.as_tensor(np.ascontiguousarray(basis(float(t))), dtype=rows.dtype).to(rows.device)
+            return torch.tensordot(w, rows, dims=1)
+        return func_delay
 
     def solve_ivp(self, y_0, params, show_progress=False):
         """quantrl/solvers/base.py:206-256."""
