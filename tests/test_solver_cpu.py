@@ -63,3 +63,27 @@ def test_delay_validation_follows_the_reference():
     with pytest.raises(AssertionError, match="step_interval"):
         B200IVPSolver(func=None, y_0=y0, T=T, solver_params={"step_interval": 5}, has_delay=True,
                       func_delay=lambda t: y0, delay_interval=11)
+
+
+@pytest.mark.parametrize("substeps,key", [(1, "rk4"), (2, "rk4x2")])
+def test_stage_callback_rk4_matches_rk4_on_the_reference_func(golden_dir, substeps, key):
+    """Fixture G2 through the solver's stage-callback integrator (the host loop that serves envs without a device
+    functor): ``step`` over every action interval == classic RK4 driven by the reference's own ``env.func``."""
+    import lyap_oracle as lo
+    import systems as sy
+    g = np.load(os.path.join(golden_dir, "lyap_optomech.npz"))
+    tag = "E5"
+    p, y0, acts, T, K = g[f"{tag}_p"], g[f"{tag}_y0"], g[f"{tag}_actions"], g[f"{tag}_T"], int(g[f"{tag}_K"])
+    rhs = lo.make_func(2, 4, lambda t, mo, u: sy.optomech_mode_rates(p, t, mo, u), lambda t, mo, u: sy.optomech_A(p, t, mo, u),
+                       lambda t, mo, u: sy.optomech_D(p, t, mo, u), p.shape[0])
+    # hooks in NumPy behind a torch signature (the integrator under test is the torch host loop, not the hooks)
+    func = lambda t, y, args: torch.as_tensor(rhs(float(t), y.numpy(), args[0].numpy()[:, 0]))  # noqa: E731
+    s = B200IVPSolver(func=func, y_0=torch.as_tensor(y0), T=torch.as_tensor(T),
+                      solver_params={"method": "rk4", "step_interval": K, "substeps": substeps})
+    y, rows = torch.as_tensor(y0), [torch.as_tensor(y0)[None]]
+    for a in range(acts.shape[0]):
+        Y = s.step(T_step=torch.as_tensor(T[a * K:(a + 1) * K + 1]), y_0=y, params=torch.as_tensor(acts[a]))
+        assert tuple(Y.shape) == (K + 1, *y0.shape) and torch.equal(Y[0], y)
+        rows.append(Y[1:])
+        y = Y[-1]
+    np.testing.assert_allclose(torch.cat(rows).numpy(), g[f"{tag}_States_{key}_reffunc"], rtol=1e-12, atol=1e-13)
