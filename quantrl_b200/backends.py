@@ -69,11 +69,16 @@ class B200Backend:
             return torch.stack([t.to(self.device) for t in tensor]).to(dtype=self.dtype_from_str(dtype))
         return torch.as_tensor(np.asarray(tensor), dtype=self.dtype_from_str(dtype), device=self.device)
 
+    @staticmethod
+    def _host(t):
+        # torch.conj() / negation views are lazy bits on the tensor; NumPy needs them materialised
+        return t.detach().resolve_conj().resolve_neg().cpu().numpy()
+
     def convert_to_numpy(self, tensor, dtype: str = None) -> np.ndarray:
         if isinstance(tensor, (list, tuple)):
-            tensor = [t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t) for t in tensor]
+            tensor = [self._host(t) if isinstance(t, torch.Tensor) else np.asarray(t) for t in tensor]
         elif isinstance(tensor, torch.Tensor):
-            tensor = tensor.detach().cpu().numpy()
+            tensor = self._host(tensor)
         return np.asarray(tensor, dtype=self.dtype_from_str(dtype, numpy=True))
 
     def generator(self, seed: int = None) -> torch.Generator:
