@@ -70,3 +70,67 @@ def test_learner_link_two_ranks_gloo(E):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, "ok"), (1, "ok")], res
+
+
+def _oracle_shard_worker(rank, world, port, E, n, K, out):
+    """CPU model of the sharded stochastic step: every rank integrates ITS block of envs with the oracle, drawing the
+    noise of the global env indices (``env_offset``), and the learner gathers the last observations / rewards."""
+    import em_oracle as eo
+    import systems as sy
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        link = LearnerLink(E, n, 1, device="cpu", dst=0)
+        A0, Au = sy.affine_matrices(n, 1, seed=0)
+        dt, seed = 0.01, 1234
+        actions = torch.as_tensor(np.random.default_rng(5).uniform(-1, 1, (E, 1)))
+
+        def interval(x0, u, env0, count, t_idx):
+            z_w, z_o = eo.philox_noise_block(seed, 0, t_idx, K, env0, count, n)
+            Y = eo.em_interval_vec(x0, sy.affine_A(A0, Au, u), np.full((count, n), 0.05), np.sqrt(dt) * z_w, dt)
+            obs = Y + 0.01 * z_o
+            return Y[-1], obs[-1], -np.sum(obs[-1] ** 2, -1)
+
+        x = np.ones((link.count, n))
+        x_full = np.ones((E, n))
+        for step in range(2):
+            u = link.scatter_actions(actions if rank == 0 else None).numpy()
+            x, obs, rew = interval(x, u, link.offset, link.count, step * K)
+            res = link.gather_step(torch.as_tensor(obs), torch.as_tensor(rew))
+            if rank == 0:   # the unsharded batch, bit for bit (SURVEY.md §8e: results invariant to the number of ranks)
+                x_full, obs_full, rew_full = interval(x_full, actions.numpy(), 0, E, step * K)
+                assert np.array_equal(res[0].numpy(), obs_full) and np.array_equal(res[1].numpy(), rew_full) and not res[2]
+        out.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        out.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_oracle_step_equals_the_unsharded_batch_gloo():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_oracle_shard_worker, args=(r, 2, port, 9, 4, 6, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(out.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, "ok"), (1, "ok")], res
+
+
+def test_make_sharded_env_slices_per_env_arguments():
+    from quantrl_b200.distributed import make_sharded_env
+
+    class FakeEnv:
+        def __init__(self, **kw):
+            self.kw = kw
+
+    params = np.arange(10 * 3).reshape(10, 3)
+    for rank, (off, cnt) in enumerate(all_shard_bounds(10, 4)):
+        env = make_sharded_env(FakeEnv, 10, rank=rank, world_size=4, system_params=params, x0=None, shared=np.ones(3),
+                               _per_env=("system_params", "x0"))
+        assert env.kw["n_envs"] == cnt and env.kw["env_offset"] == off and env.kw["x0"] is None
+        assert np.array_equal(env.kw["system_params"], params[off:off + cnt]) and env.kw["shared"].shape == (3,)
+        assert "_per_env" not in env.kw
