@@ -73,3 +73,95 @@ def test_integration_md_stub_matches_the_binding(native):
     assert [(n, getattr(doc, n).offset, getattr(doc, n).size) for n, _ in doc._fields_] == \
            [(n, getattr(ours, n).offset, getattr(ours, n).size) for n, _ in ours._fields_]
     assert f"qrl_abi_version() == {native.ABI_VERSION}" in text
+
+
+_P = 0x1000   # a non-NULL "device pointer": every case below is rejected before anything is dereferenced or launched
+
+
+def _em(**kw):
+    import quantrl_b200._native as N
+    a = N.EmArgs()
+    a.n, a.n_envs, a.K, a.rng_mode, a.t_ssz = 4, 8, 10, N.RNG_PHILOX, 0.01
+    a.x0, a.A, a.nz = _P, _P, _P
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
+
+
+def _ode(**kw):
+    import quantrl_b200._native as N
+    a = N.OdeArgs()
+    a.system, a.num_modes, a.num_quads, a.n_envs, a.K, a.method, a.substeps = N.SYS_OPTOMECH, 2, 4, 8, 10, N.ODE_RK4, 1
+    a.t_ssz, a.atol, a.rtol, a.y0, a.params, a.actions, a.n_actions = 0.01, 1e-9, 1e-6, _P, _P, _P, 1
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
+
+
+def _pack(**kw):
+    import quantrl_b200._native as N
+    a = N.PackArgs()
+    a.n_envs, a.dim, a.n_actions, a.n_obs, a.n_props, a.n_sel = 8, 11, 1, 4, 0, 1
+    a.T_step, a.actions, a.observations, a.rewards_cum, a.idxs = _P, _P, _P, _P, _P
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
+
+
+@pytest.mark.parametrize("entry,build,kw,msg", [
+    ("em_step", _em, dict(n=0), "n must be in 1..16"),
+    ("em_step", _em, dict(n=17), "n must be in 1..16"),
+    ("em_step", _em, dict(K=-1), "non-negative"),
+    ("em_step", _em, dict(n_envs=-3), "non-negative"),
+    ("em_step", _em, dict(rng_mode=7), "bad rng_mode"),
+    ("em_step", _em, dict(x0=None), "x0 is NULL"),
+    ("em_step", _em, dict(A=None), "A / nz is NULL"),
+    ("em_step", _em, dict(rng_mode=0), "fed mode needs W"),
+    ("em_step", _em, dict(reward_kind=1), "reward_w is NULL"),
+    ("em_step", _em, dict(t_idx=-1), "negative t_idx"),
+    ("em_step", _em, dict(env_offset=-1), "negative t_idx / env_offset"),
+    ("em_step", _em, dict(A_act=_P), "qrl_em_step"),                       # in-kernel drift functor without actions
+    ("em_step", _em, dict(dyn_advance=10), "qrl_em_step"),                 # last-block bookkeeping without its counter
+    ("em_step", _em, dict(minmax_out=_P, finish_counter=_P), "minmax_out needs obs_minmax"),
+    ("em_step", _em, dict(peer_flags=_P), "qrl_em_step"),                  # fused barrier without epoch / counter
+    ("em_step", _em, dict(packed=_P), "packed rows need a fused reward functor"),
+    ("em_step", _em, dict(packed=_P, reward_kind=1, reward_w=_P, rewards_cum=_P), "packed rows need T_step"),
+    ("em_step", _em, dict(packed=_P, reward_kind=1, reward_w=_P, rewards_cum=_P, T_step=_P, sel_idxs=_P, n_sel=3,
+                          packed_row_pitch=2), "packed_row_pitch < n_sel"),
+    ("em_step", _em, dict(packed=_P, reward_kind=1, reward_w=_P, rewards_cum=_P, T_step=_P, sel_idxs=_P, n_sel=3,
+                          packed_stride_e=5), "packed_stride_e too small"),
+    ("ode_step", _ode, dict(K=-1), "non-negative"),
+    ("ode_step", _ode, dict(method=99), "unknown method"),
+    ("ode_step", _ode, dict(substeps=0), "substeps must be >= 1"),
+    ("ode_step", _ode, dict(method=1, atol=0.0), "atol and rtol must be positive"),
+    ("ode_step", _ode, dict(t_ssz=0.0), "t_ssz must be positive"),
+    ("ode_step", _ode, dict(y0=None), "y0 is NULL"),
+    ("ode_step", _ode, dict(t_idx=-5), "negative t_idx"),
+    ("ode_step", _ode, dict(num_quads=6), "optomech needs num_modes=2, num_quads=4"),
+    ("ode_step", _ode, dict(params=None), "optomech needs params"),
+    ("ode_step", _ode, dict(system=2, num_modes=3, num_quads=4), "kerr_chain needs num_quads = 2 \\* num_modes"),
+    ("ode_step", _ode, dict(system=3, num_modes=2), "const_AD has no modes"),
+    ("ode_step", _ode, dict(system=3, num_modes=0, num_quads=4), "const_AD needs A and D"),
+    ("pack_rows", _pack, dict(n_obs=0), "qrl_pack_rows"),
+    ("pack_rows", _pack, dict(observations=None), "NULL input"),
+    ("pack_rows", _pack, dict(actions=None), "actions is NULL"),
+    ("pack_rows", _pack, dict(n_props=2), "properties is NULL"),
+    ("pack_rows", _pack, dict(selected=_P, idxs=None), "idxs is NULL"),
+    ("pack_rows", _pack, dict(selected=_P, n_sel=3, selected_row_pitch=2), "selected_row_pitch < n_sel"),
+    ("pack_rows", _pack, dict(packed=_P, packed_stride_e=3), "qrl_pack_rows"),
+])
+def test_every_argument_check_rejects_before_any_launch(native, entry, build, kw, msg):
+    """The C ABI validates its argument block on the host (return code < 0 + ``qrl_last_error``) before touching the
+    device: each ``QRL_REQUIRE`` of qrl_em_step / qrl_ode_step / qrl_pack_rows, exercised without a GPU."""
+    n0 = native.launch_count()
+    with pytest.raises(native.NativeError, match=msg) as e:
+        getattr(native, entry)(build(**kw), ctypes.c_void_p(0))
+    assert "invalid argument" in str(e.value) and native.launch_count() == n0
+
+
+def test_null_argument_block_and_micro_benchmarks_are_rejected(native):
+    lib = native.lib()
+    for fn in (lib.qrl_em_step, lib.qrl_ode_step, lib.qrl_pack_rows):
+        assert fn(None, None) < 0 and b"args is NULL" in lib.qrl_last_error()
+    assert lib.qrl_measure_fp64_peak(0, None) < 0 and lib.qrl_measure_fp64_latency(None) < 0
+    assert lib.qrl_host_device_pointer(None, None) < 0
