@@ -1,0 +1,79 @@
+"""TEST INFRASTRUCTURE ONLY — builds and binds oracle/em_port.c (plain-C restatement of the stochastic hot path).
+
+Used by tests/test_oracle_c_port.py (second implementation of the oracle, checked against the NumPy one and fixture
+G3) and by tools/cpu_compiled_em.py (compiled, threaded CPU comparator).  Never imported by the product."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "em_port.c")
+LIB = os.path.join(HERE, "_build", "libem_port.so")
+_lib = None
+
+
+def available():
+    return shutil.which("gcc") is not None
+
+
+def build(force=False):
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(SRC):
+        os.makedirs(os.path.dirname(LIB), exist_ok=True)
+        subprocess.run(["gcc", "-O3", "-march=native", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", SRC, "-o", LIB, "-lm"],
+                       check=True)
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        dp, i32, f64, u64 = C.POINTER(C.c_double), C.c_int, C.c_double, C.c_uint64
+        _lib.em_port_fed.argtypes = [i32, i32, i32, f64] + [dp] * 9
+        _lib.em_port_fed.restype = None
+        _lib.em_port_rng.argtypes = [i32, i32, i32, f64, u64, u64] + [dp] * 9
+        _lib.em_port_rng.restype = None
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _c(a, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a if shape is None else np.ascontiguousarray(np.broadcast_to(a, shape))
+
+
+def em_interval_fed(x0, A, nz, W, dt, obs_noise=None, weights=None):
+    """x0 (E,n); A (E,n,n) or (n,n); nz (E,n) or (n,); W (K,E,n) scaled by sqrt(dt); obs_noise (K+1,E,n) or None.
+    Returns States, Observations (K+1,E,n) and Reward (K+1,E) = -sum_c w_c obs_c^2."""
+    E, n = x0.shape
+    K = W.shape[0]
+    x0, A, nz, W = _c(x0), _c(A, (E, n, n)), _c(nz, (E, n)), _c(W)
+    ON, w = _c(obs_noise), _c(weights)
+    St, Ob, Rw = np.empty((K + 1, E, n)), np.empty((K + 1, E, n)), np.empty((K + 1, E))
+    lib().em_port_fed(E, n, K, float(dt), _p(x0), _p(A), _p(nz), _p(W), _p(ON), _p(w), _p(St), _p(Ob), _p(Rw))
+    return St, Ob, Rw
+
+
+class RngStepper:
+    """Preallocated buffers for repeated ``em_port_rng`` intervals (the timing loop of tools/cpu_compiled_em.py)."""
+
+    def __init__(self, E, n, K, dt, A, nz, stds, weights, seed=1):
+        self.E, self.n, self.K, self.dt, self.seed = E, n, K, float(dt), int(seed)
+        self.A, self.nz, self.stds, self.w = _c(A, (E, n, n)), _c(nz, (E, n)), _c(stds, (n,)), _c(weights, (n,))
+        self.St, self.Ob, self.Rw = np.empty((K + 1, E, n)), np.empty((K + 1, E, n)), np.empty((K + 1, E))
+        self.x = np.ones((E, n))
+        self.interval = 0
+
+    def step(self):
+        lib().em_port_rng(self.E, self.n, self.K, self.dt, self.seed, self.interval, _p(self.x), _p(self.A), _p(self.nz),
+                          _p(self.stds), _p(self.w), _p(self.St), _p(self.Ob), _p(self.Rw), _p(self.x))
+        self.interval += 1
+        return self.Ob[-1], self.Rw[-1]

@@ -1,0 +1,62 @@
+"""CPU: the plain-C restatement of the stochastic path (oracle/em_port.c) against the NumPy oracle and the reference's
+own ``LinearEnv`` fixture — two independently written oracles have to agree before either checks the kernel."""
+import os
+
+import numpy as np
+import pytest
+
+import em_oracle as eo
+import em_port
+import systems as sy
+
+pytestmark = pytest.mark.skipif(not em_port.available(), reason="gcc not available")
+
+
+def test_c_port_equals_numpy_oracle():
+    rng = np.random.default_rng(0)
+    for n, E, K in ((4, 37, 25), (8, 5, 10), (1, 3, 4), (16, 2, 3)):
+        A = 0.4 * rng.standard_normal((E, n, n))
+        nz = rng.uniform(0.01, 0.1, (E, n))
+        W = 0.1 * rng.standard_normal((K, E, n))
+        ON = 0.01 * rng.standard_normal((K + 1, E, n))
+        w = rng.uniform(0.5, 1.5, n)
+        x0 = rng.standard_normal((E, n))
+        St, Ob, Rw = em_port.em_interval_fed(x0, A, nz, W, 0.01, obs_noise=ON, weights=w)
+        ref = eo.em_interval_vec(x0, A, nz, W, 0.01)
+        np.testing.assert_allclose(St, ref, rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(Ob, ref + ON, rtol=1e-12, atol=1e-14)     # obs = x + noise can cancel
+        np.testing.assert_allclose(Rw, eo.reward_neg_weighted_sq(ref + ON, w), rtol=1e-12, atol=1e-15)
+    # K = 0: row 0 only
+    St, Ob, Rw = em_port.em_interval_fed(x0, A, nz, W[:0], 0.01, obs_noise=ON[:1])
+    assert St.shape == (1, E, n) and np.array_equal(St[0], x0) and np.array_equal(Ob[0], x0 + ON[0])
+
+
+@pytest.mark.parametrize("tag", ["n4", "n8"])
+def test_c_port_matches_reference_linear_env(golden_dir, tag):
+    """Fixture G3 (reference ``LinearEnv``, its own draws) through the C port, interval by interval."""
+    g = np.load(os.path.join(golden_dir, "em_linear_env.npz"))
+    A0, Au, nz, w = g[f"{tag}_A0"], g[f"{tag}_Au"], g[f"{tag}_nz"], g[f"{tag}_weights"]
+    K, S, ssz = int(g[f"{tag}_K"]), int(g[f"{tag}_S"]), float(g[f"{tag}_ssz"])
+    x = g[f"{tag}_x0"].copy()
+    for a in range(S // K):
+        t0 = a * K
+        St, Ob, Rw = em_port.em_interval_fed(
+            x, sy.affine_A(A0, Au, g[f"{tag}_actions"][:, a]), nz, np.transpose(g[f"{tag}_Ws"][:, t0:t0 + K], (1, 0, 2)), ssz,
+            obs_noise=np.transpose(g[f"{tag}_obs_noises"][:, t0:t0 + K + 1], (1, 0, 2)), weights=w)
+        np.testing.assert_allclose(np.transpose(St, (1, 0, 2)), g[f"{tag}_States"][:, t0:t0 + K + 1], rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(np.transpose(Ob, (1, 0, 2)), g[f"{tag}_Observations"][:, t0:t0 + K + 1], rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(Rw[1:].T, g[f"{tag}_Reward"][:, t0 + 1:t0 + K + 1], rtol=1e-12, atol=1e-14)
+        x = St[-1]
+
+
+def test_c_port_rng_mode_has_the_right_moments():
+    """Noise-free drift + the port's own generator: an Ornstein–Uhlenbeck ensemble reaches the stationary variance
+    ``sigma^2 / (2 theta)`` (up to the Euler–Maruyama bias) and the measurement noise has the requested std."""
+    E, n, K, dt, theta, sigma = 20000, 2, 400, 0.01, 1.0, 0.5
+    st = em_port.RngStepper(E, n, K, dt, -theta * np.eye(n), np.full(n, sigma), np.full(n, 0.2), np.ones(n), seed=3)
+    for _ in range(3):
+        st.step()
+    var = st.St[-1].var(axis=0)
+    np.testing.assert_allclose(var, sigma ** 2 / (2 * theta - theta ** 2 * dt), rtol=0.05)
+    np.testing.assert_allclose((st.Ob[-1] - st.St[-1]).std(axis=0), 0.2, rtol=0.03)
+    assert abs(np.corrcoef(st.St[-1][:, 0], st.St[-1][:, 1])[0, 1]) < 0.03
