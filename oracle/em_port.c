@@ -10,7 +10,7 @@
  *   em_port_rng   noise drawn in place (xoshiro256++ per env + libm Box–Muller), OpenMP over environments — the
  *                 "what a compiled, threaded CPU implementation achieves" comparator of tools/cpu_compiled_em.py.
  *                 Its random stream is its own (neither NumPy's PCG64 nor the kernel's Philox): throughput only.
- * Build: gcc -O3 -march=native -ffp-contract=off -fopenmp -shared -fPIC oracle/em_port.c -o oracle/_build/libem_port.so -lm
+ * Build: gcc -O3 -march=x86-64-v3 -ffp-contract=off -fopenmp -shared -fPIC oracle/em_port.c -o oracle/_build/libem_port.so -lm
  */
 #include <math.h>
 #include <stdint.h>

@@ -38,7 +38,7 @@ def main():
     for _ in range(a.steps):
         st.step()
     dt = (time.perf_counter() - t0) / a.steps
-    print(json.dumps({"config": f"oracle/em_port.c (gcc -O3 -march=native, OpenMP) E={a.envs} n={a.n} K={a.interval}, trajectory on",
+    print(json.dumps({"config": f"oracle/em_port.c (gcc -O3 -march=x86-64-v3, OpenMP) E={a.envs} n={a.n} K={a.interval}, trajectory on",
                       "threads": a.threads, "ms_per_action_step": round(dt * 1e3, 3),
                       "env_substeps_per_s": float(f"{a.envs * a.interval / dt:.4g}"),
                       "host": f"{os.cpu_count()} logical cores"}))
