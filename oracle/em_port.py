@@ -12,7 +12,10 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "em_port.c")
 LIB = os.path.join(HERE, "_build", "libem_port.so")
+LYAP_SRC = os.path.join(HERE, "lyap_port.c")
+LYAP_LIB = os.path.join(HERE, "_build", "liblyap_port.so")
 _lib = None
+_lyap = None
 
 
 def available():
@@ -20,10 +23,12 @@ def available():
 
 
 def build(force=False):
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(SRC):
-        os.makedirs(os.path.dirname(LIB), exist_ok=True)
-        subprocess.run(["gcc", "-O3", "-march=x86-64-v3", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", SRC, "-o", LIB, "-lm"],
-                       check=True)
+    """Compile both C restatements (oracle/em_port.c, oracle/lyap_port.c) into oracle/_build/; returns the EM library."""
+    for src, out in ((SRC, LIB), (LYAP_SRC, LYAP_LIB)):
+        if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            subprocess.run(["gcc", "-O3", "-march=x86-64-v3", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", src, "-o", out,
+                            "-lm"], check=True)
     return LIB
 
 
@@ -77,3 +82,18 @@ class RngStepper:
                           _p(self.stds), _p(self.w), _p(self.St), _p(self.Ob), _p(self.Rw), _p(self.x))
         self.interval += 1
         return self.Ob[-1], self.Rw[-1]
+
+
+def lyap_rk4_interval(params, actions, y0, K, t_ssz, substeps=1):
+    """oracle/lyap_port.c: optomech RK4 interval.  params (E,7), actions (E,), y0 (E,20) -> Y (K+1,E,20)."""
+    global _lyap
+    if _lyap is None:
+        build()
+        _lyap = C.CDLL(LYAP_LIB)
+        _lyap.lyap_port_rk4.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double] + [C.POINTER(C.c_double)] * 4
+        _lyap.lyap_port_rk4.restype = None
+    E = y0.shape[0]
+    params, actions, y0 = _c(params, (E, 7)), _c(actions, (E,)), _c(y0)
+    Y = np.empty((K + 1, E, 20))
+    _lyap.lyap_port_rk4(E, K, int(substeps), float(t_ssz), _p(params), _p(actions), _p(y0), _p(Y))
+    return Y

@@ -60,3 +60,23 @@ def test_c_port_rng_mode_has_the_right_moments():
     np.testing.assert_allclose(var, sigma ** 2 / (2 * theta - theta ** 2 * dt), rtol=0.05)
     np.testing.assert_allclose((st.Ob[-1] - st.St[-1]).std(axis=0), 0.2, rtol=0.03)
     assert abs(np.corrcoef(st.St[-1][:, 0], st.St[-1][:, 1])[0, 1]) < 0.03
+
+
+@pytest.mark.parametrize("substeps,key", [(1, "rk4"), (2, "rk4x2")])
+def test_c_lyapunov_port_matches_rk4_on_the_reference_func(golden_dir, substeps, key):
+    """oracle/lyap_port.c (optomech RHS + classic RK4 in plain C) against fixture G2 — RK4 driven by the reference's own
+    ``env.func`` — and against the NumPy oracle."""
+    import lyap_oracle as lo
+    g = np.load(os.path.join(golden_dir, "lyap_optomech.npz"))
+    tag = "E5"
+    p, y0, acts, T, K = g[f"{tag}_p"], g[f"{tag}_y0"], g[f"{tag}_actions"], g[f"{tag}_T"], int(g[f"{tag}_K"])
+    func = lo.make_func(2, 4, lambda t, mo, u: sy.optomech_mode_rates(p, t, mo, u), lambda t, mo, u: sy.optomech_A(p, t, mo, u),
+                        lambda t, mo, u: sy.optomech_D(p, t, mo, u), p.shape[0])
+    y, rows = y0.copy(), [y0[None].copy()]
+    for a in range(acts.shape[0]):
+        Y = em_port.lyap_rk4_interval(p, acts[a][:, 0], y, K, float(g[f"{tag}_ssz"]), substeps=substeps)
+        np.testing.assert_allclose(Y, lo.rk4_interval(func, T[a * K:(a + 1) * K + 1], y, acts[a][:, 0], substeps=substeps),
+                                   rtol=1e-12, atol=1e-13)
+        rows.append(Y[1:])
+        y = Y[-1]
+    np.testing.assert_allclose(np.concatenate(rows, 0), g[f"{tag}_States_{key}_reffunc"], rtol=1e-12, atol=1e-13)

@@ -23,11 +23,28 @@ def main():
     ap.add_argument("--interval", type=int, default=100)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--threads", type=int, default=os.cpu_count())
+    ap.add_argument("--lyap", action="store_true", help="BASELINE config 2 instead: optomech modes + Lyapunov RK4 "
+                    "(oracle/lyap_port.c), default --envs 1024")
     a = ap.parse_args()
     os.environ["OMP_NUM_THREADS"] = str(a.threads)
     import numpy as np
     import em_port
     import systems as sy
+    if a.lyap:
+        E = 1024 if a.envs == 4096 else a.envs
+        p = sy.optomech_default_params(E, seed=2)
+        y = sy.optomech_y0(p)
+        u = np.random.default_rng(3).uniform(-1, 1, E)
+        for _ in range(2):
+            y = em_port.lyap_rk4_interval(p, u, y, a.interval, 0.01)[-1]
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            y = em_port.lyap_rk4_interval(p, u, y, a.interval, 0.01)[-1]
+        dt = (time.perf_counter() - t0) / a.steps
+        print(json.dumps({"config": f"oracle/lyap_port.c (gcc -O3 -march=x86-64-v3, OpenMP) optomech RK4 E={E} K={a.interval} h=t_ssz, States rows kept",
+                          "threads": a.threads, "ms_per_action_step": round(dt * 1e3, 3),
+                          "env_substeps_per_s": float(f"{E * a.interval / dt:.4g}"), "host": f"{os.cpu_count()} logical cores"}))
+        return
     A0, Au = sy.affine_matrices(a.n, 1, seed=0)
     u = np.random.default_rng(1).uniform(-1, 1, (a.envs, 1))
     st = em_port.RngStepper(a.envs, a.n, a.interval, 0.01, sy.affine_A(A0, Au, u), np.full(a.n, 0.05), np.full(a.n, 0.01),
