@@ -13,6 +13,7 @@ Fixtures
   lyap_optomech.npz   G1/G2/G4: ``LinearizedHOVecEnv`` + SciPy at tight tolerance (dop853 and vode), default-tolerance
                       vode, RK4 driven by the reference's own ``env.func``, the single-env twin, and the packed
                       ``env.data`` cache of ``BaseSB3Env.update_data``.
+  lyap_config1.npz    G7: BASELINE config 1 exactly — one ``LinearizedHOEnv``, 1000 sub-steps (vode default, dop853 tight).
   dde_scipy.npz       G6: a delay system through ``SciPyIVPSolver.solve_ivp`` with ``has_delay=True`` (vode, tight).
   lyap_kerr.npz       same for the kerr_chain system (N=2 -> q=4, N=4 -> q=8).
 """
@@ -322,8 +323,31 @@ def golden_dde():
     print("dde_scipy.npz", Y.shape, Y[-1])
 
 
+def golden_config1():
+    """BASELINE config 1 exactly: ONE reference ``LinearizedHOEnv`` (m = 2, q = 4), kappa = 0.1,
+    gamma = 1e-3, omega_m = 1, Delta0 = -1, g0 = 1e-2, n_th = 10, A_l = 5, t_norm_max = 10 (S = 1000), K = 10, actions
+    held at ``action_maximums`` (what ``evolve`` applies): SciPy vode at the reference's default tolerances and
+    dop853 tight."""
+    p = systems.optomech_default_params(1, seed=2, jitter=False)
+    y0 = systems.optomech_y0(p)
+    K, S, ssz = 10, 1000, 0.01
+    actions = np.ones((S // K, 1, 1))
+    out = {"p": p, "y0": y0, "K": K, "S": S, "ssz": ssz}
+    for name, method, atol, rtol in (("vode_default", "vode", 1e-9, 1e-6), ("dop853_tight", "dop853", 1e-14, 1e-13)):
+        env = make_vec_env("optomech", p, 2, 4, y0, K, S, ssz, method, atol, rtol, cls=LinearizedHOEnv)
+        St, Rw, _ = run_vec(env, actions, single=True)
+        assert St.shape == (S + 1, 20), St.shape
+        out["States_" + name], out["Reward_" + name] = St, Rw
+    np.savez_compressed(os.path.join(GOLDEN, "lyap_config1.npz"), **out)
+    print("lyap_config1.npz", {k: np.shape(v) for k, v in out.items()},
+          "default vs tight:", np.max(np.abs(out["States_vode_default"] - out["States_dop853_tight"])))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
+    if "--config1-only" in sys.argv:
+        golden_config1()
+        sys.exit(0)
     if "--dde-only" in sys.argv:
         golden_dde()
         sys.exit(0)
@@ -335,3 +359,4 @@ if __name__ == "__main__":
     golden_lyap("optomech", [("E5", 5, 0)], "lyap_optomech.npz")
     golden_lyap("kerr", [("N2", 3, 2), ("N4", 2, 4)], "lyap_kerr.npz")
     golden_dde()
+    golden_config1()
