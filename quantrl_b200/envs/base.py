@@ -69,6 +69,7 @@ class PartCacheWriter:
         self.compressed = compressed
         self._q = None
         self._thread = None
+        self._error = None
 
     def _start(self):
         os.makedirs(self.disk_cache_dir, exist_ok=True)
@@ -82,9 +83,20 @@ class PartCacheWriter:
             if item is None:
                 return
             path, data = item
-            (np.savez_compressed if self.compressed else np.savez)(path, data)
+            if self._error is None:     # after a failure the queue is still drained, so that the env never blocks on it
+                try:
+                    (np.savez_compressed if self.compressed else np.savez)(path, data)
+                except Exception as e:  # noqa: BLE001
+                    self._error = e
+
+    def _raise_pending(self):
+        """A write that failed on the background thread surfaces in the caller's thread, once."""
+        if self._error is not None:
+            e, self._error = self._error, None
+            raise RuntimeError(f"writing a trajectory part file under {self.disk_cache_dir} failed") from e
 
     def dump_part_async(self, data, batch_idx, part_idx):
+        self._raise_pending()
         if self._thread is None:
             self._start()
         self._q.put((self.part_path(batch_idx, part_idx), data))
@@ -95,6 +107,7 @@ class PartCacheWriter:
             self._q.put(None)
             self._thread.join()
             self._thread = None
+        self._raise_pending()
 
     def part_path(self, batch_idx, part_idx):
         return os.path.join(self.disk_cache_dir, "_".join([
