@@ -13,6 +13,7 @@ Fixtures
   lyap_optomech.npz   G1/G2/G4: ``LinearizedHOVecEnv`` + SciPy at tight tolerance (dop853 and vode), default-tolerance
                       vode, RK4 driven by the reference's own ``env.func``, the single-env twin, and the packed
                       ``env.data`` cache of ``BaseSB3Env.update_data``.
+  lyap_optomech_props.npz  G8: vec env with ``n_properties = 2``: the full packed ``data`` cache incl. the property columns.
   lyap_config1.npz    G7: BASELINE config 1 exactly — one ``LinearizedHOEnv``, 1000 sub-steps (vode default, dop853 tight).
   dde_scipy.npz       G6: a delay system through ``SciPyIVPSolver.solve_ivp`` with ``has_delay=True`` (vode, tight).
   lyap_kerr.npz       same for the kerr_chain system (N=2 -> q=4, N=4 -> q=8).
@@ -165,7 +166,7 @@ def golden_em_time_dependent():
 # ---------------------------------------------------------------------------------------------------------
 # G1/G2/G4: deterministic LinearizedHO(Vec)Env
 # ---------------------------------------------------------------------------------------------------------
-def make_vec_env(system, p, m, q, y0, K, S, ssz, method, atol, rtol, cls=LinearizedHOVecEnv):
+def make_vec_env(system, p, m, q, y0, K, S, ssz, method, atol, rtol, cls=LinearizedHOVecEnv, n_props=0, props_fn=None):
     E = p.shape[0]
     mode_rates = getattr(systems, system + "_mode_rates")
     fA = getattr(systems, system + "_A")
@@ -199,13 +200,17 @@ def make_vec_env(system, p, m, q, y0, K, S, ssz, method, atol, rtol, cls=Lineari
             V = self.Observations[..., 2 * m:].reshape(*self.Observations.shape[:-1], q, q)
             return -np.trace(V, axis1=-2, axis2=-1)
 
+        def get_properties(self):
+            return props_fn(self.Observations)
+
     fresh_backend()
     d = 2 * m + q * q
     # the env's grid is one action interval longer than what we step, so that the vectorized env never reaches
     # ``terminated`` (its auto-reset inside ``step_wait`` would wipe ``States``/``data``; base.py:1277-1291)
     kw = dict(name=system, desc="golden", params={}, num_modes=m, num_quads=q, t_norm_max=(S + K) * ssz + ssz / 2,
-              t_norm_ssz=ssz, t_norm_mul=1.0, n_observations=d, n_properties=0, n_actions=1, action_maximums=[1.0],
-              action_interval=K, data_idxs=[0, 1, 2, 2 + d], backend_library="numpy", ode_method=method,
+              t_norm_ssz=ssz, t_norm_mul=1.0, n_observations=d, n_properties=n_props, n_actions=1, action_maximums=[1.0],
+              action_interval=K, data_idxs=[0, 1, 2, 2 + d] if n_props == 0 else list(range(1 + 1 + d + n_props + 1)),
+              backend_library="numpy", ode_method=method,
               ode_atol=atol, ode_rtol=rtol, **COMMON)
     if not single:
         kw["n_envs"] = E
@@ -323,6 +328,27 @@ def golden_dde():
     print("dde_scipy.npz", Y.shape, Y[-1])
 
 
+def optomech_props(Obs):
+    """Two properties of the observed state (shared by the generator and the tests): the covariance trace and |alpha|^2."""
+    return np.stack([Obs[..., 4] + Obs[..., 9] + Obs[..., 14] + Obs[..., 19], Obs[..., 0] ** 2 + Obs[..., 2] ** 2], axis=-1)
+
+
+def golden_props():
+    """G8: ``LinearizedHOVecEnv`` with ``n_properties = 2`` (``get_properties`` hook, envs/base.py:296-305, 464-469) and
+    every column selected: the packed ``data`` cache ``[t, action, obs(20), props(2), cumulative reward]`` of
+    ``BaseSB3Env.update_data`` (envs/base.py:1314-1372)."""
+    E, K, S, ssz = 3, 10, 50, 0.01
+    p = systems.optomech_default_params(E, seed=2)
+    y0 = systems.optomech_y0(p)
+    actions = np.random.default_rng(8).uniform(-1, 1, (S // K, E, 1))
+    env = make_vec_env("optomech", p, 2, 4, y0, K, S, ssz, "dop853", 1e-14, 1e-13, n_props=2, props_fn=optomech_props)
+    St, Rw, _ = run_vec(env, actions)
+    out = {"p": p, "y0": y0, "actions": actions, "K": K, "S": S, "ssz": ssz, "States": St, "Reward": Rw,
+           "data": np.array(env.data)[:, :S + 1], "T": np.array(env.T)[:S + 1]}
+    np.savez_compressed(os.path.join(GOLDEN, "lyap_optomech_props.npz"), **out)
+    print("lyap_optomech_props.npz", {k: np.shape(v) for k, v in out.items()})
+
+
 def golden_config1():
     """BASELINE config 1 exactly: ONE reference ``LinearizedHOEnv`` (m = 2, q = 4), kappa = 0.1,
     gamma = 1e-3, omega_m = 1, Delta0 = -1, g0 = 1e-2, n_th = 10, A_l = 5, t_norm_max = 10 (S = 1000), K = 10, actions
@@ -348,6 +374,9 @@ if __name__ == "__main__":
     if "--config1-only" in sys.argv:
         golden_config1()
         sys.exit(0)
+    if "--props-only" in sys.argv:
+        golden_props()
+        sys.exit(0)
     if "--dde-only" in sys.argv:
         golden_dde()
         sys.exit(0)
@@ -360,3 +389,4 @@ if __name__ == "__main__":
     golden_lyap("kerr", [("N2", 3, 2), ("N4", 2, 4)], "lyap_kerr.npz")
     golden_dde()
     golden_config1()
+    golden_props()
