@@ -100,6 +100,83 @@ def make_sharded_env(env_cls, n_envs_total, rank=None, world_size=None, **env_kw
     return env_cls(n_envs=count, env_offset=offset, **env_kwargs)
 
 
+class ShardedVecEnv:
+    """The learner rank's view of ONE lock-stepped batch whose environments live on all ranks (BASELINE config 5:
+    "observations/rewards all-gathered to the learner rank").
+
+    Wraps this rank's shard (an env of ``quantrl_b200.envs`` built by ``make_sharded_env``) and speaks the same
+    ``reset() / step(actions) -> (obs, reward, dones, infos)`` protocol as a single env (quantrl/envs/base.py:1185-1293),
+    for the GLOBAL batch: on the learner ``step`` takes ``(n_envs_total, n_act)`` actions and returns global
+    observations / rewards; the other ranks call ``serve()``, which mirrors the learner's calls until ``shutdown()``.
+
+    Per action step: scatter actions -> ``step_device`` on every shard (the fused kernel, no collective) -> one 1-word
+    MAX all-reduce of the truncation flag (the reference ends the episode for ALL envs when any observation leaves the
+    range, base.py:485-499, 1271-1293; termination is the same on every rank by construction) -> gather
+    ``[obs | reward]`` to the learner.  When the episode ends every shard resets and the reset observation is what
+    the learner receives (auto-reset, no ``terminal_observation``, base.py:1277-1293)."""
+
+    _STOP = float("nan")
+
+    def __init__(self, local_env, n_envs_total, dst=0, group=None, link=None):
+        self.env = local_env
+        self.device = torch.device(local_env.device)
+        self.n_envs, self.n_observations, self.n_actions = int(n_envs_total), local_env.n_observations, local_env.n_actions
+        self.action_steps, self.action_space_range = local_env.action_steps, local_env.action_space_range
+        self.link = link if link is not None else LearnerLink(n_envs_total, self.n_observations, self.n_actions,
+                                                              device=self.device, dst=dst, group=group)
+        assert self.link.count == local_env.n_envs, "the local env does not have this rank's share of the batch"
+        self.is_learner = self.link.is_learner
+        self._flag = torch.zeros((1,), dtype=torch.float64, device=self.device)
+        self._zero_reward = torch.zeros((local_env.n_envs,), dtype=torch.float64, device=self.device)
+        self.episodes = 0
+
+    def _gather(self, obs, rew):
+        res = self.link.gather_step(obs, rew, False)
+        return None if res is None else (res[0].clone(), res[1].clone())
+
+    def reset(self, seed=None, options=None):
+        obs = self.env.reset()
+        res = self._gather(obs, self._zero_reward)
+        return None if res is None else res[0]
+
+    def step(self, actions=None):
+        """Learner: ``actions (n_envs_total, n_act)`` -> ``(obs, reward, dones, infos)`` of the global batch.
+        Other ranks (through ``serve``): returns ``None``, or ``False`` once the learner has shut the loop down."""
+        a = self.link.scatter_actions(actions)
+        if self.link.world > 1 and bool(torch.isnan(a).any()):
+            return False
+        obs, rew, terminated = self.env.step_device(a)
+        self._flag[0] = 1.0 if self.env.truncation_pending() else 0.0
+        if self.link.world > 1:
+            dist.all_reduce(self._flag, op=dist.ReduceOp.MAX, group=self.link.group)
+        done = bool(terminated) or bool(self._flag[0] > 0)
+        rew = rew.clone()
+        if done:
+            self.episodes += 1
+            obs = self.env.reset()
+        res = self._gather(obs, rew)
+        if res is None:
+            return None
+        return res[0], res[1], [done] * self.n_envs, [{}] * self.n_envs
+
+    def serve(self):
+        """Non-learner ranks: follow the learner (its first ``reset`` and every ``step``) until it calls ``shutdown``."""
+        assert not self.is_learner
+        self.reset()
+        while self.step(None) is not False:
+            pass
+
+    def shutdown(self):
+        """Learner: release the ranks blocked in ``serve``."""
+        assert self.is_learner
+        if self.link.world > 1:
+            self.link.scatter_actions(torch.full((self.n_envs, self.n_actions), self._STOP, dtype=torch.float64,
+                                                 device=self.device))
+
+    def close(self, **kw):
+        self.env.close(**kw)
+
+
 class PeerGather:
     """Gather-to-learner WITHOUT a collective launch: every rank's integration kernel stores its slice of the step
     result (last observations, last reward) straight into the learner rank's buffer through NVLink peer mapping

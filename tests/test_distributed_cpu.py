@@ -134,3 +134,100 @@ def test_make_sharded_env_slices_per_env_arguments():
         assert env.kw["n_envs"] == cnt and env.kw["env_offset"] == off and env.kw["x0"] is None
         assert np.array_equal(env.kw["system_params"], params[off:off + cnt]) and env.kw["shared"].shape == (3,)
         assert "_per_env" not in env.kw
+
+
+class _FakeShard:
+    """CPU stand-in for one rank's env shard (the protocol ShardedVecEnv needs: ``reset``, ``step_device``,
+    ``truncation_pending``): x <- 0.9 x + 0.1 u + 0.05 * global_index, reward = -|x|^2, 4 action steps per episode,
+    truncation when any |x| exceeds ``limit``."""
+
+    def __init__(self, n_envs, env_offset, limit=1e9):
+        self.n_envs, self.env_offset, self.limit = n_envs, env_offset, limit
+        self.n_observations, self.n_actions, self.action_steps, self.action_space_range = 3, 1, 4, [-1.0, 1.0]
+        self.device = torch.device("cpu")
+        self.gidx = torch.arange(env_offset, env_offset + n_envs, dtype=torch.float64)[:, None]
+        self.resets = 0
+
+    def reset(self):
+        self.x = torch.ones((self.n_envs, 3), dtype=torch.float64) * (1.0 + 0.001 * self.gidx)
+        self.t = 0
+        self.resets += 1
+        return self.x.clone()
+
+    def step_device(self, a):
+        self.x = 0.9 * self.x + 0.1 * a.reshape(self.n_envs, 1) + 0.05 * self.gidx
+        self.t += 1
+        return self.x.clone(), -(self.x ** 2).sum(1), self.t >= self.action_steps
+
+    def truncation_pending(self):
+        return bool((self.x.abs() > self.limit).any())
+
+    def close(self, **kw):
+        pass
+
+
+def _sharded_env_worker(rank, world, port, E, out):
+    from quantrl_b200.distributed import ShardedVecEnv, shard_bounds
+    from quantrl_b200.learner import PPO
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # (1) lock-step protocol: the sharded batch == one unsharded env, incl. auto-reset and GLOBAL truncation
+        for limit, ends in ((1e9, [3]), (1.25, None)):
+            off, cnt = shard_bounds(E, rank, world)
+            env = ShardedVecEnv(_FakeShard(cnt, off, limit), E)
+            if rank != 0:
+                env.serve()
+                assert env.env.resets >= 2
+                continue
+            whole = _FakeShard(E, 0, limit)
+            obs = env.reset()
+            assert torch.equal(obs, whole.reset())
+            rng = np.random.default_rng(1)
+            done_steps = []
+            for step in range(6):
+                u = torch.as_tensor(rng.uniform(-1, 1, (E, 1)))
+                o, r, dones, infos = env.step(u)
+                wo, wr, wterm = whole.step_device(u)
+                wdone = wterm or whole.truncation_pending()
+                if wdone:
+                    wo = whole.reset()
+                    done_steps.append(step)
+                assert torch.equal(o, wo) and torch.equal(r, wr) and dones == [wdone] * E and infos == [{}] * E
+            if ends is not None:
+                assert done_steps == ends
+            else:   # only the LAST env (on rank 1) leaves the range: its truncation ends the episode for every rank
+                assert done_steps and done_steps[0] < 3
+            env.shutdown()
+        # (2) the learner glue on top: PPO drives the global batch on rank 0 while rank 1 serves its shard
+        off, cnt = shard_bounds(E, rank, world)
+        env = ShardedVecEnv(_FakeShard(cnt, off), E)
+        if rank == 0:
+            ppo = PPO(env, seed=0, hidden=16, epochs=1, minibatches=1)
+            hist = ppo.learn(2)
+            assert len(hist) == 2 and all(np.isfinite(h["mean_step_reward"]) for h in hist)
+            assert env.episodes == 2 and ppo.n_steps == 4
+            env.shutdown()
+        else:
+            env.serve()
+            assert env.episodes == 2
+        out.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        out.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_vec_env_serves_the_learner_gloo():
+    """ShardedVecEnv (BASELINE config 5's learner protocol) over gloo, world size 2, uneven shards (4 + 3 envs)."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_env_worker, args=(r, 2, port, 7, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(out.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, "ok"), (1, "ok")], res
