@@ -165,3 +165,32 @@ def test_null_argument_block_and_micro_benchmarks_are_rejected(native):
         assert fn(None, None) < 0 and b"args is NULL" in lib.qrl_last_error()
     assert lib.qrl_measure_fp64_peak(0, None) < 0 and lib.qrl_measure_fp64_latency(None) < 0
     assert lib.qrl_host_device_pointer(None, None) < 0
+
+
+def test_product_package_never_touches_the_oracle():
+    """``oracle/`` is test infrastructure: no module of ``quantrl_b200`` (nor the example scripts) imports it, puts it on
+    ``sys.path`` or reads the reference tree; ``bench.py`` does so only inside its CPU-baseline / reference-arm leg."""
+    import ast
+    banned = {"em_oracle", "lyap_oracle", "measure_oracle", "ref_shim", "make_golden", "em_port", "systems"}
+    pkg = os.path.join(ROOT, "quantrl_b200")
+    files = [os.path.join(d, f) for d, _, fs in os.walk(pkg) for f in fs if f.endswith(".py")]
+    files += [os.path.join(ROOT, "examples", f) for f in os.listdir(os.path.join(ROOT, "examples")) if f.endswith(".py")]
+    assert len(files) >= 12
+    for path in files:
+        src = open(path).read()
+        tree = ast.parse(src)
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Import):
+                names = [a.name.split(".")[0] for a in node.names]
+            elif isinstance(node, ast.ImportFrom) and node.level == 0:
+                names = [(node.module or "").split(".")[0]]
+            else:
+                continue
+            assert not banned.intersection(names) and "oracle" not in names, (path, names)
+        code_only = "\n".join(ln.split("#")[0] for ln in src.splitlines())
+        assert "/root/reference" not in code_only.replace('"""', ""), path
+        assert 'os.path.join(ROOT, "oracle")' not in src and "'oracle'" not in src, path
+    # bench.py: the oracle import sits inside the function that serves cpu_baseline / --impl reference
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
+    assert not any("oracle" in ast.dump(n) for n in top)
