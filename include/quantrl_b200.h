@@ -4,7 +4,7 @@
  * The reference is pure Python and has no FFI; its plugin seams are the Python ABCs
  * `BaseBackend` / `BaseIVPSolver` / `BaseEnv` and two registries.  This header is the boundary *beneath* those seams:
  * each entry point names the reference code it replaces (paths relative to the reference root).  The Python host
- * (quantrl_b200/*.py) binds it with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ * (the quantrl_b200 Python package) binds it with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
  *
  * Conventions
  *   - plain pointers and sizes only; every data pointer is a DEVICE pointer to contiguous FP64 unless the name

@@ -194,3 +194,34 @@ def test_product_package_never_touches_the_oracle():
     tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
     top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
     assert not any("oracle" in ast.dump(n) for n in top)
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(native, tmp_path):
+    """The boundary is a C ABI: ``include/quantrl_b200.h`` compiles as strict C99 and as C++ (``-Wall -Wextra -Wpedantic
+    -Werror``), and a plain C program links against ``libquantrl_b200.so``, reads the ABI version and gets an argument
+    error back through the return code + ``qrl_last_error`` — no Python, no torch types in the way."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    from quantrl_b200.build import LIB_PATH
+    src = tmp_path / "abi_client.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "quantrl_b200.h"\n'
+        "int main(void) {\n"
+        "    qrl_em_args a;\n    memset(&a, 0, sizeof a);\n    a.n = 99; a.n_envs = 1; a.K = 1;\n"
+        "    if (qrl_abi_version() != QRL_ABI_VERSION) return 2;\n"
+        "    if (qrl_em_step(&a, NULL) >= 0) return 3;\n"
+        "    if (qrl_ode_step(NULL, NULL) >= 0 || qrl_pack_rows(NULL, NULL) >= 0) return 4;\n"
+        '    printf("%d %s\\n", qrl_abi_version(), qrl_last_error());\n    return 0;\n}\n')
+    inc = os.path.join(ROOT, "include")
+    for cc, std in (("gcc", "-std=c99"), ("g++", "-std=c++11")):
+        subprocess.run([cc, std, "-Wall", "-Wextra", "-Wpedantic", "-Werror", "-I", inc, "-fsyntax-only"]
+                       + (["-x", "c++"] if cc == "g++" else []) + [str(src)], check=True)
+    exe = tmp_path / "abi_client"
+    libdir = os.path.dirname(LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-lquantrl_b200",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, (p.returncode, p.stderr)
+    assert p.stdout.split()[0] == str(native.ABI_VERSION) and "args is NULL" in p.stdout
