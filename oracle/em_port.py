@@ -14,6 +14,8 @@ SRC = os.path.join(HERE, "em_port.c")
 LIB = os.path.join(HERE, "_build", "libem_port.so")
 LYAP_SRC = os.path.join(HERE, "lyap_port.c")
 LYAP_LIB = os.path.join(HERE, "_build", "liblyap_port.so")
+PHILOX_SRC = os.path.join(HERE, "philox_port.c")
+PHILOX_LIB = os.path.join(HERE, "_build", "libphilox_port.so")
 _lib = None
 _lyap = None
 
@@ -23,8 +25,8 @@ def available():
 
 
 def build(force=False):
-    """Compile both C restatements (oracle/em_port.c, oracle/lyap_port.c) into oracle/_build/; returns the EM library."""
-    for src, out in ((SRC, LIB), (LYAP_SRC, LYAP_LIB)):
+    """Compile the C restatements (oracle/em_port.c, lyap_port.c, philox_port.c) into oracle/_build/; returns the EM library."""
+    for src, out in ((SRC, LIB), (LYAP_SRC, LYAP_LIB), (PHILOX_SRC, PHILOX_LIB)):
         if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
             os.makedirs(os.path.dirname(out), exist_ok=True)
             subprocess.run(["gcc", "-O3", "-march=x86-64-v3", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", src, "-o", out,
@@ -97,3 +99,37 @@ def lyap_rk4_interval(params, actions, y0, K, t_ssz, substeps=1):
     Y = np.empty((K + 1, E, 20))
     _lyap.lyap_port_rk4(E, K, int(substeps), float(t_ssz), _p(params), _p(actions), _p(y0), _p(Y))
     return Y
+
+
+_philox = None
+
+
+def _philox_lib():
+    global _philox
+    if _philox is None:
+        build()
+        _philox = C.CDLL(PHILOX_LIB)
+        u32p = C.POINTER(C.c_uint32)
+        _philox.philox_port_4x32_10.argtypes = [u32p, C.c_uint32, C.c_uint32, u32p]
+        _philox.philox_port_4x32_10.restype = None
+        _philox.philox_port_normals.argtypes = [C.c_uint64, C.c_uint32, u32p, u32p, u32p, C.c_int] + [C.POINTER(C.c_double)] * 2
+        _philox.philox_port_normals.restype = None
+    return _philox
+
+
+def philox4x32_10(counter, key):
+    """oracle/philox_port.c: one Philox4x32-10 block; counter (4 words), key (2 words) -> 4 words."""
+    c = (C.c_uint32 * 4)(*[int(v) & 0xFFFFFFFF for v in counter])
+    out = (C.c_uint32 * 4)()
+    _philox_lib().philox_port_4x32_10(c, int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF, out)
+    return [int(v) for v in out]
+
+
+def philox_normals_poly(seed, episode, tau, env, comp):
+    """The kernel's generator (polynomial ln / sin / cos, Goldschmidt sqrt) in C for flat uint32 arrays of counters."""
+    tau, env, comp = (np.ascontiguousarray(np.broadcast_arrays(tau, env, comp)[i], dtype=np.uint32).ravel() for i in range(3))
+    z0, z1 = np.empty(tau.size), np.empty(tau.size)
+    u32p = C.POINTER(C.c_uint32)
+    _philox_lib().philox_port_normals(int(seed) & 0xFFFFFFFFFFFFFFFF, int(episode) & 0xFFFFFFFF, tau.ctypes.data_as(u32p),
+                                      env.ctypes.data_as(u32p), comp.ctypes.data_as(u32p), tau.size, _p(z0), _p(z1))
+    return z0, z1

@@ -80,3 +80,28 @@ def test_c_lyapunov_port_matches_rk4_on_the_reference_func(golden_dir, substeps,
         rows.append(Y[1:])
         y = Y[-1]
     np.testing.assert_allclose(np.concatenate(rows, 0), g[f"{tag}_States_{key}_reffunc"], rtol=1e-12, atol=1e-13)
+
+
+def test_c_philox_known_answers_and_polynomial_normals():
+    """oracle/philox_port.c restates csrc/philox.cuh operation by operation.  (1) Random123's Philox4x32-10 known-answer
+    vectors; (2) the kernel's polynomial Box–Muller (fdlibm ln / sin / cos kernels, Goldschmidt sqrt) against the libm
+    evaluation of the same stream (oracle/em_oracle.py:philox_normals): a few ulp — the accuracy claim of philox.cuh,
+    checked without a GPU — and the moments of the polynomial normals themselves."""
+    assert em_port.philox4x32_10([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert em_port.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert em_port.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    seed, episode = 0x1234567890ABCDEF, 3
+    tau = np.arange(0, 400, dtype=np.uint64).reshape(-1, 1, 1)
+    tau[0] = 0xFFFFFFFF
+    env = (np.uint64(17) + np.arange(64, dtype=np.uint64)).reshape(1, -1, 1)
+    comp = np.arange(8, dtype=np.uint64).reshape(1, 1, -1)
+    r0, r1 = eo.philox_normals(seed, episode, tau, env, comp)
+    z0, z1 = em_port.philox_normals_poly(seed, episode, tau, env, comp)
+    z0, z1 = z0.reshape(r0.shape), z1.reshape(r1.shape)
+    for z, r in ((z0, r0), (z1, r1)):
+        assert np.max(np.abs(z - r)) < 4e-15 and np.max(np.abs(z - r) / np.maximum(np.abs(r), 1e-3)) < 2e-15
+    z = np.concatenate([z0.ravel(), z1.ravel()])
+    m = z.size
+    assert abs(z.mean()) < 5 / np.sqrt(m) and abs(z.var() - 1) < 5 * np.sqrt(2 / m) and abs((z ** 4).mean() - 3) < 5 * np.sqrt(96 / m)
+    assert abs(np.corrcoef(z0.ravel(), z1.ravel())[0, 1]) < 0.01
