@@ -331,11 +331,30 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
     def set_attr(self, attr_name, value, indices=None):
         return [setattr(self, attr_name, value) for _ in range(self._n_indices(indices))]
 
-    def validate(self):
-        """Shape checks of the user hooks (base.py:319-376, 1088-1095)."""
+    def validate_base(self, shape_reset_states, shape_get_properties, shape_get_reward):
+        """Shape checks of the user hooks on the initial state block (base.py:319-376): ``reset_states``, then — with
+        ``States`` / ``Observations`` filled with the initial states — ``get_properties`` and ``get_reward`` (skipped when
+        the reward is a fused functor of the kernel).  A missing hook raises (the reference prints and exits)."""
         states_0 = self.backend.convert_to_typed(tensor=self.reset_states(), dtype="real")
-        assert tuple(states_0.shape) == (self.n_envs, self.n_observations), \
-            f"``reset_states`` should return an array with shape ``{(self.n_envs, self.n_observations)}``"
+        assert tuple(states_0.shape) == tuple(shape_reset_states), \
+            f"``reset_states`` should return an array with shape ``{tuple(shape_reset_states)}``"
+        self._States[:] = states_0.unsqueeze(0)
+        self._Observations[:] = self._States
+        self.States, self.Observations = self._States, self._Observations
+        if self.n_properties > 0:
+            self.Properties = self.backend.convert_to_typed(tensor=self.get_properties(), dtype="real")
+            assert tuple(self.Properties.shape) == tuple(shape_get_properties), \
+                f"``get_properties`` should return an array with shape ``{tuple(shape_get_properties)}``"
+        if not self._reward_fused:
+            self.Reward = self.backend.convert_to_typed(tensor=self.get_reward(), dtype="real")
+            assert tuple(self.Reward.shape) == tuple(shape_get_reward), \
+                f"``get_reward`` should return an array with shape ``{tuple(shape_get_reward)}``"
+
+    def validate(self):
+        """``validate_base`` with the shapes of a vectorized env (base.py:1088-1095)."""
+        K1, E = self.action_interval + 1, self.n_envs
+        return self.validate_base(shape_reset_states=(E, self.n_observations),
+                                  shape_get_properties=(K1, E, self.n_properties), shape_get_reward=(K1, E))
 
     # ---- reset (base.py:378-438, 1185-1231) ------------------------------------------------------------------
     def reset(self, seed=None, options=None):
