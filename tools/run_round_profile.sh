@@ -19,3 +19,9 @@ ncu --set full --clock-control none --import-source on -k regex:rk4_split -s 3 -
 ncu --set full --clock-control none --import-source on -k regex:dopri5_lanes -s 3 -c 1 -f -o gpurun_out/prof_dopri5_lanes_$T python tools/prof_ode.py 1024 dopri5 0 >> gpurun_out/ncu_ode_$T.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:dopri5_kernel -s 3 -c 1 -f -o gpurun_out/prof_dopri5_thread_$T python tools/prof_ode.py 65536 dopri5 1 >> gpurun_out/ncu_ode_$T.log 2>&1
 grep -c "Report:" gpurun_out/ncu_ode_$T.log
+# afterwards, in the build container (no GPU needed): per-source-line breakdowns of the captures
+#   ncu -i gpurun_out/prof_tile_$T.ncu-rep --page source --csv --print-source sass,cuda > /tmp/page.csv
+#   python tools/summarize_source_page.py /tmp/page.csv --kernel-regex em_tile_kernel --regions '<file:lo-hi=name,...>' > profiles/<round>_tile_source_hotspots.md
+#   python tools/summarize_profiles.py            # raw-page summaries + profiles/traffic.json
+# pending GPU parity cases of round 2 (run once, then merge into the collected files):
+#   python -m pytest tests/pending_round2_gpu.py -m gpu -x -q
