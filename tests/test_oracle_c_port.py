@@ -105,3 +105,31 @@ def test_c_philox_known_answers_and_polynomial_normals():
     m = z.size
     assert abs(z.mean()) < 5 / np.sqrt(m) and abs(z.var() - 1) < 5 * np.sqrt(2 / m) and abs((z ** 4).mean() - 3) < 5 * np.sqrt(96 / m)
     assert abs(np.corrcoef(z0.ravel(), z1.ravel())[0, 1]) < 0.01
+
+
+def test_polynomial_normals_pass_ks_and_drive_an_ou_process_to_its_stationary_covariance():
+    """SURVEY.md §8c G5 on the CPU, with the kernel's own generator (C twin): a Kolmogorov–Smirnov test of the
+    polynomial Box–Muller normals against N(0,1), and a 4-dimensional Ornstein–Uhlenbeck ensemble integrated by the
+    oracle's Euler–Maruyama with those increments reaches the stationary covariance of the DISCRETE recurrence,
+    ``Sigma = M Sigma M^T + dt diag(nz^2)`` (``scipy.linalg.solve_discrete_lyapunov``)."""
+    from scipy.linalg import solve_discrete_lyapunov
+    from scipy.stats import kstest
+    seed, E, n, K, dt = 20251020, 4000, 4, 600, 0.01
+    tau = np.arange(K, dtype=np.uint64).reshape(-1, 1, 1)
+    env = np.arange(E, dtype=np.uint64).reshape(1, -1, 1)
+    comp = np.arange(n, dtype=np.uint64).reshape(1, 1, -1)
+    z0, z1 = em_port.philox_normals_poly(seed, 0, tau, env, comp)
+    assert kstest(z0[::7], "norm").pvalue > 1e-3 and kstest(z1[::7], "norm").pvalue > 1e-3
+    assert kstest(np.concatenate([z0[:200000], z1[:200000]]) ** 2, "chi2", args=(1,)).pvalue > 1e-3
+    rng = np.random.default_rng(0)
+    G = rng.standard_normal((n, n))
+    A = (G - G.T) - 1.0 * np.eye(n)                       # rotation + unit damping: relaxation time 1 = 100 sub-steps
+    nz = np.array([0.3, 0.5, 0.2, 0.4])
+    Y = eo.em_interval_vec(np.zeros((E, n)), np.broadcast_to(A, (E, n, n)), np.broadcast_to(nz, (E, n)),
+                           np.sqrt(dt) * z0.reshape(K, E, n), dt)
+    M = np.eye(n) + A * dt
+    Sigma = solve_discrete_lyapunov(M, dt * np.diag(nz ** 2))
+    S = np.cov(Y[-1].T)
+    scale = np.sqrt(np.outer(np.diag(Sigma), np.diag(Sigma)))
+    assert np.max(np.abs(S - Sigma) / scale) < 0.1, (S, Sigma)
+    assert np.max(np.abs(Y[-1].mean(0)) / np.sqrt(np.diag(Sigma))) < 0.08
