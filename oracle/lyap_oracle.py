@@ -314,3 +314,39 @@ def erk_interval(method, func_single, t0, t_ssz, K, y0, args_per_env, atol=1e-9,
             Y[row, e] = y
         h_last[e] = h
     return Y, n_acc, n_rej, h_last
+
+
+# ------------------------------------------------------------------------------------------------------------
+# lock-step protocol of the vectorized env (quantrl/envs/base.py:440-483, 485-499, 1233-1293)
+# ------------------------------------------------------------------------------------------------------------
+def vec_env_steps(integrate, y0, actions, K, S, T, reward_fn, obs_range=(-1e12, 1e12)):
+    """Restates ``BaseSB3Env.step_wait`` for a noise-free deterministic vec env: per call ``update`` (integrate the next
+    ``T[t_idx : t_idx+K+1]`` from ``States[-1]``, reward on all rows, ``t_idx += dim-1``, ``terminated = not t_idx+1 <
+    shape_T``), ``rewards += Reward[dim-1]``, global truncation ``max(Obs) > hi or min(Obs) < lo`` over the whole block,
+    and on ``terminated or truncated``: ``data_rewards.append(rewards)`` then reset — the RESET observation is returned.
+
+    ``integrate(T_step, y, actions_step) -> (dim, E, d)``; ``actions (n_steps, E, n_act)``.  Returns a dict of per-call
+    records with the keys of fixture G9."""
+    E = y0.shape[0]
+    rec = {k: [] for k in ("obs", "reward", "done", "t_idx", "batch_idx", "n_data_rewards", "rewards_cum")}
+    y, t_idx, batch_idx, rewards, data_rewards = y0.copy(), 0, 0, np.zeros(E), []
+    for a in range(actions.shape[0]):
+        T_step = T[t_idx:t_idx + K + 1] if t_idx + K < S + 1 else T[t_idx:]
+        dim = len(T_step)
+        Y = integrate(T_step, y, actions[a])
+        Reward = reward_fn(Y)
+        t_idx += dim - 1
+        terminated = not t_idx + 1 < S + 1
+        rewards = rewards + Reward[dim - 1]
+        truncated = bool(Y.max() > obs_range[1] or Y.min() < obs_range[0])
+        obs, y = Y[dim - 1], Y[dim - 1]
+        if terminated or truncated:
+            data_rewards.append(rewards)
+            y, t_idx, batch_idx, rewards = y0.copy(), 0, batch_idx + 1, np.zeros(E)
+            obs = y0.copy()
+        for k, v in (("obs", obs), ("reward", Reward[dim - 1]), ("done", terminated or truncated), ("t_idx", t_idx),
+                     ("batch_idx", batch_idx), ("n_data_rewards", len(data_rewards)), ("rewards_cum", rewards)):
+            rec[k].append(np.array(v))
+    out = {k: np.array(v) for k, v in rec.items()}
+    out["data_rewards"] = np.array(data_rewards)
+    return out

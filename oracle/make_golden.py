@@ -14,6 +14,7 @@ Fixtures
                       vode, RK4 driven by the reference's own ``env.func``, the single-env twin, and the packed
                       ``env.data`` cache of ``BaseSB3Env.update_data``.
   lyap_optomech_props.npz  G8: vec env with ``n_properties = 2``: the full packed ``data`` cache incl. the property columns.
+  lyap_protocol.npz   G9: the vec env's step protocol across terminations and a truncation (returns, counters, resets).
   lyap_config1.npz    G7: BASELINE config 1 exactly — one ``LinearizedHOEnv``, 1000 sub-steps (vode default, dop853 tight).
   dde_scipy.npz       G6: a delay system through ``SciPyIVPSolver.solve_ivp`` with ``has_delay=True`` (vode, tight).
   lyap_kerr.npz       same for the kerr_chain system (N=2 -> q=4, N=4 -> q=8).
@@ -166,7 +167,8 @@ def golden_em_time_dependent():
 # ---------------------------------------------------------------------------------------------------------
 # G1/G2/G4: deterministic LinearizedHO(Vec)Env
 # ---------------------------------------------------------------------------------------------------------
-def make_vec_env(system, p, m, q, y0, K, S, ssz, method, atol, rtol, cls=LinearizedHOVecEnv, n_props=0, props_fn=None):
+def make_vec_env(system, p, m, q, y0, K, S, ssz, method, atol, rtol, cls=LinearizedHOVecEnv, n_props=0, props_fn=None,
+                 **extra):
     E = p.shape[0]
     mode_rates = getattr(systems, system + "_mode_rates")
     fA = getattr(systems, system + "_A")
@@ -211,7 +213,7 @@ def make_vec_env(system, p, m, q, y0, K, S, ssz, method, atol, rtol, cls=Lineari
               t_norm_ssz=ssz, t_norm_mul=1.0, n_observations=d, n_properties=n_props, n_actions=1, action_maximums=[1.0],
               action_interval=K, data_idxs=[0, 1, 2, 2 + d] if n_props == 0 else list(range(1 + 1 + d + n_props + 1)),
               backend_library="numpy", ode_method=method,
-              ode_atol=atol, ode_rtol=rtol, **COMMON)
+              ode_atol=atol, ode_rtol=rtol, **COMMON, **extra)
     if not single:
         kw["n_envs"] = E
     return Env(**kw)
@@ -349,6 +351,40 @@ def golden_props():
     print("lyap_optomech_props.npz", {k: np.shape(v) for k, v in out.items()})
 
 
+def golden_protocol():
+    """G9: the SB3 ``VecEnv`` protocol of the reference ``LinearizedHOVecEnv`` ACROSS episode ends (envs/base.py:1233-1293):
+    S = 30, K = 10, seven ``step_async`` / ``step_wait`` calls — termination after every third step (the RESET observation
+    is returned, no ``terminal_observation``), and the same with an observation range that truncates mid-episode (any env
+    out of range ends the episode for all, base.py:485-499)."""
+    E, K, S, ssz = 3, 10, 30, 0.01
+    p = systems.optomech_default_params(E, seed=2)
+    y0 = systems.optomech_y0(p)
+    actions = np.random.default_rng(9).uniform(-1, 1, (7, E, 1))
+    out = {"p": p, "y0": y0, "actions": actions, "K": K, "S": S, "ssz": ssz}
+    for tag, rng_ in (("term", [-1e12, 1e12]), ("trunc", None)):
+        if rng_ is None:
+            # the optical amplitude grows monotonically from 0 under the drive: pick the range it crosses during step 2
+            free = out["term_obs"]
+            rng_ = [-1e12, float(0.5 * (np.abs(free[0]).max() + np.abs(free[1]).max()))]
+            out["trunc_range"] = np.array(rng_)
+        env = make_vec_env("optomech", p, 2, 4, y0, K, S - K, ssz, "dop853", 1e-14, 1e-13, observation_space_range=rng_)
+        assert env.shape_T[0] == S + 1
+        obs0 = env.reset()
+        rec = {k: [] for k in ("obs", "reward", "done", "t_idx", "batch_idx", "n_data_rewards", "rewards_cum")}
+        for a in range(actions.shape[0]):
+            env.step_async(actions[a])
+            o, r, d, info = env.step_wait()
+            assert info == [{}] * E and len(set(d)) == 1
+            for k, v in (("obs", o), ("reward", r), ("done", d[0]), ("t_idx", env.t_idx), ("batch_idx", env.batch_idx),
+                         ("n_data_rewards", len(env.data_rewards)), ("rewards_cum", env.rewards)):
+                rec[k].append(np.array(v))
+        out[tag + "_obs0"] = np.array(obs0)
+        out.update({f"{tag}_{k}": np.array(v) for k, v in rec.items()})
+        out[tag + "_data_rewards"] = np.array(env.data_rewards)
+    np.savez_compressed(os.path.join(GOLDEN, "lyap_protocol.npz"), **out)
+    print("lyap_protocol.npz", {k: (np.shape(v) if np.ndim(v) else v) for k, v in out.items() if "obs" not in k})
+
+
 def golden_config1():
     """BASELINE config 1 exactly: ONE reference ``LinearizedHOEnv`` (m = 2, q = 4), kappa = 0.1,
     gamma = 1e-3, omega_m = 1, Delta0 = -1, g0 = 1e-2, n_th = 10, A_l = 5, t_norm_max = 10 (S = 1000), K = 10, actions
@@ -377,6 +413,9 @@ if __name__ == "__main__":
     if "--props-only" in sys.argv:
         golden_props()
         sys.exit(0)
+    if "--protocol-only" in sys.argv:
+        golden_protocol()
+        sys.exit(0)
     if "--dde-only" in sys.argv:
         golden_dde()
         sys.exit(0)
@@ -390,3 +429,4 @@ if __name__ == "__main__":
     golden_dde()
     golden_config1()
     golden_props()
+    golden_protocol()
