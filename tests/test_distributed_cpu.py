@@ -69,6 +69,8 @@ def test_learner_link_two_ranks_gloo(E):
     res = sorted(out.get(timeout=120) for _ in procs)
     for p in procs:
         p.join(timeout=60)
+        if p.is_alive():        # a rank stuck in a collective after its peer failed: do not leave it behind
+            p.terminate()
     assert res == [(0, "ok"), (1, "ok")], res
 
 
@@ -117,6 +119,8 @@ def test_sharded_oracle_step_equals_the_unsharded_batch_gloo():
     res = sorted(out.get(timeout=120) for _ in procs)
     for p in procs:
         p.join(timeout=60)
+        if p.is_alive():        # a rank stuck in a collective after its peer failed: do not leave it behind
+            p.terminate()
     assert res == [(0, "ok"), (1, "ok")], res
 
 
@@ -230,4 +234,6 @@ def test_sharded_vec_env_serves_the_learner_gloo():
     res = sorted(out.get(timeout=180) for _ in procs)
     for p in procs:
         p.join(timeout=60)
+        if p.is_alive():        # a rank stuck in a collective after its peer failed: do not leave it behind
+            p.terminate()
     assert res == [(0, "ok"), (1, "ok")], res
