@@ -28,6 +28,23 @@ def _free_port():
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
 
+def _run_ranks(target, world, *args, timeout=180):
+    """Spawn ``world`` ranks of ``target(rank, world, port, *args, out)``; returns their sorted results.  Ranks that are
+    still alive afterwards (stuck in a collective because a peer failed) are terminated, whatever happened."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=target, args=(r, world, port, *args, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    try:
+        return sorted(out.get(timeout=timeout) for _ in procs)
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.terminate()
+
 
 def _worker(rank, world, port, E, n_obs, n_act, out):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -60,17 +77,7 @@ def _worker(rank, world, port, E, n_obs, n_act, out):
 
 @pytest.mark.parametrize("E", [10, 7])
 def test_learner_link_two_ranks_gloo(E):
-    ctx = mp.get_context("spawn")
-    out = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, E, 4, 1, out)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = sorted(out.get(timeout=120) for _ in procs)
-    for p in procs:
-        p.join(timeout=60)
-        if p.is_alive():        # a rank stuck in a collective after its peer failed: do not leave it behind
-            p.terminate()
+    res = _run_ranks(_worker, 2, E, 4, 1)
     assert res == [(0, "ok"), (1, "ok")], res
 
 
@@ -110,17 +117,7 @@ def _oracle_shard_worker(rank, world, port, E, n, K, out):
 
 
 def test_sharded_oracle_step_equals_the_unsharded_batch_gloo():
-    ctx = mp.get_context("spawn")
-    out = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_oracle_shard_worker, args=(r, 2, port, 9, 4, 6, out)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = sorted(out.get(timeout=120) for _ in procs)
-    for p in procs:
-        p.join(timeout=60)
-        if p.is_alive():        # a rank stuck in a collective after its peer failed: do not leave it behind
-            p.terminate()
+    res = _run_ranks(_oracle_shard_worker, 2, 9, 4, 6)
     assert res == [(0, "ok"), (1, "ok")], res
 
 
@@ -225,15 +222,5 @@ def _sharded_env_worker(rank, world, port, E, out):
 
 def test_sharded_vec_env_serves_the_learner_gloo():
     """ShardedVecEnv (BASELINE config 5's learner protocol) over gloo, world size 2, uneven shards (4 + 3 envs)."""
-    ctx = mp.get_context("spawn")
-    out = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_sharded_env_worker, args=(r, 2, port, 7, out)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = sorted(out.get(timeout=180) for _ in procs)
-    for p in procs:
-        p.join(timeout=60)
-        if p.is_alive():        # a rank stuck in a collective after its peer failed: do not leave it behind
-            p.terminate()
+    res = _run_ranks(_sharded_env_worker, 2, 7)
     assert res == [(0, "ok"), (1, "ok")], res
