@@ -225,3 +225,31 @@ def test_header_is_plain_c_and_a_c_program_links_against_the_library(native, tmp
     p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert p.returncode == 0, (p.returncode, p.stderr)
     assert p.stdout.split()[0] == str(native.ABI_VERSION) and "args is NULL" in p.stdout
+
+
+def test_every_struct_field_offset_matches_the_header(native, tmp_path):
+    """``offsetof`` of every field of qrl_em_args / qrl_ode_args / qrl_pack_args as a C compiler lays the header out ==
+    the offsets of the ctypes mirror (same field names on both sides), plus the struct sizes."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    structs = {"qrl_em_args": native.EmArgs, "qrl_ode_args": native.OdeArgs, "qrl_pack_args": native.PackArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "quantrl_b200.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'    printf("{cname} sizeof %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'    printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["    return 0;", "}"]
+    src = tmp_path / "offsets.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "offsets"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = {}
+    for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines():
+        cname, fname, off = ln.split()
+        got[(cname, fname)] = int(off)
+    for cname, cls in structs.items():
+        assert got[(cname, "sizeof")] == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
