@@ -24,6 +24,17 @@ def available():
     return shutil.which("gcc") is not None
 
 
+def usable():
+    """gcc is present AND the three C files compile here (OpenMP runtime, -march level): what the tests skip on."""
+    if not available():
+        return False
+    try:
+        build()
+        return True
+    except (subprocess.CalledProcessError, OSError):
+        return False
+
+
 def build(force=False):
     """Compile the C restatements (oracle/em_port.c, lyap_port.c, philox_port.c) into oracle/_build/; returns the EM library."""
     for src, out in ((SRC, LIB), (LYAP_SRC, LYAP_LIB), (PHILOX_SRC, PHILOX_LIB)):

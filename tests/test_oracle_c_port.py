@@ -9,7 +9,7 @@ import em_oracle as eo
 import em_port
 import systems as sy
 
-pytestmark = pytest.mark.skipif(not em_port.available(), reason="gcc not available")
+pytestmark = pytest.mark.skipif(not em_port.usable(), reason="gcc (with OpenMP) not available")
 
 
 def test_c_port_equals_numpy_oracle():
