@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define QRL_ABI_VERSION 3
+#define QRL_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define QRL_API __attribute__((visibility("default")))
@@ -50,6 +50,13 @@ extern "C" {
 
 #define QRL_E_INVALID   (-1)  /* bad argument (message in qrl_last_error) */
 #define QRL_E_UNSUPPORTED (-2) /* size/system not compiled in */
+
+/* bits OR-ed (atomically) into the `nan_flag` status word of qrl_em_args / qrl_ode_args by the kernels; the host reads
+ * the word wherever it synchronises anyway and must treat QRL_STATUS_PEER_TIMEOUT as fatal */
+#define QRL_STATUS_NONFINITE    1  /* a state became NaN / Inf (the reference carries on silently: check_truncation is
+                                    * NaN-blind, quantrl/envs/base.py:495-499) */
+#define QRL_STATUS_PEER_TIMEOUT 2  /* the fused cross-GPU barrier gave up after ~2 s: a peer never arrived, the gathered
+                                    * step results are stale or partial */
 
 #define QRL_RNG_FED    0
 #define QRL_RNG_PHILOX 1
@@ -157,7 +164,7 @@ typedef struct qrl_em_args {
     double*  rewards_cum;    /* (E,) in/out: += Reward[K]; or NULL */
 
     double*  obs_minmax;     /* [min, max] running reduction (caller initialises to [+inf, -inf]); or NULL */
-    int32_t* nan_flag;       /* set to 1 if any state is NaN/Inf; or NULL */
+    int32_t* nan_flag;       /* status word: QRL_STATUS_* bits are OR-ed in (never cleared by the library); or NULL */
 
     /* fused trajectory-cache rows (BaseSB3Env.update_data, quantrl/envs/base.py:1314-1372), n_properties == 0 only:
      *   packed[e, t, j] = column sel_idxs[j] of [T_step[t], actions[e,:], Obs[t,e,:], rewards_cum[e] (after this step)]
@@ -205,7 +212,8 @@ typedef struct qrl_em_args {
      *   peer_flags   DEVICE array of peer_world pointers; peer_flags[p] = rank p's flag array (peer_world uint64,
      *                zero-initialised, peer-mapped symmetric memory); NULL = off
      *   peer_epoch   DEVICE uint64 of this rank, zero-initialised; incremented once per launch
-     * A rank that waits longer than ~2 s raises nan_flag (if given) and returns instead of hanging the device. */
+     * A rank that waits longer than ~2 s sets QRL_STATUS_PEER_TIMEOUT in nan_flag (if given) and returns instead of
+     * hanging the device. */
     uint64_t* const* peer_flags;
     uint64_t* peer_epoch;
     int32_t   peer_rank;

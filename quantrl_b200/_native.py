@@ -7,9 +7,10 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 RNG_FED, RNG_PHILOX = 0, 1
+STATUS_NONFINITE, STATUS_PEER_TIMEOUT = 1, 2
 REWARD_NONE, REWARD_NEG_WSQ_OBS, REWARD_NEG_WSQ_STATE, REWARD_ENTAN_LN_OBS, REWARD_ENTAN_LN_STATE = 0, 1, 2, 3, 4
 REWARD_SYNC_C_OBS, REWARD_SYNC_C_STATE, REWARD_SYNC_P_OBS, REWARD_SYNC_P_STATE = 5, 6, 7, 8
 SYS_OPTOMECH, SYS_KERR_CHAIN, SYS_CONST_AD = 1, 2, 3

@@ -34,6 +34,30 @@ inline int cuda_fail(cudaError_t e, const char* where) {
         if (_e != cudaSuccess) return ::qrl::cuda_fail(_e, #call);          \
     } while (0)
 
+// Per-DEVICE caches (the header promises "current device" semantics: a process may drive several GPUs).
+constexpr int QRL_MAX_DEVICES = 64;
+inline int current_device_slot() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= QRL_MAX_DEVICES) d = 0;
+    return d;
+}
+inline int device_sm_count() {
+    static int sms[QRL_MAX_DEVICES] = {0};
+    const int d = current_device_slot();
+    if (sms[d] == 0) cudaDeviceGetAttribute(&sms[d], cudaDevAttrMultiProcessorCount, d);
+    return sms[d] > 0 ? sms[d] : 148;
+}
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device property of the function: set it once per device
+struct OncePerDevice {
+    bool done[QRL_MAX_DEVICES] = {false};
+    bool first() {
+        const int d = current_device_slot();
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 inline int after_launch(const char* name) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
@@ -169,7 +193,7 @@ __device__ __forceinline__ void em_finish_launch(const qrl_em_args& a) {
                 else seen = *reinterpret_cast<const volatile unsigned long long*>(mine + q);
                 if (seen >= epoch) break;
                 if (global_timer_ns() - t0 > 2000000000ull) {   // a peer never arrived: fail loudly, do not hang
-                    if (a.nan_flag) *a.nan_flag = 1;
+                    if (a.nan_flag) atomicOr(a.nan_flag, QRL_STATUS_PEER_TIMEOUT);
                     q = a.peer_world;
                     break;
                 }

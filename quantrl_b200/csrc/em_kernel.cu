@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(128) em_step_kernel(const qrl_em_args a_in, co
             if (a.reward_last) a.reward_last[e] = r_last;
             if (a.rewards_cum) a.rewards_cum[e] += r_last;
         }
-        if (a.nan_flag && !isfinite(x)) *a.nan_flag = 1;
+        if (a.nan_flag && !isfinite(x)) atomicOr(a.nan_flag, QRL_STATUS_NONFINITE);
     }
     if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
     em_finish_launch(a);
@@ -130,6 +130,7 @@ static int launch_em(const qrl_em_args& a, cudaStream_t st) {
 }
 
 int em_tile_launch(const qrl_em_args& a, cudaStream_t st);  // em_tile_kernel.cu
+int pack_rows_launch(const qrl_pack_args& a, int64_t dyn_bias, cudaStream_t st);  // pack_kernel.cu
 
 }  // namespace qrl
 
@@ -190,7 +191,15 @@ extern "C" int qrl_em_step(const qrl_em_args* args, void* stream) {
     p.n_envs = a.n_envs; p.dim = a.K + 1; p.n_actions = a.n_actions; p.n_obs = a.n; p.n_props = 0; p.n_sel = a.n_sel;
     p.T_step = a.T_step; p.actions = a.actions; p.observations = a.observations; p.rewards_cum = a.rewards_cum;
     p.idxs = a.sel_idxs; p.selected = a.packed; p.selected_stride_e = a.packed_stride_e;
-    p.selected_row_pitch = a.packed_row_pitch; p.dyn = a.dyn;
+    p.selected_row_pitch = a.packed_row_pitch;
     p.action_scale = a.A_act ? a.action_scale : nullptr;
-    return qrl_pack_rows(&p, stream);
+    // the time index the pack launch must see is the one the integration launch STARTED from: with QRL_EM_HOST_TIDX the
+    // host has already folded it into T_step / packed (no device-side index at all); otherwise the integration kernel's
+    // last block has advanced dyn[0] by dyn_advance before this launch runs (stream order), which the bias undoes
+    int64_t bias = 0;
+    if (a.dyn && !(a.flags & QRL_EM_HOST_TIDX)) {
+        p.dyn = a.dyn;
+        if (a.finish_counter) bias = -a.dyn_advance;
+    }
+    return pack_rows_launch(p, bias, st);
 }

@@ -527,7 +527,7 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
         bool bad = false;
 #pragma unroll
         for (int c = 0; c < N; ++c) bad |= !isfinite(x[c]);
-        if (bad) *a.nan_flag = 1;
+        if (bad) atomicOr(a.nan_flag, QRL_STATUS_NONFINITE);
     }
     // cumulative-reward column of every cache row of this interval (envs/base.py:1311, 1342-1349): one warp per env,
     // lanes along the rows of that env's contiguous run
@@ -587,11 +587,10 @@ static TilePlan plan_tiles(int E, int N, int K, int n_sel, int sms) {
 template <int N>
 static int launch_tile(const qrl_em_args& a, cudaStream_t st, int sms) {
     const TilePlan p = plan_tiles(a.n_envs, N, a.K, a.packed ? a.n_sel : 0, sms);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static OncePerDevice smem_attr;
+    if (smem_attr.first()) {
         QRL_CUDA(cudaFuncSetAttribute(em_tile_kernel<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         QRL_CUDA(cudaFuncSetAttribute(em_tile_kernel<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_set = true;
     }
     const PhiloxKeys keys = make_philox_keys(a.seed);
     cudaLaunchConfig_t cfg;
@@ -612,12 +611,7 @@ static int launch_tile(const qrl_em_args& a, cudaStream_t st, int sms) {
 
 // entry used by the qrl_em_step dispatcher (em_kernel.cu); returns QRL_E_UNSUPPORTED when the case is not tiled
 int em_tile_launch(const qrl_em_args& a, cudaStream_t st) {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        QRL_CUDA(cudaGetDevice(&dev));
-        QRL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int sms = device_sm_count();
     switch (a.n) {
         case 1: return launch_tile<1>(a, st, sms);
         case 2: return launch_tile<2>(a, st, sms);

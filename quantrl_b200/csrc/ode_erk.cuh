@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(BLOCK) erk_kernel(const __grid_constant__ qrl_
         bool bad = failed;
 #pragma unroll
         for (int d = 0; d < D; ++d) bad |= !isfinite(y[d]);
-        if (a.nan_flag && bad) *a.nan_flag = 1;
+        if (a.nan_flag && bad) atomicOr(a.nan_flag, QRL_STATUS_NONFINITE);
     }
     if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
 }
@@ -437,11 +437,9 @@ int launch_erk(const qrl_ode_args& a, cudaStream_t st, const char* name) {
     if constexpr (smem > 220 * 1024) {
         return fail(QRL_E_UNSUPPORTED, "%s", "qrl_ode_step: this method's stage storage does not fit for this state size");
     } else {
-        static bool attr_set = false;
-        if (smem > 48 * 1024 && !attr_set) {
+        static OncePerDevice attr;
+        if (smem > 48 * 1024 && attr.first())
             QRL_CUDA(cudaFuncSetAttribute(erk_kernel<Sys, TB, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
-        }
         erk_kernel<Sys, TB, BLOCK><<<(a.n_envs + BLOCK - 1) / BLOCK, BLOCK, smem, st>>>(a);
         return after_launch(name);
     }

@@ -232,7 +232,7 @@ __device__ __forceinline__ void rk4_row_out(const qrl_ode_args& a, const double2
         if (last) {
             if (yl) yl[idx2] = v;
             if (ol) ol[idx2] = o;
-            if (a.nan_flag && !(isfinite(v.x) && isfinite(v.y))) *a.nan_flag = 1;
+            if (a.nan_flag && !(isfinite(v.x) && isfinite(v.y))) atomicOr(a.nan_flag, QRL_STATUS_NONFINITE);
         }
         lo = fmin(lo, fmin(o.x, o.y));
         hi = fmax(hi, fmax(o.x, o.y));
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(BLOCK) dopri5_kernel(const __grid_constant__ q
         bool bad = next_row <= K;  // step budget exhausted
 #pragma unroll
         for (int d = 0; d < D; ++d) bad |= !isfinite(y[d]);
-        if (a.nan_flag && bad) *a.nan_flag = 1;
+        if (a.nan_flag && bad) atomicOr(a.nan_flag, QRL_STATUS_NONFINITE);
     }
     if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
 }
@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(BLOCK) rk4_lanes_kernel(const __grid_constant_
                 a.obs_last[col_v] = noise ? v + obs_noise_at(a, K, el, 2 * M + l, D) : v;
                 if (mode_lane) a.obs_last[col_m] = noise ? mv + obs_noise_at(a, K, el, l, D) : mv;
             }
-            if (a.nan_flag && !(isfinite(v) && isfinite(mv))) *a.nan_flag = 1;
+            if (a.nan_flag && !(isfinite(v) && isfinite(mv))) atomicOr(a.nan_flag, QRL_STATUS_NONFINITE);
         }
     }
     if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(EPB * 16 + 32 + 128) rk4_split_kernel(const __
                 const int64_t c2 = (int64_t)e0 * D2 + p;
                 if (a.y_last) reinterpret_cast<double2*>(a.y_last)[c2] = x;
                 if (a.obs_last) reinterpret_cast<double2*>(a.obs_last)[c2] = o;
-                if (a.nan_flag && !(isfinite(x.x) && isfinite(x.y))) *a.nan_flag = 1;
+                if (a.nan_flag && !(isfinite(x.x) && isfinite(x.y))) atomicOr(a.nan_flag, QRL_STATUS_NONFINITE);
             }
             lo = (o.x < lo) ? o.x : lo;
             lo = (o.y < lo) ? o.y : lo;
@@ -1004,7 +1004,7 @@ struct LaneEnv {
             if (has_h && a.h_state) a.h_state[e] = h;
             if (a.n_steps) { a.n_steps[2 * e] += n_acc; a.n_steps[2 * e + 1] += n_rej; }
         }
-        if (a.nan_flag && (failed || !isfinite(v) || !isfinite(mv))) *a.nan_flag = 1;
+        if (a.nan_flag && (failed || !isfinite(v) || !isfinite(mv))) atomicOr(a.nan_flag, QRL_STATUS_NONFINITE);
     }
 };
 
@@ -1180,11 +1180,9 @@ int launch_ode(const qrl_ode_args& a, cudaStream_t st) {
                 const int c_max = c_want >= 1 && c_want <= 16 ? c_want : 8;
                 const int C = NS < c_max ? (NS > 0 ? NS : 1) : c_max;
                 const size_t smem = (size_t)2 * C * 4 * 8 * (EPB + 1) * sizeof(double2) + (size_t)3 * C * EPB * D * sizeof(double);
-                static bool attr_set = false;
-                if (!attr_set) {
+                static OncePerDevice attr;
+                if (attr.first())
                     QRL_CUDA(cudaFuncSetAttribute(rk4_split_kernel<Sys, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-                    attr_set = true;
-                }
                 rk4_split_kernel<Sys, EPB><<<(a.n_envs + EPB - 1) / EPB, EPB * 16 + 32 + 128, smem, st>>>(a, C);
                 return after_launch("rk4_split_kernel");
             }
@@ -1228,11 +1226,9 @@ int launch_ode(const qrl_ode_args& a, cudaStream_t st) {
     }
     constexpr int BLOCK = 32;
     const size_t smem = (size_t)7 * D * BLOCK * sizeof(double);
-    static bool attr_set = false;
-    if (smem > 48 * 1024 && !attr_set) {
+    static OncePerDevice attr;
+    if (smem > 48 * 1024 && attr.first())
         QRL_CUDA(cudaFuncSetAttribute(dopri5_kernel<Sys, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
     const int blocks = (a.n_envs + BLOCK - 1) / BLOCK;
     dopri5_kernel<Sys, BLOCK><<<blocks, BLOCK, smem, st>>>(a);
     return after_launch("dopri5_kernel");

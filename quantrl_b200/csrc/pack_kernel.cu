@@ -12,10 +12,12 @@ namespace qrl {
 constexpr int PACK_G = 8;    // envs per tile
 constexpr int PACK_TT = 32;  // time rows per tile
 
-__global__ void __launch_bounds__(256) pack_rows_kernel(const qrl_pack_args a_in) {
+// dyn_bias: added to the device-resident time index — the pack launch that follows a generic Euler–Maruyama launch whose
+// last block has ALREADY advanced dyn[0] by K (qrl_em_args.dyn_advance) passes -K and so sees the interval's first row
+__global__ void __launch_bounds__(256) pack_rows_kernel(const qrl_pack_args a_in, const int64_t dyn_bias) {
     qrl_pack_args a = a_in;
     if (a_in.dyn) {   // CUDA-graph replay: episode bases + device-resident time index
-        const int64_t t = a_in.dyn[0];
+        const int64_t t = a_in.dyn[0] + dyn_bias;
         a.T_step += t;
         if (a.packed) a.packed += t * (2 + a.n_actions + a.n_obs + a.n_props);
         if (a.selected) a.selected += t * (a.selected_row_pitch > 0 ? a.selected_row_pitch : (int64_t)a.n_sel);
@@ -73,10 +75,8 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const qrl_pack_args a_in
 
 }  // namespace qrl
 
-extern "C" int qrl_pack_rows(const qrl_pack_args* args, void* stream) {
-    using namespace qrl;
-    QRL_REQUIRE(args != nullptr, "qrl_pack_rows: args is NULL");
-    const qrl_pack_args& a = *args;
+namespace qrl {
+int pack_rows_launch(const qrl_pack_args& a, int64_t dyn_bias, cudaStream_t st) {
     QRL_REQUIRE(a.n_envs >= 0 && a.dim >= 0 && a.n_actions >= 0 && a.n_obs >= 1 && a.n_props >= 0 && a.n_sel >= 0,
                 "qrl_pack_rows: negative size");
     if (a.n_envs == 0 || a.dim == 0) return 0;
@@ -91,9 +91,17 @@ extern "C" int qrl_pack_rows(const qrl_pack_args* args, void* stream) {
                 "qrl_pack_rows: selected_stride_e too small");
     const size_t smem = (size_t)PACK_TT * PACK_G * (a.n_obs + a.n_props) * sizeof(double);
     QRL_REQUIRE(smem <= 200 * 1024, "qrl_pack_rows: n_obs + n_props too large for the staging tile");
-    if (smem > 48 * 1024)
-        QRL_CUDA(cudaFuncSetAttribute(pack_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static OncePerDevice attr;
+    if (smem > 48 * 1024 && attr.first())
+        QRL_CUDA(cudaFuncSetAttribute(pack_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     dim3 grid((a.n_envs + PACK_G - 1) / PACK_G, (a.dim + PACK_TT - 1) / PACK_TT);
-    pack_rows_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+    pack_rows_kernel<<<grid, 256, smem, st>>>(a, dyn_bias);
     return after_launch("pack_rows_kernel");
+}
+}  // namespace qrl
+
+extern "C" int qrl_pack_rows(const qrl_pack_args* args, void* stream) {
+    using namespace qrl;
+    QRL_REQUIRE(args != nullptr, "qrl_pack_rows: args is NULL");
+    return pack_rows_launch(*args, 0, (cudaStream_t)stream);
 }

@@ -97,7 +97,7 @@ def make_sharded_env(env_cls, n_envs_total, rank=None, world_size=None, **env_kw
     for key in per_env:
         if env_kwargs.get(key) is not None:
             env_kwargs[key] = env_kwargs[key][offset:offset + count]
-    return env_cls(n_envs=count, env_offset=offset, **env_kwargs)
+    return env_cls(n_envs=count, env_offset=offset, n_envs_total=n_envs_total, **env_kwargs)
 
 
 class ShardedVecEnv:

@@ -17,6 +17,7 @@ import math
 import os
 import queue
 import threading
+import warnings
 
 import numpy as np
 import torch
@@ -63,9 +64,13 @@ class PartCacheWriter:
     named ``{b*E}_{(b+1)*E-1}_{part}.npz`` with the array under ``arr_0``.  Unlike the reference (whose "async" dump
     joins its thread immediately, io.py:74-80) the write really happens on a background thread."""
 
-    def __init__(self, disk_cache_dir, cache_dump_interval, compressed=True):
+    def __init__(self, disk_cache_dir, cache_dump_interval, compressed=True, env_offset=0, n_envs_total=None):
         self.disk_cache_dir = disk_cache_dir
         self.cache_dump_interval = cache_dump_interval
+        # sharded batches (distributed.make_sharded_env): the names carry GLOBAL env indices, so that ranks sharing one
+        # directory never overwrite each other's parts; an unsharded env gives exactly the reference's names
+        self.env_offset = int(env_offset)
+        self.n_envs_total = int(cache_dump_interval if n_envs_total is None else n_envs_total)
         self.compressed = compressed
         self._q = None
         self._thread = None
@@ -110,9 +115,9 @@ class PartCacheWriter:
         self._raise_pending()
 
     def part_path(self, batch_idx, part_idx):
+        first = batch_idx * self.n_envs_total + self.env_offset
         return os.path.join(self.disk_cache_dir, "_".join([
-            str(batch_idx * self.cache_dump_interval), str((batch_idx + 1) * self.cache_dump_interval - 1),
-            str(part_idx)]) + ".npz")
+            str(first), str(first + self.cache_dump_interval - 1), str(part_idx)]) + ".npz")
 
     def load_parts(self, batch_idx, idxs=None):
         """Read the part files of one batch back as ONE ``(E, rows, n_data)`` block (the reader the reference leaves
@@ -156,6 +161,7 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
                                      # valid until the end of the NEXT step) instead of fresh copies — the reference
                                      # returns views of its own buffers too (base.py:1293); saves two host copies per step
         "env_offset": 0,            # global index of local env 0 (multi-GPU sharding)
+        "n_envs_total": None,       # size of the global batch this env is a shard of (None: unsharded)
         "store_trajectory": True,   # keep the (K+1,E,n) States/Observations/Reward blocks (reference semantics)
         "cache_compressed": True,
     }
@@ -246,8 +252,10 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         self.data_idxs = list(data_idxs)
         self.cache_all_data = kwargs["cache_all_data"]
         self.cache_dump_interval = self.n_envs  # n_envs overrides cache_dump_interval (base.py:1040)
+        self.n_envs_total = self.n_envs if kwargs["n_envs_total"] is None else int(kwargs["n_envs_total"])
         self.io = PartCacheWriter(self.file_path_prefix + "_cache", self.cache_dump_interval,
-                                  compressed=kwargs["cache_compressed"])
+                                  compressed=kwargs["cache_compressed"], env_offset=int(kwargs["env_offset"]),
+                                  n_envs_total=self.n_envs_total)
         self.plot = False
 
         if _SB3VecEnv is not None:
@@ -270,17 +278,20 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
             self._States, self._Observations, self._Reward, self._Properties
         self.Observation_noises = None
         self._x_last = torch.empty((E, no), dtype=f64, device=self.device)
-        self._step_out = torch.empty((E * (no + 1) + 4,), dtype=f64, device=self.device)  # obs_last|reward_last|min,max|nan
+        # obs_last | reward_last | min,max | status word (QRL_STATUS_* bits, int32 in the first half of the double) | pad
+        self._step_out = torch.zeros((E * (no + 1) + 4,), dtype=f64, device=self.device)
         self._obs_last = self._step_out[:E * no].view(E, no)
         self._reward_last = self._step_out[E * no:E * (no + 1)]
         self._minmax = self._step_out[E * (no + 1):E * (no + 1) + 2]
         self._minmax_init = torch.tensor([float("inf"), float("-inf")], dtype=f64, device=self.device)
-        self._nan = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        self._nan = self._step_out[E * (no + 1) + 2:E * (no + 1) + 3].view(torch.int32)   # travels with every step's D2H
+        self.nonfinite_detected = False
         # pinned result buffers: two when step() hands out views (the kernel of step i+1 must not write where the caller
         # may still read the results of step i)
-        self._h_out_bufs = [torch.empty(self._step_out.shape, dtype=f64).pin_memory()
+        self._h_out_bufs = [torch.zeros(self._step_out.shape, dtype=f64).pin_memory()
                             for _ in range(2 if self.host_output_views else 1)]
         self._h_out_nps = [b.numpy() for b in self._h_out_bufs]
+        self._h_status_nps = [b.view(np.int32) for b in self._h_out_nps]
         self._h_sel = 0
         self._h_out, self._h_out_np = self._h_out_bufs[0], self._h_out_nps[0]
         self._h_actions = torch.empty((E, self.n_actions), dtype=f64).pin_memory()
@@ -509,8 +520,21 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         if host is None:
             self._fetch_step_outputs()
         E, no = self.n_envs, self.n_observations
+        self._check_status(int(self._h_status_nps[self._h_sel][2 * (E * (no + 1) + 2)]))
         lo, hi = self._h_out_np[E * (no + 1)], self._h_out_np[E * (no + 1) + 1]
         return bool(hi > self.observation_space_range[1] or lo < self.observation_space_range[0])
+
+    def _check_status(self, status):
+        """The kernels' status word, read wherever the host has just synchronised anyway.  A fused cross-GPU barrier that
+        timed out is fatal (the gathered step results are stale or partial); a non-finite state is reported once — the
+        reference carries on silently there (its truncation check is NaN-blind, base.py:495-499)."""
+        if status & N.STATUS_PEER_TIMEOUT:
+            raise RuntimeError("quantrl_b200: the fused cross-GPU barrier timed out (a peer rank never arrived); the "
+                               "gathered observations / rewards of this step are not valid")
+        if (status & N.STATUS_NONFINITE) and not self.nonfinite_detected:
+            self.nonfinite_detected = True
+            warnings.warn(f"quantrl_b200: non-finite states detected in batch #{self.batch_idx} (NaN / Inf); "
+                          "``env.nonfinite_detected`` is set", RuntimeWarning, stacklevel=3)
 
     def step_wait(self):
         host_step = getattr(self, "_host_step", False)

@@ -79,7 +79,6 @@ class LinearVecEnv(BaseVecEnv):
         assert not (self.use_cuda_graph and self.is_A_time_dependent), \
             "``use_cuda_graph`` needs coefficient hooks that do not depend on the time index"
         self._dyn = torch.zeros((2,), dtype=torch.int64, device=self.device)      # {t_idx, episode} read by the kernel
-        self._dyn_host = torch.zeros((2,), dtype=torch.int64).pin_memory()
         self._actions_in = torch.zeros((self.n_envs, self.n_actions), dtype=torch.float64, device=self.device)
         self._graph = self._graph_host = self._graph_host1 = None
         self._static = {}                   # cached argument blocks of the single-kernel step (_relaunch_interval)
@@ -115,8 +114,10 @@ class LinearVecEnv(BaseVecEnv):
                     generator=self.backend.generator(seed=self.seed), shape=(S1, E, n), mean=0.0, std=1.0,
                     dtype="real") * self.observation_stds.reshape(1, -1, n)
         if self.use_cuda_graph:
-            self._dyn_host[0], self._dyn_host[1] = 0, (self.batch_idx + 1) & 0xFFFFFFFF
-            self._dyn.copy_(self._dyn_host, non_blocking=True)
+            # scalar fills: the values travel as kernel arguments, so a host that runs whole episodes ahead of the GPU
+            # (device-resident loops) cannot overwrite a staging buffer before an earlier copy has executed
+            self._dyn[0].fill_(0)
+            self._dyn[1].fill_((self.batch_idx + 1) & 0xFFFFFFFF)
         return super()._reset()
 
     def set_fed_noise(self, Ws, Observation_noises=None):
@@ -237,6 +238,7 @@ class LinearVecEnv(BaseVecEnv):
                 zc = self._zero_copy()
                 if zc is not None:
                     a.obs_last, a.minmax_out = zc["out"], zc["out"] + 8 * E * (n + 1)
+                    a.nan_flag = zc["out"] + 8 * (E * (n + 1) + 2)
                     if a.reward_kind != N.REWARD_NONE:
                         a.reward_last = zc["out"] + 8 * E * n
                     if affine is not None:

@@ -72,3 +72,23 @@ def test_part_file_write_errors_surface_in_the_callers_thread(tmp_path, monkeypa
     io.dump_part_async(np.ones((4, 3, 2)), batch_idx=1, part_idx=0)
     io.close()
     assert np.array_equal(io.load_parts(1), np.ones((4, 3, 2)))
+
+
+def test_part_files_of_two_shards_sharing_a_directory_do_not_collide(tmp_path):
+    """Sharded batch (``make_sharded_env``: every rank shares ``dir_prefix`` and ``batch_idx``): the part names carry
+    GLOBAL env indices, so rank 1 never overwrites rank 0's parts and each rank reads back its own shard."""
+    from quantrl_b200.envs.base import PartCacheWriter
+    E_total, bounds = 10, [(0, 6), (6, 4)]
+    writers = [PartCacheWriter(str(tmp_path / "cache"), cache_dump_interval=cnt, env_offset=off, n_envs_total=E_total)
+               for off, cnt in bounds]
+    blocks = [np.full((cnt, 3, 2), float(r)) + np.arange(3)[None, :, None] for r, (_, cnt) in enumerate(bounds)]
+    for part in range(2):
+        for w, b in zip(writers, blocks):
+            w.dump_part_async(b + 10 * part, batch_idx=2, part_idx=part)
+    for w in writers:
+        w.flush()
+    assert sorted(os.listdir(tmp_path / "cache")) == ["20_25_0.npz", "20_25_1.npz", "26_29_0.npz", "26_29_1.npz"]
+    for r, w in enumerate(writers):
+        got = w.load_parts(2)
+        assert got.shape == (bounds[r][1], 5, 2) and got[0, 0, 0] == float(r) and got[0, -1, 0] == float(r) + 12
+        w.close()

@@ -61,7 +61,7 @@ def _worker(rank, world, port, out):
                 assert torch.equal(peer.obs_all, o_full) and torch.equal(peer.reward_all, r_full)
                 torch.testing.assert_close(peer_g.obs_all, o_full, rtol=1e-12, atol=1e-14)   # in-kernel affine drift
                 torch.testing.assert_close(peer_g.reward_all, r_full, rtol=1e-12, atol=1e-14)
-            assert int(env_g._nan.item()) == 0      # no barrier time-out
+            assert int(env_g._nan[0].item()) == 0      # no barrier time-out
         torch.cuda.synchronize()
         assert peer_g.flags.tolist()[:world] == [4] * world and int(peer_g.epoch.item()) == 4
         out.put((rank, "ok"))
