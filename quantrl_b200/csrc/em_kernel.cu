@@ -11,6 +11,7 @@
 // M = I + A dt (registers) and generates its own pair of normals (Wiener increment + measurement noise).  The n
 // components are exchanged with warp shuffles each sub-step, rows of States/Observations are written with fully
 // coalesced 8-byte-per-lane stores (one warp = 32 consecutive doubles of the (K+1,E,n) block).
+#include <stdlib.h>
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -130,6 +131,8 @@ static int launch_em(const qrl_em_args& a, cudaStream_t st) {
 }
 
 int em_tile_launch(const qrl_em_args& a, cudaStream_t st);  // em_tile_kernel.cu
+bool em_tile3_supports(const qrl_em_args& a);                // em_tile3_kernel.cu
+int em_tile3_launch(const qrl_em_args& a, cudaStream_t st);
 int pack_rows_launch(const qrl_pack_args& a, int64_t dyn_bias, cudaStream_t st);  // pack_kernel.cu
 
 }  // namespace qrl
@@ -173,10 +176,15 @@ extern "C" int qrl_em_step(const qrl_em_args* args, void* stream) {
     // n > 4: the recurrence lane cannot hold M = I + A dt (n*n doubles) in registers next to the producers' working set
     // (spills under the 128-register cap of a 512-thread CTA) and the generic kernel wins from E = 4096 on
     // (tools/variants_em.py: n = 8, E = 4096: 72 vs 108 us), so the tiled kernel is the default only up to n = 4.
-    const bool small_batch = ((int64_t)a.n_envs * a.n <= 32768 && a.n <= 4) || (a.flags & QRL_EM_FORCE_TILED);
+    // The third-generation tiled kernel (em_tile3_kernel.cu: n in {2, 4, 8}, n/2 recurrence lanes per environment) has
+    // no such limit and takes every case it supports.
+    const bool t3 = em_tile3_supports(a);
+    static const char* lanes_env = getenv("QRL_EM_TILED_MAX_LANES");   // tuning knob: crossover to the generic kernel
+    const int64_t max_lanes = lanes_env ? atoll(lanes_env) : 32768;
+    const bool small_batch = ((int64_t)a.n_envs * a.n <= max_lanes && (a.n <= 4 || t3)) || (a.flags & QRL_EM_FORCE_TILED);
     const bool tiled = a.K >= 1 && a.n <= 8 && a.A_stride_k == 0 && a.nz_stride_k == 0 && small_batch &&
                        !(a.flags & QRL_EM_FORCE_GENERIC);
-    if (tiled) return em_tile_launch(a, st);
+    if (tiled) return t3 ? em_tile3_launch(a, st) : em_tile_launch(a, st);
     QRL_REQUIRE(!a.packed || a.observations != nullptr, "qrl_em_step: the generic kernel packs from the observations block");
     int rc;
     if (a.n <= 1) rc = launch_em<1>(a, st);

@@ -1,0 +1,521 @@
+// Tiled Euler–Maruyama action interval, third generation — the fast path of qrl_em_step for n in {2, 4, 8} on sm_100a.
+//
+// Same decomposition as em_tile_kernel.cu (noise generation spread over many "worker" warps, the short sequential
+// recurrence on a few lanes, rows leaving as 16-byte pieces), rebuilt around what ncu showed on the second generation
+// (profiles/r01q_ncu_summary.md: issue slots 48 % busy, 1.8 warps per issue waiting at the per-chunk __syncthreads, one
+// 128-register allocation shared by all roles, n = 8 spilling 568 bytes in the recurrence lane):
+//   * roles synchronise through shared-memory mbarriers per ring stage instead of one CTA barrier per chunk:
+//       full_w[s]  workers -> recurrence   "the noise of the chunk in stage s is complete"
+//       full_x[s]  recurrence -> workers   "the states of that chunk are complete"
+//       empty[s]   workers -> workers      "the rows of that chunk have left, the stage may be refilled"
+//     so a warp only ever waits for the data it needs, and the recurrence drifts freely behind the producers;
+//   * the recurrence overwrites the Wiener increments IN PLACE with the new states (each element is read and written by
+//     the same lane), so a ring stage is two tiles (W/X, V) instead of 7/3 — room for deeper rings of smaller chunks;
+//   * n/2 recurrence lanes per environment, each owning one 16-byte piece (two rows of M = I + A dt, 2n doubles in
+//     registers); the pieces of a sub-step meet in the tile the row is written to anyway (STS.128, __syncwarp, LDS.128),
+//     so n = 8 needs 32 + 16 registers of state instead of 128 + 16 and nothing spills;
+//   * no role needs more than 80 registers: 768 threads per CTA (6 warps per scheduler instead of 4).
+// Arithmetic, operation order and the Philox stream are those of em_kernel.cu / em_tile_kernel.cu: States and
+// Observations agree bit for bit (tests/test_em_gpu.py).  Replaces quantrl/envs/stochastic.py:178-242,
+// envs/base.py:408-426,462,471-473,485-499 and the packed rows of BaseSB3Env.update_data (envs/base.py:1314-1372).
+#include <stdlib.h>
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace qrl {
+
+constexpr int T3_THREADS_MAX = 768;
+constexpr int T3_STAGES_MAX = 8;
+constexpr int T3_BAR_BYTES = 256;   // 3 * T3_STAGES_MAX mbarriers, rounded up: the tiles behind them stay 128-byte aligned
+
+struct T3Plan { int G, C, D, nphase, nrt, threads, grid; size_t smem; };
+
+__device__ __forceinline__ uint32_t t3_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t3_smem(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t3_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "T3_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra T3_DONE;\n"
+        "bra T3_WAIT;\n"
+        "T3_DONE:\n"
+        "}\n" ::"r"(t3_smem(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void t3_worker_barrier(int n_workers) {
+    asm volatile("bar.sync 1, %0;" ::"r"(n_workers) : "memory");
+}
+__device__ __forceinline__ void t3_minmax(double v, double& lo, double& hi) {   // NaN never wins (lo / hi are never NaN)
+    lo = (v < lo) ? v : lo;
+    hi = (v > hi) ? v : hi;
+}
+
+template <int N>
+__global__ void __launch_bounds__(T3_THREADS_MAX, 1)
+em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) {
+    static_assert(N == 2 || N == 4 || N == 8, "piece layout: n/2 lanes per environment");
+    constexpr int L = N / 2;                   // 16-byte pieces per environment row = recurrence lanes per environment
+    // programmatic dependent launch (QRL_EM_PDL): see em_tile_kernel.cu
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    qrl_em_args a = a_in;
+    extern __shared__ __align__(128) unsigned char t3_raw[];
+    const int G = pl.G, C = pl.C, D = pl.D, nphase = pl.nphase, NRT = pl.nrt;
+    const int NT = blockDim.x, NW = NT - NRT;
+    const int E = a.n_envs, K = a.K;
+    const int e0 = blockIdx.x * G;
+    const int Gl = min(G, E - e0);             // live environments of this CTA
+    const int RP = G * N;                      // doubles per tile row
+    const int tile = C * RP;                   // doubles per tile
+    uint64_t* full_w = reinterpret_cast<uint64_t*>(t3_raw);
+    uint64_t* full_x = full_w + T3_STAGES_MAX;
+    uint64_t* empty = full_x + T3_STAGES_MAX;
+    double* Wt = reinterpret_cast<double*>(t3_raw + T3_BAR_BYTES);   // [D][tile] increments, overwritten by the states
+    double* Vt = Wt + D * tile;                // [D][tile] measurement noise, already scaled by obs_std
+    double* x0S = Vt + D * tile;               // [RP] initial state (row 0)
+    double* v0S = x0S + RP;                    // [RP] measurement noise of row 0
+    double* stdS = v0S + RP;                   // [RP] measurement-noise std per (env, comp)
+    double* cumS = stdS + RP;                  // [G]  cumulative reward after this interval
+    double* wS = cumS + G;                     // [N]  reward weights
+    int* selS = reinterpret_cast<int*>(wS + N);  // [n_sel]
+
+    const int tid = threadIdx.x;
+    const bool is_rec = tid < NRT;
+    const int wt = tid - NRT;                  // worker id
+    const bool philox = a.rng_mode == QRL_RNG_PHILOX;
+    const bool has_reward = a.reward_kind != QRL_REWARD_NONE;
+    const bool reward_on_obs = a.reward_kind == QRL_REWARD_NEG_WSQ_OBS;
+    const int NC = (K + C - 1) / C;
+    const int n_data = 1 + a.n_actions + N + 1;
+    const int n_sel = a.n_sel;
+    const int pitch = a.packed ? (int)(a.packed_row_pitch > 0 ? a.packed_row_pitch : a.n_sel) : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < D; ++s) {
+            mbar_init(full_w + s, (uint32_t)NW);
+            mbar_init(full_x + s, (uint32_t)NRT);
+            mbar_init(empty + s, (uint32_t)NW);
+        }
+    }
+    // constants of a step sequence first (no step kernel writes them): behind the PDL wait they cost nothing
+    for (int i = tid; i < Gl * N; i += NT) {
+        const int el = i / N, c = i - el * N;
+        stdS[i] = (philox && a.obs_std) ? a.obs_std[(int64_t)(e0 + el) * a.obs_std_stride_e + c] : 0.0;
+    }
+    if (tid < N) wS[tid] = has_reward ? a.reward_w[tid] : 0.0;
+    if (a.packed)
+        for (int i = tid; i < n_sel; i += NT) {
+            const int s = a.sel_idxs[i];
+            selS[i] = s < 0 ? s + n_data : s;
+        }
+    if ((a.flags & QRL_EM_PDL) && is_rec && (tid % L) == 0 && tid / L < Gl) {
+        const char* Ab = reinterpret_cast<const char*>(a.A + (int64_t)(e0 + tid / L) * a.A_stride_e);
+        for (int b = 0; b < N * N * 8; b += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(Ab + b));
+    }
+    // everything below reads what the previous kernel of the stream wrote (dyn, x0, cumulative rewards, actions)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int i = tid; i < Gl * N; i += NT) x0S[i] = a.x0[(int64_t)e0 * N + i];
+    a = resolve_dyn(a_in);
+    __syncthreads();
+
+    const double sqrt_dt = sqrt(a.t_ssz);
+    const uint32_t row32 = (uint32_t)(E * N);  // doubles per time row (the dispatcher guarantees (K+1) * E * N < 2^31)
+    double lo = INFINITY, hi = -INFINITY;
+
+    if (!is_rec) {
+        // ================================= workers: produce noise, write rows ==================================
+        bool pack_rows = false;                // any cache column besides the cumulative reward (written at the end)?
+        if (a.packed)
+            for (int j = 0; j < n_sel; ++j) pack_rows |= (selS[j] != n_data - 1);
+
+        // ---- output, piece pass: one 16-byte piece (two components) of a row per worker and trip ----
+        const int PR = Gl * L;                 // pieces per live row
+        const int q_dsl = NW / PR, q_dpc = NW - q_dsl * PR;
+        const int q_sl0 = wt / PR, q_pc0 = wt - q_sl0 * PR;
+        const int q_h = wt & (L - 1);          // which piece of its environment this lane holds (adjacent lanes)
+        const double q_w0 = wS[2 * q_h], q_w1 = wS[2 * q_h + 1];
+        auto piece_pass = [&](const double* Xb, const double* Vb, int r_first, int ns) {
+            int sl = q_sl0, pc = q_pc0;
+            uint32_t g = (uint32_t)(r_first + sl) * row32 + (uint32_t)(e0 * N + 2 * pc);
+            const uint32_t g_step = (uint32_t)q_dsl * row32 + (uint32_t)(2 * q_dpc), g_wrap = row32 - (uint32_t)(2 * PR);
+            int sl_lead = __shfl_sync(0xffffffffu, sl, 0);   // warp-uniform trip count (the shuffles need all lanes)
+            while (sl_lead < ns) {
+                const bool live = sl < ns;
+                const int off = live ? sl * RP + 2 * pc : 0;
+                const double2 x2 = *reinterpret_cast<const double2*>(Xb + off);
+                const double2 v2 = *reinterpret_cast<const double2*>(Vb + off);
+                const double2 o2 = make_double2(__dadd_rn(x2.x, v2.x), __dadd_rn(x2.y, v2.y));
+                const int r = r_first + sl;
+                if (live) {
+                    if (a.states) *reinterpret_cast<double2*>(a.states + g) = x2;
+                    if (a.observations) *reinterpret_cast<double2*>(a.observations + g) = o2;
+                    t3_minmax(o2.x, lo, hi);
+                    t3_minmax(o2.y, lo, hi);
+                }
+                double rv = 0.0;
+                if (has_reward) {
+                    // -sum_c w_c s_c^2 as one chain of FMAs in component order, hopping over the L lanes of the env
+                    const double s0 = reward_on_obs ? o2.x : x2.x, s1 = reward_on_obs ? o2.y : x2.y;
+                    const double ws0 = q_w0 * s0, ws1 = q_w1 * s1;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < L; ++j) {
+                        const double t = fma(ws1, s1, fma(ws0, s0, acc));
+                        if (j == L - 1) { rv = -t; break; }
+                        const double up = __shfl_up_sync(0xffffffffu, t, 1);
+                        if (q_h == j + 1) acc = up;
+                    }
+                }
+                if (live) {
+                    const int el = pc / L, e = e0 + el;
+                    if (has_reward && q_h == L - 1 && a.reward) a.reward[(uint32_t)r * (uint32_t)E + (uint32_t)e] = rv;
+                    if (r == K) {
+                        if (has_reward && q_h == L - 1) {
+                            if (a.reward_last) a.reward_last[e] = rv;
+                            double cum = rv;
+                            if (a.rewards_cum) { cum += a.rewards_cum[e]; a.rewards_cum[e] = cum; }
+                            cumS[el] = cum;
+                        }
+                        const int64_t gl = (int64_t)e0 * N + 2 * pc;
+                        if (a.x_last) *reinterpret_cast<double2*>(a.x_last + gl) = x2;
+                        if (a.obs_last) *reinterpret_cast<double2*>(a.obs_last + gl) = o2;
+                    }
+                }
+                sl += q_dsl;
+                pc += q_dpc;
+                g += g_step;
+                if (pc >= PR) { pc -= PR; ++sl; g += g_wrap; }
+                sl_lead = __shfl_sync(0xffffffffu, sl, 0);
+            }
+        };
+        // ---- output, cache rows: packed[e, r, j] = column sel[j] of [T_step[r], actions[e,:], Obs[r,e,:], cum. reward]
+        // (envs/base.py:1314-1372); a warp walks one environment's contiguous run of ns * pitch doubles 32 at a time.
+        // The cumulative-reward column is only known after the last sub-step and is written for all rows at the end.
+        const uint32_t pk_magic = pitch > 0 ? 0xFFFFFFFFu / (uint32_t)pitch + 1u : 0u;   // idx / pitch for idx < 2^16
+        auto pack_pass = [&](const double* Xb, const double* Vb, int r_first, int ns) {
+            const int run = ns * pitch;
+            const int trips = (run + 31) >> 5;
+            const int lane = wt & 31, n_ww = NW >> 5;
+            int t = wt >> 5;
+            int el = t / trips, trip = t - el * trips;
+            const int d_el = n_ww / trips, d_trip = n_ww - d_el * trips;
+            while (el < Gl) {
+                const int idx = (trip << 5) + lane;
+                if (idx < run) {
+                    const int sl = pitch == 1 ? idx : (int)__umulhi((uint32_t)idx, pk_magic), j = idx - sl * pitch;
+                    const int col = j < n_sel ? selS[j] : n_data - 1;
+                    if (col != n_data - 1) {
+                        const int r = r_first + sl, e = e0 + el;
+                        double val;
+                        if (col == 0) val = a.T_step[r];
+                        else if (col <= a.n_actions) val = em_action(a, e, col - 1);
+                        else {
+                            const int off = sl * RP + el * N + (col - 1 - a.n_actions);
+                            val = __dadd_rn(Xb[off], Vb[off]);
+                        }
+                        a.packed[(int64_t)e * a.packed_stride_e + (int64_t)r_first * pitch + idx] = val;
+                    }
+                }
+                el += d_el;
+                trip += d_trip;
+                if (trip >= trips) { trip -= trips; ++el; }
+            }
+        };
+
+        // ---- producer: the (env, comp) column of this worker and its position in the sub-step walk ----
+        const int p_phase = wt / RP, p_col = wt - p_phase * RP;
+        const int p_el = p_col / N, p_c = p_col - p_el * N;
+        const bool p_live = p_phase < nphase && p_el < Gl;
+        const uint32_t p_env = (uint32_t)(a.env_offset + e0 + p_el);
+        const uint32_t tau_base = (uint32_t)a.t_idx;
+        double p_sd = 0.0;
+        int pj = p_phase;                      // next sub-step (within the interval) this worker generates
+        uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+
+        // ---- row 0: Observations[0] = States[0] + noise[t_idx]  (envs/base.py:462) ----
+        for (int i = wt; i < Gl * N; i += NW) {
+            const int el = i / N, c = i - el * N;
+            double v = 0.0;
+            if (philox) {
+                if (a.obs_std) {
+                    double z0, z1;
+                    const uint32_t tau = a.t_idx > 0 ? (uint32_t)(a.t_idx - 1) : 0xFFFFFFFFu;
+                    philox_normal2(keys, tau, a.episode, (uint32_t)(a.env_offset + e0 + el), (uint32_t)c, z0, z1);
+                    v = __dmul_rn(stdS[i], z1);
+                }
+            } else if (a.obs_noise) {
+                v = a.obs_noise[(int64_t)e0 * N + i];
+            }
+            v0S[i] = v;
+        }
+        if (philox && p_live) {
+            p_sd = stdS[p_col];
+            nxt = philox4x32_10(make_uint4(tau_base + (uint32_t)pj, a.episode, p_env, (uint32_t)p_c), keys);
+        }
+        t3_worker_barrier(NW);
+        piece_pass(x0S, v0S, 0, 1);
+        if (pack_rows) pack_pass(x0S, v0S, 0, 1);
+
+        int s_out = 0, s_in = 0;               // ring stages of the chunk being written out / produced
+        uint32_t par_out = 0u, par_in = 1u;    // parities: full_x of the chunk written out; empty of the stage refilled
+        for (int it = 0; it < NC + 2; ++it) {
+            // ---------------- rows of chunk `it - 2` ----------------
+            if (it >= 2) {
+                const int co = it - 2;
+                mbar_wait(full_x + s_out, par_out);
+                const double* Xb = Wt + s_out * tile;
+                const double* Vb = Vt + s_out * tile;
+                const int ns = min(C, K - co * C);
+                piece_pass(Xb, Vb, co * C + 1, ns);
+                if (pack_rows) pack_pass(Xb, Vb, co * C + 1, ns);
+                mbar_arrive(empty + s_out);
+                if (++s_out == D) { s_out = 0; par_out ^= 1u; }
+            }
+            // ---------------- noise of chunk `it` ----------------
+            if (it < NC) {
+                if (it >= D) mbar_wait(empty + s_in, par_in);     // the rows of chunk it - D have left this stage
+                const int j0 = it * C;
+                const int j_end = min(j0 + C, K);
+                double* Wb = Wt + s_in * tile;
+                double* Vb = Vt + s_in * tile;
+                if (philox) {
+                    if (p_live) {
+                        // C is a multiple of nphase (plan), so a worker's walk never straddles a chunk boundary and the
+                        // prefetched counter of its next pair stays valid across chunks
+                        double* wp = Wb + (pj - j0) * RP + p_col;
+                        double* vp = Vb + (pj - j0) * RP + p_col;
+                        for (; pj < j_end; pj += nphase, wp += nphase * RP, vp += nphase * RP) {
+                            const uint4 cur = nxt;
+                            // the rounds of the next pair are issued in the same basic block as this pair's Box–Muller
+                            nxt = philox4x32_10(make_uint4(tau_base + (uint32_t)(pj + nphase), a.episode, p_env, (uint32_t)p_c), keys);
+                            double z0, z1;
+                            normal_pair(cur, z0, z1);
+                            *wp = __dmul_rn(sqrt_dt, z0);
+                            *vp = __dmul_rn(p_sd, z1);
+                        }
+                    }
+                } else {
+                    // fed noise: 4 independent loads in flight per lane
+                    const int ns = j_end - j0;
+                    const int RL = Gl * N;
+                    const int total = ns * RL;
+                    const int64_t g0 = (int64_t)j0 * row32 + (int64_t)e0 * N;
+                    for (int base = wt; base < total; base += 4 * NW) {
+                        double wv[4], vv[4];
+                        int sidx[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int idx = base + u * NW;
+                            wv[u] = vv[u] = 0.0;
+                            sidx[u] = -1;
+                            if (idx < total) {
+                                const int s2 = idx / RL, rem = idx - s2 * RL;
+                                const int64_t gi = g0 + (int64_t)s2 * row32 + rem;
+                                sidx[u] = s2 * RP + rem;
+                                wv[u] = a.W[gi];
+                                if (a.obs_noise) vv[u] = a.obs_noise[gi + row32];
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (sidx[u] >= 0) { Wb[sidx[u]] = wv[u]; Vb[sidx[u]] = vv[u]; }
+                    }
+                }
+                mbar_arrive(full_w + s_in);
+                if (++s_in == D) { s_in = 0; par_in ^= 1u; }
+            }
+        }
+    } else {
+        // ================================= recurrence: L lanes per environment ==================================
+        // lane q of an environment owns rows 2q, 2q+1 of M = I + A dt and the matching 16-byte piece of every tile row
+        const int el_r = tid / L, q = tid - el_r * L;
+        const bool rec_live = el_r < Gl;
+        const int el_c = rec_live ? el_r : Gl - 1;     // dead lanes shadow the last environment (loads only)
+        double M[2][N], nzr[2], x[N];
+        {
+            const int e = e0 + el_c;
+            const double* Ar = a.A + (int64_t)e * a.A_stride_e + (int64_t)(2 * q) * N;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int c = 0; c < N; ++c) M[i][c] = Ar[i * N + c];
+            if (a.A_act) {
+                // action-affine drift functor, same accumulation order as em_drift(): A += u_k * A_k for k = 0, 1, ...
+#pragma unroll 1
+                for (int k = 0; k < a.n_actions; ++k) {
+                    const double u = a.actions[(int64_t)e * a.n_actions + k] * (a.action_scale ? a.action_scale[k] : 1.0);
+                    const double* Ak = a.A_act + (int64_t)k * N * N + (int64_t)(2 * q) * N;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int c = 0; c < N; ++c) M[i][c] = fma(u, Ak[i * N + c], M[i][c]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+#pragma unroll
+                for (int c = 0; c < N; ++c)
+                    M[i][c] = __dadd_rn((2 * q + i == c) ? 1.0 : 0.0, __dmul_rn(M[i][c], a.t_ssz));   // unfused like the reference
+                nzr[i] = a.nz[(int64_t)e * a.nz_stride_e + 2 * q + i];
+            }
+#pragma unroll
+            for (int c = 0; c < N; ++c) x[c] = x0S[el_c * N + c];
+        }
+        int s = 0;
+        uint32_t par = 0u;
+        for (int c = 0; c < NC; ++c) {
+            mbar_wait(full_w + s, par);
+            const int ns = min(C, K - c * C);
+            double* Wb = Wt + s * tile + el_c * N;     // this environment's run in every row of the stage
+            double2 w2 = *reinterpret_cast<const double2*>(Wb + 2 * q);
+#pragma unroll 2
+            for (int slot = 0; slot < ns; ++slot) {
+                double xn0 = __dmul_rn(M[0][0], x[0]), xn1 = __dmul_rn(M[1][0], x[0]);
+#pragma unroll
+                for (int cc = 1; cc < N; ++cc) { xn0 = fma(M[0][cc], x[cc], xn0); xn1 = fma(M[1][cc], x[cc], xn1); }
+                xn0 = fma(nzr[0], w2.x, xn0);
+                xn1 = fma(nzr[1], w2.y, xn1);
+                double* xrow = Wb + slot * RP;
+                if (slot + 1 < ns) w2 = *reinterpret_cast<const double2*>(xrow + RP + 2 * q);   // next increments: off the chain
+                if (rec_live) *reinterpret_cast<double2*>(xrow + 2 * q) = make_double2(xn0, xn1);
+                if constexpr (L == 1) {
+                    x[0] = xn0; x[1] = xn1;
+                } else {
+                    __syncwarp();              // the L lanes of an environment sit in one warp
+#pragma unroll
+                    for (int p = 0; p < L; ++p) {
+                        const double2 t = *reinterpret_cast<const double2*>(xrow + 2 * p);
+                        x[2 * p] = t.x; x[2 * p + 1] = t.y;
+                    }
+                }
+            }
+            mbar_arrive(full_x + s);
+            if (++s == D) { s = 0; par ^= 1u; }
+        }
+        if (rec_live && a.nan_flag) {
+            bool bad = false;
+#pragma unroll
+            for (int c = 0; c < N; ++c) bad |= !isfinite(x[c]);
+            if (bad) atomicOr(a.nan_flag, QRL_STATUS_NONFINITE);
+        }
+    }
+    __syncthreads();
+    // cumulative-reward column of every cache row of this interval (envs/base.py:1311, 1342-1349): one warp per env,
+    // lanes along the rows of that env's contiguous run
+    if (a.packed) {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int j = 0; j < n_sel; ++j) {
+            if (selS[j] != n_data - 1) continue;
+            for (int el = warp; el < Gl; el += NT / 32) {
+                double* dst = a.packed + (int64_t)(e0 + el) * a.packed_stride_e + j;
+                const double cum = cumS[el];
+                for (int r = lane; r <= K; r += 32) dst[(int64_t)r * pitch] = cum;
+            }
+        }
+    }
+    if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
+    em_finish_launch(a);
+}
+
+// Tile plan.  G environments per CTA (one wave of CTAs whenever the batch allows), n/2 recurrence lanes per environment,
+// every remaining warp a worker; nphase workers share one (env, comp) column and interleave its sub-steps; the ring holds
+// D stages of C sub-steps (C a multiple of nphase).  Tuning knobs: QRL_EM_T3_C, QRL_EM_T3_D, QRL_EM_T3_THREADS.
+static T3Plan t3_plan(int E, int N, int K, int n_sel, int sms) {
+    T3Plan p;
+    const int L = N / 2;
+    static const char* th_env = getenv("QRL_EM_T3_THREADS");
+    int threads = th_env ? atoi(th_env) : T3_THREADS_MAX;
+    threads = threads / 32 * 32;
+    if (threads < 128 || threads > T3_THREADS_MAX) threads = T3_THREADS_MAX;
+    // workers >= columns: G * N <= threads - (recurrence lanes rounded up to warps)
+    int g_cap = 64;
+    while (g_cap > 2 && g_cap * N + (g_cap * L + 31) / 32 * 32 > threads) g_cap -= 2;
+    int G = (E + sms - 1) / sms;
+    if (G & 1) ++G;                            // even G keeps every tile row a whole number of 16-byte pieces for n = 2 too
+    if (G > g_cap) {                           // several waves: balance them
+        const int waves = (E + g_cap * sms - 1) / (g_cap * sms);
+        G = (E + waves * sms - 1) / (waves * sms);
+        if (G & 1) ++G;
+        if (G > g_cap) G = g_cap;
+    }
+    if (G < 2) G = 2;
+    p.G = G;
+    p.grid = (E + G - 1) / G;
+    p.nrt = (G * L + 31) / 32 * 32;
+    p.threads = threads;
+    const int NW = threads - p.nrt, RP = G * N;
+    p.nphase = NW / RP;
+    if (p.nphase < 1) p.nphase = 1;
+    if (p.nphase > K) p.nphase = K;
+    static const char* d_env = getenv("QRL_EM_T3_D");
+    static const char* c_env = getenv("QRL_EM_T3_C");
+    p.D = d_env ? atoi(d_env) : 4;
+    if (p.D < 3) p.D = 3;
+    if (p.D > T3_STAGES_MAX) p.D = T3_STAGES_MAX;
+    const size_t budget = 200 * 1024;
+    const size_t fixed = T3_BAR_BYTES + (size_t)(3 * RP + G + N) * sizeof(double) + (size_t)n_sel * sizeof(int) + 64;
+    const size_t per_row = (size_t)2 * RP * sizeof(double);
+    int c_want = c_env ? atoi(c_env) : 16;
+    if (c_want < 1) c_want = 16;
+    int c_max = (int)((budget - fixed) / (per_row * p.D));
+    while (c_max < p.nphase && p.D > 3) { --p.D; c_max = (int)((budget - fixed) / (per_row * p.D)); }
+    if (c_max < p.nphase) p.nphase = c_max > 0 ? c_max : 1;
+    int C = c_want < c_max ? c_want : c_max;
+    if (C > K) C = (K + p.nphase - 1) / p.nphase * p.nphase;     // one chunk: still a multiple of nphase
+    C = C / p.nphase * p.nphase;
+    if (C < p.nphase) C = p.nphase;
+    p.C = C;
+    p.smem = fixed + per_row * p.D * p.C;
+    return p;
+}
+
+template <int N>
+static int launch_tile3(const qrl_em_args& a, cudaStream_t st, int sms) {
+    const T3Plan p = t3_plan(a.n_envs, N, a.K, a.packed ? a.n_sel : 0, sms);
+    static OncePerDevice smem_attr;
+    if (smem_attr.first())
+        QRL_CUDA(cudaFuncSetAttribute(em_tile3_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    const PhiloxKeys keys = make_philox_keys(a.seed);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(p.grid);
+    cfg.blockDim = dim3(p.threads);
+    cfg.dynamicSmemBytes = p.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (a.flags & QRL_EM_PDL) ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    QRL_CUDA(cudaLaunchKernelEx(&cfg, em_tile3_kernel<N>, a, keys, p));
+    return after_launch("em_tile3_kernel");
+}
+
+// Does the third-generation kernel take this launch?  n in {2, 4, 8}, 16-byte aligned row blocks and last-row buffers,
+// 32-bit row offsets; everything else stays with em_tile_kernel.cu / em_kernel.cu.
+bool em_tile3_supports(const qrl_em_args& a) {
+    if (!(a.n == 2 || a.n == 4 || a.n == 8) || a.K < 1 || a.A_stride_k != 0 || a.nz_stride_k != 0) return false;
+    const uintptr_t al = (uintptr_t)a.states | (uintptr_t)a.observations | (uintptr_t)a.x_last | (uintptr_t)a.obs_last;
+    if (al % 16 != 0) return false;
+    if ((int64_t)(a.K + 1) * a.n_envs * a.n >= (1ll << 31)) return false;
+    if (a.flags & (QRL_EM_ITEM_OUTPUT | 2 | 4 | 8)) return false;     // diagnostics of the second-generation kernel
+    static const char* off = getenv("QRL_EM_NO_T3");
+    return !(off && atoi(off) != 0);
+}
+
+int em_tile3_launch(const qrl_em_args& a, cudaStream_t st) {
+    const int sms = device_sm_count();
+    switch (a.n) {
+        case 2: return launch_tile3<2>(a, st, sms);
+        case 4: return launch_tile3<4>(a, st, sms);
+        case 8: return launch_tile3<8>(a, st, sms);
+        default: return QRL_E_UNSUPPORTED;
+    }
+}
+
+}  // namespace qrl
