@@ -94,6 +94,26 @@ __device__ __forceinline__ double em_drift(const qrl_em_args& a, const double* A
     }
     return v;
 }
+// One row of the Euler–Maruyama update  x'_r = sum_j M[r][j] x[j] + nz_r * w_r  (quantrl/envs/stochastic.py:229-242), as
+// every kernel of this library evaluates it: the sum is split into two INDEPENDENT fused-multiply-add chains over the
+// first H = ceil(n/2) and the remaining columns, the noise term seeds the first chain, and the halves meet in one add —
+//     lo = nz_r * w_r;  lo = fma(M[r][j], x[j], lo)  j = 0 .. H-1
+//     hi = 0;           hi = fma(M[r][j], x[j], hi)  j = H .. n-1
+//     x'_r = lo + hi
+// The recurrence is the one sequential dependency of the path: with FP64 results 8.4 cycles apart (and ~20 under pipe
+// contention, profiles/r02c) the chain per sub-step is n/2 + 1 links instead of n + 1.  All kernels use exactly this order,
+// so their trajectories agree bit for bit; against the reference (NumPy matmul) the difference is rounding (rtol 1e-12).
+template <int N>
+__device__ __forceinline__ double em_row_update(const double (&Mr)[N], const double (&x)[N], double nz, double w) {
+    constexpr int H = (N + 1) / 2;
+    double lo = __dmul_rn(nz, w), hi = 0.0;
+#pragma unroll
+    for (int j = 0; j < H; ++j) lo = fma(Mr[j], x[j], lo);
+#pragma unroll
+    for (int j = H; j < N; ++j) hi = fma(Mr[j], x[j], hi);
+    return __dadd_rn(lo, hi);
+}
+
 __device__ __forceinline__ double em_action(const qrl_em_args& a, int e, int k) {
     const double u = a.actions[(int64_t)e * a.n_actions + k];
     return (a.A_act && a.action_scale) ? u * a.action_scale[k] : u;

@@ -99,13 +99,24 @@ __global__ void __launch_bounds__(128) em_step_kernel(const qrl_em_args a_in, co
         }
         // ---- recurrence ----
         if (coeffs_vary && i > 0) load_coeffs(i);
-        double acc = 0.0;
+        // two half-sums, see em_row_update() in common.cuh (columns >= n of a padded lane group hold M = 0, x = 0)
+        double lo = __dmul_rn(nzc, w), hi = 0.0;
+        if (n == LPE) {
 #pragma unroll
-        for (int j = 0; j < LPE; ++j) {
-            const double xj = shfl_d(x, lane_base + j);
-            acc = (j == 0) ? __dmul_rn(M[0], xj) : fma(M[j], xj, acc);
+            for (int j = 0; j < LPE; ++j) {
+                const double xj = shfl_d(x, lane_base + j);
+                if (j < (LPE + 1) / 2) lo = fma(M[j], xj, lo); else hi = fma(M[j], xj, hi);
+            }
+        } else {
+            const int H = (n + 1) >> 1;
+#pragma unroll
+            for (int j = 0; j < LPE; ++j) {
+                const double xj = shfl_d(x, lane_base + j);
+                const double r = fma(M[j], xj, j < H ? lo : hi);
+                if (j < H) lo = r; else hi = r;
+            }
         }
-        x = fma(nzc, w, acc);
+        x = __dadd_rn(lo, hi);
     }
 
     if (live) {

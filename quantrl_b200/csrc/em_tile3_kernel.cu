@@ -11,9 +11,11 @@
 //     so a warp only ever waits for the data it needs, and the recurrence drifts freely behind the producers;
 //   * the recurrence overwrites the Wiener increments IN PLACE with the new states (each element is read and written by
 //     the same lane), so a ring stage is two tiles (W/X, V) instead of 7/3 — room for deeper rings of smaller chunks;
-//   * n/2 recurrence lanes per environment, each owning one 16-byte piece (two rows of M = I + A dt, 2n doubles in
-//     registers); the pieces of a sub-step meet in the tile the row is written to anyway (STS.128, __syncwarp, LDS.128),
-//     so n = 8 needs 32 + 16 registers of state instead of 128 + 16 and nothing spills;
+//   * n = 8: four recurrence lanes per environment, each owning one 16-byte piece (two rows of M = I + A dt, 2n doubles
+//     in registers); the pieces of a sub-step meet in the tile the row is written to anyway (STS.128, __syncwarp,
+//     LDS.128), so n = 8 needs 32 + 16 registers of state instead of 128 + 16 and nothing spills.  n <= 4 keeps one lane
+//     per environment and the state in registers.  The row update itself is two independent half-chains
+//     (em_row_update, common.cuh): the recurrence is the slowest pipeline stage when its FP64 chain is long;
 //   * no role needs more than 80 registers: 768 threads per CTA (6 warps per scheduler instead of 4).
 // Arithmetic, operation order and the Philox stream are those of em_kernel.cu / em_tile_kernel.cu: States and
 // Observations agree bit for bit (tests/test_em_gpu.py).  Replaces quantrl/envs/stochastic.py:178-242,
@@ -28,7 +30,7 @@ constexpr int T3_THREADS_MAX = 768;
 constexpr int T3_STAGES_MAX = 8;
 constexpr int T3_BAR_BYTES = 256;   // 3 * T3_STAGES_MAX mbarriers, rounded up: the tiles behind them stay 128-byte aligned
 
-struct T3Plan { int G, C, D, nphase, nrt, threads, grid; size_t smem; };
+struct T3Plan { int G, C, D, nphase, nrt, threads, grid, split; size_t smem; };
 
 __device__ __forceinline__ uint32_t t3_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -42,27 +44,48 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "T3_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"   // suspend-time hint: park, do not spin
         "@p bra T3_DONE;\n"
         "bra T3_WAIT;\n"
         "T3_DONE:\n"
         "}\n" ::"r"(t3_smem(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void t3_worker_barrier(int n_workers) {
-    asm volatile("bar.sync 1, %0;" ::"r"(n_workers) : "memory");
 }
 __device__ __forceinline__ void t3_minmax(double v, double& lo, double& hi) {   // NaN never wins (lo / hi are never NaN)
     lo = (v < lo) ? v : lo;
     hi = (v > hi) ? v : hi;
 }
 
-template <int N>
+// Development instrumentation (tools/microbench/t3_timeline.cu builds this file with -DQRL_T3_TIMELINE): per warp, the
+// cycles spent producing / writing rows / waiting on each kind of mbarrier, and absolute times of the kernel's phases.
+#ifdef QRL_T3_TIMELINE
+__device__ unsigned long long t3_tl[256][32][8];
+#define T3_TL_DECL long long tl_t0 = 0; unsigned long long tl_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define T3_TL_BEGIN tl_t0 = clock64();
+#define T3_TL_END(slot) tl_acc[slot] += (unsigned long long)(clock64() - tl_t0);
+#define T3_TL_MARK(slot) tl_acc[slot] = global_timer_ns();
+__device__ unsigned long long t3_trace[2][256];
+#define T3_TRACE(who, idx) if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (who == 0 ? threadIdx.x == 0 : threadIdx.x == NRT) && (idx) < 256) t3_trace[who][idx] = global_timer_ns();
+#define T3_TL_FLUSH if ((threadIdx.x & 31) == 0 && blockIdx.x < 256) { for (int i_ = 0; i_ < 8; ++i_) t3_tl[blockIdx.x][threadIdx.x >> 5][i_] = tl_acc[i_]; }
+#else
+#define T3_TL_DECL
+#define T3_TL_BEGIN
+#define T3_TL_END(slot)
+#define T3_TL_MARK(slot)
+#define T3_TL_FLUSH
+#define T3_TRACE(who, idx)
+#endif
+
+template <int N, int LR>
 __global__ void __launch_bounds__(T3_THREADS_MAX, 1)
 em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) {
     static_assert(N == 2 || N == 4 || N == 8, "piece layout: n/2 lanes per environment");
-    constexpr int L = N / 2;                   // 16-byte pieces per environment row = recurrence lanes per environment
+    static_assert(N % LR == 0 && LR <= 8, "LR recurrence lanes per environment, N / LR rows each");
+    constexpr int L = N / 2;                   // 16-byte pieces per environment row
+    constexpr int RO = N / LR;                 // rows of M per recurrence lane
     // programmatic dependent launch (QRL_EM_PDL): see em_tile_kernel.cu
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    T3_TL_DECL
+    T3_TL_MARK(0)
     qrl_em_args a = a_in;
     extern __shared__ __align__(128) unsigned char t3_raw[];
     const int G = pl.G, C = pl.C, D = pl.D, nphase = pl.nphase, NRT = pl.nrt;
@@ -82,7 +105,8 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
     double* stdS = v0S + RP;                   // [RP] measurement-noise std per (env, comp)
     double* cumS = stdS + RP;                  // [G]  cumulative reward after this interval
     double* wS = cumS + G;                     // [N]  reward weights
-    int* selS = reinterpret_cast<int*>(wS + N);  // [n_sel]
+    double* mmS = wS + N;                      // [64] per-warp min / max partials
+    int* selS = reinterpret_cast<int*>(mmS + 64);  // [n_sel]
 
     const int tid = threadIdx.x;
     const bool is_rec = tid < NRT;
@@ -113,8 +137,8 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
             const int s = a.sel_idxs[i];
             selS[i] = s < 0 ? s + n_data : s;
         }
-    if ((a.flags & QRL_EM_PDL) && is_rec && (tid % L) == 0 && tid / L < Gl) {
-        const char* Ab = reinterpret_cast<const char*>(a.A + (int64_t)(e0 + tid / L) * a.A_stride_e);
+    if ((a.flags & QRL_EM_PDL) && is_rec && (tid % LR) == 0 && tid / LR < Gl) {
+        const char* Ab = reinterpret_cast<const char*>(a.A + (int64_t)(e0 + tid / LR) * a.A_stride_e);
         for (int b = 0; b < N * N * 8; b += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(Ab + b));
     }
     // everything below reads what the previous kernel of the stream wrote (dyn, x0, cumulative rewards, actions)
@@ -122,6 +146,8 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
     for (int i = tid; i < Gl * N; i += NT) x0S[i] = a.x0[(int64_t)e0 * N + i];
     a = resolve_dyn(a_in);
     __syncthreads();
+    T3_TL_MARK(1)
+    T3_TRACE(0, 252)
 
     const double sqrt_dt = sqrt(a.t_ssz);
     const uint32_t row32 = (uint32_t)(E * N);  // doubles per time row (the dispatcher guarantees (K+1) * E * N < 2^31)
@@ -133,65 +159,69 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
         if (a.packed)
             for (int j = 0; j < n_sel; ++j) pack_rows |= (selS[j] != n_data - 1);
 
-        // ---- output, piece pass: one 16-byte piece (two components) of a row per worker and trip ----
+        // ---- output, row pass: a worker owns ONE 16-byte piece column (environment, component pair) and walks the rows with
+        // a fixed stride, like the producers walk the sub-steps: environment, weights and the piece's position in a row are
+        // loop invariants, the running offsets advance by constants.  Per row: LDS.128 of states and noise, two adds,
+        // STG.128 into the States / Observations blocks (a warp writes 512 contiguous bytes), NaN-ignoring min/max, and
+        // the reward as ONE chain of FMAs in component order that hops over the L adjacent lanes of the environment.
+        // Row 0 (States[0] = x0, Observations[0] = x0 + noise[t_idx], envs/base.py:462) is one more row of the walk, taken
+        // from x0S / v0S together with chunk 0 — nothing of it sits in front of the first produced chunk.
         const int PR = Gl * L;                 // pieces per live row
-        const int q_dsl = NW / PR, q_dpc = NW - q_dsl * PR;
-        const int q_sl0 = wt / PR, q_pc0 = wt - q_sl0 * PR;
+        const int o_np = NW / PR;              // row phases (>= 1: the plan keeps G * N <= workers)
+        const int o_phase = wt / PR, o_pc = wt - o_phase * PR;
+        const bool o_live = o_phase < o_np;
         const int q_h = wt & (L - 1);          // which piece of its environment this lane holds (adjacent lanes)
+        const unsigned q_mask = L == 1 ? 0u : (((1u << L) - 1u) << ((wt & 31) & ~(L - 1)));   // the lanes of this environment
         const double q_w0 = wS[2 * q_h], q_w1 = wS[2 * q_h + 1];
-        auto piece_pass = [&](const double* Xb, const double* Vb, int r_first, int ns) {
-            int sl = q_sl0, pc = q_pc0;
-            uint32_t g = (uint32_t)(r_first + sl) * row32 + (uint32_t)(e0 * N + 2 * pc);
-            const uint32_t g_step = (uint32_t)q_dsl * row32 + (uint32_t)(2 * q_dpc), g_wrap = row32 - (uint32_t)(2 * PR);
-            int sl_lead = __shfl_sync(0xffffffffu, sl, 0);   // warp-uniform trip count (the shuffles need all lanes)
-            while (sl_lead < ns) {
-                const bool live = sl < ns;
-                const int off = live ? sl * RP + 2 * pc : 0;
-                const double2 x2 = *reinterpret_cast<const double2*>(Xb + off);
-                const double2 v2 = *reinterpret_cast<const double2*>(Vb + off);
-                const double2 o2 = make_double2(__dadd_rn(x2.x, v2.x), __dadd_rn(x2.y, v2.y));
-                const int r = r_first + sl;
-                if (live) {
-                    if (a.states) *reinterpret_cast<double2*>(a.states + g) = x2;
-                    if (a.observations) *reinterpret_cast<double2*>(a.observations + g) = o2;
-                    t3_minmax(o2.x, lo, hi);
-                    t3_minmax(o2.y, lo, hi);
-                }
-                double rv = 0.0;
-                if (has_reward) {
-                    // -sum_c w_c s_c^2 as one chain of FMAs in component order, hopping over the L lanes of the env
-                    const double s0 = reward_on_obs ? o2.x : x2.x, s1 = reward_on_obs ? o2.y : x2.y;
-                    const double ws0 = q_w0 * s0, ws1 = q_w1 * s1;
-                    double acc = 0.0;
+        const int o_el = o_pc / L, o_e = e0 + o_el;
+        int orow = o_phase + 1 == o_np ? 0 : o_phase + 1;          // next row of this worker: r = o_phase + 1 (mod o_np)
+        const uint32_t o_g0 = (uint32_t)(e0 * N + 2 * o_pc);       // element offset of the piece inside a row
+        auto one_row = [&](const double* xp, const double* vp, int r) {
+            const double2 x2 = *reinterpret_cast<const double2*>(xp);
+            const double2 v2 = *reinterpret_cast<const double2*>(vp);
+            const double2 o2 = make_double2(__dadd_rn(x2.x, v2.x), __dadd_rn(x2.y, v2.y));
+            const uint32_t g = (uint32_t)r * row32 + o_g0;
+            if (a.states) *reinterpret_cast<double2*>(a.states + g) = x2;
+            if (a.observations) *reinterpret_cast<double2*>(a.observations + g) = o2;
+            t3_minmax(o2.x, lo, hi);
+            t3_minmax(o2.y, lo, hi);
+            double rv = 0.0;
+            if (has_reward) {
+                // -sum_c w_c s_c^2 as one chain of FMAs in component order, hopping over the L lanes of the env
+                const double s0 = reward_on_obs ? o2.x : x2.x, s1 = reward_on_obs ? o2.y : x2.y;
+                const double ws0 = q_w0 * s0, ws1 = q_w1 * s1;
+                double acc = 0.0;
 #pragma unroll
-                    for (int j = 0; j < L; ++j) {
-                        const double t = fma(ws1, s1, fma(ws0, s0, acc));
-                        if (j == L - 1) { rv = -t; break; }
-                        const double up = __shfl_up_sync(0xffffffffu, t, 1);
-                        if (q_h == j + 1) acc = up;
-                    }
+                for (int j = 0; j < L; ++j) {
+                    const double t = fma(ws1, s1, fma(ws0, s0, acc));
+                    if (j == L - 1) { rv = -t; break; }
+                    const double up = __shfl_up_sync(q_mask, t, 1);
+                    if (q_h == j + 1) acc = up;
                 }
-                if (live) {
-                    const int el = pc / L, e = e0 + el;
-                    if (has_reward && q_h == L - 1 && a.reward) a.reward[(uint32_t)r * (uint32_t)E + (uint32_t)e] = rv;
-                    if (r == K) {
-                        if (has_reward && q_h == L - 1) {
-                            if (a.reward_last) a.reward_last[e] = rv;
-                            double cum = rv;
-                            if (a.rewards_cum) { cum += a.rewards_cum[e]; a.rewards_cum[e] = cum; }
-                            cumS[el] = cum;
-                        }
-                        const int64_t gl = (int64_t)e0 * N + 2 * pc;
-                        if (a.x_last) *reinterpret_cast<double2*>(a.x_last + gl) = x2;
-                        if (a.obs_last) *reinterpret_cast<double2*>(a.obs_last + gl) = o2;
-                    }
-                }
-                sl += q_dsl;
-                pc += q_dpc;
-                g += g_step;
-                if (pc >= PR) { pc -= PR; ++sl; g += g_wrap; }
-                sl_lead = __shfl_sync(0xffffffffu, sl, 0);
+                if (q_h == L - 1 && a.reward) a.reward[(uint32_t)r * (uint32_t)E + (uint32_t)o_e] = rv;
             }
+            if (r == K) {
+                if (has_reward && q_h == L - 1) {
+                    if (a.reward_last) a.reward_last[o_e] = rv;
+                    double cum = rv;
+                    if (a.rewards_cum) { cum += a.rewards_cum[o_e]; a.rewards_cum[o_e] = cum; }
+                    cumS[o_el] = cum;
+                }
+                if (a.x_last) *reinterpret_cast<double2*>(a.x_last + o_g0) = x2;
+                if (a.obs_last) *reinterpret_cast<double2*>(a.obs_last + o_g0) = o2;
+            }
+        };
+        // rows r_first .. r_first + ns - 1 sit in slots 0 .. ns-1 of Xb / Vb
+        auto piece_pass = [&](const double* Xb, const double* Vb, int r_first, int ns) {
+            if (!o_live) return;
+            if (orow == 0) {                   // only reached with chunk 0 (r_first == 1)
+                one_row(x0S + 2 * o_pc, v0S + 2 * o_pc, 0);
+                orow = o_np;
+            }
+            const int r_end = r_first + ns;
+            const double* xp = Xb + (orow - r_first) * RP + 2 * o_pc;
+            const double* vp = Vb + (orow - r_first) * RP + 2 * o_pc;
+            for (; orow < r_end; orow += o_np, xp += o_np * RP, vp += o_np * RP) one_row(xp, vp, orow);
         };
         // ---- output, cache rows: packed[e, r, j] = column sel[j] of [T_step[r], actions[e,:], Obs[r,e,:], cum. reward]
         // (envs/base.py:1314-1372); a warp walks one environment's contiguous run of ns * pitch doubles 32 at a time.
@@ -237,52 +267,67 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
         int pj = p_phase;                      // next sub-step (within the interval) this worker generates
         uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
 
-        // ---- row 0: Observations[0] = States[0] + noise[t_idx]  (envs/base.py:462) ----
-        for (int i = wt; i < Gl * N; i += NW) {
-            const int el = i / N, c = i - el * N;
-            double v = 0.0;
-            if (philox) {
-                if (a.obs_std) {
-                    double z0, z1;
-                    const uint32_t tau = a.t_idx > 0 ? (uint32_t)(a.t_idx - 1) : 0xFFFFFFFFu;
-                    philox_normal2(keys, tau, a.episode, (uint32_t)(a.env_offset + e0 + el), (uint32_t)c, z0, z1);
-                    v = __dmul_rn(stdS[i], z1);
-                }
-            } else if (a.obs_noise) {
-                v = a.obs_noise[(int64_t)e0 * N + i];
-            }
-            v0S[i] = v;
-        }
         if (philox && p_live) {
             p_sd = stdS[p_col];
             nxt = philox4x32_10(make_uint4(tau_base + (uint32_t)pj, a.episode, p_env, (uint32_t)p_c), keys);
         }
-        t3_worker_barrier(NW);
-        piece_pass(x0S, v0S, 0, 1);
-        if (pack_rows) pack_pass(x0S, v0S, 0, 1);
+        // measurement noise of row 0 (time index t_idx: z1 of the previous sub-step's call, or of the reset call): produced
+        // with chunk 0 by the first-phase owner of each column; fed mode copies it
+        auto produce_row0 = [&]() {
+            if (philox) {
+                if (p_phase == 0 && p_el < Gl) {
+                    double v = 0.0;
+                    if (a.obs_std) {
+                        double z0, z1;
+                        const uint32_t tau = a.t_idx > 0 ? (uint32_t)(a.t_idx - 1) : 0xFFFFFFFFu;
+                        philox_normal2(keys, tau, a.episode, p_env, (uint32_t)p_c, z0, z1);
+                        v = __dmul_rn(p_sd, z1);
+                    }
+                    v0S[p_col] = v;
+                }
+            } else {
+                for (int i = wt; i < Gl * N; i += NW) v0S[i] = a.obs_noise ? a.obs_noise[(int64_t)e0 * N + i] : 0.0;
+            }
+        };
 
         int s_out = 0, s_in = 0;               // ring stages of the chunk being written out / produced
         uint32_t par_out = 0u, par_in = 1u;    // parities: full_x of the chunk written out; empty of the stage refilled
-        for (int it = 0; it < NC + 2; ++it) {
-            // ---------------- rows of chunk `it - 2` ----------------
+        // ---------------- rows of chunk `it - 2` ----------------
+        auto rows_out = [&](int it) {
             if (it >= 2) {
                 const int co = it - 2;
+                T3_TL_BEGIN
+                T3_TRACE(1, 4 * it + 0)
                 mbar_wait(full_x + s_out, par_out);
+                T3_TRACE(1, 4 * it + 1)
+                T3_TL_END(4)
+                T3_TL_BEGIN
                 const double* Xb = Wt + s_out * tile;
                 const double* Vb = Vt + s_out * tile;
                 const int ns = min(C, K - co * C);
                 piece_pass(Xb, Vb, co * C + 1, ns);
-                if (pack_rows) pack_pass(Xb, Vb, co * C + 1, ns);
+                if (pack_rows) {
+                    if (co == 0) pack_pass(x0S, v0S, 0, 1);
+                    pack_pass(Xb, Vb, co * C + 1, ns);
+                }
+                T3_TL_END(3)
                 mbar_arrive(empty + s_out);
                 if (++s_out == D) { s_out = 0; par_out ^= 1u; }
             }
-            // ---------------- noise of chunk `it` ----------------
+        };
+        // ---------------- noise of chunk `it` ----------------
+        auto produce = [&](int it) {
             if (it < NC) {
+                T3_TL_BEGIN
                 if (it >= D) mbar_wait(empty + s_in, par_in);     // the rows of chunk it - D have left this stage
+                T3_TRACE(1, 4 * it + 2)
+                T3_TL_END(5)
+                T3_TL_BEGIN
                 const int j0 = it * C;
                 const int j_end = min(j0 + C, K);
                 double* Wb = Wt + s_in * tile;
                 double* Vb = Vt + s_in * tile;
+                if (it == 0) produce_row0();
                 if (philox) {
                     if (p_live) {
                         // C is a multiple of nphase (plan), so a worker's walk never straddles a chunk boundary and the
@@ -326,22 +371,34 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
                             if (sidx[u] >= 0) { Wb[sidx[u]] = wv[u]; Vb[sidx[u]] = vv[u]; }
                     }
                 }
+                T3_TL_END(2)
+                T3_TRACE(1, 4 * it + 3)
                 mbar_arrive(full_w + s_in);
                 if (++s_in == D) { s_in = 0; par_in ^= 1u; }
             }
+        };
+        // Half of the worker warps write rows first and produce afterwards, the other half the other way round: at any
+        // time some warps run the generator (ALU / FP64 bound) while others run the row pass (shared / global memory
+        // latency bound), instead of every warp hitting the same pipes in the same phase.
+        const bool produce_first = pl.split && ((wt >> 5) & 1);
+        for (int it = 0; it < NC + 2; ++it) {
+            if (produce_first) { produce(it); rows_out(it); }
+            else { rows_out(it); produce(it); }
         }
     } else {
-        // ================================= recurrence: L lanes per environment ==================================
-        // lane q of an environment owns rows 2q, 2q+1 of M = I + A dt and the matching 16-byte piece of every tile row
-        const int el_r = tid / L, q = tid - el_r * L;
+        // ================================= recurrence: LR lanes per environment ==================================
+        // lane q of an environment owns RO = N / LR consecutive rows of M = I + A dt and the matching 16-byte pieces of
+        // every tile row.  n <= 4: one lane per environment, the state never leaves its registers; n = 8: four lanes, whose
+        // pieces meet in the tile the row is written to anyway (STS.128, __syncwarp, LDS.128)
+        const int el_r = tid / LR, q = tid - el_r * LR;
         const bool rec_live = el_r < Gl;
         const int el_c = rec_live ? el_r : Gl - 1;     // dead lanes shadow the last environment (loads only)
-        double M[2][N], nzr[2], x[N];
+        double M[RO][N], nzr[RO], x[N];
         {
             const int e = e0 + el_c;
-            const double* Ar = a.A + (int64_t)e * a.A_stride_e + (int64_t)(2 * q) * N;
+            const double* Ar = a.A + (int64_t)e * a.A_stride_e + (int64_t)(RO * q) * N;
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
+            for (int i = 0; i < RO; ++i)
 #pragma unroll
                 for (int c = 0; c < N; ++c) M[i][c] = Ar[i * N + c];
             if (a.A_act) {
@@ -349,19 +406,19 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
 #pragma unroll 1
                 for (int k = 0; k < a.n_actions; ++k) {
                     const double u = a.actions[(int64_t)e * a.n_actions + k] * (a.action_scale ? a.action_scale[k] : 1.0);
-                    const double* Ak = a.A_act + (int64_t)k * N * N + (int64_t)(2 * q) * N;
+                    const double* Ak = a.A_act + (int64_t)k * N * N + (int64_t)(RO * q) * N;
 #pragma unroll
-                    for (int i = 0; i < 2; ++i)
+                    for (int i = 0; i < RO; ++i)
 #pragma unroll
                         for (int c = 0; c < N; ++c) M[i][c] = fma(u, Ak[i * N + c], M[i][c]);
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < RO; ++i) {
 #pragma unroll
                 for (int c = 0; c < N; ++c)
-                    M[i][c] = __dadd_rn((2 * q + i == c) ? 1.0 : 0.0, __dmul_rn(M[i][c], a.t_ssz));   // unfused like the reference
-                nzr[i] = a.nz[(int64_t)e * a.nz_stride_e + 2 * q + i];
+                    M[i][c] = __dadd_rn((RO * q + i == c) ? 1.0 : 0.0, __dmul_rn(M[i][c], a.t_ssz));   // unfused like the reference
+                nzr[i] = a.nz[(int64_t)e * a.nz_stride_e + RO * q + i];
             }
 #pragma unroll
             for (int c = 0; c < N; ++c) x[c] = x0S[el_c * N + c];
@@ -369,31 +426,57 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
         int s = 0;
         uint32_t par = 0u;
         for (int c = 0; c < NC; ++c) {
+            T3_TL_BEGIN
+            T3_TRACE(0, 2 * c)
             mbar_wait(full_w + s, par);
+            T3_TRACE(0, 2 * c + 1)
+            T3_TL_END(4)
+            T3_TL_BEGIN
             const int ns = min(C, K - c * C);
-            double* Wb = Wt + s * tile + el_c * N;     // this environment's run in every row of the stage
-            double2 w2 = *reinterpret_cast<const double2*>(Wb + 2 * q);
+            double* Wb = Wt + s * tile + el_c * N + RO * q;     // this lane's pieces in every row of the stage
+            double w[RO];
+            auto load_w = [&](const double* src) {
+                if constexpr (RO == 1) {
+                    w[0] = src[0];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < RO / 2; ++i) {
+                        const double2 t = *reinterpret_cast<const double2*>(src + 2 * i);
+                        w[2 * i] = t.x; w[2 * i + 1] = t.y;
+                    }
+                }
+            };
+            load_w(Wb);
 #pragma unroll 2
             for (int slot = 0; slot < ns; ++slot) {
-                double xn0 = __dmul_rn(M[0][0], x[0]), xn1 = __dmul_rn(M[1][0], x[0]);
+                double xn[RO];
 #pragma unroll
-                for (int cc = 1; cc < N; ++cc) { xn0 = fma(M[0][cc], x[cc], xn0); xn1 = fma(M[1][cc], x[cc], xn1); }
-                xn0 = fma(nzr[0], w2.x, xn0);
-                xn1 = fma(nzr[1], w2.y, xn1);
+                for (int i = 0; i < RO; ++i) xn[i] = em_row_update<N>(M[i], x, nzr[i], w[i]);
                 double* xrow = Wb + slot * RP;
-                if (slot + 1 < ns) w2 = *reinterpret_cast<const double2*>(xrow + RP + 2 * q);   // next increments: off the chain
-                if (rec_live) *reinterpret_cast<double2*>(xrow + 2 * q) = make_double2(xn0, xn1);
-                if constexpr (L == 1) {
-                    x[0] = xn0; x[1] = xn1;
-                } else {
-                    __syncwarp();              // the L lanes of an environment sit in one warp
+                if (slot + 1 < ns) load_w(xrow + RP);      // next increments: off the chain
+                if (rec_live) {
+                    if constexpr (RO == 1) {
+                        xrow[0] = xn[0];
+                    } else {
 #pragma unroll
-                    for (int p = 0; p < L; ++p) {
-                        const double2 t = *reinterpret_cast<const double2*>(xrow + 2 * p);
+                        for (int i = 0; i < RO / 2; ++i)
+                            *reinterpret_cast<double2*>(xrow + 2 * i) = make_double2(xn[2 * i], xn[2 * i + 1]);
+                    }
+                }
+                if constexpr (LR == 1) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) x[i] = xn[i];
+                } else {
+                    __syncwarp();              // the LR lanes of an environment sit in one warp
+                    const double* xall = xrow - RO * q;
+#pragma unroll
+                    for (int p = 0; p < N / 2; ++p) {
+                        const double2 t = *reinterpret_cast<const double2*>(xall + 2 * p);
                         x[2 * p] = t.x; x[2 * p + 1] = t.y;
                     }
                 }
             }
+            T3_TL_END(2)
             mbar_arrive(full_x + s);
             if (++s == D) { s = 0; par ^= 1u; }
         }
@@ -404,7 +487,20 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
             if (bad) atomicOr(a.nan_flag, QRL_STATUS_NONFINITE);
         }
     }
+    T3_TL_MARK(6)
+    T3_TRACE(0, 254)
+    T3_TRACE(1, 254)
+    // block min / max: warp partials meet in shared memory across the barrier that ends the pipeline anyway
+    if (a.obs_minmax) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fmin(lo, shfl_xor_d(lo, o));
+            hi = fmax(hi, shfl_xor_d(hi, o));
+        }
+        if ((tid & 31) == 0) { mmS[tid >> 5] = lo; mmS[32 + (tid >> 5)] = hi; }
+    }
     __syncthreads();
+    T3_TRACE(0, 255)
     // cumulative-reward column of every cache row of this interval (envs/base.py:1311, 1342-1349): one warp per env,
     // lanes along the rows of that env's contiguous run
     if (a.packed) {
@@ -418,16 +514,41 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
             }
         }
     }
-    if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
+    if (a.obs_minmax && tid < 32) {            // one atomic pair per CTA (NaN never wins, like the reference's comparisons)
+        lo = tid < NT / 32 ? mmS[tid] : INFINITY;
+        hi = tid < NT / 32 ? mmS[32 + tid] : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fmin(lo, shfl_xor_d(lo, o));
+            hi = fmax(hi, shfl_xor_d(hi, o));
+        }
+        if (tid == 0) {
+            atomic_min_d(a.obs_minmax + 0, lo);
+            atomic_max_d(a.obs_minmax + 1, hi);
+        }
+    }
+    T3_TL_MARK(7)
+    T3_TL_FLUSH
     em_finish_launch(a);
 }
 
 // Tile plan.  G environments per CTA (one wave of CTAs whenever the batch allows), n/2 recurrence lanes per environment,
 // every remaining warp a worker; nphase workers share one (env, comp) column and interleave its sub-steps; the ring holds
 // D stages of C sub-steps (C a multiple of nphase).  Tuning knobs: QRL_EM_T3_C, QRL_EM_T3_D, QRL_EM_T3_THREADS.
+static int t3_rec_lanes(int N) {
+    static const char* lr_env = getenv("QRL_EM_T3_LR");
+    // measured on B200 (tools/microbench/t3_timeline.cu): under FP64-pipe contention a recurrence warp advances at ~12
+    // cycles per FP64 instruction, so the stage time is set by the FP64 instructions PER LANE and sub-step: n = 4 with one
+    // lane per environment (24) takes 16-18 us per 100 sub-steps, two lanes (12) 8 us, four lanes (6 + exchange) 6.6 us
+    const int dflt = N == 8 ? 4 : (N == 4 ? 2 : 1);
+    int lr = lr_env ? atoi(lr_env) : dflt;
+    if (lr < 1 || lr > N || (N % lr) != 0 || (N == 8 && lr < 4)) lr = dflt;   // n = 8 needs <= 2 rows per lane
+    return lr;
+}
+
 static T3Plan t3_plan(int E, int N, int K, int n_sel, int sms) {
     T3Plan p;
-    const int L = N / 2;
+    const int L = t3_rec_lanes(N);             // recurrence lanes per environment (LR of the kernel)
     static const char* th_env = getenv("QRL_EM_T3_THREADS");
     int threads = th_env ? atoi(th_env) : T3_THREADS_MAX;
     threads = threads / 32 * 32;
@@ -454,14 +575,14 @@ static T3Plan t3_plan(int E, int N, int K, int n_sel, int sms) {
     if (p.nphase > K) p.nphase = K;
     static const char* d_env = getenv("QRL_EM_T3_D");
     static const char* c_env = getenv("QRL_EM_T3_C");
-    p.D = d_env ? atoi(d_env) : 4;
+    p.D = d_env ? atoi(d_env) : 3;
     if (p.D < 3) p.D = 3;
     if (p.D > T3_STAGES_MAX) p.D = T3_STAGES_MAX;
     const size_t budget = 200 * 1024;
-    const size_t fixed = T3_BAR_BYTES + (size_t)(3 * RP + G + N) * sizeof(double) + (size_t)n_sel * sizeof(int) + 64;
+    const size_t fixed = T3_BAR_BYTES + (size_t)(3 * RP + G + N + 64) * sizeof(double) + (size_t)n_sel * sizeof(int) + 64;
     const size_t per_row = (size_t)2 * RP * sizeof(double);
-    int c_want = c_env ? atoi(c_env) : 16;
-    if (c_want < 1) c_want = 16;
+    int c_want = c_env ? atoi(c_env) : 36;     // few, long chunks: every chunk costs ~0.2 us of hand-over per role
+    if (c_want < 1) c_want = 36;
     int c_max = (int)((budget - fixed) / (per_row * p.D));
     while (c_max < p.nphase && p.D > 3) { --p.D; c_max = (int)((budget - fixed) / (per_row * p.D)); }
     if (c_max < p.nphase) p.nphase = c_max > 0 ? c_max : 1;
@@ -471,15 +592,17 @@ static T3Plan t3_plan(int E, int N, int K, int n_sel, int sms) {
     if (C < p.nphase) C = p.nphase;
     p.C = C;
     p.smem = fixed + per_row * p.D * p.C;
+    static const char* split_env = getenv("QRL_EM_T3_SPLIT");
+    p.split = split_env ? atoi(split_env) : 0;
     return p;
 }
 
-template <int N>
+template <int N, int LR>
 static int launch_tile3(const qrl_em_args& a, cudaStream_t st, int sms) {
     const T3Plan p = t3_plan(a.n_envs, N, a.K, a.packed ? a.n_sel : 0, sms);
     static OncePerDevice smem_attr;
     if (smem_attr.first())
-        QRL_CUDA(cudaFuncSetAttribute(em_tile3_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        QRL_CUDA(cudaFuncSetAttribute(em_tile3_kernel<N, LR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     const PhiloxKeys keys = make_philox_keys(a.seed);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -492,7 +615,7 @@ static int launch_tile3(const qrl_em_args& a, cudaStream_t st, int sms) {
     attr[0].val.programmaticStreamSerializationAllowed = (a.flags & QRL_EM_PDL) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    QRL_CUDA(cudaLaunchKernelEx(&cfg, em_tile3_kernel<N>, a, keys, p));
+    QRL_CUDA(cudaLaunchKernelEx(&cfg, em_tile3_kernel<N, LR>, a, keys, p));
     return after_launch("em_tile3_kernel");
 }
 
@@ -510,10 +633,15 @@ bool em_tile3_supports(const qrl_em_args& a) {
 
 int em_tile3_launch(const qrl_em_args& a, cudaStream_t st) {
     const int sms = device_sm_count();
-    switch (a.n) {
-        case 2: return launch_tile3<2>(a, st, sms);
-        case 4: return launch_tile3<4>(a, st, sms);
-        case 8: return launch_tile3<8>(a, st, sms);
+    const int lr = t3_rec_lanes(a.n);
+    switch (a.n * 16 + lr) {
+        case 2 * 16 + 1: return launch_tile3<2, 1>(a, st, sms);
+        case 2 * 16 + 2: return launch_tile3<2, 2>(a, st, sms);
+        case 4 * 16 + 1: return launch_tile3<4, 1>(a, st, sms);
+        case 4 * 16 + 2: return launch_tile3<4, 2>(a, st, sms);
+        case 4 * 16 + 4: return launch_tile3<4, 4>(a, st, sms);
+        case 8 * 16 + 4: return launch_tile3<8, 4>(a, st, sms);
+        case 8 * 16 + 8: return launch_tile3<8, 8>(a, st, sms);
         default: return QRL_E_UNSUPPORTED;
     }
 }

@@ -501,12 +501,7 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
             for (int slot = 0; slot < ns; ++slot) {
                 double xn[N];
 #pragma unroll
-                for (int r = 0; r < N; ++r) {
-                    double acc = __dmul_rn(M[r][0], x[0]);
-#pragma unroll
-                    for (int c = 1; c < N; ++c) acc = fma(M[r][c], x[c], acc);
-                    xn[r] = fma(nz[r], w[r], acc);
-                }
+                for (int r = 0; r < N; ++r) xn[r] = em_row_update<N>(M[r], x, nz[r], w[r]);
                 if (slot + 1 < ns) load_w(slot + 1);   // the next increments arrive while this sub-step's chain drains
 #pragma unroll
                 for (int c = 0; c < N; ++c) x[c] = xn[c];
