@@ -105,6 +105,12 @@ __device__ __forceinline__ double em_drift(const qrl_em_args& a, const double* A
 // so their trajectories agree bit for bit; against the reference (NumPy matmul) the difference is rounding (rtol 1e-12).
 template <int N>
 __device__ __forceinline__ double em_row_update(const double (&Mr)[N], const double (&x)[N], double nz, double w) {
+#ifdef QRL_EM_CHAIN_UPDATE   // experiment only: the single chain of rounds 1
+    double acc = __dmul_rn(Mr[0], x[0]);
+#pragma unroll
+    for (int j = 1; j < N; ++j) acc = fma(Mr[j], x[j], acc);
+    return fma(nz, w, acc);
+#endif
     constexpr int H = (N + 1) / 2;
     double lo = __dmul_rn(nz, w), hi = 0.0;
 #pragma unroll

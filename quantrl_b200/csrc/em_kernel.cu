@@ -187,11 +187,13 @@ extern "C" int qrl_em_step(const qrl_em_args* args, void* stream) {
     // n > 4: the recurrence lane cannot hold M = I + A dt (n*n doubles) in registers next to the producers' working set
     // (spills under the 128-register cap of a 512-thread CTA) and the generic kernel wins from E = 4096 on
     // (tools/variants_em.py: n = 8, E = 4096: 72 vs 108 us), so the tiled kernel is the default only up to n = 4.
-    // The third-generation tiled kernel (em_tile3_kernel.cu: n in {2, 4, 8}, n/2 recurrence lanes per environment) has
-    // no such limit and takes every case it supports.
+    // The third-generation tiled kernel (em_tile3_kernel.cu: n in {2, 4, 8}, several recurrence lanes per environment for
+    // n = 8) has no such limit.  Measured on B200 with the cumulative-reward cache column fused (tools/t3_sweep.py, us per
+    // 100 sub-steps, tiled vs generic + pack launch): n = 8: E = 8192 89 vs 122, 16384 168 vs 227, 65536 622 vs 851;
+    // n = 4: E = 8192 47 vs 85, 65536 317 vs 410 (287 without cache rows) — it takes every case it supports up to 2^19 lanes.
     const bool t3 = em_tile3_supports(a);
     static const char* lanes_env = getenv("QRL_EM_TILED_MAX_LANES");   // tuning knob: crossover to the generic kernel
-    const int64_t max_lanes = lanes_env ? atoll(lanes_env) : 32768;
+    const int64_t max_lanes = lanes_env ? atoll(lanes_env) : (t3 ? 524288 : 32768);
     const bool small_batch = ((int64_t)a.n_envs * a.n <= max_lanes && (a.n <= 4 || t3)) || (a.flags & QRL_EM_FORCE_TILED);
     const bool tiled = a.K >= 1 && a.n <= 8 && a.A_stride_k == 0 && a.nz_stride_k == 0 && small_batch &&
                        !(a.flags & QRL_EM_FORCE_GENERIC);

@@ -30,7 +30,7 @@ constexpr int T3_THREADS_MAX = 768;
 constexpr int T3_STAGES_MAX = 8;
 constexpr int T3_BAR_BYTES = 256;   // 3 * T3_STAGES_MAX mbarriers, rounded up: the tiles behind them stay 128-byte aligned
 
-struct T3Plan { int G, C, D, nphase, nrt, threads, grid, split; size_t smem; };
+struct T3Plan { int G, C, D, nphase, nrt, threads, grid; size_t smem; };
 
 __device__ __forceinline__ uint32_t t3_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -101,8 +101,7 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
     double* Wt = reinterpret_cast<double*>(t3_raw + T3_BAR_BYTES);   // [D][tile] increments, overwritten by the states
     double* Vt = Wt + D * tile;                // [D][tile] measurement noise, already scaled by obs_std
     double* x0S = Vt + D * tile;               // [RP] initial state (row 0)
-    double* v0S = x0S + RP;                    // [RP] measurement noise of row 0
-    double* stdS = v0S + RP;                   // [RP] measurement-noise std per (env, comp)
+    double* stdS = x0S + RP;                   // [RP] measurement-noise std per (env, comp)
     double* cumS = stdS + RP;                  // [G]  cumulative reward after this interval
     double* wS = cumS + G;                     // [N]  reward weights
     double* mmS = wS + N;                      // [64] per-warp min / max partials
@@ -114,7 +113,7 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
     const bool philox = a.rng_mode == QRL_RNG_PHILOX;
     const bool has_reward = a.reward_kind != QRL_REWARD_NONE;
     const bool reward_on_obs = a.reward_kind == QRL_REWARD_NEG_WSQ_OBS;
-    const int NC = (K + C - 1) / C;
+    const int NC = (K + C) / C;                // chunks of C rows over the K+1 rows of the interval
     const int n_data = 1 + a.n_actions + N + 1;
     const int n_sel = a.n_sel;
     const int pitch = a.packed ? (int)(a.packed_row_pitch > 0 ? a.packed_row_pitch : a.n_sel) : 0;
@@ -153,75 +152,80 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
     const uint32_t row32 = (uint32_t)(E * N);  // doubles per time row (the dispatcher guarantees (K+1) * E * N < 2^31)
     double lo = INFINITY, hi = -INFINITY;
 
+    // Chunks are cut over ROWS: chunk c holds rows c*C .. c*C+C-1 of the K+1 rows of the interval, row r in slot r - c*C.
+    // Row 0 (States[0] = x0, Observations[0] = x0 + noise[t_idx], envs/base.py:462) is simply the first row of chunk 0;
+    // row r >= 1 is the result of sub-step r-1.  Every role therefore has ONE loop body for all rows (one inlined copy
+    // of each pass: the kernel is sensitive to instruction-cache pressure).
     if (!is_rec) {
         // ================================= workers: produce noise, write rows ==================================
         bool pack_rows = false;                // any cache column besides the cumulative reward (written at the end)?
         if (a.packed)
             for (int j = 0; j < n_sel; ++j) pack_rows |= (selS[j] != n_data - 1);
 
-        // ---- output, row pass: a worker owns ONE 16-byte piece column (environment, component pair) and walks the rows with
-        // a fixed stride, like the producers walk the sub-steps: environment, weights and the piece's position in a row are
-        // loop invariants, the running offsets advance by constants.  Per row: LDS.128 of states and noise, two adds,
-        // STG.128 into the States / Observations blocks (a warp writes 512 contiguous bytes), NaN-ignoring min/max, and
-        // the reward as ONE chain of FMAs in component order that hops over the L adjacent lanes of the environment.
-        // Row 0 (States[0] = x0, Observations[0] = x0 + noise[t_idx], envs/base.py:462) is one more row of the walk, taken
-        // from x0S / v0S together with chunk 0 — nothing of it sits in front of the first produced chunk.
+        // ---- output, piece pass: one 16-byte piece (two components) of a row per worker and trip: LDS.128 of states and
+        // noise, two adds, STG.128 into the States / Observations blocks (a warp writes 512 contiguous bytes), NaN-ignoring
+        // min/max, and the reward as ONE chain of FMAs in component order that hops over the L adjacent lanes of an
+        // environment.  (A pass in which every worker owns one piece column and walks the rows with loop-invariant
+        // addressing was measured too: fewer instructions per row, but workers / (pieces per row) is rarely an integer and
+        // the idle remainder costs more than the invariants save — n = 8, G = 56: 94 vs 85 us.)
         const int PR = Gl * L;                 // pieces per live row
-        const int o_np = NW / PR;              // row phases (>= 1: the plan keeps G * N <= workers)
-        const int o_phase = wt / PR, o_pc = wt - o_phase * PR;
-        const bool o_live = o_phase < o_np;
+        const int q_dsl = NW / PR, q_dpc = NW - q_dsl * PR;
+        const int q_sl0 = wt / PR, q_pc0 = wt - q_sl0 * PR;
         const int q_h = wt & (L - 1);          // which piece of its environment this lane holds (adjacent lanes)
-        const unsigned q_mask = L == 1 ? 0u : (((1u << L) - 1u) << ((wt & 31) & ~(L - 1)));   // the lanes of this environment
         const double q_w0 = wS[2 * q_h], q_w1 = wS[2 * q_h + 1];
-        const int o_el = o_pc / L, o_e = e0 + o_el;
-        int orow = o_phase + 1 == o_np ? 0 : o_phase + 1;          // next row of this worker: r = o_phase + 1 (mod o_np)
-        const uint32_t o_g0 = (uint32_t)(e0 * N + 2 * o_pc);       // element offset of the piece inside a row
-        auto one_row = [&](const double* xp, const double* vp, int r) {
-            const double2 x2 = *reinterpret_cast<const double2*>(xp);
-            const double2 v2 = *reinterpret_cast<const double2*>(vp);
-            const double2 o2 = make_double2(__dadd_rn(x2.x, v2.x), __dadd_rn(x2.y, v2.y));
-            const uint32_t g = (uint32_t)r * row32 + o_g0;
-            if (a.states) *reinterpret_cast<double2*>(a.states + g) = x2;
-            if (a.observations) *reinterpret_cast<double2*>(a.observations + g) = o2;
-            t3_minmax(o2.x, lo, hi);
-            t3_minmax(o2.y, lo, hi);
-            double rv = 0.0;
-            if (has_reward) {
-                // -sum_c w_c s_c^2 as one chain of FMAs in component order, hopping over the L lanes of the env
-                const double s0 = reward_on_obs ? o2.x : x2.x, s1 = reward_on_obs ? o2.y : x2.y;
-                const double ws0 = q_w0 * s0, ws1 = q_w1 * s1;
-                double acc = 0.0;
-#pragma unroll
-                for (int j = 0; j < L; ++j) {
-                    const double t = fma(ws1, s1, fma(ws0, s0, acc));
-                    if (j == L - 1) { rv = -t; break; }
-                    const double up = __shfl_up_sync(q_mask, t, 1);
-                    if (q_h == j + 1) acc = up;
-                }
-                if (q_h == L - 1 && a.reward) a.reward[(uint32_t)r * (uint32_t)E + (uint32_t)o_e] = rv;
-            }
-            if (r == K) {
-                if (has_reward && q_h == L - 1) {
-                    if (a.reward_last) a.reward_last[o_e] = rv;
-                    double cum = rv;
-                    if (a.rewards_cum) { cum += a.rewards_cum[o_e]; a.rewards_cum[o_e] = cum; }
-                    cumS[o_el] = cum;
-                }
-                if (a.x_last) *reinterpret_cast<double2*>(a.x_last + o_g0) = x2;
-                if (a.obs_last) *reinterpret_cast<double2*>(a.obs_last + o_g0) = o2;
-            }
-        };
-        // rows r_first .. r_first + ns - 1 sit in slots 0 .. ns-1 of Xb / Vb
         auto piece_pass = [&](const double* Xb, const double* Vb, int r_first, int ns) {
-            if (!o_live) return;
-            if (orow == 0) {                   // only reached with chunk 0 (r_first == 1)
-                one_row(x0S + 2 * o_pc, v0S + 2 * o_pc, 0);
-                orow = o_np;
+            int sl = q_sl0, pc = q_pc0;
+            uint32_t g = (uint32_t)(r_first + sl) * row32 + (uint32_t)(e0 * N + 2 * pc);
+            const uint32_t g_step = (uint32_t)q_dsl * row32 + (uint32_t)(2 * q_dpc), g_wrap = row32 - (uint32_t)(2 * PR);
+            int sl_lead = __shfl_sync(0xffffffffu, sl, 0);   // warp-uniform trip count (the shuffles need all lanes)
+            while (sl_lead < ns) {
+                const bool live = sl < ns;
+                const int off = live ? sl * RP + 2 * pc : 0;
+                const double2 x2 = *reinterpret_cast<const double2*>(Xb + off);
+                const double2 v2 = *reinterpret_cast<const double2*>(Vb + off);
+                const double2 o2 = make_double2(__dadd_rn(x2.x, v2.x), __dadd_rn(x2.y, v2.y));
+                const int r = r_first + sl;
+                if (live) {
+                    if (a.states) *reinterpret_cast<double2*>(a.states + g) = x2;
+                    if (a.observations) *reinterpret_cast<double2*>(a.observations + g) = o2;
+                    t3_minmax(o2.x, lo, hi);
+                    t3_minmax(o2.y, lo, hi);
+                }
+                double rv = 0.0;
+                if (has_reward) {
+                    // -sum_c w_c s_c^2 as one chain of FMAs in component order, hopping over the L lanes of the env
+                    const double s0 = reward_on_obs ? o2.x : x2.x, s1 = reward_on_obs ? o2.y : x2.y;
+                    const double ws0 = q_w0 * s0, ws1 = q_w1 * s1;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < L; ++j) {
+                        const double t = fma(ws1, s1, fma(ws0, s0, acc));
+                        if (j == L - 1) { rv = -t; break; }
+                        const double up = __shfl_up_sync(0xffffffffu, t, 1);
+                        if (q_h == j + 1) acc = up;
+                    }
+                }
+                if (live) {
+                    const int el = pc / L, e = e0 + el;
+                    if (has_reward && q_h == L - 1 && a.reward) a.reward[(uint32_t)r * (uint32_t)E + (uint32_t)e] = rv;
+                    if (r == K) {
+                        if (has_reward && q_h == L - 1) {
+                            if (a.reward_last) a.reward_last[e] = rv;
+                            double cum = rv;
+                            if (a.rewards_cum) { cum += a.rewards_cum[e]; a.rewards_cum[e] = cum; }
+                            cumS[el] = cum;
+                        }
+                        const int64_t gl = (int64_t)e0 * N + 2 * pc;
+                        if (a.x_last) *reinterpret_cast<double2*>(a.x_last + gl) = x2;
+                        if (a.obs_last) *reinterpret_cast<double2*>(a.obs_last + gl) = o2;
+                    }
+                }
+                sl += q_dsl;
+                pc += q_dpc;
+                g += g_step;
+                if (pc >= PR) { pc -= PR; ++sl; g += g_wrap; }
+                sl_lead = __shfl_sync(0xffffffffu, sl, 0);
             }
-            const int r_end = r_first + ns;
-            const double* xp = Xb + (orow - r_first) * RP + 2 * o_pc;
-            const double* vp = Vb + (orow - r_first) * RP + 2 * o_pc;
-            for (; orow < r_end; orow += o_np, xp += o_np * RP, vp += o_np * RP) one_row(xp, vp, orow);
         };
         // ---- output, cache rows: packed[e, r, j] = column sel[j] of [T_step[r], actions[e,:], Obs[r,e,:], cum. reward]
         // (envs/base.py:1314-1372); a warp walks one environment's contiguous run of ns * pitch doubles 32 at a time.
@@ -257,43 +261,26 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
             }
         };
 
-        // ---- producer: the (env, comp) column of this worker and its position in the sub-step walk ----
+        // ---- producer: the (env, comp) column of this worker and its position in the row walk ----
+        // the call with tau = t_idx + r - 1 gives z0 -> Wiener increment of sub-step r-1 (row r's input) and z1 -> measurement
+        // noise of row r; row 0's measurement noise is z1 of the call before (tau = t_idx - 1, or the reset call)
         const int p_phase = wt / RP, p_col = wt - p_phase * RP;
         const int p_el = p_col / N, p_c = p_col - p_el * N;
         const bool p_live = p_phase < nphase && p_el < Gl;
         const uint32_t p_env = (uint32_t)(a.env_offset + e0 + p_el);
-        const uint32_t tau_base = (uint32_t)a.t_idx;
+        const uint32_t tau_base = (uint32_t)a.t_idx - 1u;   // tau of row r is tau_base + r (row 0 of an episode: 0xFFFFFFFF, the reset call)
         double p_sd = 0.0;
-        int pj = p_phase;                      // next sub-step (within the interval) this worker generates
+        int pr = p_phase;                      // next row this worker generates (phase 0 starts with row 0)
         uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
-
         if (philox && p_live) {
             p_sd = stdS[p_col];
-            nxt = philox4x32_10(make_uint4(tau_base + (uint32_t)pj, a.episode, p_env, (uint32_t)p_c), keys);
+            nxt = philox4x32_10(make_uint4(tau_base + (uint32_t)pr, a.episode, p_env, (uint32_t)p_c), keys);
         }
-        // measurement noise of row 0 (time index t_idx: z1 of the previous sub-step's call, or of the reset call): produced
-        // with chunk 0 by the first-phase owner of each column; fed mode copies it
-        auto produce_row0 = [&]() {
-            if (philox) {
-                if (p_phase == 0 && p_el < Gl) {
-                    double v = 0.0;
-                    if (a.obs_std) {
-                        double z0, z1;
-                        const uint32_t tau = a.t_idx > 0 ? (uint32_t)(a.t_idx - 1) : 0xFFFFFFFFu;
-                        philox_normal2(keys, tau, a.episode, p_env, (uint32_t)p_c, z0, z1);
-                        v = __dmul_rn(p_sd, z1);
-                    }
-                    v0S[p_col] = v;
-                }
-            } else {
-                for (int i = wt; i < Gl * N; i += NW) v0S[i] = a.obs_noise ? a.obs_noise[(int64_t)e0 * N + i] : 0.0;
-            }
-        };
 
         int s_out = 0, s_in = 0;               // ring stages of the chunk being written out / produced
         uint32_t par_out = 0u, par_in = 1u;    // parities: full_x of the chunk written out; empty of the stage refilled
-        // ---------------- rows of chunk `it - 2` ----------------
-        auto rows_out = [&](int it) {
+        for (int it = 0; it < NC + 2; ++it) {
+            // ---------------- rows of chunk `it - 2` ----------------
             if (it >= 2) {
                 const int co = it - 2;
                 T3_TL_BEGIN
@@ -304,52 +291,46 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
                 T3_TL_BEGIN
                 const double* Xb = Wt + s_out * tile;
                 const double* Vb = Vt + s_out * tile;
-                const int ns = min(C, K - co * C);
-                piece_pass(Xb, Vb, co * C + 1, ns);
-                if (pack_rows) {
-                    if (co == 0) pack_pass(x0S, v0S, 0, 1);
-                    pack_pass(Xb, Vb, co * C + 1, ns);
-                }
+                const int ns = min(C, K + 1 - co * C);
+                piece_pass(Xb, Vb, co * C, ns);
+                if (pack_rows) pack_pass(Xb, Vb, co * C, ns);
                 T3_TL_END(3)
                 mbar_arrive(empty + s_out);
                 if (++s_out == D) { s_out = 0; par_out ^= 1u; }
             }
-        };
-        // ---------------- noise of chunk `it` ----------------
-        auto produce = [&](int it) {
+            // ---------------- noise of chunk `it` ----------------
             if (it < NC) {
                 T3_TL_BEGIN
                 if (it >= D) mbar_wait(empty + s_in, par_in);     // the rows of chunk it - D have left this stage
                 T3_TRACE(1, 4 * it + 2)
                 T3_TL_END(5)
                 T3_TL_BEGIN
-                const int j0 = it * C;
-                const int j_end = min(j0 + C, K);
+                const int r0 = it * C;
+                const int r_end = min(r0 + C, K + 1);
                 double* Wb = Wt + s_in * tile;
                 double* Vb = Vt + s_in * tile;
-                if (it == 0) produce_row0();
                 if (philox) {
                     if (p_live) {
                         // C is a multiple of nphase (plan), so a worker's walk never straddles a chunk boundary and the
                         // prefetched counter of its next pair stays valid across chunks
-                        double* wp = Wb + (pj - j0) * RP + p_col;
-                        double* vp = Vb + (pj - j0) * RP + p_col;
-                        for (; pj < j_end; pj += nphase, wp += nphase * RP, vp += nphase * RP) {
+                        double* wp = Wb + (pr - r0) * RP + p_col;
+                        double* vp = Vb + (pr - r0) * RP + p_col;
+                        for (; pr < r_end; pr += nphase, wp += nphase * RP, vp += nphase * RP) {
                             const uint4 cur = nxt;
                             // the rounds of the next pair are issued in the same basic block as this pair's Box–Muller
-                            nxt = philox4x32_10(make_uint4(tau_base + (uint32_t)(pj + nphase), a.episode, p_env, (uint32_t)p_c), keys);
+                            nxt = philox4x32_10(make_uint4(tau_base + (uint32_t)(pr + nphase), a.episode, p_env, (uint32_t)p_c), keys);
                             double z0, z1;
                             normal_pair(cur, z0, z1);
-                            *wp = __dmul_rn(sqrt_dt, z0);
+                            *wp = __dmul_rn(sqrt_dt, z0);          // (row 0: never read — the recurrence puts x0 there)
                             *vp = __dmul_rn(p_sd, z1);
                         }
                     }
                 } else {
-                    // fed noise: 4 independent loads in flight per lane
-                    const int ns = j_end - j0;
+                    // fed noise: 4 independent loads in flight per lane.  Row r takes W[r-1] (r >= 1) and obs_noise[r]
+                    const int ns = r_end - r0;
                     const int RL = Gl * N;
                     const int total = ns * RL;
-                    const int64_t g0 = (int64_t)j0 * row32 + (int64_t)e0 * N;
+                    const int64_t g0 = (int64_t)r0 * row32 + (int64_t)e0 * N;
                     for (int base = wt; base < total; base += 4 * NW) {
                         double wv[4], vv[4];
                         int sidx[4];
@@ -362,8 +343,8 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
                                 const int s2 = idx / RL, rem = idx - s2 * RL;
                                 const int64_t gi = g0 + (int64_t)s2 * row32 + rem;
                                 sidx[u] = s2 * RP + rem;
-                                wv[u] = a.W[gi];
-                                if (a.obs_noise) vv[u] = a.obs_noise[gi + row32];
+                                if (r0 + s2 > 0) wv[u] = a.W[gi - row32];
+                                if (a.obs_noise) vv[u] = a.obs_noise[gi];
                             }
                         }
 #pragma unroll
@@ -376,20 +357,12 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
                 mbar_arrive(full_w + s_in);
                 if (++s_in == D) { s_in = 0; par_in ^= 1u; }
             }
-        };
-        // Half of the worker warps write rows first and produce afterwards, the other half the other way round: at any
-        // time some warps run the generator (ALU / FP64 bound) while others run the row pass (shared / global memory
-        // latency bound), instead of every warp hitting the same pipes in the same phase.
-        const bool produce_first = pl.split && ((wt >> 5) & 1);
-        for (int it = 0; it < NC + 2; ++it) {
-            if (produce_first) { produce(it); rows_out(it); }
-            else { rows_out(it); produce(it); }
         }
     } else {
         // ================================= recurrence: LR lanes per environment ==================================
-        // lane q of an environment owns RO = N / LR consecutive rows of M = I + A dt and the matching 16-byte pieces of
-        // every tile row.  n <= 4: one lane per environment, the state never leaves its registers; n = 8: four lanes, whose
-        // pieces meet in the tile the row is written to anyway (STS.128, __syncwarp, LDS.128)
+        // lane q of an environment owns RO = N / LR consecutive rows of M = I + A dt and the matching pieces of every tile
+        // row.  One lane per environment keeps the state in registers; with several lanes the pieces of a sub-step meet in
+        // the tile the row is written to anyway (STS, __syncwarp, LDS.128 broadcast)
         const int el_r = tid / LR, q = tid - el_r * LR;
         const bool rec_live = el_r < Gl;
         const int el_c = rec_live ? el_r : Gl - 1;     // dead lanes shadow the last environment (loads only)
@@ -432,7 +405,7 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
             T3_TRACE(0, 2 * c + 1)
             T3_TL_END(4)
             T3_TL_BEGIN
-            const int ns = min(C, K - c * C);
+            const int ns = min(C, K + 1 - c * C);
             double* Wb = Wt + s * tile + el_c * N + RO * q;     // this lane's pieces in every row of the stage
             double w[RO];
             auto load_w = [&](const double* src) {
@@ -446,23 +419,31 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
                     }
                 }
             };
-            load_w(Wb);
+            auto store_x = [&](double* dst, const double (&v)[RO]) {
+                if constexpr (RO == 1) {
+                    dst[0] = v[0];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < RO / 2; ++i) *reinterpret_cast<double2*>(dst + 2 * i) = make_double2(v[2 * i], v[2 * i + 1]);
+                }
+            };
+            int slot = 0;
+            if (c == 0) {                      // row 0 = the initial state
+                double x0r[RO];
+#pragma unroll
+                for (int i = 0; i < RO; ++i) x0r[i] = x0S[el_c * N + RO * q + i];
+                if (rec_live) store_x(Wb, x0r);
+                slot = 1;
+            }
+            if (slot < ns) load_w(Wb + slot * RP);
 #pragma unroll 2
-            for (int slot = 0; slot < ns; ++slot) {
+            for (; slot < ns; ++slot) {
                 double xn[RO];
 #pragma unroll
                 for (int i = 0; i < RO; ++i) xn[i] = em_row_update<N>(M[i], x, nzr[i], w[i]);
                 double* xrow = Wb + slot * RP;
                 if (slot + 1 < ns) load_w(xrow + RP);      // next increments: off the chain
-                if (rec_live) {
-                    if constexpr (RO == 1) {
-                        xrow[0] = xn[0];
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < RO / 2; ++i)
-                            *reinterpret_cast<double2*>(xrow + 2 * i) = make_double2(xn[2 * i], xn[2 * i + 1]);
-                    }
-                }
+                if (rec_live) store_x(xrow, xn);
                 if constexpr (LR == 1) {
 #pragma unroll
                     for (int i = 0; i < N; ++i) x[i] = xn[i];
@@ -470,9 +451,9 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
                     __syncwarp();              // the LR lanes of an environment sit in one warp
                     const double* xall = xrow - RO * q;
 #pragma unroll
-                    for (int p = 0; p < N / 2; ++p) {
-                        const double2 t = *reinterpret_cast<const double2*>(xall + 2 * p);
-                        x[2 * p] = t.x; x[2 * p + 1] = t.y;
+                    for (int p2 = 0; p2 < N / 2; ++p2) {
+                        const double2 t = *reinterpret_cast<const double2*>(xall + 2 * p2);
+                        x[2 * p2] = t.x; x[2 * p2 + 1] = t.y;
                     }
                 }
             }
@@ -579,7 +560,7 @@ static T3Plan t3_plan(int E, int N, int K, int n_sel, int sms) {
     if (p.D < 3) p.D = 3;
     if (p.D > T3_STAGES_MAX) p.D = T3_STAGES_MAX;
     const size_t budget = 200 * 1024;
-    const size_t fixed = T3_BAR_BYTES + (size_t)(3 * RP + G + N + 64) * sizeof(double) + (size_t)n_sel * sizeof(int) + 64;
+    const size_t fixed = T3_BAR_BYTES + (size_t)(2 * RP + G + N + 64) * sizeof(double) + (size_t)n_sel * sizeof(int) + 64;
     const size_t per_row = (size_t)2 * RP * sizeof(double);
     int c_want = c_env ? atoi(c_env) : 36;     // few, long chunks: every chunk costs ~0.2 us of hand-over per role
     if (c_want < 1) c_want = 36;
@@ -587,13 +568,11 @@ static T3Plan t3_plan(int E, int N, int K, int n_sel, int sms) {
     while (c_max < p.nphase && p.D > 3) { --p.D; c_max = (int)((budget - fixed) / (per_row * p.D)); }
     if (c_max < p.nphase) p.nphase = c_max > 0 ? c_max : 1;
     int C = c_want < c_max ? c_want : c_max;
-    if (C > K) C = (K + p.nphase - 1) / p.nphase * p.nphase;     // one chunk: still a multiple of nphase
+    if (C > K + 1) C = (K + p.nphase) / p.nphase * p.nphase;     // one chunk of K+1 rows: still a multiple of nphase
     C = C / p.nphase * p.nphase;
     if (C < p.nphase) C = p.nphase;
     p.C = C;
     p.smem = fixed + per_row * p.D * p.C;
-    static const char* split_env = getenv("QRL_EM_T3_SPLIT");
-    p.split = split_env ? atoi(split_env) : 0;
     return p;
 }
 

@@ -2,7 +2,10 @@
 // cycle accumulators around every phase and mbarrier wait) and prints, for a config-3-sized launch, the per-role
 // averages.    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DQRL_T3_TIMELINE -o t3_timeline t3_timeline.cu
 //              ./t3_timeline [E] [n] [K]          (knobs: QRL_EM_T3_C / QRL_EM_T3_D / QRL_EM_T3_THREADS)
-#include "../../quantrl_b200/csrc/em_tile3_kernel.cu"
+#ifndef T3_SRC
+#define T3_SRC "../../quantrl_b200/csrc/em_tile3_kernel.cu"
+#endif
+#include T3_SRC
 #include <vector>
 namespace qrl {
 thread_local char g_err[512] = "";
@@ -41,14 +44,17 @@ int main(int argc, char** argv) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    for (int i = 0; i < 20; ++i) em_tile3_launch(a, 0);
+    for (int i = 0; i < 200; ++i) em_tile3_launch(a, 0);
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     float ms;
     cudaEventElapsedTime(&ms, e0, e1);
     const T3Plan p = t3_plan(E, n, K, 1, device_sm_count());
     printf("E=%d n=%d K=%d: %.2f us per launch; plan G=%d C=%d D=%d nphase=%d rec threads=%d threads=%d grid=%d smem=%zu\n", E, n, K,
-           ms * 1e3 / 20, p.G, p.C, p.D, p.nphase, p.nrt, p.threads, p.grid, p.smem);
+           ms * 1e3 / 200, p.G, p.C, p.D, p.nphase, p.nrt, p.threads, p.grid, p.smem);
+#ifndef QRL_T3_TIMELINE
+    return 0;
+#else
     static unsigned long long tl[256][32][8];
     CK(cudaMemcpyFromSymbol(tl, t3_tl, sizeof(tl)));
     const int nw = p.threads / 32, nrw = p.nrt / 32;
@@ -85,4 +91,5 @@ int main(int argc, char** argv) {
                (tr[0][255] - t0) * 1e-3, (tl[0][0][7] - t0) * 1e-3);
     }
     return 0;
+#endif
 }
