@@ -218,6 +218,22 @@ typedef struct qrl_em_args {
     uint64_t* peer_epoch;
     int32_t   peer_rank;
     int32_t   peer_world;
+
+    /* publish-only exchange (ABI 4, flags & QRL_EM_PEER_PUBLISH) — what the sharded path uses: the step results stay in
+     * THIS rank's memory (obs_last / reward_last point into a ring of slices that the host rotates launch by launch),
+     * every block fences at device scope only, and the last block releases at system scope and stores
+     * peer_publish_value into peer_flags[peer_dst][peer_rank] — one 8-byte NVLink store per launch; nobody waits.  The
+     * learner rank gathers the slices with qrl_peer_pull, which polls those flags.  Flow control: when peer_pulled is
+     * non-NULL the launch spins at its start until *peer_pulled >= peer_pulled_min (the learner has gathered the epoch
+     * that last used the ring slice this launch overwrites); ~2 s time-out -> QRL_STATUS_PEER_TIMEOUT. */
+    uint64_t  peer_publish_value;
+    const uint64_t* peer_pulled;
+    uint64_t  peer_pulled_min;
+    int32_t   peer_dst;
+    int32_t   _pad1;
+    /* optional second copy of the last rows (e.g. obs_last -> pinned host memory for step(), obs_last_b -> the ring) */
+    double*   obs_last_b;
+    double*   reward_last_b;
 } qrl_em_args;
 
 #define QRL_EM_FORCE_GENERIC 1   /* flags: always use the generic lane-per-component kernel (A/B testing) */
@@ -229,6 +245,7 @@ typedef struct qrl_em_args {
                                  * completion before reading anything), which hides the launch latency between the
                                  * back-to-back step kernels of a device-resident loop */
 #define QRL_EM_PACK_TMA     128 /* flags: reserved (accepted and ignored; the cache rows are written from registers) */
+#define QRL_EM_PEER_PUBLISH 8192 /* flags: publish-only exchange (see peer_publish_value); needs peer_flags + finish_counter */
 #define QRL_EM_HOST_TIDX    64  /* flags: `dyn` is only ADVANCED by this launch (dyn_advance), not read: t_idx, episode and the
                                  * pointers that depend on t_idx (W, obs_noise, T_step, packed) were set by the host for
                                  * this launch — a host that re-enqueues every step anyway saves the kernel one global round
@@ -335,6 +352,37 @@ typedef struct qrl_pack_args {
 } qrl_pack_args;
 
 QRL_API int qrl_pack_rows(const qrl_pack_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Learner-side gather of one action step of the env-sharded path (the only exchange step: SURVEY.md §8e; replaces an
+ * NCCL all_gather of [obs | reward] per step).  Rank p keeps the last rows of epoch e in slice e % out_slots of its own
+ * ring (peer-mapped symmetric memory) and its step kernel stores e into flags[p] of the learner (QRL_EM_PEER_PUBLISH).
+ * This launch — on the learner, typically on a side stream so that it overlaps the next step — gathers epoch
+ * e = *pull_epoch + 1: the blocks that copy rank p's slice first poll flags[p] >= e, so slices of early ranks move
+ * while late ranks still integrate; the last block then advances *pull_epoch and stores e into every rank's `pulled`
+ * word (the credit that lets rank p reuse the ring slice).  Ring slice of rank p (count_p environments):
+ *   [ obs (count_p, n_obs) | reward (count_p,) ]   at peer_ring[p] + (e % out_slots) * slot_stride[p]   (doubles)
+ * A rank that does not publish within ~2 s sets QRL_STATUS_PEER_TIMEOUT in *status and the launch returns.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct qrl_peer_pull_args {
+    int32_t  world;               /* number of ranks */
+    int32_t  n_obs;
+    int32_t  out_slots;           /* slices per ring */
+    int32_t  blocks_per_rank;     /* 0 = default */
+    const uint64_t* flags;        /* (world,) this rank's flag array, written by the step kernels of all ranks */
+    const double* const* peer_ring; /* DEVICE table (world,): rank p's ring, mapped into this process */
+    const int64_t* slot_stride;   /* DEVICE (world,) doubles between the slices of rank p's ring */
+    const int64_t* env_offset;    /* DEVICE (world,) global index of rank p's first environment */
+    const int64_t* env_count;     /* DEVICE (world,) environments of rank p */
+    double*  obs_all;             /* (E_total, n_obs) gathered observations */
+    double*  reward_all;          /* (E_total,) gathered rewards */
+    uint64_t* pull_epoch;         /* DEVICE counter of this rank, zero-initialised */
+    uint64_t* const* peer_pulled; /* DEVICE table (world,): rank p's `pulled` word, mapped into this process */
+    uint32_t* finish_counter;     /* DEVICE scratch, 0 before the launch and after it */
+    int32_t*  status;             /* QRL_STATUS_* bits; or NULL */
+} qrl_peer_pull_args;
+
+QRL_API int qrl_peer_pull(const qrl_peer_pull_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Machine-peak micro-benchmarks used as roofline denominators (synchronous; return the measurement).

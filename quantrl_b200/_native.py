@@ -21,6 +21,7 @@ ODE_METHODS = {"rk4": (ODE_RK4, False), "dopri5": (ODE_DOPRI5, True), "bosh3": (
                "fehlberg2": (ODE_FEHLBERG2, True), "dop853": (ODE_DOP853, True), "DOP853": (ODE_DOP853, True),
                "dopri8": (ODE_DOP853, True), "euler": (ODE_EULER, False), "midpoint": (ODE_MIDPOINT, False)}
 EM_FORCE_GENERIC, EM_FORCE_TILED, EM_ITEM_OUTPUT, EM_PACK_TMA, EM_PDL, EM_HOST_TIDX = 1, 16, 32, 128, 256, 64
+EM_PEER_PUBLISH = 8192
 ODE_FORCE_THREAD, ODE_FORCE_LANES, ODE_LANES_SINGLE = 1, 2, 4
 
 _dp = C.c_void_p  # device pointers travel as integers
@@ -45,6 +46,8 @@ class EmArgs(C.Structure):
         ("n_actions", C.c_int32), ("n_sel", C.c_int32), ("dyn", _dp), ("A_act", _dp), ("action_scale", _dp),
         ("finish_counter", _dp), ("minmax_out", _dp), ("dyn_advance", C.c_int64),
         ("peer_flags", _dp), ("peer_epoch", _dp), ("peer_rank", C.c_int32), ("peer_world", C.c_int32),
+        ("peer_publish_value", C.c_uint64), ("peer_pulled", _dp), ("peer_pulled_min", C.c_uint64),
+        ("peer_dst", C.c_int32), ("_pad1", C.c_int32), ("obs_last_b", _dp), ("reward_last_b", _dp),
     ]
 
 
@@ -73,6 +76,15 @@ class PackArgs(C.Structure):
     ]
 
 
+class PeerPullArgs(C.Structure):
+    _fields_ = [
+        ("world", C.c_int32), ("n_obs", C.c_int32), ("out_slots", C.c_int32), ("blocks_per_rank", C.c_int32),
+        ("flags", _dp), ("peer_ring", _dp), ("slot_stride", _dp), ("env_offset", _dp), ("env_count", _dp),
+        ("obs_all", _dp), ("reward_all", _dp), ("pull_epoch", _dp), ("peer_pulled", _dp), ("finish_counter", _dp),
+        ("status", _dp),
+    ]
+
+
 # every symbol include/quantrl_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "qrl_abi_version": (C.c_int, []),
@@ -84,6 +96,7 @@ SYMBOLS = {
     "qrl_em_step": (C.c_int, [C.POINTER(EmArgs), C.c_void_p]),
     "qrl_ode_step": (C.c_int, [C.POINTER(OdeArgs), C.c_void_p]),
     "qrl_pack_rows": (C.c_int, [C.POINTER(PackArgs), C.c_void_p]),
+    "qrl_peer_pull": (C.c_int, [C.POINTER(PeerPullArgs), C.c_void_p]),
     "qrl_measure_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "qrl_measure_fp64_latency": (C.c_int, [C.POINTER(C.c_double)]),
 }
@@ -149,6 +162,10 @@ def ode_step(args: OdeArgs, stream=None):
 
 def pack_rows(args: PackArgs, stream=None):
     check(lib().qrl_pack_rows(C.byref(args), stream if stream is not None else current_stream()), "qrl_pack_rows")
+
+
+def peer_pull(args: PeerPullArgs, stream=None):
+    check(lib().qrl_peer_pull(C.byref(args), stream if stream is not None else current_stream()), "qrl_peer_pull")
 
 
 def host_device_pointer(t) -> int:

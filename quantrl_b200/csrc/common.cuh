@@ -172,16 +172,52 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 
+// Flow control of the publish-only exchange (qrl_em_args.peer_pulled): one thread per block, at the start of the launch,
+// before anything is written — the learner must have gathered the epoch that last used the ring slice this launch
+// overwrites.  Almost always true already (the learner trails by one step, the ring has three slices).
+__device__ __forceinline__ void em_wait_pulled(const qrl_em_args& a) {
+    if (a.peer_pulled == nullptr || a.peer_pulled_min == 0ull) return;
+    const unsigned long long t0 = global_timer_ns();
+    while (true) {
+        unsigned long long seen;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.peer_pulled) : "memory");
+        if (seen >= a.peer_pulled_min) return;
+        if (global_timer_ns() - t0 > 2000000000ull) {
+            if (a.nan_flag) atomicOr(a.nan_flag, QRL_STATUS_PEER_TIMEOUT);
+            return;
+        }
+        __nanosleep(100);
+    }
+}
+
 // Last-block-done bookkeeping of qrl_em_args (finish_counter / minmax_out / dyn_advance / peer barrier); call once per
 // block, by all threads, after block_minmax_commit (whose atomics are issued by thread 0, like the counter increment).
 __device__ __forceinline__ void em_finish_launch(const qrl_em_args& a) {
     if (a.finish_counter == nullptr) return;
     __syncthreads();                                    // every thread of the block has read dyn and is done
     if (threadIdx.x != 0) return;
-    // this block's min/max atomics, dyn reads and (peer barrier) its stores into the learner's buffer come first
-    if (a.peer_flags && !(a.flags & 512)) __threadfence_system(); else __threadfence();
+    const bool publish_only = (a.flags & QRL_EM_PEER_PUBLISH) && a.peer_flags;
+    // this block's min/max atomics, dyn reads and (peer barrier) its stores into the learner's buffer come first.
+    // Publish-only exchange: the outputs are local, a device-scope fence per block is enough — the last block's
+    // system-scope release below is cumulative over what it has observed through the counter
+    if (a.peer_flags && !publish_only && !(a.flags & 512)) __threadfence_system(); else __threadfence();
     const unsigned prev = atomicAdd(a.finish_counter, 1u);
     if (prev != gridDim.x - 1) return;
+    if (publish_only) {
+        __threadfence_system();
+        if (a.minmax_out && a.obs_minmax) {
+            volatile double* acc = a.obs_minmax;
+            a.minmax_out[0] = acc[0];
+            a.minmax_out[1] = acc[1];
+            acc[0] = INFINITY;
+            acc[1] = -INFINITY;
+        }
+        if (a.dyn && a.dyn_advance != 0) const_cast<int64_t*>(a.dyn)[0] += a.dyn_advance;
+        *a.finish_counter = 0u;
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(a.peer_flags[a.peer_dst]) + a.peer_rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"((unsigned long long)a.peer_publish_value) : "memory");
+        return;
+    }
     // last block.  Cross-GPU barrier, part 1: publish this rank's new epoch in every rank's flag array FIRST — the
     // release fence then has nothing of this thread's own bookkeeping to wait for, and the flags travel over NVLink
     // while the local bookkeeping below is done.  (The other blocks' stores were fenced at system scope before their

@@ -20,6 +20,10 @@ namespace qrl {
 template <int LPE>
 __global__ void __launch_bounds__(128) em_step_kernel(const qrl_em_args a_in, const PhiloxKeys keys) {
     const qrl_em_args a = resolve_dyn(a_in);
+    if (a.peer_pulled) {               // publish-only exchange: flow control before anything is written
+        if (threadIdx.x == 0) em_wait_pulled(a);
+        __syncthreads();
+    }
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int e = tid / LPE;
     const int c = tid % LPE;
@@ -122,8 +126,10 @@ __global__ void __launch_bounds__(128) em_step_kernel(const qrl_em_args a_in, co
     if (live) {
         if (a.x_last) a.x_last[off] = x;
         if (a.obs_last) a.obs_last[off] = obs;
+        if (a.obs_last_b) a.obs_last_b[off] = obs;
         if (c == 0 && a.reward_kind != QRL_REWARD_NONE) {
             if (a.reward_last) a.reward_last[e] = r_last;
+            if (a.reward_last_b) a.reward_last_b[e] = r_last;
             if (a.rewards_cum) a.rewards_cum[e] += r_last;
         }
         if (a.nan_flag && !isfinite(x)) atomicOr(a.nan_flag, QRL_STATUS_NONFINITE);
@@ -168,9 +174,12 @@ extern "C" int qrl_em_step(const qrl_em_args* args, void* stream) {
     QRL_REQUIRE(a.finish_counter != nullptr || (a.minmax_out == nullptr && a.dyn_advance == 0),
                 "qrl_em_step: minmax_out / dyn_advance need finish_counter");
     QRL_REQUIRE(a.minmax_out == nullptr || a.obs_minmax != nullptr, "qrl_em_step: minmax_out needs obs_minmax");
-    QRL_REQUIRE(a.peer_flags == nullptr || (a.finish_counter != nullptr && a.peer_epoch != nullptr && a.peer_world >= 1 &&
-                                            a.peer_rank >= 0 && a.peer_rank < a.peer_world),
-                "qrl_em_step: the peer barrier needs finish_counter, peer_epoch and 0 <= peer_rank < peer_world");
+    QRL_REQUIRE(a.peer_flags == nullptr || (a.finish_counter != nullptr && ((a.flags & QRL_EM_PEER_PUBLISH) || a.peer_epoch != nullptr) &&
+                                            a.peer_world >= 1 && a.peer_rank >= 0 && a.peer_rank < a.peer_world),
+                "qrl_em_step: the peer exchange needs finish_counter, peer_epoch (barrier mode) and 0 <= peer_rank < peer_world");
+    QRL_REQUIRE(!(a.flags & QRL_EM_PEER_PUBLISH) || (a.peer_flags != nullptr && a.peer_dst >= 0 && a.peer_dst < a.peer_world),
+                "qrl_em_step: the publish-only exchange needs peer_flags and 0 <= peer_dst < peer_world");
+    QRL_REQUIRE(a.reward_last_b == nullptr || a.reward_kind != QRL_REWARD_NONE, "qrl_em_step: reward_last_b needs a fused reward");
     if (a.packed) {
         QRL_REQUIRE(a.reward_kind != QRL_REWARD_NONE && a.rewards_cum != nullptr,
                     "qrl_em_step: packed rows need a fused reward functor and rewards_cum");

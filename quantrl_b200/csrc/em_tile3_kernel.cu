@@ -144,6 +144,7 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
     asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int i = tid; i < Gl * N; i += NT) x0S[i] = a.x0[(int64_t)e0 * N + i];
     a = resolve_dyn(a_in);
+    if (a.peer_pulled && tid == 0) em_wait_pulled(a);     // publish-only exchange: flow control before anything is written
     __syncthreads();
     T3_TL_MARK(1)
     T3_TRACE(0, 252)
@@ -211,6 +212,7 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
                     if (r == K) {
                         if (has_reward && q_h == L - 1) {
                             if (a.reward_last) a.reward_last[e] = rv;
+                            if (a.reward_last_b) a.reward_last_b[e] = rv;
                             double cum = rv;
                             if (a.rewards_cum) { cum += a.rewards_cum[e]; a.rewards_cum[e] = cum; }
                             cumS[el] = cum;
@@ -218,6 +220,7 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
                         const int64_t gl = (int64_t)e0 * N + 2 * pc;
                         if (a.x_last) *reinterpret_cast<double2*>(a.x_last + gl) = x2;
                         if (a.obs_last) *reinterpret_cast<double2*>(a.obs_last + gl) = o2;
+                        if (a.obs_last_b) *reinterpret_cast<double2*>(a.obs_last_b + gl) = o2;
                     }
                 }
                 sl += q_dsl;
@@ -602,7 +605,8 @@ static int launch_tile3(const qrl_em_args& a, cudaStream_t st, int sms) {
 // 32-bit row offsets; everything else stays with em_tile_kernel.cu / em_kernel.cu.
 bool em_tile3_supports(const qrl_em_args& a) {
     if (!(a.n == 2 || a.n == 4 || a.n == 8) || a.K < 1 || a.A_stride_k != 0 || a.nz_stride_k != 0) return false;
-    const uintptr_t al = (uintptr_t)a.states | (uintptr_t)a.observations | (uintptr_t)a.x_last | (uintptr_t)a.obs_last;
+    const uintptr_t al = (uintptr_t)a.states | (uintptr_t)a.observations | (uintptr_t)a.x_last | (uintptr_t)a.obs_last |
+                         (uintptr_t)a.obs_last_b;
     if (al % 16 != 0) return false;
     if ((int64_t)(a.K + 1) * a.n_envs * a.n >= (1ll << 31)) return false;
     if (a.flags & (QRL_EM_ITEM_OUTPUT | 2 | 4 | 8)) return false;     // diagnostics of the second-generation kernel

@@ -127,6 +127,7 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
             if (i < Gl * N) x0S[i] = x0r[u];
         }
     }
+    if (a.peer_pulled && tid == 0) em_wait_pulled(a);     // publish-only exchange: flow control before anything is written
     __syncthreads();
     // does any selected cache column have to be written row by row?  (the cumulative-reward column is only known
     // after the last sub-step and is written for all K+1 rows at the end)
@@ -208,6 +209,7 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
                 if (r == K) {
                     if (has_reward) {
                         if (a.reward_last) a.reward_last[e] = rv;
+                        if (a.reward_last_b) a.reward_last_b[e] = rv;
                         double cum = rv;
                         if (a.rewards_cum) { cum += a.rewards_cum[e]; a.rewards_cum[e] = cum; }
                         cumS[el] = cum;
@@ -216,6 +218,7 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
                     for (int c = 0; c < N; ++c) {
                         if (a.x_last) a.x_last[(int64_t)e * N + c] = xv[c];
                         if (a.obs_last) a.obs_last[(int64_t)e * N + c] = ov[c];
+                        if (a.obs_last_b) a.obs_last_b[(int64_t)e * N + c] = ov[c];
                     }
                 }
             }
@@ -276,10 +279,12 @@ em_tile_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const int G, const
                     if (r == K) {
                         if (has_reward && q_h == L - 1) {
                             if (a.reward_last) a.reward_last[e] = rv;
+                            if (a.reward_last_b) a.reward_last_b[e] = rv;
                             double cum = rv;
                             if (a.rewards_cum) { cum += a.rewards_cum[e]; a.rewards_cum[e] = cum; }
                             cumS[el] = cum;
                         }
+                        if (a.obs_last_b) { a.obs_last_b[(int64_t)e0 * N + 2 * pc] = o2.x; a.obs_last_b[(int64_t)e0 * N + 2 * pc + 1] = o2.y; }
                         // last rows: one 16-byte store per piece (obs_last may be the learner's peer-mapped buffer:
                         // 8-byte stores would double the NVLink write packets)
                         const int64_t gl = (int64_t)e0 * N + 2 * pc;

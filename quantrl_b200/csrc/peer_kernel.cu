@@ -1,0 +1,90 @@
+// Learner-side gather of the env-sharded path (qrl_peer_pull) — sm_100a, NVLink peer memory.
+//
+// The reference has no multi-GPU path; this is the one exchange step of ours: per action step the learner
+// rank needs [obs | reward] of every rank's environments.  Instead of an NCCL all_gather launch per step (latency bound:
+// 40-160 KB per rank), every rank's step kernel leaves its last rows in its OWN memory (a ring of slices, symmetric
+// memory mapped into the learner's process) and stores one epoch word into the learner's flag array when it is done
+// (qrl_em_args, QRL_EM_PEER_PUBLISH).  This kernel runs on the learner, usually on a side stream next to the following
+// step: the blocks that copy rank p's slice poll flags[p] first (one thread, nanosleep back-off), so the slices of ranks
+// that have finished move over NVLink while the others still integrate; 16-byte loads from peer memory, 16-byte stores to
+// the gathered block.  The last block advances the learner's epoch counter and hands every rank the credit (`pulled`)
+// that lets it reuse the ring slice.
+#include "common.cuh"
+
+namespace qrl {
+
+constexpr int PULL_THREADS = 128;   // small on purpose: such a block is co-resident with a 768-thread step CTA (registers)
+
+__global__ void __launch_bounds__(PULL_THREADS) peer_pull_kernel(const qrl_peer_pull_args a, const int bpr) {
+    const int p = blockIdx.x / bpr, b = blockIdx.x - p * bpr;
+    const unsigned long long epoch = *a.pull_epoch + 1ull;
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+        int ok = 1;
+        const unsigned long long t0 = global_timer_ns();
+        while (true) {
+            unsigned long long seen;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.flags + p) : "memory");
+            if (seen >= epoch) break;
+            if (global_timer_ns() - t0 > 2000000000ull) {   // a rank never published: fail loudly, do not hang
+                if (a.status) atomicOr(a.status, QRL_STATUS_PEER_TIMEOUT);
+                ok = 0;
+                break;
+            }
+            __nanosleep(200);
+        }
+        s_ok = ok;
+    }
+    __syncthreads();
+    if (s_ok) {
+        const int64_t cnt = a.env_count[p], off = a.env_offset[p];
+        const double* src = a.peer_ring[p] + (int64_t)(epoch % (unsigned long long)a.out_slots) * a.slot_stride[p];
+        // slice = [obs (cnt, n_obs) | reward (cnt,)]; both parts are whole numbers of doubles, copied as 16-byte pieces
+        // where the alignment allows (ring slices and the gathered blocks are 16-byte aligned when cnt * n_obs is even)
+        const int64_t n_o = cnt * a.n_obs, n_r = cnt;
+        double* dst_o = a.obs_all + off * a.n_obs;
+        double* dst_r = a.reward_all + off;
+        const int64_t stride = (int64_t)bpr * PULL_THREADS;
+        const int64_t t = (int64_t)b * PULL_THREADS + threadIdx.x;
+        const bool vec_o = ((n_o & 1) == 0) && (((uintptr_t)src | (uintptr_t)dst_o) % 16 == 0);
+        if (vec_o) {
+            const double2* s2 = reinterpret_cast<const double2*>(src);
+            double2* d2 = reinterpret_cast<double2*>(dst_o);
+            const int64_t n2 = n_o >> 1;
+            int64_t i = t;
+            for (; i + 3 * stride < n2; i += 4 * stride) {      // 4 independent 16-byte loads in flight per thread
+                const double2 v0 = s2[i], v1 = s2[i + stride], v2 = s2[i + 2 * stride], v3 = s2[i + 3 * stride];
+                d2[i] = v0; d2[i + stride] = v1; d2[i + 2 * stride] = v2; d2[i + 3 * stride] = v3;
+            }
+            for (; i < n2; i += stride) d2[i] = s2[i];
+        } else {
+            for (int64_t i = t; i < n_o; i += stride) dst_o[i] = src[i];
+        }
+        for (int64_t i = t; i < n_r; i += stride) dst_r[i] = src[n_o + i];
+    }
+    // last block: advance the epoch, hand out the credits
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    __threadfence();
+    const unsigned prev = atomicAdd(a.finish_counter, 1u);
+    if (prev != gridDim.x - 1) return;
+    __threadfence_system();
+    *a.finish_counter = 0u;
+    *a.pull_epoch = epoch;
+    for (int q = 0; q < a.world; ++q)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.peer_pulled[q]), "l"(epoch) : "memory");
+}
+
+}  // namespace qrl
+
+extern "C" int qrl_peer_pull(const qrl_peer_pull_args* args, void* stream) {
+    using namespace qrl;
+    QRL_REQUIRE(args != nullptr, "qrl_peer_pull: args is NULL");
+    const qrl_peer_pull_args& a = *args;
+    QRL_REQUIRE(a.world >= 1 && a.n_obs >= 1 && a.out_slots >= 1 && a.blocks_per_rank >= 0, "qrl_peer_pull: bad sizes");
+    QRL_REQUIRE(a.flags && a.peer_ring && a.slot_stride && a.env_offset && a.env_count && a.obs_all && a.reward_all &&
+                a.pull_epoch && a.peer_pulled && a.finish_counter, "qrl_peer_pull: NULL argument");
+    const int bpr = a.blocks_per_rank > 0 ? a.blocks_per_rank : 8;
+    peer_pull_kernel<<<a.world * bpr, PULL_THREADS, 0, (cudaStream_t)stream>>>(a, bpr);
+    return after_launch("peer_pull_kernel");
+}

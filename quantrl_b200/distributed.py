@@ -178,54 +178,107 @@ class ShardedVecEnv:
 
 
 class PeerGather:
-    """Gather-to-learner WITHOUT a collective launch: every rank's integration kernel stores its slice of the step
-    result (last observations, last reward) straight into the learner rank's buffer through NVLink peer mapping
-    (torch symmetric memory), i.e. the gather is fused into the epilogue of ``qrl_em_step`` / ``qrl_ode_step``.
-    ``fence()`` is the only cross-GPU synchronisation: a device-side barrier on the current stream after which the
-    learner may read ``obs_all`` / ``reward_all``.
+    """Gather-to-learner WITHOUT a collective launch and without a barrier (the one exchange step of the sharded path).
+
+    Every rank keeps the last rows of an action step — ``[obs (E_loc, n) | reward (E_loc,)]`` — in its OWN memory, in a
+    ring of ``SLOTS`` slices of torch symmetric memory (mapped into the learner's process over NVLink); its step kernel
+    stores one epoch word into the learner's flag array when the slice is complete (``qrl_em_args``,
+    ``QRL_EM_PEER_PUBLISH``: device-scope fences per block, one system-scope release by the last block, nobody waits).
+    The learner gathers with ``pull()`` — ``qrl_peer_pull`` on a side stream, whose blocks poll the flags rank by rank
+    and copy the slices with 16-byte peer loads, so the gather of step ``i`` overlaps step ``i+1`` — and hands every rank
+    a credit (``pulled``) that lets it reuse the slice: a rank can run at most ``SLOTS`` steps ahead of the learner.
 
     The NCCL path (``LearnerLink.gather_step``) stays as the fallback and as the measured comparison.
     """
 
+    SLOTS = 3
+
     def __init__(self, n_envs_total, n_observations, device, dst=0, group=None):
         import torch.distributed._symmetric_memory as symm_mem
+        from . import _native as N
         assert dist.is_initialized()
+        self._N = N
         self.group = group if group is not None else dist.group.WORLD
+        gname = self.group.group_name if hasattr(self.group, "group_name") else self.group
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
         self.dst, self.E, self.n_obs = dst, n_envs_total, n_observations
-        self.offset, self.count = shard_bounds(n_envs_total, self.rank, self.world)
-        n_words = n_envs_total * (n_observations + 1)
-        self.buf = symm_mem.empty(n_words + (n_words & 1), dtype=torch.float64, device=device)
-        self.buf.zero_()
-        self.hdl = symm_mem.rendezvous(self.buf, self.group.group_name if hasattr(self.group, "group_name") else self.group)
-        base = int(self.hdl.buffer_ptrs[dst])
-        self.obs_ptr = base + 8 * self.offset * n_observations
-        self.reward_ptr = base + 8 * (n_envs_total * n_observations + self.offset)
+        self.device = torch.device(device)
+        self.bounds = all_shard_bounds(n_envs_total, self.world)
+        self.offset, self.count = self.bounds[self.rank]
         self.is_learner = self.rank == dst
-        self.obs_all = self.buf[:n_envs_total * n_observations].view(n_envs_total, n_observations)
-        self.reward_all = self.buf[n_envs_total * n_observations:n_words]
-        # in-kernel barrier (qrl_em_args.peer_flags): one uint64 epoch flag per rank in every rank's symmetric buffer
-        self.flags = symm_mem.empty(max(self.world, 2), dtype=torch.int64, device=device)
+        n = n_observations
+        words = max(c for _, c in self.bounds) * (n + 1)
+        self.slot_words = words + (words & 1)                       # even: every slice starts 16-byte aligned
+        self.ring = symm_mem.empty(self.SLOTS * self.slot_words, dtype=torch.float64, device=device)
+        self.ring.zero_()
+        self.ring_hdl = symm_mem.rendezvous(self.ring, gname)
+        # flags[0:world] = epoch published by rank p (only the learner's copy is written), flags[world] = `pulled` credit
+        self.flags = symm_mem.empty(self.world + 2, dtype=torch.int64, device=device)
         self.flags.zero_()
-        self.flags_hdl = symm_mem.rendezvous(self.flags, self.group.group_name if hasattr(self.group, "group_name") else self.group)
+        self.flags_hdl = symm_mem.rendezvous(self.flags, gname)
         self.flag_ptrs = torch.tensor([int(p) for p in self.flags_hdl.buffer_ptrs], dtype=torch.int64, device=device)
-        self.epoch = torch.zeros((1,), dtype=torch.int64, device=device)
-        self.hdl.barrier(channel=0)      # everybody's flags are zeroed before the first fused barrier
-        self._env = None
+        self.pulled_ptr = self.flags.data_ptr() + 8 * self.world
+        self.epoch = 0                                              # launches published by this rank
+        self.pulls = 0
+        self._slot_views = []
+        for s in range(self.SLOTS):
+            base = s * self.slot_words
+            self._slot_views.append((self.ring[base:base + self.count * n].view(self.count, n),
+                                     self.ring[base + self.count * n:base + self.count * (n + 1)]))
+        if self.is_learner:
+            i64 = dict(dtype=torch.int64, device=device)
+            self.obs_all = torch.zeros((n_envs_total, n), dtype=torch.float64, device=device)
+            self.reward_all = torch.zeros((n_envs_total,), dtype=torch.float64, device=device)
+            self._ring_ptrs = torch.tensor([int(p) for p in self.ring_hdl.buffer_ptrs], **i64)
+            self._strides = torch.full((self.world,), self.slot_words, **i64)
+            self._offsets = torch.tensor([o for o, _ in self.bounds], **i64)
+            self._counts = torch.tensor([c for _, c in self.bounds], **i64)
+            self._pulled_ptrs = torch.tensor([int(p) + 8 * self.world for p in self.flags_hdl.buffer_ptrs], **i64)
+            self._pull_epoch = torch.zeros((1,), **i64)
+            self._finish = torch.zeros((1,), dtype=torch.int32, device=device)
+            self._status = torch.zeros((1,), dtype=torch.int32, device=device)
+            self.side = torch.cuda.Stream(device=device)
+            a = N.PeerPullArgs()
+            a.world, a.n_obs, a.out_slots, a.blocks_per_rank = self.world, n, self.SLOTS, 8
+            a.flags, a.peer_ring, a.slot_stride = self.flags.data_ptr(), N.ptr(self._ring_ptrs), N.ptr(self._strides)
+            a.env_offset, a.env_count = N.ptr(self._offsets), N.ptr(self._counts)
+            a.obs_all, a.reward_all, a.pull_epoch = N.ptr(self.obs_all), N.ptr(self.reward_all), N.ptr(self._pull_epoch)
+            a.peer_pulled, a.finish_counter, a.status = N.ptr(self._pulled_ptrs), N.ptr(self._finish), N.ptr(self._status)
+            self._pull_args = a
+            import ctypes as C
+            self._side_raw = C.c_void_p(self.side.cuda_stream)
+        torch.cuda.synchronize(device)
+        self.ring_hdl.barrier(channel=0)      # everybody's ring and flags are zeroed before the first publish
 
     def attach(self, env):
-        """Point the env's step outputs at the learner's buffer (before the first step / graph capture)."""
+        """Route the env's step outputs through the ring (before its first step)."""
         assert env.n_envs == self.count and env.n_observations == self.n_obs
-        obs_view = self.obs_all[self.offset:self.offset + self.count] if self.is_learner else None
-        rew_view = self.reward_all[self.offset:self.offset + self.count] if self.is_learner else None
-        env.attach_step_output(self.obs_ptr, self.reward_ptr, obs_view, rew_view)
-        if hasattr(env, "attach_peer_barrier"):
-            env.attach_peer_barrier(self.flag_ptrs, self.epoch, self.rank, self.world)
-            self._env = env
+        env.attach_peer(self)
 
-    def fence(self):
-        """Cross-GPU barrier after a step.  Steps that went through a captured graph already ended with the barrier
-        fused into the kernel (``qrl_em_args.peer_flags``): nothing to launch then."""
-        if self._env is not None and getattr(self._env, "last_step_peer_fenced", False):
-            return
-        self.hdl.barrier(channel=0)
+    def next_launch(self):
+        """Called by the env for every integration launch it enqueues: ``(epoch, obs_ptr, reward_ptr, pulled_min,
+        obs_view, reward_view)`` of the ring slice this launch writes."""
+        self.epoch += 1
+        e = self.epoch
+        s = e % self.SLOTS
+        obs_v, rew_v = self._slot_views[s]
+        return e, obs_v.data_ptr(), rew_v.data_ptr(), max(0, e - self.SLOTS), obs_v, rew_v
+
+    def pull(self):
+        """Learner: enqueue the gather of the next epoch on the side stream (one call per published step, in order)."""
+        assert self.is_learner
+        self.pulls += 1
+        self._N.peer_pull(self._pull_args, self._side_raw)
+
+    def wait(self):
+        """Learner: the current stream waits for every gather enqueued so far (``obs_all`` / ``reward_all`` then hold the
+        last pulled epoch)."""
+        if self.is_learner:
+            torch.cuda.current_stream().wait_stream(self.side)
+
+    def check(self):
+        """Synchronise the side stream and raise if a gather timed out (a rank never published)."""
+        if self.is_learner:
+            self.side.synchronize()
+            if int(self._status.item()) & self._N.STATUS_PEER_TIMEOUT:
+                raise RuntimeError("quantrl_b200: qrl_peer_pull timed out waiting for a rank's step result")

@@ -56,7 +56,8 @@ class LinearVecEnv(BaseVecEnv):
         # actions from, and writes obs_last / reward_last / [min,max] to, pinned host memory directly (no copy nodes)
         self.host_zero_copy = bool(kwargs.pop("host_zero_copy", True))
         self._zc = None
-        self._peer_barrier = None           # (flag pointer table, epoch, rank, world) of distributed.PeerGather
+        self._peer_barrier = None           # (flag pointer table, epoch, rank, world): ABI-3 fused barrier (kept for A/B)
+        self._peer = None                   # distributed.PeerGather: publish-only exchange, outputs in a local ring
         self.last_step_peer_fenced = False
         self.reward_functor = kwargs.pop("reward_functor", None)
         reward_weights = kwargs.pop("reward_weights", None)
@@ -162,6 +163,8 @@ class LinearVecEnv(BaseVecEnv):
 
     def _launch(self, K, x0, write_traj=True, graph_mode=None):
         a, keep = self.interval_args(K, x0, write_traj, graph_mode)
+        if self._peer is not None and K > 0:
+            self._peer_patch(a, host_io=getattr(self, "_host_step", False))
         ev = getattr(self, "_em_events", None)
         if ev is not None and K > 0:  # live per-launch timing on the launch stream (bench.py roofline)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -228,6 +231,13 @@ class LinearVecEnv(BaseVecEnv):
             a.rewards_cum = N.ptr(self.rewards)
         a.obs_minmax = N.ptr(self._minmax)
         a.nan_flag = N.ptr(self._nan)
+        if self._peer is not None and K > 0:
+            # publish-only exchange: constant part (the per-launch part — ring slice, epoch — is patched in by _peer_patch)
+            pg = self._peer
+            a.finish_counter = N.ptr(self._finish)
+            a.peer_flags, a.peer_rank, a.peer_world, a.peer_dst = N.ptr(pg.flag_ptrs), pg.rank, pg.world, pg.dst
+            a.peer_pulled = pg.pulled_ptr
+            a.flags |= N.EM_PEER_PUBLISH
         if graph_mode is not None:
             a.finish_counter, a.dyn_advance = N.ptr(self._finish), K
             if self._peer_barrier is not None:
@@ -258,9 +268,28 @@ class LinearVecEnv(BaseVecEnv):
             a.sel_idxs, a.n_sel = N.ptr(self._sel_idxs), n_sel
             self._packed_by_kernel = True
         if self.force_generic_kernel:
-            a.flags = N.EM_FORCE_GENERIC
+            a.flags |= N.EM_FORCE_GENERIC
         a.flags |= int(os.environ.get("QRL_EM_DEBUG_FLAGS", "0"))    # development knob (kernel diagnostics bits)
         return a, keep
+
+    def attach_peer(self, peer):
+        """Route the step outputs through ``distributed.PeerGather``'s ring: every integration launch (K > 0) writes its
+        last rows into the next ring slice and publishes its epoch to the learner rank."""
+        assert not (self.use_cuda_graph and not self._single_kernel_step()), \
+            "the peer exchange rotates the output slice launch by launch: it needs eager launches or the single-kernel step"
+        self._peer = peer
+        self._graph = self._graph_host = self._graph_host1 = None
+        self._static = {}
+
+    def _peer_patch(self, a, host_io):
+        """Per-launch part of the publish-only exchange: the ring slice of this epoch, its number, the credit it needs."""
+        e, obs_ptr, rew_ptr, pulled_min, obs_v, rew_v = self._peer.next_launch()
+        if host_io:     # the primary outputs go to (pinned) host memory for step(); the ring gets the second copy
+            a.obs_last_b, a.reward_last_b = obs_ptr, rew_ptr
+        else:
+            a.obs_last, a.reward_last = obs_ptr, rew_ptr
+            self._obs_last, self._reward_last = obs_v, rew_v
+        a.peer_publish_value, a.peer_pulled_min = e, pulled_min
 
     def attach_peer_barrier(self, flag_ptrs, epoch, rank, world):
         """Fuse the per-step cross-GPU barrier of the sharded path into the captured step kernel (ABI 3)."""
@@ -308,6 +337,10 @@ class LinearVecEnv(BaseVecEnv):
             self._actions_src = src = None
         if not self.use_cuda_graph:
             self._launch(dim - 1, self._x_last)
+        elif dim == self.action_interval + 1 and self._single_kernel_step() and self._peer is not None:
+            # sharded path: the output ring slice rotates launch by launch, so the host round trip re-enqueues its block too
+            self._relaunch_interval(host_io=getattr(self, "_host_step", False), actions_src=src)
+            self._actions_src = None
         elif dim == self.action_interval + 1 and self._single_kernel_step() and not getattr(self, "_host_step", False):
             # device-resident step: direct launch, actions read in place.  (The host round trip keeps its captured
             # graph: its pointers never change and a replay costs ~4 us less host time than a ctypes launch.)
@@ -330,11 +363,11 @@ class LinearVecEnv(BaseVecEnv):
         """Single-kernel step: the ``qrl_em_args`` block of one full action interval is built once (device-resident time
         index, last-block bookkeeping) and enqueued again every step with only the actions pointer updated — the
         caller's CUDA tensor for ``step_device``, the pinned host buffer (zero-copy) or the staging buffer otherwise."""
-        key = "host" if host_io else "device"
+        key = ("host", self._h_sel) if host_io else "device"    # one block per pinned result buffer (host_output_views)
         st = self._static.get(key)
         if st is None:
             zc = self._zero_copy() if host_io else None
-            a, keep = self.interval_args(self.action_interval, self._x_last, True, graph_mode=key)
+            a, keep = self.interval_args(self.action_interval, self._x_last, True, graph_mode="host" if host_io else "device")
             if not host_io:
                 # back-to-back step kernels of a device-resident loop: programmatic dependent launch hides the launch
                 # latency between them (measured 32.2 -> 30.3 us per step at config 3); the host re-enqueues the block
@@ -365,6 +398,8 @@ class LinearVecEnv(BaseVecEnv):
             if st["packed"]:
                 a.packed = st["packed"] + 8 * t * (a.packed_row_pitch if a.packed_row_pitch > 0 else a.n_sel)
         self._packed_by_kernel = st["packs"]
+        if self._peer is not None:
+            self._peer_patch(a, host_io)
         N.em_step(a, st["stream"])
         if host_io and st["zc"] is None:
             self._h_out.copy_(self._step_out, non_blocking=True)
@@ -378,6 +413,7 @@ class LinearVecEnv(BaseVecEnv):
         ``[obs_last | reward_last | min,max]`` to pinned host memory over PCIe, so the graph is still one kernel;
         otherwise it starts with the H2D copy of the actions and ends with the D2H copy of the results."""
         # the host graph is captured per pinned result buffer (two of them when step() hands out views)
+        assert self._peer is None, "the peer exchange needs the single-kernel step (fused_coefficients + reward_functor)"
         key = ("_graph_host" if self._h_sel == 0 else "_graph_host1") if host_io else "_graph"
         if getattr(self, key, None) is None:
             K = self.action_interval

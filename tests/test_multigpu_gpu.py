@@ -1,6 +1,7 @@
 """GPU, needs >= 2 devices (skipped on a single-GPU box): environment sharding is invisible in the results and the
-peer-store gather (obs|reward written by the kernel epilogue into the learner's buffer over NVLink) equals the NCCL
-gather.  One process per GPU — never two ranks on one device (device-side barriers would wait on one another)."""
+publish / pull gather (every rank keeps its last rows in a ring of its own memory and publishes an epoch flag; the
+learner's qrl_peer_pull copies the slices over NVLink) equals the NCCL gather and the unsharded env, bit for bit.
+One process per GPU."""
 import os
 import socket
 
@@ -27,46 +28,59 @@ def _worker(rank, world, port, out):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        E, n, K = 600, 4, 10
+        E, n, K = 601, 4, 10                                      # uneven shards: 301 + 300
         A0, Au = affine_matrices(n, 1, seed=0)
         kw = dict(n=n, A0=A0, Au=Au, noise_prefixes=0.05, x0=1.0, t_norm_max=0.505, t_norm_ssz=0.01, action_interval=K,
                   observation_stds=[0.01] * n, seed=4, dir_prefix="/tmp/qrl_test")
-        env = make_sharded_env(AffineLinearVecEnv, E, **kw)
-        peer = PeerGather(E, n, dev, dst=0)
-        peer.attach(env)
         link = LearnerLink(E, n, 1, dev, dst=0)
-        env.reset()
-        actions = torch.as_tensor(np.random.default_rng(0).uniform(-1, 1, (E, 1)), device=dev)
+        # three flavours of the same shard, each publishing through its own ring: eager launches (torch hooks), the
+        # re-enqueued single-kernel step (device-resident loop), and the host round trip of step()
+        env = make_sharded_env(AffineLinearVecEnv, E, **kw)
+        env_d = make_sharded_env(AffineLinearVecEnv, E, use_cuda_graph=True, fused_coefficients=True, **kw)
+        env_h = make_sharded_env(AffineLinearVecEnv, E, use_cuda_graph=True, fused_coefficients=True, return_numpy=True, **kw)
+        peers = [PeerGather(E, n, dev, dst=0) for _ in range(3)]
+        for e_, p_ in zip((env, env_d, env_h), peers):
+            p_.attach(e_)
+            e_.reset()
         full = AffineLinearVecEnv(n_envs=E, **kw) if rank == 0 else None   # the unsharded twin on the learner
         if full is not None:
             full.reset()
-        # the same shard once more with the step captured in a CUDA graph: the cross-GPU barrier is then fused into the
-        # kernel's last block (qrl_em_args.peer_flags) and peer.fence() launches nothing
-        env_g = make_sharded_env(AffineLinearVecEnv, E, use_cuda_graph=True, fused_coefficients=True, **kw)
-        peer_g = PeerGather(E, n, dev, dst=0)
-        peer_g.attach(env_g)
-        env_g.reset()
-        for step in range(4):
+        rng = np.random.default_rng(0)
+        for step in range(8):                                     # more steps than ring slices, across an episode end
+            actions = torch.as_tensor(rng.uniform(-1, 1, (E, 1)), device=dev)
             a_loc = link.scatter_actions(actions if rank == 0 else None)
-            env.step_device(a_loc)
-            peer.fence()
-            env_g.step_device(a_loc)
-            assert env_g.last_step_peer_fenced
-            peer_g.fence()
+            o_loc, r_loc, _ = env.step_device(a_loc)
+            o_d, r_d, _ = env_d.step_device(a_loc.clone())
+            o_h, r_h, done_h, _ = env_h.step(a_loc.cpu().numpy())
+            torch.testing.assert_close(o_d, o_loc, rtol=1e-12, atol=1e-14)                      # in-kernel affine drift
+            np.testing.assert_allclose(o_h, o_loc.cpu().numpy() if not done_h[0] else o_h, rtol=1e-12, atol=1e-14)
             res = link.gather_step(env.Observations[-1], env.Reward[-1])
             if rank == 0:
-                o_full, r_full, _ = full.step_device(actions)
+                for p_ in peers:
+                    p_.pull()
+                    p_.wait()
+                o_full, r_full, term = full.step_device(actions)
                 torch.cuda.synchronize()
-                assert torch.equal(peer.obs_all, res[0]) and torch.equal(peer.reward_all, res[1])
-                assert torch.equal(peer.obs_all, o_full) and torch.equal(peer.reward_all, r_full)
-                torch.testing.assert_close(peer_g.obs_all, o_full, rtol=1e-12, atol=1e-14)   # in-kernel affine drift
-                torch.testing.assert_close(peer_g.reward_all, r_full, rtol=1e-12, atol=1e-14)
-            assert int(env_g._nan[0].item()) == 0      # no barrier time-out
+                assert torch.equal(peers[0].obs_all, res[0]) and torch.equal(peers[0].reward_all, res[1])
+                assert torch.equal(peers[0].obs_all, o_full) and torch.equal(peers[0].reward_all, r_full)   # bit for bit
+                for p_ in peers[1:]:
+                    torch.testing.assert_close(p_.obs_all, o_full, rtol=1e-12, atol=1e-14)
+                    torch.testing.assert_close(p_.reward_all, r_full, rtol=1e-12, atol=1e-14)
+                if term:
+                    full.reset()
+            if env.t_idx + 1 >= env.shape_T[0]:
+                env.reset(); env_d.reset()
+            assert int(env_d._nan[0].item()) == 0 and int(env._nan[0].item()) == 0      # no flow-control time-out
+        for p_ in peers:
+            p_.check()
         torch.cuda.synchronize()
-        assert peer_g.flags.tolist()[:world] == [4] * world and int(peer_g.epoch.item()) == 4
+        dist.barrier()
+        assert peers[1].epoch == 8 and (rank != 0 or peers[1].flags.tolist()[:world] == [8] * world)
+        assert int(peers[1].flags[world].item()) == 8                                  # every rank got its credits
         out.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
-        out.put((rank, repr(e)))
+        import traceback
+        out.put((rank, repr(e) + traceback.format_exc()[-800:]))
     finally:
         dist.destroy_process_group()
 
