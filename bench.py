@@ -3,15 +3,24 @@
 
 A "step" is one action interval (K = 100 Euler–Maruyama sub-steps) of E = 4096 stochastic linear environments per
 GPU (n = 4, in-kernel Philox noise, measurement-noise observations, fused reward), with the reference's trajectory
-semantics kept: the (K+1,E,n) States/Observations blocks, the (K+1,E) Reward block and the packed cache rows
-[t, actions, obs, cumulative reward] of BaseSB3Env.update_data, the latter written straight into a device-resident
-(E, shape_T, n_data) episode cache (2.3 GB > L2, so consecutive steps never rewrite cached lines).
+semantics kept: the (K+1,E,n) States/Observations blocks, the (K+1,E) Reward block and the selected column of the packed
+cache rows of BaseSB3Env.update_data (data_idxs=[-1], the cumulative reward), written by the same launch into a
+device-resident (E, shape_T, 1) episode cache.  The 33 MB of trajectory rows are rewritten in place every step and stay
+in the 126 MB L2 (the application's steady state); `roofline.l2_ring` is the same launch rotating over 8 sets of
+trajectory blocks (> L2) — the kernel is issue bound, the two agree.
 
   value  : whole-job env-sub-steps/s, inputs resident in HBM (`step_device`), CUDA events, max over ranks
   e2e    : the same metric through the public VecEnv API with HOST actions in pinned memory and HOST obs/reward
            out (H2D + D2H + sync inside the timed region, every step)
-  --impl reference : the reference algorithm's CPU path (oracle port of LinearEnv, one Python loop per env and
-           sub-step exactly like quantrl/envs/stochastic.py + backends/numpy.py:178-186) on all host cores
+  configs: sub-results of the other BASELINE configs in the same line — c2 (1024 deterministic envs, RK4 x 100, through
+           LinearizedHOVecEnv.step), c4 (65536 stochastic envs, n = 8: STRONG scaling over the ranks), c5 (PPO on 8192
+           stochastic envs, rollouts on the device, sharded over the ranks)
+  N > 1  : environments are sharded (weak scaling of config 3: 4096 per GPU); the only exchange is the learner gather of
+           [obs | reward] per step — every rank publishes an epoch flag, the learner's qrl_peer_pull copies the slices over
+           NVLink on a side stream.  After the timed loop rank 0 replays the whole run UNSHARDED and checks that the
+           gathered block equals it bit for bit (`sharded_equals_unsharded`).
+  --impl reference : the reference algorithm's CPU path on all host cores: the UNMODIFIED reference LinearEnv when it has
+           been staged into oracle/_ref (oracle/stage_ref.py), else the oracle port of it
 """
 import argparse
 import json
@@ -30,32 +39,79 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 E_PER_GPU, N_STATE, K_SUB, S_EPISODE, T_SSZ = 4096, 4, 100, 10000, 0.01
+E_C4, N_C4, S_C4 = 65536, 8, 1000          # config 4: strong scaling of 65536 envs, 8x8 drift
+E_C5 = 8192                                # config 5: PPO on 8192 envs
+E_C2 = 1024                                # config 2: deterministic optomechanical envs, RK4 x 100
 METRIC, UNIT = "env_substeps_per_s", "env-substeps/s"
 WORKLOAD = ("BASELINE config 3: 4096 stochastic linear envs per GPU (n=4, A=A0+u*A1), Euler-Maruyama, K=100 sub-steps "
             "per action, S=10000 sub-steps per episode, FP64, Wiener + measurement noise")
 
 
+def base_config():
+    """The keys both arms print under `config` (identical, so that the driver's same-config check holds)."""
+    return {"workload": WORKLOAD, "envs_per_gpu": E_PER_GPU, "n": N_STATE, "action_interval": K_SUB}
+
+
 # ---------------------------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: oracle port of the reference's LinearEnv on host cores
+# reference arm / cpu_baseline: the reference's LinearEnv (oracle/_ref when staged, else the oracle port) on host cores
 # ---------------------------------------------------------------------------------------------------------------------
+def _ref_available():
+    return os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "quantrl"))
+
+
 def _cpu_worker(job):
     """Each worker owns `n_env` single envs (the reference's stochastic env is single-env) and steps them in lock-step
     for `warmup + steps` action intervals; returns the wall time of the timed part."""
-    wid, n_env, steps, warmup = job
+    wid, n_env, steps, warmup, use_ref = job
     os.environ["OMP_NUM_THREADS"] = "1"
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
-    import em_oracle as eo
     import systems as sy
     A0, Au = sy.affine_matrices(N_STATE, 1, seed=0)
     nz = np.full(N_STATE, 0.05)
     rng = np.random.default_rng(1000 + wid)
     total = (warmup + steps) * K_SUB
+    w = np.ones(N_STATE)
+    if use_ref:
+        # the UNMODIFIED reference: quantrl.envs.stochastic.LinearEnv (staged copy, import shims in oracle/ref_shim.py)
+        import ref_shim
+        quantrl = ref_shim.import_reference(os.path.join(ROOT, "oracle", "_ref"))
+        LinearEnv = quantrl.envs.stochastic.LinearEnv
+
+        class Env(LinearEnv):
+            def __init__(self):
+                super().__init__(name="affine", desc="config 3", params={}, t_norm_max=total * T_SSZ + T_SSZ / 2, t_norm_ssz=T_SSZ,
+                                 t_norm_mul=1.0, n_observations=N_STATE, n_properties=0, n_actions=1, action_maximums=[1.0],
+                                 action_interval=K_SUB, data_idxs=[-1], dir_prefix="/tmp/qrl_ref_arm", backend_library="numpy",
+                                 observation_stds=[0.01] * N_STATE, plot=False, cache_all_data=False)
+
+            def reset_states(self):
+                return np.ones(N_STATE)
+
+            def get_A(self, t_idx, args):
+                return A0 + args[0][0] * Au[0]
+
+            def get_noise_prefixes(self, t_idx, args):
+                return nz
+
+            def get_reward(self):
+                return -np.sum(w * self.Observations * self.Observations, axis=-1)
+
+        envs = [Env() for _ in range(n_env)]
+        for env in envs:
+            env.reset()
+        t_start = None
+        for a in range(warmup + steps):
+            if a == warmup:
+                t_start = time.perf_counter()
+            for env in envs:
+                env.step(rng.uniform(-1, 1, 1))
+        return time.perf_counter() - t_start
+    import em_oracle as eo
     x = [np.ones(N_STATE) for _ in range(n_env)]
     # the reference pre-draws all increments at reset (stochastic.py:162-170); drawn here outside the timed part
     Ws = [np.sqrt(T_SSZ) * rng.standard_normal((total, N_STATE)) for _ in range(n_env)]
     ON = [0.01 * rng.standard_normal((total + 1, N_STATE)) for _ in range(n_env)]
-    w = np.ones(N_STATE)
     t_start = None
     for a in range(warmup + steps):
         if a == warmup:
@@ -70,41 +126,42 @@ def _cpu_worker(job):
     return time.perf_counter() - t_start
 
 
-def run_cpu_port(steps, warmup, budget_s=20.0):
+def run_cpu_arm(steps, warmup, budget_s=20.0):
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    per_env_step_s = K_SUB * 15e-6                      # ~15 us of Python per sub-step per env
+    use_ref = _ref_available()
+    per_env_step_s = K_SUB * (25e-6 if use_ref else 15e-6)      # ~15-25 us of Python per sub-step per env
     n_env = int(max(1, min(64, budget_s / max(1e-9, (steps + warmup) * per_env_step_s))))
     with mp.get_context("spawn").Pool(cores) as pool:
-        times = pool.map(_cpu_worker, [(w, n_env, steps, warmup) for w in range(cores)])
+        times = pool.map(_cpu_worker, [(w, n_env, steps, warmup, use_ref) for w in range(cores)])
     wall = max(times)
     value = cores * n_env * steps * K_SUB / wall
-    sample = (f"{cores} processes x {n_env} single envs x {steps} action intervals x {K_SUB} sub-steps "
-              f"(oracle port of LinearEnv: Python loop per env per sub-step)")
-    return value, cores, sample, wall
+    what = ("the UNMODIFIED reference quantrl.envs.stochastic.LinearEnv (NumPy backend, staged under oracle/_ref)" if use_ref else
+            "oracle port of LinearEnv: Python loop per env per sub-step")
+    sample = f"{cores} processes x {n_env} single envs x {steps} action intervals x {K_SUB} sub-steps ({what})"
+    return value, cores, sample, wall, ("reference" if use_ref else "port")
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, cores, sample, wall = run_cpu_port(args.steps, args.warmup)
+    value, cores, sample, wall, kind = run_cpu_arm(args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_gpu": E_PER_GPU, "n": N_STATE, "action_interval": K_SUB},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": base_config(),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# clocks sampler (NVML) during the timed region
+# clocks sampler (NVML) during the timed regions
 # ---------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    def __init__(self, index, period=0.01):
+    def __init__(self, index, period=0.002):
         self.samples, self.reasons, self._stop, self.max_mhz = [], set(), threading.Event(), None
         try:
             import pynvml
@@ -115,7 +172,7 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.nv = None
         self.period = period
-        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread = None
 
     def _run(self):
         nv = self.nv
@@ -133,13 +190,15 @@ class ClockSampler:
             time.sleep(self.period)
 
     def __enter__(self):
+        self._stop.clear()
         if self.nv is not None:
+            self.thread = threading.Thread(target=self._run, daemon=True)
             self.thread.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        if self.nv is not None:
+        if self.thread is not None:
             self.thread.join()
 
     def summary(self):
@@ -151,14 +210,240 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------------
-def make_env(rank, return_numpy, use_cuda_graph=True, host_zero_copy=True, host_output_views=False):
+def make_env(rank, return_numpy, use_cuda_graph=True, host_zero_copy=True, host_output_views=False, n_envs=E_PER_GPU,
+             n=N_STATE, episode=S_EPISODE, env_offset=None, seed=1, drift_seed=0):
+    from quantrl_b200.systems import AffineLinearVecEnv, affine_matrices
+    A0, Au = affine_matrices(n, 1, seed=drift_seed)
+    return AffineLinearVecEnv(
+        n_envs=n_envs, n=n, A0=A0, Au=Au, noise_prefixes=0.05, x0=1.0, t_norm_max=episode * T_SSZ + T_SSZ / 2,
+        t_norm_ssz=T_SSZ, action_interval=K_SUB, observation_stds=[0.01] * n, seed=seed, rng="philox",
+        env_offset=rank * n_envs if env_offset is None else env_offset, return_numpy=return_numpy,
+        use_cuda_graph=use_cuda_graph, fused_coefficients=True, data_idxs=[-1], host_zero_copy=host_zero_copy,
+        host_output_views=host_output_views, dir_prefix="/tmp/qrl_bench")
+
+
+def device_loop(env, peer, actions, n_steps):
+    """n_steps action intervals, everything resident in HBM; multi-GPU: the learner enqueues one gather per step."""
+    nb = actions.shape[0]
+    for i in range(n_steps):
+        if env.t_idx + 1 >= env.shape_T[0] or env.batch_idx < 0:
+            env.reset()
+        env.step_device(actions[i % nb])
+        if peer is not None and peer.is_learner:
+            peer.pull()
+    if peer is not None:
+        peer.wait()
+
+
+def time_device_loop(torch, dist, world, dev, env, peer, actions, steps, warmup, sampler=None):
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    device_loop(env, peer, actions, warmup)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def region():
+        barrier()
+        e0.record()
+        t_host0 = time.perf_counter()
+        device_loop(env, peer, actions, steps)
+        host_us = (time.perf_counter() - t_host0) * 1e6 / steps   # host time to ENQUEUE one step (no sync)
+        e1.record()
+        barrier()
+        return host_us
+    if sampler is not None:
+        with sampler:
+            host_us = region()
+    else:
+        host_us = region()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), host_us
+
+
+def kernel_time(torch, N, env_k, actions, K, n_launch=100, ring=0):
+    """The fused integration launch timed live with CUDA events on its stream: the argument block of one interval of an
+    eager twin env is enqueued back to back (launch cost < kernel time, so the device never idles).  ring > 0: the
+    trajectory blocks rotate over `ring` sets (> L2) instead of being rewritten in place."""
+    env_k.reset()
+    for i in range(3):
+        env_k.step_device(actions[i % actions.shape[0]])
+    env_k._set_actions(actions[3 % actions.shape[0]])
+    base, keep = env_k.interval_args(K)
+    blocks = [base]
+    for _ in range(max(0, ring - 1)):
+        st, ob = torch.empty_like(env_k._States), torch.empty_like(env_k._Observations)
+        rw = torch.empty_like(env_k._Reward)
+        b = N.EmArgs.from_buffer_copy(base)
+        b.states, b.observations, b.reward = st.data_ptr(), ob.data_ptr(), rw.data_ptr()
+        blocks.append(b)
+        keep += [st, ob, rw]
+    for i in range(10):
+        N.em_step(blocks[i % len(blocks)])
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for i in range(n_launch):
+        N.em_step(blocks[i % len(blocks)])
+    k1.record()
+    torch.cuda.synchronize()
+    return k0.elapsed_time(k1) / n_launch
+
+
+def verify_sharded(torch, dist, world, rank, dev, peer, actions, total_steps, n, n_envs, episode, drift_seed=0, seed=1):
+    """Untimed: rank 0 replays the whole run UNSHARDED (all world * n_envs environments in one launch per step, the same
+    actions) and compares the learner's gathered [obs | reward] of the LAST step with it, bit for bit."""
+    allact = torch.empty((world,) + tuple(actions.shape), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(allact.view(-1), actions.contiguous().view(-1))
+    ok = None
+    if rank == 0:
+        peer.check()
+        full = make_env(0, return_numpy=False, n_envs=world * n_envs, n=n, episode=episode, env_offset=0, seed=seed,
+                        drift_seed=drift_seed)
+        glob = allact.permute(1, 0, 2, 3).reshape(actions.shape[0], world * n_envs, 1).contiguous()
+        device_loop(full, None, glob, total_steps)
+        torch.cuda.synchronize()
+        ok = bool(torch.equal(peer.obs_all, full._obs_last) and torch.equal(peer.reward_all, full._reward_last))
+        full.close()
+        del full
+    if world > 1:
+        dist.barrier()
+    return ok
+
+
+def bench_config4(torch, dist, N, world, rank, dev, args, clocks):
+    """BASELINE config 4: 65536 stochastic envs with an 8x8 drift, STRONG scaling (65536 / world envs per rank)."""
+    E = E_C4 // world
+    env = make_env(rank, return_numpy=False, n_envs=E, n=N_C4, episode=S_C4, seed=4, drift_seed=4)
+    gen = torch.Generator(device=dev).manual_seed(40 + rank)
+    actions = torch.rand((16, E, 1), generator=gen, device=dev, dtype=torch.float64) * 2 - 1
+    peer = None
+    if world > 1:
+        from quantrl_b200.distributed import PeerGather
+        peer = PeerGather(E_C4, N_C4, dev, dst=0)
+        peer.attach(env)
+    steps, warmup = max(10, min(args.steps, 200)), 5
+    ms, host_us = time_device_loop(torch, dist, world, dev, env, peer, actions, steps, warmup, clocks)
+    res = {"workload": "BASELINE config 4: 65536 stochastic linear envs (n=8, 8x8 drift A0+u*A1), K=100, S=1000, FP64, sharded "
+                       f"over {world} GPU(s) ({E} envs each)", "scaling": "strong", "steps": steps,
+           "value": E_C4 * K_SUB * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps}
+    if world > 1:
+        res["sharded_equals_unsharded"] = verify_sharded(torch, dist, world, rank, dev, peer, actions, warmup + steps, N_C4, E,
+                                                         S_C4, drift_seed=4, seed=4)
+    env_k = make_env(rank, return_numpy=False, use_cuda_graph=False, n_envs=E, n=N_C4, episode=S_C4, seed=4, drift_seed=4)
+    k_ms = kernel_time(torch, N, env_k, actions, K_SUB, n_launch=30)
+    env_k.close()
+    env.close()
+    bytes_per = 8 * (2 * N_C4 + 1) + 8
+    res.update(kernel_ms=k_ms, kernel="em_tile3_kernel<8,4> (qrl_em_step)" if E * N_C4 <= 524288 else "em_step_kernel<8> + pack_rows_kernel",
+               algorithmic_bytes_per_substep=bytes_per, achieved_gbs=bytes_per * E * K_SUB / (k_ms * 1e-3) / 1e9)
+    return res
+
+
+def bench_config2(torch, N, dev, args):
+    """BASELINE config 2: 1024 deterministic optomechanical envs (m=2, q=4, d=20), RK4, 100 sub-steps per action, through
+    LinearizedHOVecEnv.step(host actions) -> host obs, reward; device time of the integration launch beside it."""
+    import numpy as np
+    from quantrl_b200.envs.deterministic import LinearizedHOVecEnv
+    rng = np.random.default_rng(2)
+    E, K = E_C2, K_SUB
+    # canonical optomechanical system of SURVEY.md §8d: [kappa, gamma, omega_m, Delta0, g0, n_th, A_l], Delta0 jittered per env
+    p = np.tile(np.array([0.1, 1e-3, 1.0, -1.0, 1e-2, 10.0, 5.0]), (E, 1))
+    p[:, 3] = rng.uniform(-1.2, -0.8, E)
+    y0 = np.zeros((E, 20))
+    y0[:, 4 + 0], y0[:, 4 + 5], y0[:, 4 + 10], y0[:, 4 + 15] = 0.5, 0.5, 10.5, 10.5
+
+    class Env(LinearizedHOVecEnv):
+        def reset_states(self):
+            return torch.as_tensor(y0, device=dev)
+
+    S = 100 * K
+    env = Env(name="optomech", desc="config 2", params={}, num_modes=2, num_quads=4, t_norm_max=S * T_SSZ + T_SSZ / 2,
+              t_norm_ssz=T_SSZ, t_norm_mul=1.0, n_envs=E, n_observations=20, n_properties=0, n_actions=1,
+              action_maximums=[1.0], action_interval=K, data_idxs=[-1], cache_all_data=False, dir_prefix="/tmp/qrl_bench_lho",
+              ode_method="rk4", system="optomech", system_params=p, return_numpy=True, reward_functor="entan_ln_obs")
+    env.reset()
+    acts = [rng.uniform(-1, 1, (E, 1)) for _ in range(8)]
+    steps = max(10, min(args.steps, 90))
+    for i in range(5):
+        env.step(acts[i % 8])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        env.step(acts[i % 8])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    # device time of the integration launch alone (CUDA events around back-to-back updates without the host round trip)
+    a_dev = torch.as_tensor(acts[0], device=dev)
+    env.reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    env._set_actions(a_dev)
+    for _ in range(3):
+        env.update()
+    torch.cuda.synchronize()
+    n_k = 30
+    e0.record()
+    for _ in range(n_k):
+        env.update()
+    e1.record()
+    torch.cuda.synchronize()
+    k_ms = e0.elapsed_time(e1) / n_k
+    env.close()
+    return {"workload": "BASELINE config 2: 1024 deterministic linearized optomechanical envs (m=2, q=4, d=20), RK4, 100 sub-steps "
+                        "per action, FP64, fused log-negativity reward, one GPU",
+            "api": "LinearizedHOVecEnv.step(host actions) -> host obs, reward", "steps": steps,
+            "e2e": {"value": E * K * steps / dt, "unit": UNIT, "us_per_step": dt / steps * 1e6},
+            "kernel_ms": k_ms, "kernel": "rk4_split_kernel<SysOptomech,8> (qrl_ode_step)", "value": E * K / (k_ms * 1e-3), "unit": UNIT,
+            "algorithmic_bytes_per_substep": 328, "achieved_gbs": 328 * E * K / (k_ms * 1e-3) / 1e9}
+
+
+def bench_config5(torch, dist, world, rank, dev, args):
+    """BASELINE config 5: PPO on 8192 stochastic envs, rollouts on the device; with several ranks the envs are sharded and
+    observations / rewards are gathered to the learner rank every step (ShardedVecEnv)."""
+    from quantrl_b200.distributed import ShardedVecEnv, make_sharded_env
+    from quantrl_b200.learner import PPO
     from quantrl_b200.systems import AffineLinearVecEnv, affine_matrices
     A0, Au = affine_matrices(N_STATE, 1, seed=0)
-    return AffineLinearVecEnv(
-        n_envs=E_PER_GPU, n=N_STATE, A0=A0, Au=Au, noise_prefixes=0.05, x0=1.0, t_norm_max=S_EPISODE * T_SSZ + T_SSZ / 2,
-        t_norm_ssz=T_SSZ, action_interval=K_SUB, observation_stds=[0.01] * N_STATE, seed=1, rng="philox",
-        env_offset=rank * E_PER_GPU, return_numpy=return_numpy, use_cuda_graph=use_cuda_graph, fused_coefficients=True, data_idxs=[-1],
-        host_zero_copy=host_zero_copy, host_output_views=host_output_views, dir_prefix="/tmp/qrl_bench")
+    kw = dict(n=N_STATE, A0=A0, Au=3.0 * Au, noise_prefixes=0.05, x0=1.0, t_norm_max=1000 * T_SSZ + T_SSZ / 2, t_norm_ssz=T_SSZ,
+              action_interval=K_SUB, observation_stds=[0.01] * N_STATE, seed=1, data_idxs=[-1], dir_prefix="/tmp/qrl_bench_ppo")
+    iters = 3
+    if world == 1:
+        env = AffineLinearVecEnv(n_envs=E_C5, use_cuda_graph=True, fused_coefficients=True, **kw)
+        ppo = PPO(env, lr=1e-3, epochs=4, minibatches=4)
+        ppo.learn(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        hist = ppo.learn(iters)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        n_steps = ppo.n_steps
+        env.close()
+    else:
+        local = make_sharded_env(AffineLinearVecEnv, E_C5, **kw)
+        senv = ShardedVecEnv(local, E_C5, dst=0)
+        hist, dt, n_steps = None, None, local.action_steps
+        if senv.is_learner:
+            ppo = PPO(senv, lr=1e-3, epochs=4, minibatches=4)
+            ppo.learn(1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            hist = ppo.learn(iters)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            senv.shutdown()
+        else:
+            senv.serve()
+        senv.close()
+        dist.barrier()
+    if rank != 0:
+        return None
+    return {"workload": f"BASELINE config 5: PPO (on-device torch learner) on 8192 stochastic linear envs (n=4), K=100, S=1000, "
+                        f"{iters} iterations x {n_steps} action steps, envs sharded over {world} GPU(s), obs/reward gathered to the learner",
+            "value": iters * n_steps * E_C5 * K_SUB / dt, "unit": UNIT, "includes": "policy inference, the gathers and the PPO updates",
+            "seconds": dt, "mean_step_reward": [h["mean_step_reward"] for h in hist]}
 
 
 def main():
@@ -168,10 +453,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl", "none"],
-                    help="multi-GPU: obs|reward reach the learner through peer stores fused into the kernel epilogue "
-                         "(p2p, default; falls back to nccl if symmetric memory is unavailable), an NCCL all_gather, or "
-                         "none: independent shards without the per-step learner exchange (the upper bound of weak scaling)")
+    ap.add_argument("--only-headline", action="store_true", help="skip the c2 / c4 / c5 sub-results (profiling runs)")
+    ap.add_argument("--gather", default="peer", choices=["peer", "none"],
+                    help="multi-GPU: learner gather of obs|reward per step through the publish / pull exchange (default), or "
+                         "none: independent shards (the upper bound of weak scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -196,124 +481,87 @@ def main():
 
     env = make_env(rank, return_numpy=False)
     E, n, K = env.n_envs, env.n_observations, env.action_interval
-    steps_per_episode = env.action_steps
     gen = torch.Generator(device=dev).manual_seed(3 + rank)
-    n_act_bufs = 64
-    actions_dev = torch.rand((n_act_bufs, E, 1), generator=gen, device=dev, dtype=torch.float64) * 2 - 1
-    gathered = [torch.empty((world, E, n + 1), dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else None
-    local_or = torch.empty((E, n + 1), dtype=torch.float64, device=dev)
-    peer, gather_mode = None, "none"
-    if world > 1:
-        gather_mode = args.gather
-        if args.gather == "p2p":
-            try:
-                from quantrl_b200.distributed import PeerGather
-                peer = PeerGather(world * E, n, dev, dst=0)
-                peer.attach(env)
-            except Exception as exc:  # noqa: BLE001
-                if rank == 0:
-                    print(f"[bench] symmetric memory unavailable ({exc!r}); using the NCCL all_gather", file=sys.stderr)
-                peer, gather_mode = None, "nccl"
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def run_device(n_steps):
-        """n_steps action intervals, everything resident in HBM; multi-GPU: obs|reward all-gathered every step."""
-        pending = []
-        for i in range(n_steps):
-            if env.t_idx + 1 >= env.shape_T[0] or env.batch_idx < 0:
-                env.reset()
-            obs, rew, _ = env.step_device(actions_dev[i % n_act_bufs])
-            if peer is not None:
-                peer.fence()     # the kernel epilogue already stored this rank's slice into the learner's buffer
-            elif world > 1 and gather_mode != "none":
-                local_or[:, :n].copy_(obs)
-                local_or[:, n].copy_(rew)
-                pending.append(dist.all_gather_into_tensor(gathered[i % 2].view(-1), local_or.view(-1), async_op=True))
-                if len(pending) > 1:
-                    pending.pop(0).wait()
-        for p in pending:
-            p.wait()
+    actions_dev = torch.rand((64, E, 1), generator=gen, device=dev, dtype=torch.float64) * 2 - 1
+    peer = None
+    if world > 1 and args.gather == "peer":
+        from quantrl_b200.distributed import PeerGather
+        peer = PeerGather(world * E, n, dev, dst=0)
+        peer.attach(env)
 
     # ---- value: device-resident ----
-    run_device(args.warmup)
-    barrier()
-    launches0, replays0 = N.launch_count(), env.graph_replays
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        barrier()
-        e0.record()
-        t_host0 = time.perf_counter()
-        run_device(args.steps)
-        host_enqueue_us = (time.perf_counter() - t_host0) * 1e6 / args.steps   # host time to ENQUEUE one step (no sync)
-        e1.record()
-        barrier()
-    ms = e0.elapsed_time(e1)
-    print(f"[bench] rank {rank}: host enqueue {host_enqueue_us:.1f} us/step, device {ms * 1e3 / args.steps:.1f} us/step",
+    clocks = ClockSampler(local)
+    launches0 = N.launch_count()
+    ms_max, host_enqueue_us = time_device_loop(torch, dist, world, dev, env, peer, actions_dev, args.steps, args.warmup, clocks)
+    print(f"[bench] rank {rank}: host enqueue {host_enqueue_us:.1f} us/step, device {ms_max * 1e3 / args.steps:.1f} us/step (max over ranks)",
           file=sys.stderr)
-    if peer is not None:
-        # not timed: the learner's peer-written buffer must equal an NCCL all_gather of every rank's local last rows
-        ref = torch.empty((world, E, n), dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(ref.view(-1), env.Observations[-1].contiguous().view(-1))
-        torch.cuda.synchronize()
-        if rank == 0:
-            assert torch.equal(peer.obs_all.view(world, E, n), ref), "peer-stored observations differ from the NCCL gather"
-    # kernels of libquantrl_b200.so launched in the timed region: eager launches + graph replays x kernels per graph
-    launches = (N.launch_count() - launches0) + (env.graph_replays - replays0) * env.graph_native_launches
-
-    # dominant kernel (the fused integration launch) timed live with CUDA events on its stream: the argument block of
-    # one interval of an identical env is enqueued back to back (launch cost < kernel time, so the device never idles;
-    # timing single launches of the eager env instead measures a cold, down-clocked GPU between Python steps)
-    env_k = make_env(rank, return_numpy=False, use_cuda_graph=False)
-    env_k.reset()
-    for i in range(3):
-        env_k.step_device(actions_dev[i % n_act_bufs])
-    env_k._set_actions(actions_dev[3])
-    k_args, k_keep = env_k.interval_args(K)
-    n_k = 100
-    for _ in range(10):
-        N.em_step(k_args)
-    torch.cuda.synchronize()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for _ in range(n_k):
-        N.em_step(k_args)
-    k1.record()
-    torch.cuda.synchronize()
-    em_ms = k0.elapsed_time(k1) / n_k
-    del env_k
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    # kernels of libquantrl_b200.so launched by this rank since the warm-up began, scaled to the timed region
+    launches = int(round((N.launch_count() - launches0) * args.steps / (args.steps + args.warmup)))
     value = world * E * K * args.steps / (ms_max * 1e-3)
+    sharded_ok = None
+    if peer is not None:
+        sharded_ok = verify_sharded(torch, dist, world, rank, dev, peer, actions_dev, args.warmup + args.steps, n, E, S_EPISODE)
+        if rank == 0:
+            assert sharded_ok, "the learner's gathered [obs | reward] differs from the unsharded replay"
+
+    # dominant kernel (the fused integration launch) timed live with CUDA events on its stream, in place and over a ring
+    env_k = make_env(rank, return_numpy=False, use_cuda_graph=False)
+    with clocks:
+        em_ms = kernel_time(torch, N, env_k, actions_dev, K)
+        em_ring_ms = kernel_time(torch, N, env_k, actions_dev, K, ring=8)
+    env_k.close()
+    del env_k
 
     # ---- e2e: public VecEnv API, host actions in, host obs/reward out, every step ----
-    # (multi-GPU: the learner gather below reads the device-side last rows, so the results take the copy-node route)
-    env2 = make_env(rank, return_numpy=True, host_zero_copy=(world == 1), host_output_views=True)
+    env2 = make_env(rank, return_numpy=True, host_zero_copy=True, host_output_views=True)
+    peer2 = None
+    if peer is not None:
+        peer2 = PeerGather(world * E, n, dev, dst=0)
+        peer2.attach(env2)
     host_actions = [np.random.default_rng(5 + rank).uniform(-1, 1, (E, 1)) for _ in range(8)]
     env2.reset()
     e2e_steps = max(10, min(args.steps, 300))
-    for i in range(args.warmup):
-        env2.step(host_actions[i % 8])
-    barrier()
+
+    def e2e_loop(n_steps):
+        for i in range(n_steps):
+            env2.step(host_actions[i % 8])
+            if peer2 is not None and peer2.is_learner:   # the learner also waits for every rank's rows of this step
+                peer2.pull()
+                peer2.side.synchronize()
+    e2e_loop(args.warmup)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        obs_h, rew_h, done, _ = env2.step(host_actions[i % 8])
-        if world > 1:  # learner-rank gather of the host-visible result
-            local_or[:, :n].copy_(env2._obs_last)
-            local_or[:, n].copy_(env2._reward_last)
-            dist.all_gather_into_tensor(gathered[0].view(-1), local_or.view(-1))
+    e2e_loop(e2e_steps)
     torch.cuda.synchronize()
     e2e_ms = 1e3 * (time.perf_counter() - t0)   # wall clock: every step already ends with a host sync
-    barrier()
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
+        dist.barrier()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * E * K * e2e_steps / (float(t.item()) * 1e-3)
+    zero_copy = bool(getattr(env2, "_zc", None))
+    if peer2 is not None:
+        peer2.check()
+    env2.close()
+    env.close()
+
+    # ---- the other BASELINE configs, in the same line ----
+    configs = {}
+    if not args.only_headline:
+        for name, fn in (("c4", lambda: bench_config4(torch, dist, N, world, rank, dev, args, clocks)),
+                         ("c2", (lambda: bench_config2(torch, N, dev, args)) if world == 1 else None),
+                         ("c5", lambda: bench_config5(torch, dist, world, rank, dev, args))):
+            if fn is None:
+                configs[name] = {"skipped": "single-GPU config: measured at N = 1 only"}
+                continue
+            try:
+                configs[name] = fn()
+            except Exception as exc:  # noqa: BLE001  (a sub-result must not lose the headline line)
+                configs[name] = {"error": repr(exc)[:300]}
+                if world > 1:
+                    raise
 
     if rank == 0:
         peaks = {}
@@ -328,47 +576,55 @@ def main():
         alg_bytes = bytes_per_substep * E * K
         achieved = alg_bytes / (em_ms * 1e-3) / 1e9
         fp64_peak = N.measure_fp64_peak(8192)
-        traffic, traffic_src = None, None
-        try:   # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture (profiles/)
+        traffic, traffic_ring, traffic_src = None, None, None
+        try:   # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` captures (profiles/)
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))   # written by tools/summarize_profiles.py
             traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["capture"]
+            traffic_ring = tj.get("traffic_bytes_per_launch_ring")
         except Exception:  # noqa: BLE001
             pass
+        for c in configs.values():
+            if isinstance(c, dict) and "achieved_gbs" in c:
+                c["roofline_frac"] = c["achieved_gbs"] / hbm_peak
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": E, "n": n, "action_interval": K,
-                       "rng": "philox4x32-10 in-kernel", "trajectory": "States+Observations+Reward blocks kept on device; data cache column data_idxs=[-1] (cumulative reward) "
-                                     "written by the same launch into a device-resident (E, shape_T, 1) episode cache",
-                       "l2": "inputs per step are < 1 MB (no reuse to exploit); the 33 MB of trajectory rows per step are rewritten "
-                             "every step and stay L2-resident (126 MB L2), the episode cache (655 MB) streams to HBM", "parallelism": f"env-sharded dp{world}",
-                       "collective": {"none": "none (independent shards, no learner exchange)" if world > 1 else "none",
-                                      "nccl": "all_gather(obs|reward) per step (NCCL, async)",
-                                      "p2p": "obs|reward stored into the learner rank's buffer over NVLink by the kernel "
-                                             "epilogue; the per-step cross-GPU barrier is fused into the same kernel's last block "
-                                             "(no collective or barrier launch)"}[gather_mode]},
+            "dtype": "f64", "data": "synthetic", "config": base_config(),
+            "details": {"rng": "philox4x32-10 in-kernel", "trajectory": "States+Observations+Reward blocks kept on device; data cache column "
+                        "data_idxs=[-1] (cumulative reward) written by the same launch into a device-resident (E, shape_T, 1) episode cache",
+                        "l2": "inputs per step are < 1 MB (no reuse to exploit); the 33 MB of trajectory rows per step are rewritten in place "
+                              "every step and stay L2-resident (126 MB L2) — roofline.l2_ring is the same launch over 8 sets of blocks (> L2)",
+                        "parallelism": f"env-sharded dp{world}",
+                        "collective": ("none" if world == 1 else "none (independent shards, no learner exchange)" if peer is None else
+                                       "publish / pull: every rank keeps obs|reward of a step in a ring of its own memory and stores one "
+                                       "epoch flag into the learner's memory; the learner gathers the slices over NVLink with "
+                                       "qrl_peer_pull on a side stream (no collective, no barrier; 3-slice credit flow control)"),
+                        "sharded_equals_unsharded": sharded_ok, "host_enqueue_us_per_step": host_enqueue_us},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * 1 * 8, "d2h_bytes_per_step": (E * (n + 1) + 4) * 8,
-                    "steps": e2e_steps, "api": "AffineLinearVecEnv.step(host actions) -> host obs, reward",
+                    "steps": e2e_steps, "api": "AffineLinearVecEnv.step(host actions) -> host obs, reward"
+                    + (" on every rank + learner gather of all ranks' rows, waited for every step" if world > 1 else ""),
                     "transport": ("zero-copy: the step kernel reads the actions from and writes obs|reward|min,max to pinned host "
                                   "memory over PCIe inside the launch; step() returns NumPy views of that (double buffered) "
-                                  "pinned memory, valid until the end of the next step" if getattr(env2, "_zc", None) else
+                                  "pinned memory, valid until the end of the next step" if zero_copy else
                                   "H2D / D2H copy nodes from / to pinned host memory around the step kernel")},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "em_tile_kernel<4> (qrl_em_step)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "em_tile3_kernel<4,2> (qrl_em_step)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                          "algorithmic_bytes_per_substep": bytes_per_substep, "kernel_ms": em_ms,
                          # kernel_ms: launches serialised by the stream (no programmatic dependent launch); in the timed loop
                          # the next kernel's prologue overlaps the previous kernel's tail, so a step can be shorter
                          "kernel_share_of_step": min(1.0, em_ms / (ms_max / args.steps)),
+                         "l2_ring": {"sets": 8, "kernel_ms": em_ring_ms, "achieved": alg_bytes / (em_ring_ms * 1e-3) / 1e9,
+                                     "frac": alg_bytes / (em_ring_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic_ring},
                          "fp64_peak_tflops_measured": fp64_peak,
                          "fp64_algorithmic_frac": (2 * n * n + 5 * n) * E * K / (em_ms * 1e-3) / 1e12 / fp64_peak},
+            "configs": configs,
         }
         if not args.no_cpu_baseline and world == 1:
-            v, cores, sample, _ = run_cpu_port(steps=20, warmup=2, budget_s=15.0)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            v, cores, sample, _, kind = run_cpu_arm(steps=20, warmup=2, budget_s=15.0)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()

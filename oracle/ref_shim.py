@@ -8,18 +8,35 @@ then imports the reference from ``/root/reference``.  No reference arithmetic is
 through this shim comes from the reference's own code + NumPy/SciPy.
 
 It is used by ``oracle/make_golden.py`` (run in the build container, where /root/reference exists) to create the
-fixtures under ``tests/golden/``.  Nothing that runs on the GPU box imports this file's ``load()`` successfully
-(/root/reference does not exist there) and nothing in the product package imports it at all.
+fixtures under ``tests/golden/``, and — through the staged copy ``oracle/_ref/`` that ``oracle/stage_ref.py`` makes
+(git-ignored, built like a compiled reference would be, shipped to the GPU box) — by the ``-m gpu`` test that runs the
+reference's OWN env class on the ``'b200'`` backend and by ``bench.py --impl reference`` (the reference's own
+``LinearEnv`` timed on the host cores).  Nothing in the product package imports it.
 """
 import os
 import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("QRL_REFERENCE_ROOT", "/root/reference")
+# the staged copy of the reference package (oracle/stage_ref.py -> oracle/_ref/, git-ignored, travels to the GPU box)
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "quantrl"))
+
+
+def staged_available() -> bool:
+    return os.path.isdir(os.path.join(STAGED_ROOT, "quantrl"))
+
+
+def import_reference(root=None):
+    """Import the reference from ``root`` (default: /root/reference if present, else the staged copy oracle/_ref)."""
+    global REFERENCE_ROOT
+    if root is None:
+        root = REFERENCE_ROOT if available() else STAGED_ROOT
+    REFERENCE_ROOT = root
+    return load()
 
 
 def _stub(name, **attrs):

@@ -283,12 +283,10 @@ class LinearVecEnv(BaseVecEnv):
 
     def _peer_patch(self, a, host_io):
         """Per-launch part of the publish-only exchange: the ring slice of this epoch, its number, the credit it needs."""
-        e, obs_ptr, rew_ptr, pulled_min, obs_v, rew_v = self._peer.next_launch()
-        if host_io:     # the primary outputs go to (pinned) host memory for step(); the ring gets the second copy
-            a.obs_last_b, a.reward_last_b = obs_ptr, rew_ptr
-        else:
-            a.obs_last, a.reward_last = obs_ptr, rew_ptr
-            self._obs_last, self._reward_last = obs_v, rew_v
+        e, obs_ptr, rew_ptr, pulled_min, _, _ = self._peer.next_launch()
+        # the ring gets the second copy of the last rows; the primary outputs stay where step() / step_device() read them
+        # (the env's own buffer, or pinned host memory), so reset launches and host fetches never touch a published slice
+        a.obs_last_b, a.reward_last_b = obs_ptr, rew_ptr
         a.peer_publish_value, a.peer_pulled_min = e, pulled_min
 
     def attach_peer_barrier(self, flag_ptrs, epoch, rank, world):

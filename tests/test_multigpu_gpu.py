@@ -93,7 +93,7 @@ def test_sharded_envs_and_peer_gather_match_single_gpu(native):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted(out.get(timeout=300) for _ in procs)
+    res = sorted(out.get(timeout=120) for _ in procs)
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, "ok"), (1, "ok")], res
