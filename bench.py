@@ -161,7 +161,7 @@ def reference_arm(args):
 # clocks sampler (NVML) during the timed regions
 # ---------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    def __init__(self, index, period=0.002):
+    def __init__(self, index, period=0.01):
         self.samples, self.reasons, self._stop, self.max_mhz = [], set(), threading.Event(), None
         try:
             import pynvml
@@ -230,7 +230,7 @@ def device_loop(env, peer, actions, n_steps):
             env.reset()
         env.step_device(actions[i % nb])
         if peer is not None and peer.is_learner:
-            peer.pull()
+            peer.gather()
     if peer is not None:
         peer.wait()
 
@@ -293,9 +293,10 @@ def kernel_time(torch, N, env_k, actions, K, n_launch=100, ring=0):
     return k0.elapsed_time(k1) / n_launch
 
 
-def verify_sharded(torch, dist, world, rank, dev, peer, actions, total_steps, n, n_envs, episode, drift_seed=0, seed=1):
+def verify_sharded(torch, dist, world, rank, dev, peer, actions, segments, n, n_envs, episode, drift_seed=0, seed=1):
     """Untimed: rank 0 replays the whole run UNSHARDED (all world * n_envs environments in one launch per step, the same
-    actions) and compares the learner's gathered [obs | reward] of the LAST step with it, bit for bit."""
+    actions in the same order: `segments` = the step counts of the device_loop calls made so far) and compares the
+    learner's gathered [obs | reward] of the LAST step with it, bit for bit."""
     allact = torch.empty((world,) + tuple(actions.shape), dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(allact.view(-1), actions.contiguous().view(-1))
     ok = None
@@ -304,7 +305,8 @@ def verify_sharded(torch, dist, world, rank, dev, peer, actions, total_steps, n,
         full = make_env(0, return_numpy=False, n_envs=world * n_envs, n=n, episode=episode, env_offset=0, seed=seed,
                         drift_seed=drift_seed)
         glob = allact.permute(1, 0, 2, 3).reshape(actions.shape[0], world * n_envs, 1).contiguous()
-        device_loop(full, None, glob, total_steps)
+        for seg in segments:
+            device_loop(full, None, glob, seg)
         torch.cuda.synchronize()
         ok = bool(torch.equal(peer.obs_all, full._obs_last) and torch.equal(peer.reward_all, full._reward_last))
         full.close()
@@ -323,7 +325,7 @@ def bench_config4(torch, dist, N, world, rank, dev, args, clocks):
     peer = None
     if world > 1:
         from quantrl_b200.distributed import PeerGather
-        peer = PeerGather(E_C4, N_C4, dev, dst=0)
+        peer = PeerGather(E_C4, N_C4, dev, dst=0, mode=args.gather if args.gather != "none" else "push")
         peer.attach(env)
     steps, warmup = max(10, min(args.steps, 200)), 5
     ms, host_us = time_device_loop(torch, dist, world, dev, env, peer, actions, steps, warmup, clocks)
@@ -331,7 +333,7 @@ def bench_config4(torch, dist, N, world, rank, dev, args, clocks):
                        f"over {world} GPU(s) ({E} envs each)", "scaling": "strong", "steps": steps,
            "value": E_C4 * K_SUB * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps}
     if world > 1:
-        res["sharded_equals_unsharded"] = verify_sharded(torch, dist, world, rank, dev, peer, actions, warmup + steps, N_C4, E,
+        res["sharded_equals_unsharded"] = verify_sharded(torch, dist, world, rank, dev, peer, actions, (warmup, steps), N_C4, E,
                                                          S_C4, drift_seed=4, seed=4)
     env_k = make_env(rank, return_numpy=False, use_cuda_graph=False, n_envs=E, n=N_C4, episode=S_C4, seed=4, drift_seed=4)
     k_ms = kernel_time(torch, N, env_k, actions, K_SUB, n_launch=30)
@@ -454,9 +456,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only-headline", action="store_true", help="skip the c2 / c4 / c5 sub-results (profiling runs)")
-    ap.add_argument("--gather", default="peer", choices=["peer", "none"],
-                    help="multi-GPU: learner gather of obs|reward per step through the publish / pull exchange (default), or "
-                         "none: independent shards (the upper bound of weak scaling)")
+    ap.add_argument("--gather", default="push", choices=["push", "pull", "none"],
+                    help="multi-GPU: learner gather of obs|reward per step — push: every rank's copy engine moves its rows into the "
+                         "learner's block behind each step (default); pull: epoch flag stored by the step kernel + gather kernel "
+                         "on the learner; none: independent shards (the upper bound of weak scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -484,9 +487,9 @@ def main():
     gen = torch.Generator(device=dev).manual_seed(3 + rank)
     actions_dev = torch.rand((64, E, 1), generator=gen, device=dev, dtype=torch.float64) * 2 - 1
     peer = None
-    if world > 1 and args.gather == "peer":
+    if world > 1 and args.gather != "none":
         from quantrl_b200.distributed import PeerGather
-        peer = PeerGather(world * E, n, dev, dst=0)
+        peer = PeerGather(world * E, n, dev, dst=0, mode=args.gather)
         peer.attach(env)
 
     # ---- value: device-resident ----
@@ -500,7 +503,7 @@ def main():
     value = world * E * K * args.steps / (ms_max * 1e-3)
     sharded_ok = None
     if peer is not None:
-        sharded_ok = verify_sharded(torch, dist, world, rank, dev, peer, actions_dev, args.warmup + args.steps, n, E, S_EPISODE)
+        sharded_ok = verify_sharded(torch, dist, world, rank, dev, peer, actions_dev, (args.warmup, args.steps), n, E, S_EPISODE)
         if rank == 0:
             assert sharded_ok, "the learner's gathered [obs | reward] differs from the unsharded replay"
 
@@ -516,7 +519,7 @@ def main():
     env2 = make_env(rank, return_numpy=True, host_zero_copy=True, host_output_views=True)
     peer2 = None
     if peer is not None:
-        peer2 = PeerGather(world * E, n, dev, dst=0)
+        peer2 = PeerGather(world * E, n, dev, dst=0, mode=args.gather)
         peer2.attach(env2)
     host_actions = [np.random.default_rng(5 + rank).uniform(-1, 1, (E, 1)) for _ in range(8)]
     env2.reset()
@@ -526,8 +529,9 @@ def main():
         for i in range(n_steps):
             env2.step(host_actions[i % 8])
             if peer2 is not None and peer2.is_learner:   # the learner also waits for every rank's rows of this step
-                peer2.pull()
-                peer2.side.synchronize()
+                peer2.gather()
+                peer2.wait()
+                torch.cuda.current_stream().synchronize()
     e2e_loop(args.warmup)
     if world > 1:
         dist.barrier()
@@ -596,9 +600,12 @@ def main():
                               "every step and stay L2-resident (126 MB L2) — roofline.l2_ring is the same launch over 8 sets of blocks (> L2)",
                         "parallelism": f"env-sharded dp{world}",
                         "collective": ("none" if world == 1 else "none (independent shards, no learner exchange)" if peer is None else
-                                       "publish / pull: every rank keeps obs|reward of a step in a ring of its own memory and stores one "
-                                       "epoch flag into the learner's memory; the learner gathers the slices over NVLink with "
-                                       "qrl_peer_pull on a side stream (no collective, no barrier; 3-slice credit flow control)"),
+                                       "push: every rank keeps obs|reward of a step in a ring of its own memory; behind each step launch its "
+                                       "copy engine moves the slice into the learner's (double buffered) block over NVLink and stores an "
+                                       "epoch word (events + cudaMemcpyAsync on a side stream: no collective, no barrier, no SM)"
+                                       if peer.mode == "push" else
+                                       "pull: the step kernel's last block stores an epoch flag into the learner's memory; the learner "
+                                       "gathers the slices over NVLink with qrl_peer_pull on a side stream (credit flow control)"),
                         "sharded_equals_unsharded": sharded_ok, "host_enqueue_us_per_step": host_enqueue_us},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * 1 * 8, "d2h_bytes_per_step": (E * (n + 1) + 4) * 8,

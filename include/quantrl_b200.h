@@ -385,6 +385,36 @@ typedef struct qrl_peer_pull_args {
 QRL_API int qrl_peer_pull(const qrl_peer_pull_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Copy-engine variant of the same exchange (the default of the sharded path): nothing changes in the step kernel, no SM
+ * is involved.  After the step launch of epoch e on `main_stream` a rank calls qrl_peer_push, which enqueues
+ *   main_stream:  record(step_done)
+ *   side_stream:  wait(step_done); copy ring slice -> the learner's gathered block (peer-mapped, NVLink, copy engine);
+ *                 copy the 8-byte epoch word -> learner.flags[rank]; record(copy_done)
+ * so the transfer of step e overlaps step e+1 and the step stream never waits.  The epoch word follows the data on the
+ * same stream, so a flag value >= e means the slice of epoch e has landed.  The caller owns streams and events
+ * (cudaStream_t / cudaEvent_t passed as void*); before it reuses a ring slice it passes that slice's copy_done event to
+ * qrl_peer_event_wait (returns at once when the copy has finished — it always has, the ring being several steps deep).
+ * The learner waits for an epoch with qrl_peer_wait: one warp that polls flags[0..world) >= epoch on `stream`
+ * (~2 s time-out -> QRL_STATUS_PEER_TIMEOUT in *status).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct qrl_peer_push_args {
+    const void* src;          /* this rank's ring slice of the epoch (device): observations */
+    void*       dst;          /* this rank's slice of the learner's gathered block (peer-mapped device pointer) */
+    int64_t     bytes;
+    const void* src2;         /* second piece (rewards), or NULL */
+    void*       dst2;
+    int64_t     bytes2;
+    const void* flag_src;     /* 8-byte epoch word: pinned HOST memory written by the caller, or device memory */
+    void*       flag_dst;     /* learner.flags[rank] (peer-mapped device pointer) */
+    void*       step_done;    /* cudaEvent_t */
+    void*       copy_done;    /* cudaEvent_t */
+} qrl_peer_push_args;
+
+QRL_API int qrl_peer_push(const qrl_peer_push_args* args, void* main_stream, void* side_stream);
+QRL_API int qrl_peer_event_wait(void* event);   /* cudaEventSynchronize */
+QRL_API int qrl_peer_wait(const uint64_t* flags, int32_t world, uint64_t epoch, int32_t* status, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Machine-peak micro-benchmarks used as roofline denominators (synchronous; return the measurement).
  * ------------------------------------------------------------------------------------------------------------ */
 /* dependent-free DFMA stream on every SM: returns achieved FP64 TFLOP/s (FMA = 2 flop) in *tflops */

@@ -85,6 +85,12 @@ class PeerPullArgs(C.Structure):
     ]
 
 
+class PeerPushArgs(C.Structure):
+    _fields_ = [("src", _dp), ("dst", _dp), ("bytes", C.c_int64), ("src2", _dp), ("dst2", _dp), ("bytes2", C.c_int64),
+                ("flag_src", _dp), ("flag_dst", _dp),
+                ("step_done", _dp), ("copy_done", _dp)]
+
+
 # every symbol include/quantrl_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "qrl_abi_version": (C.c_int, []),
@@ -97,6 +103,9 @@ SYMBOLS = {
     "qrl_ode_step": (C.c_int, [C.POINTER(OdeArgs), C.c_void_p]),
     "qrl_pack_rows": (C.c_int, [C.POINTER(PackArgs), C.c_void_p]),
     "qrl_peer_pull": (C.c_int, [C.POINTER(PeerPullArgs), C.c_void_p]),
+    "qrl_peer_push": (C.c_int, [C.POINTER(PeerPushArgs), C.c_void_p, C.c_void_p]),
+    "qrl_peer_event_wait": (C.c_int, [C.c_void_p]),
+    "qrl_peer_wait": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p]),
     "qrl_measure_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "qrl_measure_fp64_latency": (C.c_int, [C.POINTER(C.c_double)]),
 }
@@ -166,6 +175,18 @@ def pack_rows(args: PackArgs, stream=None):
 
 def peer_pull(args: PeerPullArgs, stream=None):
     check(lib().qrl_peer_pull(C.byref(args), stream if stream is not None else current_stream()), "qrl_peer_pull")
+
+
+def peer_push(args: PeerPushArgs, main_stream, side_stream):
+    check(lib().qrl_peer_push(C.byref(args), main_stream, side_stream), "qrl_peer_push")
+
+
+def peer_event_wait(event):
+    check(lib().qrl_peer_event_wait(event), "qrl_peer_event_wait")
+
+
+def peer_wait(flags_ptr, world, epoch, status_ptr, stream=None):
+    check(lib().qrl_peer_wait(flags_ptr, world, epoch, status_ptr, stream if stream is not None else current_stream()), "qrl_peer_wait")
 
 
 def host_device_pointer(t) -> int:

@@ -13,9 +13,14 @@
 
 namespace qrl {
 
-constexpr int PULL_THREADS = 128;   // small on purpose: such a block is co-resident with a 768-thread step CTA (registers)
+// Small on purpose.  The gather of step i is enqueued right behind step i and polls while step i+1 already runs, so a
+// gather block must be CO-RESIDENT with a step CTA: em_tile3_kernel takes 768 threads x 80 registers = 61440 of the SM's
+// 65536 registers and ~200 KB of its shared memory, which leaves room for exactly 128 threads x 32 registers.  (A block
+// that does not fit waits for the step CTA to exit, the next step's CTA then waits for the gather, and the gather waits
+// for the other ranks: measured 50 instead of 27 us per step with 40 registers per thread.)
+constexpr int PULL_THREADS = 128;
 
-__global__ void __launch_bounds__(PULL_THREADS) peer_pull_kernel(const qrl_peer_pull_args a, const int bpr) {
+__global__ void __launch_bounds__(PULL_THREADS, 16) peer_pull_kernel(const qrl_peer_pull_args a, const int bpr) {
     const int p = blockIdx.x / bpr, b = blockIdx.x - p * bpr;
     const unsigned long long epoch = *a.pull_epoch + 1ull;
     __shared__ int s_ok;
@@ -23,9 +28,9 @@ __global__ void __launch_bounds__(PULL_THREADS) peer_pull_kernel(const qrl_peer_
         int ok = 1;
         const unsigned long long t0 = global_timer_ns();
         while (true) {
-            unsigned long long seen;
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.flags + p) : "memory");
-            if (seen >= epoch) break;
+            unsigned long long seen;       // relaxed polling (L2), one acquire fence once the epoch has arrived
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.flags + p) : "memory");
+            if (seen >= epoch) { __threadfence_system(); break; }
             if (global_timer_ns() - t0 > 2000000000ull) {   // a rank never published: fail loudly, do not hang
                 if (a.status) atomicOr(a.status, QRL_STATUS_PEER_TIMEOUT);
                 ok = 0;
@@ -75,7 +80,56 @@ __global__ void __launch_bounds__(PULL_THREADS) peer_pull_kernel(const qrl_peer_
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.peer_pulled[q]), "l"(epoch) : "memory");
 }
 
+// one warp: lane p polls flags[p] until it has reached `epoch`
+__global__ void __launch_bounds__(32) peer_wait_kernel(const uint64_t* flags, int world, unsigned long long epoch, int* status) {
+    const unsigned long long t0 = global_timer_ns();
+    for (int p = threadIdx.x; p < world; p += 32) {
+        while (true) {
+            unsigned long long seen;
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flags + p) : "memory");
+            if (seen >= epoch) break;
+            if (global_timer_ns() - t0 > 2000000000ull) {
+                if (status) atomicOr(status, QRL_STATUS_PEER_TIMEOUT);
+                break;
+            }
+            __nanosleep(100);
+        }
+    }
+    __threadfence_system();
+}
+
 }  // namespace qrl
+
+extern "C" int qrl_peer_push(const qrl_peer_push_args* args, void* main_stream, void* side_stream) {
+    using namespace qrl;
+    QRL_REQUIRE(args != nullptr, "qrl_peer_push: args is NULL");
+    const qrl_peer_push_args& a = *args;
+    QRL_REQUIRE(a.src && a.dst && a.bytes >= 0 && a.flag_src && a.flag_dst && a.step_done && a.copy_done,
+                "qrl_peer_push: NULL argument");
+    QRL_REQUIRE(main_stream != side_stream, "qrl_peer_push: the copies need a stream of their own");
+    cudaStream_t ms = (cudaStream_t)main_stream, ss = (cudaStream_t)side_stream;
+    QRL_CUDA(cudaEventRecord((cudaEvent_t)a.step_done, ms));
+    QRL_CUDA(cudaStreamWaitEvent(ss, (cudaEvent_t)a.step_done, 0));
+    if (a.bytes > 0) QRL_CUDA(cudaMemcpyAsync(a.dst, a.src, (size_t)a.bytes, cudaMemcpyDefault, ss));
+    if (a.src2 && a.dst2 && a.bytes2 > 0) QRL_CUDA(cudaMemcpyAsync(a.dst2, a.src2, (size_t)a.bytes2, cudaMemcpyDefault, ss));
+    QRL_CUDA(cudaMemcpyAsync(a.flag_dst, a.flag_src, 8, cudaMemcpyDefault, ss));
+    QRL_CUDA(cudaEventRecord((cudaEvent_t)a.copy_done, ss));
+    return 0;
+}
+
+extern "C" int qrl_peer_event_wait(void* event) {
+    using namespace qrl;
+    QRL_REQUIRE(event != nullptr, "qrl_peer_event_wait: event is NULL");
+    QRL_CUDA(cudaEventSynchronize((cudaEvent_t)event));
+    return 0;
+}
+
+extern "C" int qrl_peer_wait(const uint64_t* flags, int32_t world, uint64_t epoch, int32_t* status, void* stream) {
+    using namespace qrl;
+    QRL_REQUIRE(flags != nullptr && world >= 1, "qrl_peer_wait: bad arguments");
+    peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, world, (unsigned long long)epoch, status);
+    return after_launch("peer_wait_kernel");
+}
 
 extern "C" int qrl_peer_pull(const qrl_peer_pull_args* args, void* stream) {
     using namespace qrl;

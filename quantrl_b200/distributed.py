@@ -181,23 +181,30 @@ class PeerGather:
     """Gather-to-learner WITHOUT a collective launch and without a barrier (the one exchange step of the sharded path).
 
     Every rank keeps the last rows of an action step — ``[obs (E_loc, n) | reward (E_loc,)]`` — in its OWN memory, in a
-    ring of ``SLOTS`` slices of torch symmetric memory (mapped into the learner's process over NVLink); its step kernel
-    stores one epoch word into the learner's flag array when the slice is complete (``qrl_em_args``,
-    ``QRL_EM_PEER_PUBLISH``: device-scope fences per block, one system-scope release by the last block, nobody waits).
-    The learner gathers with ``pull()`` — ``qrl_peer_pull`` on a side stream, whose blocks poll the flags rank by rank
-    and copy the slices with 16-byte peer loads, so the gather of step ``i`` overlaps step ``i+1`` — and hands every rank
-    a credit (``pulled``) that lets it reuse the slice: a rank can run at most ``SLOTS`` steps ahead of the learner.
+    ring of ``SLOTS`` slices of torch symmetric memory; they reach the learner's gathered block
+    ``obs_all (E, n) | reward_all (E,)`` in one of two ways:
 
+    * ``mode='push'`` (default): copy engines.  After every integration launch the rank enqueues, on a side stream that
+      waits for that launch through an event, a peer-to-peer ``cudaMemcpyAsync`` of its slice into the learner's block
+      and an 8-byte epoch word into the learner's flag array (``qrl_peer_push``).  The step kernel is untouched, no SM is
+      involved, the transfer of step ``i`` overlaps step ``i+1``.  The learner's block is double buffered by epoch parity.
+    * ``mode='pull'``: kernels.  The step kernel's last block stores the epoch word itself (``QRL_EM_PEER_PUBLISH``) and the
+      learner runs ``qrl_peer_pull`` on a side stream, which polls the flags and copies the slices with 16-byte peer loads;
+      credits (``pulled``) let a rank reuse a slice.  (Kept as the measured comparison: a polling gather block has to be
+      co-resident with the next step's CTAs, which costs the learner a few microseconds per step.)
+
+    ``wait()`` on the learner makes the current stream wait until every rank's rows of the latest epoch have arrived.
     The NCCL path (``LearnerLink.gather_step``) stays as the fallback and as the measured comparison.
     """
 
-    SLOTS = 3
+    SLOTS = 4
 
-    def __init__(self, n_envs_total, n_observations, device, dst=0, group=None):
+    def __init__(self, n_envs_total, n_observations, device, dst=0, group=None, mode="push"):
+        import ctypes as C
         import torch.distributed._symmetric_memory as symm_mem
         from . import _native as N
-        assert dist.is_initialized()
-        self._N = N
+        assert dist.is_initialized() and mode in ("push", "pull")
+        self._N, self.mode = N, mode
         self.group = group if group is not None else dist.group.WORLD
         gname = self.group.group_name if hasattr(self.group, "group_name") else self.group
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
@@ -219,16 +226,41 @@ class PeerGather:
         self.flag_ptrs = torch.tensor([int(p) for p in self.flags_hdl.buffer_ptrs], dtype=torch.int64, device=device)
         self.pulled_ptr = self.flags.data_ptr() + 8 * self.world
         self.epoch = 0                                              # launches published by this rank
-        self.pulls = 0
         self._slot_views = []
         for s in range(self.SLOTS):
             base = s * self.slot_words
             self._slot_views.append((self.ring[base:base + self.count * n].view(self.count, n),
                                      self.ring[base + self.count * n:base + self.count * (n + 1)]))
-        if self.is_learner:
+        self._status = torch.zeros((1,), dtype=torch.int32, device=device)
+        self.side = torch.cuda.Stream(device=device)
+        self._side_raw = C.c_void_p(self.side.cuda_stream)
+        gwords = n_envs_total * (n + 1)
+        self._gwords = gwords + (gwords & 1)
+        if mode == "push":
+            # the learner's gathered block, double buffered by epoch parity (symmetric: every rank maps the learner's copy)
+            self.gathered = symm_mem.empty(2 * self._gwords, dtype=torch.float64, device=device)
+            self.gathered.zero_()
+            self.gathered_hdl = symm_mem.rendezvous(self.gathered, gname)
+            self._g_dst = int(self.gathered_hdl.buffer_ptrs[dst])
+            self._flag_dst = int(self.flags_hdl.buffer_ptrs[dst]) + 8 * self.rank
+            self._epoch_words = torch.zeros((self.SLOTS,), dtype=torch.int64).pin_memory()
+            self._ev_step = [torch.cuda.Event() for _ in range(self.SLOTS)]
+            self._ev_copy = [torch.cuda.Event() for _ in range(self.SLOTS)]
+            for ev in self._ev_step + self._ev_copy:
+                ev.record()                                         # materialise the cudaEvent_t handles
+            self._push = []
+            for s in range(self.SLOTS):
+                a = N.PeerPushArgs()
+                obs_v, rew_v = self._slot_views[s]
+                a.src, a.bytes = obs_v.data_ptr(), 8 * self.count * n
+                a.src2, a.bytes2 = rew_v.data_ptr(), 8 * self.count
+                a.flag_src = self._epoch_words.data_ptr() + 8 * s
+                a.flag_dst = self._flag_dst
+                a.step_done, a.copy_done = self._ev_step[s].cuda_event, self._ev_copy[s].cuda_event
+                self._push.append(a)
+        elif self.is_learner:
             i64 = dict(dtype=torch.int64, device=device)
-            self.obs_all = torch.zeros((n_envs_total, n), dtype=torch.float64, device=device)
-            self.reward_all = torch.zeros((n_envs_total,), dtype=torch.float64, device=device)
+            self.gathered = torch.zeros((self._gwords,), dtype=torch.float64, device=device)
             self._ring_ptrs = torch.tensor([int(p) for p in self.ring_hdl.buffer_ptrs], **i64)
             self._strides = torch.full((self.world,), self.slot_words, **i64)
             self._offsets = torch.tensor([o for o, _ in self.bounds], **i64)
@@ -236,49 +268,89 @@ class PeerGather:
             self._pulled_ptrs = torch.tensor([int(p) + 8 * self.world for p in self.flags_hdl.buffer_ptrs], **i64)
             self._pull_epoch = torch.zeros((1,), **i64)
             self._finish = torch.zeros((1,), dtype=torch.int32, device=device)
-            self._status = torch.zeros((1,), dtype=torch.int32, device=device)
-            self.side = torch.cuda.Stream(device=device)
             a = N.PeerPullArgs()
             a.world, a.n_obs, a.out_slots, a.blocks_per_rank = self.world, n, self.SLOTS, 8
             a.flags, a.peer_ring, a.slot_stride = self.flags.data_ptr(), N.ptr(self._ring_ptrs), N.ptr(self._strides)
             a.env_offset, a.env_count = N.ptr(self._offsets), N.ptr(self._counts)
-            a.obs_all, a.reward_all, a.pull_epoch = N.ptr(self.obs_all), N.ptr(self.reward_all), N.ptr(self._pull_epoch)
+            a.obs_all, a.reward_all = self.gathered.data_ptr(), self.gathered.data_ptr() + 8 * n_envs_total * n
+            a.pull_epoch = N.ptr(self._pull_epoch)
             a.peer_pulled, a.finish_counter, a.status = N.ptr(self._pulled_ptrs), N.ptr(self._finish), N.ptr(self._status)
             self._pull_args = a
-            import ctypes as C
-            self._side_raw = C.c_void_p(self.side.cuda_stream)
         torch.cuda.synchronize(device)
-        self.ring_hdl.barrier(channel=0)      # everybody's ring and flags are zeroed before the first publish
+        self.ring_hdl.barrier(channel=0)      # everybody's ring, flags and gathered block are zeroed before the first epoch
+
+    # ---- the learner's view of the latest epoch -----------------------------------------------------------------------
+    def _block(self):
+        base = (self.epoch % 2) * self._gwords if self.mode == "push" else 0
+        return self.gathered[base:base + self._gwords]
+
+    @property
+    def obs_all(self):
+        return self._block()[:self.E * self.n_obs].view(self.E, self.n_obs)
+
+    @property
+    def reward_all(self):
+        return self._block()[self.E * self.n_obs:self.E * (self.n_obs + 1)]
 
     def attach(self, env):
         """Route the env's step outputs through the ring (before its first step)."""
         assert env.n_envs == self.count and env.n_observations == self.n_obs
         env.attach_peer(self)
 
+    # ---- called by the env around every integration launch it enqueues ------------------------------------------------------
     def next_launch(self):
-        """Called by the env for every integration launch it enqueues: ``(epoch, obs_ptr, reward_ptr, pulled_min,
-        obs_view, reward_view)`` of the ring slice this launch writes."""
+        """``(epoch, obs_ptr, reward_ptr, pulled_min)`` of the ring slice the next launch writes."""
         self.epoch += 1
         e = self.epoch
         s = e % self.SLOTS
+        if self.mode == "push" and e > self.SLOTS:
+            # the copy that last read this slice (epoch e - SLOTS) has long finished; this returns at once
+            self._N.peer_event_wait(self._ev_copy[s].cuda_event)
+        if self.mode == "push" and self.is_learner:
+            # the learner's own rows need no transfer: its launch writes them straight into its slice of the gathered block
+            # (a local device-to-device copy would run on SMs and hold up the next step's CTAs: measured 36.6 vs 27.6 us)
+            base = self.gathered.data_ptr() + 8 * (e % 2) * self._gwords
+            return e, base + 8 * self.offset * self.n_obs, base + 8 * (self.E * self.n_obs + self.offset), 0
         obs_v, rew_v = self._slot_views[s]
-        return e, obs_v.data_ptr(), rew_v.data_ptr(), max(0, e - self.SLOTS), obs_v, rew_v
+        return e, obs_v.data_ptr(), rew_v.data_ptr(), (max(0, e - self.SLOTS) if self.mode == "pull" else 0)
 
-    def pull(self):
-        """Learner: enqueue the gather of the next epoch on the side stream (one call per published step, in order)."""
-        assert self.is_learner
-        self.pulls += 1
-        self._N.peer_pull(self._pull_args, self._side_raw)
+    def after_launch(self, main_stream_raw):
+        """push mode: enqueue the transfer of the epoch just launched (events + copy engine, no kernel)."""
+        if self.mode != "push":
+            return
+        e = self.epoch
+        s = e % self.SLOTS
+        a = self._push[s]
+        self._epoch_words[s] = e
+        base = self._g_dst + 8 * (e % 2) * self._gwords
+        a.dst = base + 8 * self.offset * self.n_obs
+        a.dst2 = base + 8 * (self.E * self.n_obs + self.offset)
+        if self.is_learner:
+            a.bytes = a.bytes2 = 0          # rows already in place; only the epoch word follows the launch
+        self._N.peer_push(a, main_stream_raw, self._side_raw)
+
+    # ---- learner ------------------------------------------------------------------------------------------------------
+    def gather(self):
+        """Learner, once per published step, in order: pull mode enqueues the gather kernel on the side stream; push mode
+        has nothing to do (every rank pushes its own rows)."""
+        if self.mode == "pull" and self.is_learner:
+            self._N.peer_pull(self._pull_args, self._side_raw)
+
+    pull = gather
 
     def wait(self):
-        """Learner: the current stream waits for every gather enqueued so far (``obs_all`` / ``reward_all`` then hold the
-        last pulled epoch)."""
-        if self.is_learner:
+        """Learner: the current stream waits until the rows of the latest epoch of every rank are in ``obs_all`` /
+        ``reward_all``.  Other ranks: nothing."""
+        if not self.is_learner:
+            return
+        if self.mode == "pull":
             torch.cuda.current_stream().wait_stream(self.side)
+        else:
+            self._N.peer_wait(self.flags.data_ptr(), self.world, self.epoch, self._N.ptr(self._status))
 
     def check(self):
-        """Synchronise the side stream and raise if a gather timed out (a rank never published)."""
-        if self.is_learner:
-            self.side.synchronize()
-            if int(self._status.item()) & self._N.STATUS_PEER_TIMEOUT:
-                raise RuntimeError("quantrl_b200: qrl_peer_pull timed out waiting for a rank's step result")
+        """Synchronise and raise if an exchange step timed out (a rank never delivered)."""
+        self.side.synchronize()
+        torch.cuda.current_stream().synchronize()
+        if int(self._status.item()) & self._N.STATUS_PEER_TIMEOUT:
+            raise RuntimeError("quantrl_b200: the learner gather timed out waiting for a rank's step result")

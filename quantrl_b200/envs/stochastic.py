@@ -163,7 +163,8 @@ class LinearVecEnv(BaseVecEnv):
 
     def _launch(self, K, x0, write_traj=True, graph_mode=None):
         a, keep = self.interval_args(K, x0, write_traj, graph_mode)
-        if self._peer is not None and K > 0:
+        peer = self._peer if K > 0 else None
+        if peer is not None:
             self._peer_patch(a, host_io=getattr(self, "_host_step", False))
         ev = getattr(self, "_em_events", None)
         if ev is not None and K > 0:  # live per-launch timing on the launch stream (bench.py roofline)
@@ -174,6 +175,8 @@ class LinearVecEnv(BaseVecEnv):
             ev.append((e0, e1))
         else:
             N.em_step(a)
+        if peer is not None:
+            peer.after_launch(N.current_stream())
         return keep
 
     def interval_args(self, K, x0=None, write_traj=True, graph_mode=None):
@@ -231,7 +234,7 @@ class LinearVecEnv(BaseVecEnv):
             a.rewards_cum = N.ptr(self.rewards)
         a.obs_minmax = N.ptr(self._minmax)
         a.nan_flag = N.ptr(self._nan)
-        if self._peer is not None and K > 0:
+        if self._peer is not None and K > 0 and self._peer.mode == "pull":
             # publish-only exchange: constant part (the per-launch part — ring slice, epoch — is patched in by _peer_patch)
             pg = self._peer
             a.finish_counter = N.ptr(self._finish)
@@ -283,7 +286,7 @@ class LinearVecEnv(BaseVecEnv):
 
     def _peer_patch(self, a, host_io):
         """Per-launch part of the publish-only exchange: the ring slice of this epoch, its number, the credit it needs."""
-        e, obs_ptr, rew_ptr, pulled_min, _, _ = self._peer.next_launch()
+        e, obs_ptr, rew_ptr, pulled_min = self._peer.next_launch()
         # the ring gets the second copy of the last rows; the primary outputs stay where step() / step_device() read them
         # (the env's own buffer, or pinned host memory), so reset launches and host fetches never touch a published slice
         a.obs_last_b, a.reward_last_b = obs_ptr, rew_ptr
@@ -399,6 +402,8 @@ class LinearVecEnv(BaseVecEnv):
         if self._peer is not None:
             self._peer_patch(a, host_io)
         N.em_step(a, st["stream"])
+        if self._peer is not None:
+            self._peer.after_launch(st["stream"])
         if host_io and st["zc"] is None:
             self._h_out.copy_(self._step_out, non_blocking=True)
         self._host_graph_done = host_io

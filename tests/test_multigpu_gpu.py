@@ -19,7 +19,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, mode):
     import torch.distributed as dist
     from quantrl_b200.distributed import LearnerLink, PeerGather, make_sharded_env
     from quantrl_b200.systems import AffineLinearVecEnv, affine_matrices
@@ -38,7 +38,7 @@ def _worker(rank, world, port, out):
         env = make_sharded_env(AffineLinearVecEnv, E, **kw)
         env_d = make_sharded_env(AffineLinearVecEnv, E, use_cuda_graph=True, fused_coefficients=True, **kw)
         env_h = make_sharded_env(AffineLinearVecEnv, E, use_cuda_graph=True, fused_coefficients=True, return_numpy=True, **kw)
-        peers = [PeerGather(E, n, dev, dst=0) for _ in range(3)]
+        peers = [PeerGather(E, n, dev, dst=0, mode=mode) for _ in range(3)]
         for e_, p_ in zip((env, env_d, env_h), peers):
             p_.attach(e_)
             e_.reset()
@@ -57,7 +57,7 @@ def _worker(rank, world, port, out):
             res = link.gather_step(env.Observations[-1], env.Reward[-1])
             if rank == 0:
                 for p_ in peers:
-                    p_.pull()
+                    p_.gather()
                     p_.wait()
                 o_full, r_full, term = full.step_device(actions)
                 torch.cuda.synchronize()
@@ -76,7 +76,7 @@ def _worker(rank, world, port, out):
         torch.cuda.synchronize()
         dist.barrier()
         assert peers[1].epoch == 8 and (rank != 0 or peers[1].flags.tolist()[:world] == [8] * world)
-        assert int(peers[1].flags[world].item()) == 8                                  # every rank got its credits
+        assert mode == "push" or int(peers[1].flags[world].item()) == 8                # pull mode: every rank got its credits
         out.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         import traceback
@@ -85,12 +85,13 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_sharded_envs_and_peer_gather_match_single_gpu(native):
+@pytest.mark.parametrize("mode", ["push", "pull"])
+def test_sharded_envs_and_peer_gather_match_single_gpu(native, mode):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out, mode)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted(out.get(timeout=120) for _ in procs)
