@@ -366,7 +366,8 @@ def bench_config2(torch, N, dev, args):
     env = Env(name="optomech", desc="config 2", params={}, num_modes=2, num_quads=4, t_norm_max=S * T_SSZ + T_SSZ / 2,
               t_norm_ssz=T_SSZ, t_norm_mul=1.0, n_envs=E, n_observations=20, n_properties=0, n_actions=1,
               action_maximums=[1.0], action_interval=K, data_idxs=[-1], cache_all_data=False, dir_prefix="/tmp/qrl_bench_lho",
-              ode_method="rk4", system="optomech", system_params=p, return_numpy=True, reward_functor="entan_ln_obs")
+              ode_method="rk4", system="optomech", system_params=p, return_numpy=True, host_output_views=True,
+              reward_functor="entan_ln_obs")
     env.reset()
     acts = [rng.uniform(-1, 1, (E, 1)) for _ in range(8)]
     steps = max(10, min(args.steps, 90))
@@ -520,18 +521,16 @@ def main():
     peer2 = None
     if peer is not None:
         peer2 = PeerGather(world * E, n, dev, dst=0, mode=args.gather)
-        peer2.attach(env2)
+        peer2.attach(env2, wait_in_step=True)
     host_actions = [np.random.default_rng(5 + rank).uniform(-1, 1, (E, 1)) for _ in range(8)]
     env2.reset()
     e2e_steps = max(10, min(args.steps, 300))
 
     def e2e_loop(n_steps):
         for i in range(n_steps):
+            # (multi-GPU: on the learner the gather wait is enqueued behind the step launch — PeerGather.attach(...,
+            # wait_in_step=True) — so the sync that ends step() also covers "every rank's rows of this step have arrived")
             env2.step(host_actions[i % 8])
-            if peer2 is not None and peer2.is_learner:   # the learner also waits for every rank's rows of this step
-                peer2.gather()
-                peer2.wait()
-                torch.cuda.current_stream().synchronize()
     e2e_loop(args.warmup)
     if world > 1:
         dist.barrier()

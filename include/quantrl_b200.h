@@ -311,6 +311,9 @@ typedef struct qrl_ode_args {
     double*  reward;         /* (K+1,E) or NULL */
     double*  reward_last;    /* (E,) = Reward[K]; or NULL */
     double*  rewards_cum;    /* (E,) in/out: += Reward[K]; or NULL */
+    /* ABI 4: when non-NULL, `actions` holds the RAW actions (e.g. read in place from pinned host memory) and the functors
+     * see actions[e,k] * action_scale[k]  (= float(action) * action_maximums, quantrl/envs/base.py:1244-1248) */
+    const double* action_scale; /* (n_actions,) or NULL */
 } qrl_ode_args;
 
 /* Kernel selection of qrl_ode_step at num_quads = 4 (all variants perform the same operations; measured crossovers on

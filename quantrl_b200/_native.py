@@ -63,6 +63,7 @@ class OdeArgs(C.Structure):
         ("env_offset", C.c_int64), ("obs_std", _dp), ("obs_std_stride_e", C.c_int64),
         ("h_state", _dp), ("n_steps", _dp), ("obs_minmax", _dp), ("nan_flag", _dp),
         ("flags", C.c_int32), ("reward_kind", C.c_int32), ("reward", _dp), ("reward_last", _dp), ("rewards_cum", _dp),
+        ("action_scale", _dp),
     ]
 
 

@@ -63,7 +63,15 @@ __device__ __forceinline__ void load_system(Sys& s, const qrl_ode_args& a, int e
     if constexpr (is_const_ad<Sys>::value) {
         s.load_AD(a.A + (int64_t)e * a.A_stride_e, a.D + (int64_t)e * a.D_stride_e);
     } else {
-        s.load(a.params + (int64_t)e * a.params_stride_e, a.actions + (int64_t)e * a.n_actions);
+        const double* u = a.actions + (int64_t)e * a.n_actions;
+        if (a.action_scale) {          // raw actions (possibly in pinned host memory): scale a private copy
+            double us[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) us[k] = k < a.n_actions ? u[k] * a.action_scale[k] : 0.0;
+            s.load(a.params + (int64_t)e * a.params_stride_e, us);
+        } else {
+            s.load(a.params + (int64_t)e * a.params_stride_e, u);
+        }
     }
 }
 

@@ -32,6 +32,7 @@ extern "C" int qrl_ode_step(const qrl_ode_args* args, void* stream) {
                 "qrl_ode_step: reward_kind must be NONE, ENTAN_LN_*, SYNC_C_* or SYNC_P_* (num_quads == 4)");
     QRL_REQUIRE(a.reward_kind < QRL_REWARD_SYNC_P_OBS || a.num_modes >= 2,
                 "qrl_ode_step: SYNC_P_* needs the amplitudes of two modes (num_modes >= 2)");
+    QRL_REQUIRE(a.action_scale == nullptr || (a.n_actions >= 1 && a.n_actions <= 4), "qrl_ode_step: action_scale needs 1..4 actions");
     cudaStream_t st = (cudaStream_t)stream;
     const int m = a.num_modes, q = a.num_quads;
     switch (a.system) {

@@ -269,6 +269,7 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         self.t_idx, self.t, self.action_idx, self._idx_s = 0, self.numpy_real(0.0), 0, 0
         self.batch_idx = -1
         self.actions = None
+        self._raw_actions_ptr = None
         self._t_range = None
         self._States = torch.empty((K1, E, no), dtype=f64, device=self.device)
         self._Observations = torch.empty((K1, E, no), dtype=f64, device=self.device)
@@ -308,6 +309,19 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         self._dones_true, self._dones_false, self._infos = [True] * E, [False] * E, [{}] * E
         self._host_step = False
         self._obs_last_ptr = self._reward_last_ptr = None
+
+    # ``actions`` = float(action) * action_maximums (base.py:1244-1248).  Fast paths hand the RAW actions to the kernels
+    # (which scale them in place) and materialise this tensor only when something reads it (user hooks, the pack launch)
+    @property
+    def actions(self):
+        lazy = self.__dict__.get("_actions_lazy")
+        if lazy is not None:
+            self._actions_val, self._actions_lazy = lazy(), None
+        return self.__dict__.get("_actions_val")
+
+    @actions.setter
+    def actions(self, value):
+        self._actions_val, self._actions_lazy = value, None
 
     # ---- hooks the interfaced environment implements (base.py:272-317) ------------------------------------------
     def _update_states(self):
@@ -413,6 +427,9 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
             if getattr(self, "use_cuda_graph", False):
                 self._host_step = True      # H2D of the actions and D2H of the results are nodes of the captured graph
                 return
+            if self._host_actions_in_place():
+                self._host_step = True      # the integration launch reads the pinned actions itself (zero-copy)
+                return
             a = self._h_actions
         self._host_step = False
         self._set_actions(a)
@@ -432,6 +449,10 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
 
     def _direct_actions(self, a):
         """Hook: environments whose captured step is a single native kernel may consume the actions tensor in place."""
+        return False
+
+    def _host_actions_in_place(self):
+        """Hook: True when the env's integration launch reads ``_h_actions`` (pinned host memory) directly."""
         return False
 
     def step(self, actions):
@@ -484,22 +505,29 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         if getattr(self, "_packed_by_kernel", False):
             self._data_host = None
             return  # the integration kernel already wrote this interval's cache rows
-        a = N.PackArgs()
-        a.n_envs, a.dim, a.n_actions, a.n_obs, a.n_props = self.n_envs, dim, self.n_actions, self.n_observations, self.n_properties
-        a.n_sel = len(self.data_idxs)
+        a = self.__dict__.get("_pack_args")
+        if a is None:       # the constant part of the argument block is built once
+            a = self._pack_args = N.PackArgs()
+            a.n_envs, a.n_actions, a.n_obs, a.n_props = self.n_envs, self.n_actions, self.n_observations, self.n_properties
+            a.n_sel = len(self.data_idxs)
+            a.observations = N.ptr(self._Observations)
+            a.rewards_cum = N.ptr(self.rewards)
+            a.idxs = N.ptr(self._sel_idxs)
+            if self._packed is not None:
+                a.packed, a.packed_stride_e = N.ptr(self._packed), (self.action_interval + 1) * self.n_data
+            a.selected_stride_e = self.shape_T[0] * self._data_pitch
+            a.selected_row_pitch = self._data_pitch
+        a.dim = dim
         a.T_step = N.ptr(self.T) + 8 * (self.t_idx - dim + 1)
-        a.actions = N.ptr(self.actions)
-        a.observations = N.ptr(self._Observations)
+        raw = self.__dict__.get("_raw_actions_ptr")
+        if raw is not None and self.__dict__.get("_actions_lazy") is not None:
+            a.actions, a.action_scale = raw, N.ptr(self.action_maximums)     # raw actions, scaled by the pack kernel
+        else:
+            a.actions, a.action_scale = N.ptr(self.actions), None
         a.properties = N.ptr(self.Properties.contiguous()) if self.n_properties > 0 else None
-        a.rewards_cum = N.ptr(self.rewards)
-        a.idxs = N.ptr(self._sel_idxs)
-        if self._packed is not None:
-            a.packed, a.packed_stride_e = N.ptr(self._packed), (self.action_interval + 1) * self.n_data
         # rows t_idx-dim+1 .. t_idx of the (E, shape_T, n_sel) cache; row 0 of a block overwrites the last row of
         # the previous one exactly as in the reference (base.py:1370-1372)
         a.selected = N.ptr(self._data_dev) + 8 * (self.t_idx - dim + 1) * self._data_pitch
-        a.selected_stride_e = self.shape_T[0] * self._data_pitch
-        a.selected_row_pitch = self._data_pitch
         N.pack_rows(a)
         self._data_host = None
         if self.cache_all_data:
@@ -540,6 +568,9 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         host_step = getattr(self, "_host_step", False)
         observations, reward, terminated = self.update(reset_minmax=not host_step)
         self.update_data()
+        hook = getattr(self, "_pre_sync_hook", None)
+        if hook is not None:        # e.g. the learner's gather wait of the sharded path: enqueued behind the step, covered by
+            hook()                  # the one stream synchronisation below
         if host_step and getattr(self, "_host_graph_done", False):
             self._replay_stream.synchronize()     # the replayed graph already delivered the results to pinned memory
             host = self._h_out

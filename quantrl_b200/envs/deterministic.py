@@ -162,10 +162,84 @@ class LinearizedHOVecEnv(BaseVecEnv):
         self.solver.integrate(T_step=self.T[:1], y_0=states_0, params=self.action_maximums_batch, out=self._States[:1])
         return self._obs_last.clone()
 
+    # ---- fast host path of the fused mode (BASELINE config 2 through step()) ------------------------------------------
+    # The step used to be an eager chain around the integration kernel: H2D of the actions, a scaling kernel, a freshly
+    # built argument block (~40 ctypes stores), the launch, the pack launch, D2H (profiles/r01p: 153 us around a 54 us
+    # kernel).  Now the kernel reads the RAW actions in place (pinned host memory over PCIe for step(host array), the
+    # caller's tensor for CUDA tensors) and scales them itself (qrl_ode_args.action_scale), and the argument block of a
+    # full interval is built once and patched (t0, time index, episode) per step.
+    def _host_actions_in_place(self):
+        if self.system is None or self.system["system"] == "const_AD" or self.n_actions > 4:
+            return False
+        if self.__dict__.get("_h_act_dev") is None:
+            try:
+                self._h_act_dev = N.host_device_pointer(self._h_actions)
+            except N.NativeError:
+                self._h_act_dev = False
+        if not self._h_act_dev:
+            return False
+        h = self._h_actions     # ``self.actions`` (scaled, on the device) materialises only if something reads it
+        self._raw_actions_ptr = self._h_act_dev
+        self._actions_lazy = lambda: h.to(self.device, non_blocking=True) * self.action_maximums_batch
+        return True
+
+    def _set_actions(self, a):
+        if self.system is None or self.system["system"] == "const_AD" or self.n_actions > 4:
+            return super()._set_actions(a)
+        self._host_step = False
+        a = a if a.is_cuda else a.to(self.device, non_blocking=True)
+        self._raw_actions = a.reshape(self.n_envs, self.n_actions).to(torch.float64).contiguous()   # no copy when already so
+        self._raw_actions_ptr = self._raw_actions.data_ptr()
+        self._actions_lazy = lambda: self._raw_actions * self.action_maximums_batch
+
+    def _fused_args(self, dim):
+        """Cached ``qrl_ode_args`` of a full interval (``dim == K + 1``): everything that does not change from step to step."""
+        a = self.__dict__.get("_ode_args")
+        if a is not None:
+            return a
+        sysd, sp = self.system, self.solver.solver_params
+        a = N.OdeArgs()
+        a.system, a.num_modes, a.num_quads = SYSTEMS[sysd["system"]], sysd["num_modes"], sysd["num_quads"]
+        a.n_envs, a.K = self.n_envs, dim - 1
+        a.method, adaptive = N.ODE_METHODS[sp["method"]]
+        a.substeps, a.t_ssz, a.atol, a.rtol = int(sp["substeps"]), self.t_ssz, float(sp["atol"]), float(sp["rtol"])
+        P = sysd["params"]
+        a.params, a.params_stride_e = N.ptr(P), (P.shape[-1] if P.dim() == 2 else 0)
+        a.n_actions, a.action_scale = self.n_actions, N.ptr(self.action_maximums)
+        a.y0, a.y_last, a.states = N.ptr(self._x_last), N.ptr(self._x_last), N.ptr(self._States)
+        a.observations, a.obs_last = N.ptr(self._Observations), N.ptr(self._obs_last)
+        a.obs_minmax, a.nan_flag = N.ptr(self._minmax), N.ptr(self._nan)
+        if self.reward_functor is not None:
+            a.reward_kind, a.reward = _REWARD_KINDS[self.reward_functor], N.ptr(self._Reward)
+            a.reward_last, a.rewards_cum = N.ptr(self._reward_last), N.ptr(self.rewards)
+        if self.observation_stds is not None and self.rng != "fed":
+            a.obs_std, a.obs_std_stride_e = N.ptr(self.observation_stds), (self.n_observations if self.observation_stds.dim() == 2 else 0)
+            a.seed, a.env_offset = self._philox_seed, self.env_offset
+        if adaptive:
+            if self.solver.h_state is None or self.solver.h_state.shape[0] != self.n_envs:
+                self.solver.h_state = torch.zeros((self.n_envs,), dtype=torch.float64, device=self.device)
+                self.solver.n_steps = torch.zeros((self.n_envs, 2), dtype=torch.int32, device=self.device)
+            a.h_state, a.n_steps = N.ptr(self.solver.h_state), N.ptr(self.solver.n_steps)
+        self._ode_args = a
+        return a
+
     def _update_states(self):
         dim = self._dim
         t0 = self.t_idx
+        fast = (self.system is not None and self.system["system"] != "const_AD" and dim == self.action_interval + 1
+                and self.n_actions <= 4 and (self._host_step or self.__dict__.get("_actions_lazy") is not None))
+        if fast:
+            a = self._fused_args(dim)
+            a.actions = self._raw_actions_ptr      # pinned host memory (step(host array)) or the caller's CUDA tensor
+            if self._host_step:
+                self._minmax.copy_(self._minmax_init, non_blocking=True)
+            a.t0, a.t_idx, a.episode = float(self._T_host[t0]), t0, self.batch_idx & 0xFFFFFFFF
+            if self.observation_stds is not None and self.rng == "fed":
+                a.obs_noise = N.ptr(self.Observation_noises) + 8 * t0 * self.n_envs * self.n_observations
+            N.ode_step(a)
+            return self._States
         if self.system is not None:
+            _ = self.actions                # (materialise the scaled actions for the generic launch below)
             self.system["T_host"] = self._T_step_host
             self.solver.epilogue = dict(
                 self._noise_epilogue(t0), observations=N.ptr(self._Observations), y_last=N.ptr(self._x_last),
