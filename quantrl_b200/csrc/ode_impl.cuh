@@ -92,7 +92,9 @@ __device__ __forceinline__ double obs_noise_at(const qrl_ode_args& a, int row, i
     if (a.obs_std) {
         const double2 z = philox_normal2_call(a.seed, (uint32_t)(a.t_idx + row), a.episode, (uint32_t)(a.env_offset + e),
                                               0x10000u + (uint32_t)(d >> 1));
-        return a.obs_std[(int64_t)e * a.obs_std_stride_e + d] * ((d & 1) ? z.y : z.x);
+        // explicitly rounded product: `state + noise` must not become a fused multiply-add in one kernel and a separate
+        // multiply and add in another (the kernel variants are held to each other bit for bit)
+        return __dmul_rn(a.obs_std[(int64_t)e * a.obs_std_stride_e + d], (d & 1) ? z.y : z.x);
     }
     return 0.0;
 }
@@ -183,8 +185,8 @@ __device__ __forceinline__ double2 emit_row_thread(const qrl_ode_args& a, int ro
         } else if (sd) {
             const double2 z = philox_normal2_call(a.seed, (uint32_t)(a.t_idx + row), a.episode, (uint32_t)(a.env_offset + e),
                                                   0x10000u + (uint32_t)c);
-            o.x = v.x + sd[2 * c] * z.x;
-            o.y = v.y + sd[2 * c + 1] * z.y;
+            o.x = __dadd_rn(v.x, __dmul_rn(sd[2 * c], z.x));      // (explicit roundings: see obs_noise_at)
+            o.y = __dadd_rn(v.y, __dmul_rn(sd[2 * c + 1], z.y));
         }
         if (st) st[c] = v;
         if (ob) ob[c] = o;
@@ -232,8 +234,8 @@ __device__ __forceinline__ void rk4_row_out(const qrl_ode_args& a, const double2
             const double2 z = philox_normal2_call(a.seed, (uint32_t)(a.t_idx + row), a.episode,
                                                   (uint32_t)(a.env_offset + e0 + elx), 0x10000u + (uint32_t)c);
             const double* sd = a.obs_std + (int64_t)(e0 + elx) * a.obs_std_stride_e + 2 * c;
-            o.x = v.x + sd[0] * z.x;
-            o.y = v.y + sd[1] * z.y;
+            o.x = __dadd_rn(v.x, __dmul_rn(sd[0], z.x));
+            o.y = __dadd_rn(v.y, __dmul_rn(sd[1], z.y));
         }
         if (st) st[idx2] = v;
         if (ob) ob[idx2] = o;
@@ -665,6 +667,180 @@ __global__ void __launch_bounds__(BLOCK) rk4_lanes_kernel(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// RK4 with q LANES per environment (num_quads 6 and 8: the "warp for larger mode counts" of the north_star).
+// One thread per environment needs 2 q^2 + 5 (2m + q^2) doubles of state at q = 8 — 255 registers and 8-22 KB of
+// spills (profiles/r01r_ptxas_resources.md: 6.4e8 sub-steps/s at E = 16384).  Here lane i of an environment owns ROW i
+// of the covariance V and of the drift matrix A (RowSys, systems.cuh) and the replicated mode amplitudes: per RK stage
+// the lanes publish their rows of V and A in shared memory (double buffered over the stages: one __syncwarp each), then
+//     (A V)_ij   = sum_k A_ik V_kj   own A row from registers, row k of V as LDS.128 broadcasts
+//     (V A^T)_ij = sum_k V_ik A_jk   own V row from registers, row j of A as LDS.128 broadcasts
+// — 2 q^2 FMAs in 2q independent chains per lane and stage, same order of operations as rhs() (k ascending, then
+// (av + va) + D_ij), so the trajectories are bit-identical to the thread-per-env kernel (the structural zeros it skips
+// contribute exact zeros).  32 / q environments per warp; a row of the (K+1, E, d) blocks leaves as q-double runs.
+// ------------------------------------------------------------------------------------------------------------------
+template <class Sys, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) rk4_rows_kernel(const __grid_constant__ qrl_ode_args a) {
+    constexpr int M = Sys::M, Q = Sys::Q, D = Dim<Sys>::D;
+    constexpr int M2 = 2 * M > 0 ? 2 * M : 1;
+    static_assert(Q % 2 == 0 && Q <= 8 && BLOCK % 32 == 0, "row lanes: even q <= 8");
+    constexpr int EPW = 32 / Q, EPB = (BLOCK / 32) * EPW;              // envs per warp / per block
+    // exchange tiles, padded: row pitch Q + 2 doubles (the 8 lanes of an environment store their 16-byte pieces into 8
+    // distinct bank groups) and environment pitch + 2 (the 32 / Q environments of a warp read their pieces of the same
+    // row from different banks) — with dense [Q][Q] tiles 58 % of the shared-memory wavefronts were conflicts (ncu r02j)
+    constexpr int RPITCH = Q + 2, EPITCH = Q * RPITCH + 2;
+    __shared__ __align__(16) double sA[2][EPB * EPITCH], sV[2][EPB * EPITCH];
+    const int E = a.n_envs, K = a.K;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gw = lane / Q, i = lane - gw * Q;                        // env within the warp, my row
+    const bool lane_used = gw < EPW;
+    const int g = warp * EPW + (lane_used ? gw : 0);                   // env slot within the block
+    const int e = blockIdx.x * EPB + g;
+    const bool live = lane_used && e < E;
+    const int el = e < E ? e : E - 1;
+
+    RowSys<Sys> s;
+    {
+        const double* prm = a.params ? a.params + (int64_t)el * a.params_stride_e : nullptr;
+        double us[4] = {0.0, 0.0, 0.0, 0.0};
+        if (a.actions) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < a.n_actions) us[k] = a.actions[(int64_t)el * a.n_actions + k] * (a.action_scale ? a.action_scale[k] : 1.0);
+        }
+        s.load(prm, us, a.A ? a.A + (int64_t)el * a.A_stride_e : nullptr, a.D ? a.D + (int64_t)el * a.D_stride_e : nullptr, i);
+    }
+    double ym[M2], v[Q], drow[Q];
+#pragma unroll
+    for (int c = 0; c < 2 * M; ++c) ym[c] = a.y0[(int64_t)el * D + c];
+#pragma unroll
+    for (int j = 0; j < Q; ++j) { v[j] = a.y0[(int64_t)el * D + 2 * M + i * Q + j]; drow[j] = s.Drow(j); }
+    const int noise = a.obs_noise ? 1 : (a.obs_std ? 2 : 0);
+    // my elements of a row: V row i at columns 2M + i*Q .. +Q-1; lanes i < 2M also write mode component i
+    const bool mode_lane = i < 2 * M;
+    const int64_t col_v = (int64_t)el * D + 2 * M + i * Q, col_m = (int64_t)el * D + i, row_pitch = (int64_t)E * D;
+    double lo = INFINITY, hi = -INFINITY;
+    auto my_mode = [&]() {
+        double mv = 0.0;
+#pragma unroll
+        for (int c = 0; c < 2 * M; ++c) mv = (i == c) ? ym[c] : mv;
+        return mv;
+    };
+    auto emit = [&](int row, bool last) {
+        const double mv = my_mode();
+        double ov[Q], om = mv;
+#pragma unroll
+        for (int j = 0; j < Q; ++j) ov[j] = noise ? v[j] + obs_noise_at(a, row, el, 2 * M + i * Q + j, D) : v[j];
+        if (noise && mode_lane) om = mv + obs_noise_at(a, row, el, i, D);
+        if (live) {
+            const int64_t r0 = (int64_t)row * row_pitch;
+            if (a.states) {
+#pragma unroll
+                for (int j = 0; j < Q; j += 2) *reinterpret_cast<double2*>(a.states + r0 + col_v + j) = make_double2(v[j], v[j + 1]);
+                if (mode_lane) a.states[r0 + col_m] = mv;
+            }
+            if (a.observations) {
+#pragma unroll
+                for (int j = 0; j < Q; j += 2) *reinterpret_cast<double2*>(a.observations + r0 + col_v + j) = make_double2(ov[j], ov[j + 1]);
+                if (mode_lane) a.observations[r0 + col_m] = om;
+            }
+#pragma unroll
+            for (int j = 0; j < Q; ++j) { lo = fmin(lo, ov[j]); hi = fmax(hi, ov[j]); }
+            if (mode_lane) { lo = fmin(lo, om); hi = fmax(hi, om); }
+            if (last) {
+                if (a.y_last) {
+#pragma unroll
+                    for (int j = 0; j < Q; j += 2) *reinterpret_cast<double2*>(a.y_last + col_v + j) = make_double2(v[j], v[j + 1]);
+                    if (mode_lane) a.y_last[col_m] = mv;
+                }
+                if (a.obs_last) {
+#pragma unroll
+                    for (int j = 0; j < Q; j += 2) *reinterpret_cast<double2*>(a.obs_last + col_v + j) = make_double2(ov[j], ov[j + 1]);
+                    if (mode_lane) a.obs_last[col_m] = om;
+                }
+                bool bad = !isfinite(mv);
+#pragma unroll
+                for (int j = 0; j < Q; ++j) bad |= !isfinite(v[j]);
+                if (a.nan_flag && bad) atomicOr(a.nan_flag, QRL_STATUS_NONFINITE);
+            }
+        }
+    };
+    // one right-hand side at (modes ymt, my row vt) through exchange buffer `buf`: fills dv (my row of dV/dt) and dm
+    auto rhs_row = [&](int buf, double t, const double* ymt, const double (&vt)[Q], double (&dv)[Q], double* dm) {
+        double Arow[Q];
+        s.rates(t, ymt, dm);
+        s.row(t, ymt, Arow);
+        if (lane_used) {
+#pragma unroll
+            for (int j = 0; j < Q; j += 2) {
+                *reinterpret_cast<double2*>(&sV[buf][g * EPITCH + i * RPITCH + j]) = make_double2(vt[j], vt[j + 1]);
+                *reinterpret_cast<double2*>(&sA[buf][g * EPITCH + i * RPITCH + j]) = make_double2(Arow[j], Arow[j + 1]);
+            }
+        }
+        __syncwarp();
+        double av[Q];
+#pragma unroll
+        for (int j = 0; j < Q; ++j) av[j] = 0.0;
+#pragma unroll
+        for (int k = 0; k < Q; ++k) {          // (A V)_ij: row k of V, broadcast to the lanes of the env
+            double vk[Q];
+#pragma unroll
+            for (int j = 0; j < Q; j += 2) {
+                const double2 t2 = *reinterpret_cast<const double2*>(&sV[buf][g * EPITCH + k * RPITCH + j]);
+                vk[j] = t2.x; vk[j + 1] = t2.y;
+            }
+#pragma unroll
+            for (int j = 0; j < Q; ++j) av[j] = fma(Arow[k], vk[j], av[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {          // (V A^T)_ij: row j of A
+            double aj[Q];
+#pragma unroll
+            for (int k = 0; k < Q; k += 2) {
+                const double2 t2 = *reinterpret_cast<const double2*>(&sA[buf][g * EPITCH + j * RPITCH + k]);
+                aj[k] = t2.x; aj[k + 1] = t2.y;
+            }
+            double va = 0.0;
+#pragma unroll
+            for (int k = 0; k < Q; ++k) va = fma(vt[k], aj[k], va);
+            dv[j] = (av[j] + va) + drow[j];    // same association as deterministic.py:713-732
+        }
+    };
+
+    emit(0, K == 0);
+    const int nsub = a.substeps;
+    const double h = a.t_ssz / (double)nsub, hh = 0.5 * h, h6 = h / 6.0;
+    for (int row = 1; row <= K; ++row) {
+        const double t_row = a.t0 + (double)(row - 1) * a.t_ssz;
+        for (int sub = 0; sub < nsub; ++sub) {
+            const double t = t_row + (double)sub * h;
+            double dm[M2], ymt[M2], accm[M2], k[Q], accv[Q], vt[Q];
+            rhs_row(0, t, ym, v, k, dm);
+#pragma unroll
+            for (int j = 0; j < Q; ++j) { accv[j] = k[j]; vt[j] = fma(hh, k[j], v[j]); }
+#pragma unroll
+            for (int c = 0; c < 2 * M; ++c) { accm[c] = dm[c]; ymt[c] = fma(hh, dm[c], ym[c]); }
+            rhs_row(1, t + hh, ymt, vt, k, dm);
+#pragma unroll
+            for (int j = 0; j < Q; ++j) { accv[j] = fma(2.0, k[j], accv[j]); vt[j] = fma(hh, k[j], v[j]); }
+#pragma unroll
+            for (int c = 0; c < 2 * M; ++c) { accm[c] = fma(2.0, dm[c], accm[c]); ymt[c] = fma(hh, dm[c], ym[c]); }
+            rhs_row(0, t + hh, ymt, vt, k, dm);
+#pragma unroll
+            for (int j = 0; j < Q; ++j) { accv[j] = fma(2.0, k[j], accv[j]); vt[j] = fma(h, k[j], v[j]); }
+#pragma unroll
+            for (int c = 0; c < 2 * M; ++c) { accm[c] = fma(2.0, dm[c], accm[c]); ymt[c] = fma(h, dm[c], ym[c]); }
+            rhs_row(1, t + h, ymt, vt, k, dm);
+#pragma unroll
+            for (int j = 0; j < Q; ++j) v[j] = fma(h6, accv[j] + k[j], v[j]);
+#pragma unroll
+            for (int c = 0; c < 2 * M; ++c) ym[c] = fma(h6, accm[c] + dm[c], ym[c]);
+        }
+        emit(row, row == K);
+    }
+    if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // RK4, warp-specialised small-batch kernel (q = 4).  With E = 1024 there is at most one warp per scheduler, so every
 // instruction of a lane's loop is on the critical path.  The classical mode amplitudes do not depend on the
 // covariance, and writing a row does not feed back into the integration, so both are taken OUT of the covariance
@@ -773,8 +949,8 @@ __global__ void __launch_bounds__(EPB * 16 + 32 + 128) rk4_split_kernel(const __
                 const double2 z = philox_normal2_call(a.seed, (uint32_t)(a.t_idx + row), a.episode,
                                                       (uint32_t)(a.env_offset + e0 + elx), 0x10000u + (uint32_t)c);
                 const double* sd = a.obs_std + (int64_t)(e0 + elx) * a.obs_std_stride_e + 2 * c;
-                o.x = x.x + sd[0] * z.x;
-                o.y = x.y + sd[1] * z.y;
+                o.x = __dadd_rn(x.x, __dmul_rn(sd[0], z.x));
+                o.y = __dadd_rn(x.y, __dmul_rn(sd[1], z.y));
             }
             if (a.states) reinterpret_cast<double2*>(a.states)[g2] = x;
             if (a.observations) reinterpret_cast<double2*>(a.observations)[g2] = o;
@@ -1193,6 +1369,18 @@ int launch_ode(const qrl_ode_args& a, cudaStream_t st) {
                     QRL_CUDA(cudaFuncSetAttribute(rk4_split_kernel<Sys, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
                 rk4_split_kernel<Sys, EPB><<<(a.n_envs + EPB - 1) / EPB, EPB * 16 + 32 + 128, smem, st>>>(a, C);
                 return after_launch("rk4_split_kernel");
+            }
+        }
+        if constexpr (Sys::Q > 4 && Sys::Q % 2 == 0) {
+            // q = 6, 8: q lanes per environment.  Measured on B200 (tools/prof_ode.py, kerr_chain, 100 sub-steps, sub-steps/s,
+            // row lanes vs one thread per env): q = 8 (the thread kernel spills 8-22 KB): E = 1024 3.5e8 vs 6.6e7, 4096 9.8e8 vs
+            // 2.5e8, 16384 1.12e9 vs 7.0e8, 65536 1.17e9 vs 8.8e8; q = 6 (no spills): E = 16384 1.9e9 vs 3.2e9 — row lanes
+            // for every batch at q = 8, for small batches at q = 6
+            const bool rows = Sys::Q == 8 || a.n_envs <= 6144 || (a.flags & QRL_ODE_FORCE_LANES);
+            if (rows && !(a.flags & QRL_ODE_FORCE_THREAD)) {
+                constexpr int BR = 128, EPB = (BR / 32) * (32 / Sys::Q);
+                rk4_rows_kernel<Sys, BR><<<(a.n_envs + EPB - 1) / EPB, BR, 0, st>>>(a);
+                return after_launch("rk4_rows_kernel");
             }
         }
         constexpr int BLOCK = 32;

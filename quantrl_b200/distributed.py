@@ -197,7 +197,7 @@ class PeerGather:
     The NCCL path (``LearnerLink.gather_step``) stays as the fallback and as the measured comparison.
     """
 
-    SLOTS = 4
+    SLOTS = 16          # ring depth = how many steps the host may run ahead of the copies (jitter tolerance), 16 x 164 KB at config 3
 
     def __init__(self, n_envs_total, n_observations, device, dst=0, group=None, mode="push"):
         import ctypes as C
