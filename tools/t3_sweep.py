@@ -32,7 +32,7 @@ if __name__ == "__main__":
     cases = [(4096, 4), (8192, 8), (8192, 4)] if quick else [(4096, 4), (1024, 4), (8192, 4), (8192, 8), (16384, 8), (32768, 8), (65536, 8), (65536, 4)]
     for E, n in cases:
         print(f"E={E} n={n}: gen3 {run({}, E, n)} us | gen2 {run({'QRL_EM_NO_T3': '1'}, E, n)} us | generic {run({}, E, n, flags=1)} us", flush=True)
-    if quick:
+    if quick or not (len(sys.argv) > 1 and sys.argv[1] == "knobs"):
         sys.exit(0)
     for E, n in [(4096, 4), (8192, 8)]:
         for th in (512, 640, 768):
