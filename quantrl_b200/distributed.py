@@ -244,6 +244,7 @@ class PeerGather:
             self._g_dst = int(self.gathered_hdl.buffer_ptrs[dst])
             self._flag_dst = int(self.flags_hdl.buffer_ptrs[dst]) + 8 * self.rank
             self._epoch_words = torch.zeros((self.SLOTS,), dtype=torch.int64).pin_memory()
+            self._epoch_np = self._epoch_words.numpy()              # (a NumPy store costs a fraction of a tensor item store)
             self._ev_step = [torch.cuda.Event() for _ in range(self.SLOTS)]
             self._ev_copy = [torch.cuda.Event() for _ in range(self.SLOTS)]
             for ev in self._ev_step + self._ev_copy:
@@ -328,7 +329,7 @@ class PeerGather:
         e = self.epoch
         s = e % self.SLOTS
         a = self._push[s]
-        self._epoch_words[s] = e
+        self._epoch_np[s] = e
         base = self._g_dst + 8 * (e % 2) * self._gwords
         a.dst = base + 8 * self.offset * self.n_obs
         a.dst2 = base + 8 * (self.E * self.n_obs + self.offset)

@@ -182,8 +182,6 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         assert len(kwargs["observation_space_range"]) == 2 and len(kwargs["action_space_range"]) == 2
         assert kwargs["action_space_type"] in ["binary", "box"], "parameter ``action_space_type`` can be either ``'binary'`` or ``'box'``"
         assert kwargs["rng"] in ["philox", "fed"], "parameter ``rng`` can be either ``'philox'`` or ``'fed'``"
-        assert not kwargs["has_delay"], \
-            "delay (DDE) systems are supported at the solver level only (B200IVPSolver, stage-callback mode), not by the vectorized envs"
 
         N.lib()  # fail loudly, now, if the CUDA extension is missing
         self.backend = backend
@@ -222,7 +220,7 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         self.action_maximums_batch = self.action_maximums.reshape(1, self.n_actions).repeat(self.n_envs, 1).contiguous()
         self.action_interval = int(action_interval)
         self.action_steps = int(math.ceil((self.shape_T[0] - 1) / self.action_interval))
-        self.has_delay = False
+        self.has_delay = bool(kwargs["has_delay"])     # honoured by LinearizedHOVecEnv in its stage-callback mode (base.py:214-216)
 
         # measurement noise: per-env stds (E,n_obs) or shared (n_obs,) (base.py:179-184, 417-424)
         stds = kwargs["observation_stds"]

@@ -79,12 +79,17 @@ class LinearizedHOVecEnv(BaseVecEnv):
         if self.reward_functor is not None:
             assert sysd is not None and q == 4, "fused reward functors need a device functor system with num_quads == 4"
             self._reward_fused = self._cum_fused = True
+        # delay systems (quantrl/envs/base.py:214-216, solvers/base.py:96-112, 198-202): the history function is an argument
+        # of the user's torch hooks (``args[2]``), refitted by the solver after every action interval — stage-callback mode
+        assert not (self.has_delay and sysd is not None), \
+            "delay (DDE) systems run in the stage-callback mode (no ``system=``): the device functors have no history argument"
+        self._func_delay_0 = getattr(self, "func_delay", None)
         self.solver = IVPSolver(
             func=self.func, y_0=self._States[-1], T=self.T,
             solver_params={"method": ode["ode_method"], "atol": ode["ode_atol"], "rtol": ode["ode_rtol"], "is_stiff": False,
                            "step_interval": self.action_interval, "substeps": ode["ode_substeps"]},
-            func_controls=getattr(self, "func_controls", None), has_delay=False,
-            func_delay=getattr(self, "func_delay", None), delay_interval=self.action_interval, backend=self.backend,
+            func_controls=getattr(self, "func_controls", None), has_delay=self.has_delay,
+            func_delay=self._func_delay_0, delay_interval=self.action_interval, backend=self.backend,
             system=sysd)
 
     # ---- user hooks (deterministic.py:748-818) ------------------------------------------------------------------
@@ -137,6 +142,8 @@ class LinearizedHOVecEnv(BaseVecEnv):
                 generator=self.backend.generator(seed=self.seed), shape=(S1, E, d), mean=0.0, std=1.0,
                 dtype="real") * self.observation_stds.reshape(1, -1, d)
         self.solver.reset_controller()
+        if self.has_delay:      # an episode starts from the history the env was built with, not from the last episode's window
+            self.solver.func_delay = self._func_delay_0
         return super()._reset()
 
     def set_fed_noise(self, Observation_noises):

@@ -72,6 +72,7 @@ class LinearVecEnv(BaseVecEnv):
             file_prefix="lin_vec_env", **kwargs)
         n = self.n_observations
         assert 1 <= n <= 16, "qrl_em_step supports 1 <= n_observations <= 16"
+        assert not self.has_delay, "the Euler-Maruyama path has no history argument (the reference's LinearEnv has none either)"
         # (shape_T - 1) % action_interval != 0 is supported: the last interval is shorter (dim < K+1, base.py:454-458);
         # the reference's own LinearEnv raises there (its States block keeps K+1 rows, base.py:462)
         self.I = torch.eye(n, dtype=torch.float64, device=self.device)
