@@ -414,6 +414,16 @@ typedef struct qrl_peer_push_args {
 } qrl_peer_push_args;
 
 QRL_API int qrl_peer_push(const qrl_peer_push_args* args, void* main_stream, void* side_stream);
+/* The same with the driver calls off the caller's thread: a context owns a worker thread (bound to the current device) and
+ * `side_stream`.  qrl_peer_ctx_push records step_done on `main_stream` itself (that must happen in stream order, right
+ * behind the step launch: one driver call) and queues the rest — stream wait, copies, copy_done record — for the worker;
+ * it returns a sequence number.  qrl_peer_ctx_wait(ctx, seq) blocks until job `seq` has been issued AND its copy_done event
+ * has completed (seq 0: nothing to wait for).  A step loop that is device bound at ~27 us per step stays device bound:
+ * the five driver calls of qrl_peer_push cost the calling thread ~12 us, this path ~3 us. */
+QRL_API int      qrl_peer_ctx_create(void** ctx, void* side_stream);
+QRL_API uint64_t qrl_peer_ctx_push(void* ctx, const qrl_peer_push_args* args, void* main_stream);   /* 0 = error */
+QRL_API int      qrl_peer_ctx_wait(void* ctx, uint64_t seq);
+QRL_API int      qrl_peer_ctx_destroy(void* ctx);
 QRL_API int qrl_peer_event_wait(void* event);   /* cudaEventSynchronize */
 QRL_API int qrl_peer_wait(const uint64_t* flags, int32_t world, uint64_t epoch, int32_t* status, void* stream);
 

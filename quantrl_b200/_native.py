@@ -106,6 +106,10 @@ SYMBOLS = {
     "qrl_peer_pull": (C.c_int, [C.POINTER(PeerPullArgs), C.c_void_p]),
     "qrl_peer_push": (C.c_int, [C.POINTER(PeerPushArgs), C.c_void_p, C.c_void_p]),
     "qrl_peer_event_wait": (C.c_int, [C.c_void_p]),
+    "qrl_peer_ctx_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p]),
+    "qrl_peer_ctx_push": (C.c_uint64, [C.c_void_p, C.POINTER(PeerPushArgs), C.c_void_p]),
+    "qrl_peer_ctx_wait": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "qrl_peer_ctx_destroy": (C.c_int, [C.c_void_p]),
     "qrl_peer_wait": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p]),
     "qrl_measure_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "qrl_measure_fp64_latency": (C.c_int, [C.POINTER(C.c_double)]),
@@ -180,6 +184,27 @@ def peer_pull(args: PeerPullArgs, stream=None):
 
 def peer_push(args: PeerPushArgs, main_stream, side_stream):
     check(lib().qrl_peer_push(C.byref(args), main_stream, side_stream), "qrl_peer_push")
+
+
+def peer_ctx_create(side_stream):
+    ctx = C.c_void_p(0)
+    check(lib().qrl_peer_ctx_create(C.byref(ctx), side_stream), "qrl_peer_ctx_create")
+    return ctx
+
+
+def peer_ctx_push(ctx, args: PeerPushArgs, main_stream) -> int:
+    seq = int(lib().qrl_peer_ctx_push(ctx, C.byref(args), main_stream))
+    if seq == 0:
+        check(-1, "qrl_peer_ctx_push")
+    return seq
+
+
+def peer_ctx_wait(ctx, seq):
+    check(lib().qrl_peer_ctx_wait(ctx, seq), "qrl_peer_ctx_wait")
+
+
+def peer_ctx_destroy(ctx):
+    lib().qrl_peer_ctx_destroy(ctx)
 
 
 def peer_event_wait(event):

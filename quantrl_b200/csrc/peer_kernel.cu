@@ -9,6 +9,11 @@
 // that have finished move over NVLink while the others still integrate; 16-byte loads from peer memory, 16-byte stores to
 // the gathered block.  The last block advances the learner's epoch counter and hands every rank the credit (`pulled`)
 // that lets it reuse the ring slice.
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+
 #include "common.cuh"
 
 namespace qrl {
@@ -114,6 +119,113 @@ extern "C" int qrl_peer_push(const qrl_peer_push_args* args, void* main_stream, 
     if (a.src2 && a.dst2 && a.bytes2 > 0) QRL_CUDA(cudaMemcpyAsync(a.dst2, a.src2, (size_t)a.bytes2, cudaMemcpyDefault, ss));
     QRL_CUDA(cudaMemcpyAsync(a.flag_dst, a.flag_src, 8, cudaMemcpyDefault, ss));
     QRL_CUDA(cudaEventRecord((cudaEvent_t)a.copy_done, ss));
+    return 0;
+}
+
+// ---- worker-thread context of the push exchange -------------------------------------------------------------------
+namespace qrl {
+struct PeerCtx {
+    int device = 0;
+    cudaStream_t side = nullptr;
+    std::mutex mu;
+    std::condition_variable cv_job, cv_done;
+    std::deque<std::pair<uint64_t, qrl_peer_push_args>> jobs;
+    uint64_t next_seq = 1, issued = 0;
+    cudaEvent_t copy_done_of[64] = {nullptr};      // copy_done event of job seq (ring indexed by seq % 64)
+    int error = 0;
+    bool stop = false;
+    std::thread worker;
+
+    void run() {
+        cudaSetDevice(device);
+        for (;;) {
+            std::pair<uint64_t, qrl_peer_push_args> job;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_job.wait(lk, [&] { return stop || !jobs.empty(); });
+                if (jobs.empty()) return;
+                job = jobs.front();
+                jobs.pop_front();
+            }
+            const qrl_peer_push_args& a = job.second;
+            cudaError_t e = cudaStreamWaitEvent(side, (cudaEvent_t)a.step_done, 0);
+            if (e == cudaSuccess && a.bytes > 0) e = cudaMemcpyAsync(a.dst, a.src, (size_t)a.bytes, cudaMemcpyDefault, side);
+            if (e == cudaSuccess && a.src2 && a.dst2 && a.bytes2 > 0) e = cudaMemcpyAsync(a.dst2, a.src2, (size_t)a.bytes2, cudaMemcpyDefault, side);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(a.flag_dst, a.flag_src, 8, cudaMemcpyDefault, side);
+            if (e == cudaSuccess) e = cudaEventRecord((cudaEvent_t)a.copy_done, side);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (e != cudaSuccess && error == 0) error = (int)e;
+                copy_done_of[job.first % 64] = (cudaEvent_t)a.copy_done;
+                issued = job.first;
+            }
+            cv_done.notify_all();
+        }
+    }
+};
+}  // namespace qrl
+
+extern "C" int qrl_peer_ctx_create(void** ctx, void* side_stream) {
+    using namespace qrl;
+    QRL_REQUIRE(ctx != nullptr && side_stream != nullptr, "qrl_peer_ctx_create: NULL argument");
+    PeerCtx* c = new PeerCtx();
+    QRL_CUDA(cudaGetDevice(&c->device));
+    c->side = (cudaStream_t)side_stream;
+    c->worker = std::thread([c] { c->run(); });
+    *ctx = c;
+    return 0;
+}
+
+extern "C" uint64_t qrl_peer_ctx_push(void* ctx, const qrl_peer_push_args* args, void* main_stream) {
+    using namespace qrl;
+    if (ctx == nullptr || args == nullptr || !args->src || !args->dst || !args->flag_src || !args->flag_dst || !args->step_done ||
+        !args->copy_done) {
+        fail(QRL_E_INVALID, "%s", "qrl_peer_ctx_push: NULL argument");
+        return 0;
+    }
+    PeerCtx* c = static_cast<PeerCtx*>(ctx);
+    // in stream order, right behind the step launch: this one call stays on the caller's thread
+    cudaError_t e = cudaEventRecord((cudaEvent_t)args->step_done, (cudaStream_t)main_stream);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaEventRecord(step_done)"); return 0; }
+    uint64_t seq;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (c->error != 0) { cuda_fail((cudaError_t)c->error, "qrl_peer_ctx worker"); return 0; }
+        seq = c->next_seq++;
+        c->jobs.emplace_back(seq, *args);
+    }
+    c->cv_job.notify_one();
+    return seq;
+}
+
+extern "C" int qrl_peer_ctx_wait(void* ctx, uint64_t seq) {
+    using namespace qrl;
+    QRL_REQUIRE(ctx != nullptr, "qrl_peer_ctx_wait: ctx is NULL");
+    if (seq == 0) return 0;
+    PeerCtx* c = static_cast<PeerCtx*>(ctx);
+    cudaEvent_t ev = nullptr;
+    {
+        std::unique_lock<std::mutex> lk(c->mu);
+        QRL_REQUIRE(seq < c->next_seq, "qrl_peer_ctx_wait: unknown sequence number");
+        c->cv_done.wait(lk, [&] { return c->issued >= seq || c->error != 0; });
+        if (c->error != 0) return cuda_fail((cudaError_t)c->error, "qrl_peer_ctx worker");
+        if (c->issued - seq < 64) ev = c->copy_done_of[seq % 64];     // older jobs: their events have long been re-recorded
+    }
+    if (ev) QRL_CUDA(cudaEventSynchronize(ev));
+    return 0;
+}
+
+extern "C" int qrl_peer_ctx_destroy(void* ctx) {
+    using namespace qrl;
+    if (ctx == nullptr) return 0;
+    PeerCtx* c = static_cast<PeerCtx*>(ctx);
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        c->stop = true;
+    }
+    c->cv_job.notify_all();
+    if (c->worker.joinable()) c->worker.join();
+    delete c;
     return 0;
 }
 
