@@ -9,8 +9,11 @@
 // that have finished move over NVLink while the others still integrate; 16-byte loads from peer memory, 16-byte stores to
 // the gathered block.  The last block advances the learner's epoch counter and hands every rank the credit (`pulled`)
 // that lets it reuse the ring slice.
+#include <chrono>
+#if defined(__linux__)
+#include <sys/prctl.h>
+#endif
 #include <condition_variable>
-#include <deque>
 #include <mutex>
 #include <thread>
 
@@ -123,43 +126,59 @@ extern "C" int qrl_peer_push(const qrl_peer_push_args* args, void* main_stream, 
 }
 
 // ---- worker-thread context of the push exchange -------------------------------------------------------------------
+// Single producer (the stepping thread) / single consumer (the worker) ring of jobs, lock free on the producer's side.
+// While a step loop is running the worker polls the ring with short timed sleeps (~25-70 us): a condition-variable
+// wake-up per step costs the stepping thread a futex system call (measured 36 instead of 27 us per step on two of eight
+// ranks), a busy-polling worker takes a core that eight ranks on one box do not have to spare (34.6 us) — and the
+// transfer is not latency critical (the ring of slices is 16 steps deep).  After ~20 ms without a job the worker sleeps on
+// a condition variable and the next push wakes it.
 namespace qrl {
 struct PeerCtx {
+    static constexpr uint64_t RING = 256;
     int device = 0;
     cudaStream_t side = nullptr;
+    qrl_peer_push_args ring[RING];
+    std::atomic<uint64_t> head{0};             // jobs produced (sequence number of the newest job)
+    std::atomic<uint64_t> issued{0};           // jobs whose driver calls have been made
+    std::atomic<int> error{0};
+    std::atomic<bool> sleeping{false}, stop{false};
     std::mutex mu;
-    std::condition_variable cv_job, cv_done;
-    std::deque<std::pair<uint64_t, qrl_peer_push_args>> jobs;
-    uint64_t next_seq = 1, issued = 0;
-    cudaEvent_t copy_done_of[64] = {nullptr};      // copy_done event of job seq (ring indexed by seq % 64)
-    int error = 0;
-    bool stop = false;
+    std::condition_variable cv;
     std::thread worker;
 
     void run() {
         cudaSetDevice(device);
+#if defined(__linux__)
+        prctl(PR_SET_TIMERSLACK, 1000UL, 0UL, 0UL, 0UL);   // 1 us instead of the default 50 us of timer slack for this thread
+#endif
+        uint64_t done = 0;
+        int idle = 0;
         for (;;) {
-            std::pair<uint64_t, qrl_peer_push_args> job;
-            {
-                std::unique_lock<std::mutex> lk(mu);
-                cv_job.wait(lk, [&] { return stop || !jobs.empty(); });
-                if (jobs.empty()) return;
-                job = jobs.front();
-                jobs.pop_front();
+            if (done < head.load(std::memory_order_acquire)) {
+                idle = 0;
+                const uint64_t seq = done + 1;
+                const qrl_peer_push_args a = ring[seq % RING];
+                cudaError_t e = cudaStreamWaitEvent(side, (cudaEvent_t)a.step_done, 0);
+                if (e == cudaSuccess && a.bytes > 0) e = cudaMemcpyAsync(a.dst, a.src, (size_t)a.bytes, cudaMemcpyDefault, side);
+                if (e == cudaSuccess && a.src2 && a.dst2 && a.bytes2 > 0) e = cudaMemcpyAsync(a.dst2, a.src2, (size_t)a.bytes2, cudaMemcpyDefault, side);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(a.flag_dst, a.flag_src, 8, cudaMemcpyDefault, side);
+                if (e == cudaSuccess) e = cudaEventRecord((cudaEvent_t)a.copy_done, side);
+                if (e != cudaSuccess && error.load() == 0) error.store((int)e);
+                done = seq;
+                issued.store(seq, std::memory_order_release);
+                continue;
             }
-            const qrl_peer_push_args& a = job.second;
-            cudaError_t e = cudaStreamWaitEvent(side, (cudaEvent_t)a.step_done, 0);
-            if (e == cudaSuccess && a.bytes > 0) e = cudaMemcpyAsync(a.dst, a.src, (size_t)a.bytes, cudaMemcpyDefault, side);
-            if (e == cudaSuccess && a.src2 && a.dst2 && a.bytes2 > 0) e = cudaMemcpyAsync(a.dst2, a.src2, (size_t)a.bytes2, cudaMemcpyDefault, side);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(a.flag_dst, a.flag_src, 8, cudaMemcpyDefault, side);
-            if (e == cudaSuccess) e = cudaEventRecord((cudaEvent_t)a.copy_done, side);
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                if (e != cudaSuccess && error == 0) error = (int)e;
-                copy_done_of[job.first % 64] = (cudaEvent_t)a.copy_done;
-                issued = job.first;
+            if (stop.load()) return;
+            if (++idle < 400) {                // ~20 ms of timed polling
+                std::this_thread::sleep_for(std::chrono::microseconds(20));
+                continue;
             }
-            cv_done.notify_all();
+            std::unique_lock<std::mutex> lk(mu);
+            sleeping.store(true);
+            if (done >= head.load(std::memory_order_acquire) && !stop.load())
+                cv.wait_for(lk, std::chrono::milliseconds(50));
+            sleeping.store(false);
+            idle = 0;
         }
     }
 };
@@ -184,17 +203,18 @@ extern "C" uint64_t qrl_peer_ctx_push(void* ctx, const qrl_peer_push_args* args,
         return 0;
     }
     PeerCtx* c = static_cast<PeerCtx*>(ctx);
+    if (c->error.load() != 0) { cuda_fail((cudaError_t)c->error.load(), "qrl_peer_ctx worker"); return 0; }
     // in stream order, right behind the step launch: this one call stays on the caller's thread
     cudaError_t e = cudaEventRecord((cudaEvent_t)args->step_done, (cudaStream_t)main_stream);
     if (e != cudaSuccess) { cuda_fail(e, "cudaEventRecord(step_done)"); return 0; }
-    uint64_t seq;
-    {
+    const uint64_t seq = c->head.load(std::memory_order_relaxed) + 1;
+    while (seq - c->issued.load(std::memory_order_acquire) >= PeerCtx::RING) std::this_thread::yield();   // (never in practice)
+    c->ring[seq % PeerCtx::RING] = *args;
+    c->head.store(seq, std::memory_order_release);
+    if (c->sleeping.load()) {
         std::lock_guard<std::mutex> lk(c->mu);
-        if (c->error != 0) { cuda_fail((cudaError_t)c->error, "qrl_peer_ctx worker"); return 0; }
-        seq = c->next_seq++;
-        c->jobs.emplace_back(seq, *args);
+        c->cv.notify_one();
     }
-    c->cv_job.notify_one();
     return seq;
 }
 
@@ -203,15 +223,15 @@ extern "C" int qrl_peer_ctx_wait(void* ctx, uint64_t seq) {
     QRL_REQUIRE(ctx != nullptr, "qrl_peer_ctx_wait: ctx is NULL");
     if (seq == 0) return 0;
     PeerCtx* c = static_cast<PeerCtx*>(ctx);
-    cudaEvent_t ev = nullptr;
-    {
-        std::unique_lock<std::mutex> lk(c->mu);
-        QRL_REQUIRE(seq < c->next_seq, "qrl_peer_ctx_wait: unknown sequence number");
-        c->cv_done.wait(lk, [&] { return c->issued >= seq || c->error != 0; });
-        if (c->error != 0) return cuda_fail((cudaError_t)c->error, "qrl_peer_ctx worker");
-        if (c->issued - seq < 64) ev = c->copy_done_of[seq % 64];     // older jobs: their events have long been re-recorded
+    QRL_REQUIRE(seq <= c->head.load(), "qrl_peer_ctx_wait: unknown sequence number");
+    while (c->issued.load(std::memory_order_acquire) < seq) {
+        if (c->error.load() != 0) return cuda_fail((cudaError_t)c->error.load(), "qrl_peer_ctx worker");
+        std::this_thread::yield();
     }
-    if (ev) QRL_CUDA(cudaEventSynchronize(ev));
+    if (c->error.load() != 0) return cuda_fail((cudaError_t)c->error.load(), "qrl_peer_ctx worker");
+    // the slot of job `seq` still holds its arguments unless RING newer jobs have been produced since (then its copy has
+    // long finished and its event has been re-recorded for a later job)
+    if (c->head.load() - seq < PeerCtx::RING - 1) QRL_CUDA(cudaEventSynchronize((cudaEvent_t)c->ring[seq % PeerCtx::RING].copy_done));
     return 0;
 }
 
@@ -219,11 +239,11 @@ extern "C" int qrl_peer_ctx_destroy(void* ctx) {
     using namespace qrl;
     if (ctx == nullptr) return 0;
     PeerCtx* c = static_cast<PeerCtx*>(ctx);
+    c->stop.store(true);
     {
         std::lock_guard<std::mutex> lk(c->mu);
-        c->stop = true;
+        c->cv.notify_all();
     }
-    c->cv_job.notify_all();
     if (c->worker.joinable()) c->worker.join();
     delete c;
     return 0;
