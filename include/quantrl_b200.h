@@ -20,9 +20,9 @@
  * RNG stream (in-kernel noise, `rng_mode == QRL_RNG_PHILOX`), restated by oracle/em_oracle.py:philox_normals
  *   (x0,x1,x2,x3) = Philox4x32-10(counter = (tau, episode, env_global, comp), key = (seed lo32, seed hi32))
  *   u1 = 2 - bits(0x3FF<<52 | x1<<20 | x0>>12 | 1) in (0,1);  r = sqrt(-2 ln u1)
- *   B = x3<<20 | x2>>12 (52 bits);  alpha = (B mod 2^49) / 2^49 * pi/4;  (s, c) = (sin alpha, cos alpha);
- *   bit 49 of B swaps (s, c), bit 50 negates the first, bit 51 the second (the octant symmetries: a uniform direction);
- *   z0 = r s;  z1 = r c     (Box-Muller; ln/sqrt/sin/cos are evaluated by polynomial kernels accurate to < 1e-15)
+ *   j = x3>>24 (8 bits);  frac = ((x3 & 0xFFFFFF)<<28 | x2>>4) / 2^52;  theta = (j + frac) * 2 pi / 256;
+ *   z0 = r sin theta;  z1 = r cos theta     (Box-Muller; ln and sin/cos are evaluated from 256-entry tables + short
+ *   polynomials, sqrt by one third-order correction of the hardware seed: |dz| <= 5 * 2^-53 * r against libm)
  *   Stochastic path (qrl_em_step): the call with tau = global sub-step index k gives z0 -> Wiener increment of sub-step
  *   k -> k+1 (scaled by sqrt(t_ssz)) and z1 -> measurement noise of time index k+1 (scaled by obs_std), so every
  *   trajectory row after the first depends on exactly one call; the measurement noise of time index 0 (the reset

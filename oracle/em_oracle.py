@@ -162,26 +162,21 @@ def _bits_to_double(hi20, lo32):
 
 def philox_normals(seed, episode, tau, env, comp):
     """Two N(0,1) per counter (tau, episode, env, comp), key = (seed lo, seed hi): the stream of
-    include/quantrl_b200.h ("RNG stream"), evaluated with NumPy's libm instead of the kernel's polynomial kernels.
+    include/quantrl_b200.h ("RNG stream"), evaluated with NumPy's libm in extended precision (np.longdouble: 64-bit
+    mantissa on x86) instead of the kernel's table + polynomial kernels, then rounded to double.
 
       u1 = 2 - bits(0x3FF<<52 | x1<<20 | x0>>12 | 1)   in (0,1);   radius = sqrt(-2 ln u1)
-      B  = x3<<20 | x2>>12 (52 bits);  alpha = (B mod 2^49) / 2^49 * pi/4;  (s, c) = (sin alpha, cos alpha)
-      bit 49 of B swaps (s, c), bit 50 negates the first, bit 51 the second;  z0 = radius * s,  z1 = radius * c
+      j = x3 >> 24 (8 bits);  frac = ((x3 & 0xFFFFFF) << 28 | x2 >> 4) / 2^52;  theta = (j + frac) * 2 pi / 256
+      z0 = radius * sin theta,  z1 = radius * cos theta
     """
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     x0, x1, x2, x3 = philox4x32_10(tau, episode, env, comp, seed & 0xFFFFFFFF, seed >> 32)
-    u64 = np.uint64
+    u64, ld = np.uint64, np.longdouble
     d1 = _bits_to_double(x1 >> u64(12), ((x1 << u64(20)) & _MASK) | (x0 >> u64(12)) | u64(1))
-    radius = np.sqrt(-2.0 * np.log(2.0 - d1))
-    mant_hi = ((x3 << u64(3)) & _MASK) >> u64(12)
-    mant_lo = ((x3 << u64(23)) & _MASK) | ((x2 >> u64(9)) & u64(0xFFFFFFF8))
-    alpha = (_bits_to_double(mant_hi, mant_lo) - 1.0) * (np.pi / 4)
-    sn, cs = np.sin(alpha), np.cos(alpha)
-    swap = ((x3 >> u64(29)) & u64(1)) == 1
-    s0, c0 = np.where(swap, cs, sn), np.where(swap, sn, cs)
-    s0 = np.where(((x3 >> u64(30)) & u64(1)) == 1, -s0, s0)
-    c0 = np.where(((x3 >> u64(31)) & u64(1)) == 1, -c0, c0)
-    return radius * s0, radius * c0
+    radius = np.sqrt(-2 * np.log((2.0 - d1).astype(ld)))
+    frac = _bits_to_double((x3 >> u64(4)) & u64(0xFFFFF), ((x3 << u64(28)) & _MASK) | (x2 >> u64(4))) - 1.0
+    theta = ((x3 >> u64(24)).astype(ld) + frac.astype(ld)) * (ld("3.14159265358979323846264338327950288") / 128)
+    return (radius * np.sin(theta)).astype(np.float64), (radius * np.cos(theta)).astype(np.float64)
 
 
 def philox_noise_block(seed, episode, t_idx, K, env0, E, n):

@@ -38,7 +38,8 @@ def usable():
 def build(force=False):
     """Compile the C restatements (oracle/em_port.c, lyap_port.c, philox_port.c) into oracle/_build/; returns the EM library."""
     for src, out in ((SRC, LIB), (LYAP_SRC, LYAP_LIB), (PHILOX_SRC, PHILOX_LIB)):
-        if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        newest = max(os.path.getmtime(src), os.path.getmtime(os.path.join(HERE, "rng_tables.h")))
+        if force or not os.path.exists(out) or os.path.getmtime(out) < newest:
             os.makedirs(os.path.dirname(out), exist_ok=True)
             subprocess.run(["gcc", "-O3", "-march=x86-64-v3", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", src, "-o", out,
                             "-lm"], check=True)

@@ -29,6 +29,7 @@ namespace qrl {
 constexpr int T3_THREADS_MAX = 768;
 constexpr int T3_STAGES_MAX = 8;
 constexpr int T3_BAR_BYTES = 256;   // 3 * T3_STAGES_MAX mbarriers, rounded up: the tiles behind them stay 128-byte aligned
+constexpr int T3_TAB_BYTES = 8192;  // shared-memory copy of the generator's two lookup tables (philox.cuh)
 
 struct T3Plan { int G, C, D, nphase, nrt, threads, grid; size_t smem; };
 
@@ -104,7 +105,7 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
     uint64_t* full_w = reinterpret_cast<uint64_t*>(t3_raw);
     uint64_t* full_x = full_w + T3_STAGES_MAX;
     uint64_t* empty = full_x + T3_STAGES_MAX;
-    double* Wt = reinterpret_cast<double*>(t3_raw + T3_BAR_BYTES);   // [D][tile] increments, overwritten by the states
+    double* Wt = reinterpret_cast<double*>(t3_raw + T3_BAR_BYTES + T3_TAB_BYTES);   // [D][tile] increments, overwritten by the states
     double* Vt = Wt + D * tile;                // [D][tile] measurement noise, already scaled by obs_std
     double* x0S = Vt + D * tile;               // [RP] initial state (row 0)
     double* stdS = x0S + RP;                   // [RP] measurement-noise std per (env, comp)
@@ -132,6 +133,7 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
         }
     }
     // constants of a step sequence first (no step kernel writes them): behind the PDL wait they cost nothing
+    const RngTabSmem rng_tab = rng_tables_to_smem(t3_raw + T3_BAR_BYTES, tid, NT);
     for (int i = tid; i < Gl * N; i += NT) {
         const int el = i / N, c = i - el * N;
         stdS[i] = (philox && a.obs_std) ? a.obs_std[(int64_t)(e0 + el) * a.obs_std_stride_e + c] : 0.0;
@@ -329,7 +331,7 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
                             // the rounds of the next pair are issued in the same basic block as this pair's Box–Muller
                             nxt = philox4x32_10(make_uint4(tau_base + (uint32_t)(pr + nphase), a.episode, p_env, (uint32_t)p_c), keys);
                             double z0, z1;
-                            normal_pair(cur, z0, z1);
+                            normal_pair(cur, rng_tab, z0, z1);
                             *wp = __dmul_rn(sqrt_dt, z0);          // (row 0: never read — the recurrence puts x0 there)
                             *vp = __dmul_rn(p_sd, z1);
                         }
@@ -568,8 +570,8 @@ static T3Plan t3_plan(int E, int N, int K, int n_sel, int sms) {
     p.D = d_env ? atoi(d_env) : 3;
     if (p.D < 3) p.D = 3;
     if (p.D > T3_STAGES_MAX) p.D = T3_STAGES_MAX;
-    const size_t budget = 200 * 1024;
-    const size_t fixed = T3_BAR_BYTES + (size_t)(2 * RP + G + N + 64) * sizeof(double) + (size_t)n_sel * sizeof(int) + 64;
+    const size_t budget = 208 * 1024;
+    const size_t fixed = T3_BAR_BYTES + T3_TAB_BYTES + (size_t)(2 * RP + G + N + 64) * sizeof(double) + (size_t)n_sel * sizeof(int) + 64;
     const size_t per_row = (size_t)2 * RP * sizeof(double);
     int c_want = c_env ? atoi(c_env) : 36;     // few, long chunks: every chunk costs ~0.2 us of hand-over per role
     if (c_want < 1) c_want = 36;

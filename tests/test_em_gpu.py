@@ -101,6 +101,34 @@ def test_philox_pathwise_matches_oracle_stream(native, cuda):
     np.testing.assert_allclose(out["observations"].cpu().numpy(), ref + std * z_o, rtol=1e-10, atol=1e-12)
 
 
+def test_philox_normals_accuracy_against_libm(native, cuda):
+    """The generator itself, read out of the kernel exactly.  With A = 0, x0 = 0, dt = 1: nz = 1 makes the first state
+    row 0 + 1 * (1 * z0) = z0 of the call with tau = t_idx; nz = 0 and obs_std = 1 make Observations[1] = 0 + z1.  Both
+    kernels (tiled: tables in shared memory; generic: tables behind L1) against the extended-precision libm evaluation
+    of the same stream (oracle/em_oracle.py:philox_normals): |dz| <= 5 * 2^-53 * radius (philox.cuh's accuracy claim, the
+    same bound oracle/philox_port.c is held to on the CPU), and tiled == generic bit for bit."""
+    E, n, K = 4096, 4, 1
+    ph = dict(seed=0xFEEDFACE12345678, episode=5, t_idx=77, env_offset=3)
+    z0s, z1s = [], []
+    for flags in (0, N.EM_FORCE_GENERIC):
+        out = em_step(np.zeros((E, n)), np.zeros((n, n)), np.ones(n), 1.0, K, philox=ph, obs_std=np.ones(n), flags=flags)
+        z0s.append(out["states"][1].cpu().numpy())
+        out = em_step(np.zeros((E, n)), np.zeros((n, n)), np.zeros(n), 1.0, K, philox=ph, obs_std=np.ones(n), flags=flags)
+        z1s.append(out["observations"][1].cpu().numpy())
+    np.testing.assert_array_equal(z0s[0], z0s[1])
+    np.testing.assert_array_equal(z1s[0], z1s[1])
+    tau = np.full((1, 1, 1), ph["t_idx"], dtype=np.uint64)
+    env = (np.uint64(ph["env_offset"]) + np.arange(E, dtype=np.uint64)).reshape(1, -1, 1)
+    comp = np.arange(n, dtype=np.uint64).reshape(1, 1, -1)
+    r0, r1 = eo.philox_normals(ph["seed"], ph["episode"], tau, env, comp)
+    radius = np.hypot(r0[0], r1[0])
+    for z, r in ((z0s[0], r0[0]), (z1s[0], r1[0])):
+        err = np.abs(z - r)
+        assert np.max(err / radius) < 5 * 2.0 ** -53, np.max(err / radius) * 2.0 ** 53
+        assert np.mean(err > 2 * np.spacing(np.abs(r))) < 0.01
+    assert np.max(np.abs(np.hypot(z0s[0], z1s[0]) - radius) / radius) < 7 * 2.0 ** -53
+
+
 def test_philox_sharding_invariance_full_size(native, cuda):
     """BASELINE config 3 size (E=4096, n=4, K=100): two half shards with env_offset == one full launch, bitwise."""
     rng = np.random.default_rng(1)

@@ -84,9 +84,9 @@ def test_c_lyapunov_port_matches_rk4_on_the_reference_func(golden_dir, substeps,
 
 def test_c_philox_known_answers_and_polynomial_normals():
     """oracle/philox_port.c restates csrc/philox.cuh operation by operation.  (1) Random123's Philox4x32-10 known-answer
-    vectors; (2) the kernel's polynomial Box–Muller (fdlibm ln / sin / cos kernels, Goldschmidt sqrt) against the libm
-    evaluation of the same stream (oracle/em_oracle.py:philox_normals): a few ulp — the accuracy claim of philox.cuh,
-    checked without a GPU — and the moments of the polynomial normals themselves."""
+    vectors; (2) the kernel's table-driven Box–Muller (256-bin ln and sin / cos tables + short polynomials, third-order
+    sqrt) against the extended-precision libm evaluation of the same stream (oracle/em_oracle.py:philox_normals): the
+    accuracy claim of philox.cuh, |dz| <= 5 * 2^-53 * radius, checked without a GPU — and the moments of those normals."""
     assert em_port.philox4x32_10([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
     assert em_port.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert em_port.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
@@ -99,8 +99,13 @@ def test_c_philox_known_answers_and_polynomial_normals():
     r0, r1 = eo.philox_normals(seed, episode, tau, env, comp)
     z0, z1 = em_port.philox_normals_poly(seed, episode, tau, env, comp)
     z0, z1 = z0.reshape(r0.shape), z1.reshape(r1.shape)
+    radius = np.hypot(r0, r1)
     for z, r in ((z0, r0), (z1, r1)):
-        assert np.max(np.abs(z - r)) < 4e-15 and np.max(np.abs(z - r) / np.maximum(np.abs(r), 1e-3)) < 2e-15
+        err = np.abs(z - r)
+        assert np.max(err) < 4e-15 and np.max(err / radius) < 5 * 2.0 ** -53
+        assert np.mean(err > 2 * np.spacing(np.abs(r))) < 0.01          # more than 2 ulp of the value itself: < 1 %
+    # radius alone (sin^2 + cos^2 = 1 up to the direction's error): -2 ln u1 and its square root within 2 ulp
+    assert np.max(np.abs(np.hypot(z0, z1) - radius) / radius) < 7 * 2.0 ** -53
     z = np.concatenate([z0.ravel(), z1.ravel()])
     m = z.size
     assert abs(z.mean()) < 5 / np.sqrt(m) and abs(z.var() - 1) < 5 * np.sqrt(2 / m) and abs((z ** 4).mean() - 3) < 5 * np.sqrt(96 / m)
