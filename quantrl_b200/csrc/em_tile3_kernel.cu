@@ -107,11 +107,8 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
     uint64_t* empty = full_x + T3_STAGES_MAX;
     double* Wt = reinterpret_cast<double*>(t3_raw + T3_BAR_BYTES + T3_TAB_BYTES);   // [D][tile] increments, overwritten by the states
     double* Vt = Wt + D * tile;                // [D][tile] measurement noise, already scaled by obs_std
-    double* x0S = Vt + D * tile;               // [RP] initial state (row 0)
-    double* stdS = x0S + RP;                   // [RP] measurement-noise std per (env, comp)
-    double* cumS = stdS + RP;                  // [G]  cumulative reward after this interval
-    double* wS = cumS + G;                     // [N]  reward weights
-    double* mmS = wS + N;                      // [64] per-warp min / max partials
+    double* cumS = Vt + D * tile;              // [G]  cumulative reward before (prologue) / after (last row) this interval
+    double* mmS = cumS + G;                    // [64] per-warp min / max partials
     int* selS = reinterpret_cast<int*>(mmS + 64);  // [n_sel]
 
     const int tid = threadIdx.x;
@@ -132,30 +129,45 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
             mbar_init(empty + s, (uint32_t)NW);
         }
     }
-    // constants of a step sequence first (no step kernel writes them): behind the PDL wait they cost nothing
-    const RngTabSmem rng_tab = rng_tables_to_smem(t3_raw + T3_BAR_BYTES, tid, NT);
-    for (int i = tid; i < Gl * N; i += NT) {
-        const int el = i / N, c = i - el * N;
-        stdS[i] = (philox && a.obs_std) ? a.obs_std[(int64_t)(e0 + el) * a.obs_std_stride_e + c] : 0.0;
-    }
-    if (tid < N) wS[tid] = has_reward ? a.reward_w[tid] : 0.0;
-    if (a.packed)
-        for (int i = tid; i < n_sel; i += NT) {
-            const int s = a.sel_idxs[i];
-            selS[i] = s < 0 ? s + n_data : s;
-        }
+    // ---- prologue.  Every global load of the launch's set-up is ISSUED before the first of them is consumed, in both
+    // roles: one round trip to L2 instead of four serial ones (tables, noise scales, x0, drift rows; the timeline of round
+    // 2's first version showed 2.1 us from kernel entry to the barrier and 3.4 us to the first pair of normals).
+    // Constants of a step sequence first (no step kernel writes them): behind the PDL wait they cost nothing.
+    double2 tab_v = make_double2(0.0, 0.0);
+    if (tid < 512) tab_v = tid < 256 ? kRngLogTab[tid] : kRngSinCosTab[tid - 256];
+    int sel_v = 0;
+    if (a.packed && tid < n_sel) sel_v = a.sel_idxs[tid];
     if ((a.flags & QRL_EM_PDL) && is_rec && (tid % LR) == 0 && tid / LR < Gl) {
         const char* Ab = reinterpret_cast<const char*>(a.A + (int64_t)(e0 + tid / LR) * a.A_stride_e);
         for (int b = 0; b < N * N * 8; b += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(Ab + b));
     }
     // everything below reads what the previous kernel of the stream wrote (dyn, x0, cumulative rewards, actions)
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    for (int i = tid; i < Gl * N; i += NT) x0S[i] = a.x0[(int64_t)e0 * N + i];
     a = resolve_dyn(a_in);
-    if (a.peer_pulled && tid == 0) em_wait_pulled(a);     // publish-only exchange: flow control before anything is written
-    __syncthreads();
-    T3_TL_MARK(1)
-    T3_TRACE(0, 252)
+    double cum_v = 0.0;
+    if (tid < Gl && a.rewards_cum) cum_v = a.rewards_cum[e0 + tid];
+    RngTabSmem rng_tab;
+    rng_tab.lg_base = t3_smem(t3_raw + T3_BAR_BYTES);
+    rng_tab.sc_base = rng_tab.lg_base + 4096u;
+    // second half of the prologue, called by either role once ITS loads are in flight: shared-memory copies, then the
+    // CTA barrier (bar.sync 0 from two call sites: roles are whole warps)
+    auto publish_prologue = [&]() {
+        double2* tabS = reinterpret_cast<double2*>(t3_raw + T3_BAR_BYTES);
+        if (tid < 512) tabS[tid] = tab_v;
+        for (int i = tid + NT; i < 512; i += NT) tabS[i] = i < 256 ? kRngLogTab[i] : kRngSinCosTab[i - 256];   // (CTAs below 512 threads)
+        if (a.packed) {
+            if (tid < n_sel) selS[tid] = sel_v < 0 ? sel_v + n_data : sel_v;
+            for (int i = tid + NT; i < n_sel; i += NT) {
+                const int s2 = a.sel_idxs[i];
+                selS[i] = s2 < 0 ? s2 + n_data : s2;
+            }
+        }
+        if (tid < Gl) cumS[tid] = cum_v;       // cumulative reward BEFORE this interval (the last row adds to it)
+        if (a.peer_pulled && tid == 0) em_wait_pulled(a);     // publish-only exchange: flow control before anything is written
+        asm volatile("bar.sync 0;" ::: "memory");
+        T3_TL_MARK(1)
+        T3_TRACE(0, 252)
+    };
 
     const double sqrt_dt = sqrt(a.t_ssz);
     const uint32_t row32 = (uint32_t)(E * N);  // doubles per time row (the dispatcher guarantees (K+1) * E * N < 2^31)
@@ -167,9 +179,6 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
     // of each pass: the kernel is sensitive to instruction-cache pressure).
     if (!is_rec) {
         // ================================= workers: produce noise, write rows ==================================
-        bool pack_rows = false;                // any cache column besides the cumulative reward (written at the end)?
-        if (a.packed)
-            for (int j = 0; j < n_sel; ++j) pack_rows |= (selS[j] != n_data - 1);
 
         // ---- output, piece pass: one 16-byte piece (two components) of a row per worker and trip: LDS.128 of states and
         // noise, two adds, STG.128 into the States / Observations blocks (a warp writes 512 contiguous bytes), NaN-ignoring
@@ -181,7 +190,7 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
         const int q_dsl = NW / PR, q_dpc = NW - q_dsl * PR;
         const int q_sl0 = wt / PR, q_pc0 = wt - q_sl0 * PR;
         const int q_h = wt & (L - 1);          // which piece of its environment this lane holds (adjacent lanes)
-        const double q_w0 = wS[2 * q_h], q_w1 = wS[2 * q_h + 1];
+        const double q_w0 = has_reward ? a.reward_w[2 * q_h] : 0.0, q_w1 = has_reward ? a.reward_w[2 * q_h + 1] : 0.0;
         auto piece_pass = [&](const double* Xb, const double* Vb, int r_first, int ns) {
             int sl = q_sl0, pc = q_pc0;
             uint32_t g = (uint32_t)(r_first + sl) * row32 + (uint32_t)(e0 * N + 2 * pc);
@@ -284,9 +293,13 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
         int pr = p_phase;                      // next row this worker generates (phase 0 starts with row 0)
         uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
         if (philox && p_live) {
-            p_sd = stdS[p_col];
+            if (a.obs_std) p_sd = a.obs_std[(int64_t)(e0 + p_el) * a.obs_std_stride_e + p_c];
             nxt = philox4x32_10(make_uint4(tau_base + (uint32_t)pr, a.episode, p_env, (uint32_t)p_c), keys);
         }
+        publish_prologue();
+        bool pack_rows = false;                // any cache column besides the cumulative reward (written at the end)?
+        if (a.packed)
+            for (int j = 0; j < n_sel; ++j) pack_rows |= (selS[j] != n_data - 1);
 
         int s_out = 0, s_in = 0;               // ring stages of the chunk being written out / produced
         uint32_t par_out = 0u, par_in = 1u;    // parities: full_x of the chunk written out; empty of the stage refilled
@@ -405,8 +418,12 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
                 nzr[i] = a.nz[(int64_t)e * a.nz_stride_e + RO * q + i];
             }
 #pragma unroll
-            for (int c = 0; c < N; ++c) x[c] = x0S[el_c * N + c];
+            for (int c = 0; c < N; ++c) x[c] = a.x0[(int64_t)e * N + c];
         }
+        double x0r[RO];                        // this lane's piece of row 0
+#pragma unroll
+        for (int i = 0; i < RO; ++i) x0r[i] = a.x0[(int64_t)(e0 + el_c) * N + RO * q + i];
+        publish_prologue();
         int s = 0;
         uint32_t par = 0u;
         for (int c = 0; c < NC; ++c) {
@@ -440,9 +457,6 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
             };
             int slot = 0;
             if (c == 0) {                      // row 0 = the initial state
-                double x0r[RO];
-#pragma unroll
-                for (int i = 0; i < RO; ++i) x0r[i] = x0S[el_c * N + RO * q + i];
                 if (rec_live) store_x(Wb, x0r);
                 slot = 1;
             }
@@ -571,7 +585,7 @@ static T3Plan t3_plan(int E, int N, int K, int n_sel, int sms) {
     if (p.D < 3) p.D = 3;
     if (p.D > T3_STAGES_MAX) p.D = T3_STAGES_MAX;
     const size_t budget = 208 * 1024;
-    const size_t fixed = T3_BAR_BYTES + T3_TAB_BYTES + (size_t)(2 * RP + G + N + 64) * sizeof(double) + (size_t)n_sel * sizeof(int) + 64;
+    const size_t fixed = T3_BAR_BYTES + T3_TAB_BYTES + (size_t)(G + 64) * sizeof(double) + (size_t)n_sel * sizeof(int) + 64;
     const size_t per_row = (size_t)2 * RP * sizeof(double);
     int c_want = c_env ? atoi(c_env) : 36;     // few, long chunks: every chunk costs ~0.2 us of hand-over per role
     if (c_want < 1) c_want = 36;
