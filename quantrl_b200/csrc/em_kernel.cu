@@ -20,10 +20,14 @@ namespace qrl {
 template <int LPE>
 __global__ void __launch_bounds__(128) em_step_kernel(const qrl_em_args a_in, const PhiloxKeys keys) {
     const qrl_em_args a = resolve_dyn(a_in);
-    if (a.peer_pulled) {               // publish-only exchange: flow control before anything is written
-        if (threadIdx.x == 0) em_wait_pulled(a);
-        __syncthreads();
-    }
+    // the generator's lookup tables in shared memory (philox.cuh): random 16-byte reads cost ~10 shared-memory wavefronts per
+    // warp, ~16+ L1 tag look-ups when they go through the read-only path (config-3 size: 72.5 vs 65.5 us per interval)
+    __shared__ __align__(16) unsigned char rng_tab_smem[8192];
+    RngTabSmem rng_tab;
+    rng_tab.lg_base = rng_tab.sc_base = 0u;
+    if (a.rng_mode == QRL_RNG_PHILOX) rng_tab = rng_tables_to_smem(rng_tab_smem, threadIdx.x, blockDim.x);
+    if (a.peer_pulled && threadIdx.x == 0) em_wait_pulled(a);     // publish-only exchange: flow control before anything is written
+    __syncthreads();
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int e = tid / LPE;
     const int c = tid % LPE;
@@ -67,7 +71,7 @@ __global__ void __launch_bounds__(128) em_step_kernel(const qrl_em_args a_in, co
     if (philox && a.obs_std) {
         double z0, z1;
         const uint32_t tau = a.t_idx > 0 ? (uint32_t)(a.t_idx - 1) : 0xFFFFFFFFu;
-        philox_normal2(keys, tau, a.episode, env_g, (uint32_t)c, z0, z1);
+        normal_pair(philox4x32_10(make_uint4(tau, a.episode, env_g, (uint32_t)c), keys), rng_tab, z0, z1);
         v = __dmul_rn(std_c, z1);
     }
 
@@ -95,7 +99,7 @@ __global__ void __launch_bounds__(128) em_step_kernel(const qrl_em_args a_in, co
         double w;
         if (philox) {
             double z0, z1;
-            philox_normal2(keys, (uint32_t)(a.t_idx + i), a.episode, env_g, (uint32_t)c, z0, z1);
+            normal_pair(philox4x32_10(make_uint4((uint32_t)(a.t_idx + i), a.episode, env_g, (uint32_t)c), keys), rng_tab, z0, z1);
             w = __dmul_rn(sqrt_dt, z0);
             v = __dmul_rn(std_c, z1);
         } else {

@@ -230,8 +230,8 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
                         if (has_reward && q_h == L - 1) {
                             if (a.reward_last) a.reward_last[e] = rv;
                             if (a.reward_last_b) a.reward_last_b[e] = rv;
-                            double cum = rv;
-                            if (a.rewards_cum) { cum += a.rewards_cum[e]; a.rewards_cum[e] = cum; }
+                            const double cum = a.rewards_cum ? rv + cumS[el] : rv;   // (the old value was fetched in the prologue)
+                            if (a.rewards_cum) a.rewards_cum[e] = cum;
                             cumS[el] = cum;
                         }
                         const int64_t gl = (int64_t)e0 * N + 2 * pc;

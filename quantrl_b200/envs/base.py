@@ -533,7 +533,13 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
             self.io.dump_part_async(data=part, batch_idx=self.batch_idx, part_idx=self.action_idx - 1)
 
     def _fetch_step_outputs(self):
-        """One D2H of [obs_last | reward_last | min,max] into pinned memory, then a stream sync."""
+        """One D2H of [obs_last | reward_last | min,max] into pinned memory, then a stream sync.  An env whose launch has
+        already delivered the results (zero-copy) leaves an event in ``_host_event``: the host then waits for that point of
+        the stream only — launches enqueued after it (cache rows) do not hold the step up."""
+        ev = self.__dict__.pop("_host_event", None)
+        if ev is not None:
+            ev.synchronize()
+            return self._h_out
         self._h_out.copy_(self._step_out, non_blocking=True)
         raw = N.current_raw_stream()
         if raw != getattr(self, "_sync_raw", None):     # the Stream object is looked up again only when the stream changes

@@ -190,6 +190,37 @@ class LinearizedHOVecEnv(BaseVecEnv):
         self._actions_lazy = lambda: h.to(self.device, non_blocking=True) * self.action_maximums_batch
         return True
 
+    def _zero_copy_out(self):
+        """Device-side views of the pinned result buffer of this step (``return_numpy`` envs with a fused reward functor on
+        platforms that map pinned memory), else ``None``: the D2H copy of ``[obs | reward | min,max]`` is then one node."""
+        zc = self.__dict__.get("_zc_out")
+        if zc is None:
+            zc = False
+            if getattr(self, "host_zero_copy", True) and self.return_numpy and self._reward_fused and self._obs_last_ptr is None:
+                try:
+                    E, no = self.n_envs, self.n_observations
+                    zc = []
+                    for b in self._h_out_bufs:
+                        base = N.host_device_pointer(b)
+                        zc.append({"obs": base, "reward": base + 8 * E * no, "tail_host": b[E * (no + 1):]})
+                    self._step_tail = self._step_out[E * (no + 1):]
+                    self._fetch_event = torch.cuda.Event()
+                    n_data = 1 + self.n_actions + no + self.n_properties + 1
+                    self._pack_reads_actions = self._packed is not None or any(
+                        1 <= (i + n_data if i < 0 else i) <= self.n_actions for i in self.data_idxs)
+                    self._host_event_after_pack = False
+                except N.NativeError:
+                    zc = False    # pinned memory not mapped on this platform: keep the D2H copy
+            self._zc_out = zc
+        return zc[self._h_sel] if zc else None
+
+    def update_data(self):
+        super().update_data()
+        if self.__dict__.get("_host_event_after_pack"):
+            self._host_event_after_pack = False
+            self._fetch_event.record()
+            self._host_event = self._fetch_event
+
     def _set_actions(self, a):
         if self.system is None or self.system["system"] == "const_AD" or self.n_actions > 4:
             return super()._set_actions(a)
@@ -215,10 +246,12 @@ class LinearizedHOVecEnv(BaseVecEnv):
         a.n_actions, a.action_scale = self.n_actions, N.ptr(self.action_maximums)
         a.y0, a.y_last, a.states = N.ptr(self._x_last), N.ptr(self._x_last), N.ptr(self._States)
         a.observations, a.obs_last = N.ptr(self._Observations), N.ptr(self._obs_last)
+        self._obs_last_dev_ptr, self._reward_last_dev_ptr = N.ptr(self._obs_last), None
         a.obs_minmax, a.nan_flag = N.ptr(self._minmax), N.ptr(self._nan)
         if self.reward_functor is not None:
             a.reward_kind, a.reward = _REWARD_KINDS[self.reward_functor], N.ptr(self._Reward)
             a.reward_last, a.rewards_cum = N.ptr(self._reward_last), N.ptr(self.rewards)
+            self._reward_last_dev_ptr = N.ptr(self._reward_last)
         if self.observation_stds is not None and self.rng != "fed":
             a.obs_std, a.obs_std_stride_e = N.ptr(self.observation_stds), (self.n_observations if self.observation_stds.dim() == 2 else 0)
             a.seed, a.env_offset = self._philox_seed, self.env_offset
@@ -238,12 +271,28 @@ class LinearizedHOVecEnv(BaseVecEnv):
         if fast:
             a = self._fused_args(dim)
             a.actions = self._raw_actions_ptr      # pinned host memory (step(host array)) or the caller's CUDA tensor
-            if self._host_step:
-                self._minmax.copy_(self._minmax_init, non_blocking=True)
+            # (no per-step reset of the min/max accumulators: they run over the episode — reset() re-arms them — and
+            # "max > hi or min < lo so far" is the reference's per-block check (base.py:485-499) at every step, because the
+            # first block that leaves the range ends the episode)
             a.t0, a.t_idx, a.episode = float(self._T_host[t0]), t0, self.batch_idx & 0xFFFFFFFF
             if self.observation_stds is not None and self.rng == "fed":
                 a.obs_noise = N.ptr(self.Observation_noises) + 8 * t0 * self.n_envs * self.n_observations
-            N.ode_step(a)
+            zc = self._zero_copy_out() if self._host_step else None
+            if zc is not None:
+                # step(host actions) -> host results: the kernel writes the last observations and rewards straight into the
+                # pinned result buffer (zero-copy over PCIe); only [min, max | status] (32 bytes) is copied, an event marks
+                # the point the host waits for, and the cache-row launch that follows runs behind the host's back
+                a.obs_last, a.reward_last = zc["obs"], zc["reward"]
+                N.ode_step(a)
+                zc["tail_host"].copy_(self._step_tail, non_blocking=True)
+                if self._pack_reads_actions:      # the cache-row launch reads the pinned actions: the host waits for it too
+                    self._host_event_after_pack = True
+                else:
+                    self._fetch_event.record()
+                    self._host_event = self._fetch_event
+            else:
+                a.obs_last, a.reward_last = self._obs_last_dev_ptr, self._reward_last_dev_ptr
+                N.ode_step(a)
             return self._States
         if self.system is not None:
             _ = self.actions                # (materialise the scaled actions for the generic launch below)
