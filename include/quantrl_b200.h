@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define QRL_ABI_VERSION 4
+#define QRL_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define QRL_API __attribute__((visibility("default")))
@@ -234,6 +234,15 @@ typedef struct qrl_em_args {
     /* optional second copy of the last rows (e.g. obs_last -> pinned host memory for step(), obs_last_b -> the ring) */
     double*   obs_last_b;
     double*   reward_last_b;
+    /* completion word (ABI 5; needs finish_counter) — for a host that waits for THIS step's results and nothing else
+     * (BaseSB3Env.step_wait, quantrl/envs/base.py:1250-1293): when done_flag is non-NULL every block fences at SYSTEM
+     * scope before it counts itself done, and the last block, after the bookkeeping above, stores done_value to
+     * *done_flag with a system-scope release.  done_flag is normally the device-side address of a pinned host word
+     * (qrl_host_device_pointer) next to obs_last / reward_last / minmax_out in pinned memory: a host that reads
+     * done_value there may read those results — without waiting for the grid to drain and the stream to report
+     * completion (qrl_em_step_host does exactly this). */
+    uint64_t* done_flag;
+    uint64_t  done_value;
 } qrl_em_args;
 
 #define QRL_EM_FORCE_GENERIC 1   /* flags: always use the generic lane-per-component kernel (A/B testing) */
@@ -255,6 +264,15 @@ typedef struct qrl_em_args {
  * synchronised; extra system fence after the flag stores / volatile polling + trailing system fence: A/B variants) */
 
 QRL_API int qrl_em_step(const qrl_em_args* args, void* stream);
+
+/* ABI 5: qrl_em_step + the host-side wait for the step's results in ONE call — the body of BaseSB3Env.step_wait
+ * (quantrl/envs/base.py:1250-1293) between "actions are in pinned memory" and "observations / reward are in pinned
+ * memory".  done_host NULL: enqueue, then cudaStreamSynchronize(stream).  done_host non-NULL (the HOST address of the
+ * pinned word args->done_flag points to): enqueue, then spin on *done_host until it equals args->done_value; the launch
+ * may still be draining when the call returns (later work on the stream is ordered behind it as usual).  After
+ * timeout_ms (0 = 2000) without the word, falls back to cudaStreamSynchronize and reports what that returns; a word still
+ * missing after a successful synchronisation is QRL_E_INVALID (done_flag / done_host do not name the same memory). */
+QRL_API int qrl_em_step_host(const qrl_em_args* args, void* stream, const volatile uint64_t* done_host, int32_t timeout_ms);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Deterministic action interval: modes + Lyapunov covariance  dV/dt = A V + V A^T + D  for E environments.

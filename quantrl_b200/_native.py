@@ -7,7 +7,7 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 RNG_FED, RNG_PHILOX = 0, 1
 STATUS_NONFINITE, STATUS_PEER_TIMEOUT = 1, 2
@@ -48,6 +48,7 @@ class EmArgs(C.Structure):
         ("peer_flags", _dp), ("peer_epoch", _dp), ("peer_rank", C.c_int32), ("peer_world", C.c_int32),
         ("peer_publish_value", C.c_uint64), ("peer_pulled", _dp), ("peer_pulled_min", C.c_uint64),
         ("peer_dst", C.c_int32), ("_pad1", C.c_int32), ("obs_last_b", _dp), ("reward_last_b", _dp),
+        ("done_flag", _dp), ("done_value", C.c_uint64),
     ]
 
 
@@ -101,6 +102,7 @@ SYMBOLS = {
     "qrl_launch_count": (C.c_uint64, []),
     "qrl_host_device_pointer": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "qrl_em_step": (C.c_int, [C.POINTER(EmArgs), C.c_void_p]),
+    "qrl_em_step_host": (C.c_int, [C.POINTER(EmArgs), C.c_void_p, C.c_void_p, C.c_int32]),
     "qrl_ode_step": (C.c_int, [C.POINTER(OdeArgs), C.c_void_p]),
     "qrl_pack_rows": (C.c_int, [C.POINTER(PackArgs), C.c_void_p]),
     "qrl_peer_pull": (C.c_int, [C.POINTER(PeerPullArgs), C.c_void_p]),

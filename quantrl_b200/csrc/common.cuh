@@ -202,7 +202,9 @@ __device__ __forceinline__ void em_finish_launch(const qrl_em_args& a) {
     // this block's min/max atomics, dyn reads and (peer barrier) its stores into the learner's buffer come first.
     // Publish-only exchange: the outputs are local, a device-scope fence per block is enough — the last block's
     // system-scope release below is cumulative over what it has observed through the counter
-    if (a.peer_flags && !publish_only && !(a.flags & 512)) __threadfence_system(); else __threadfence();
+    // Completion word (ABI 5): the rows this block stored to pinned host memory must be ordered before the word the
+    // last block stores there, so the block fences at system scope as well.
+    if ((a.peer_flags && !publish_only && !(a.flags & 512)) || a.done_flag) __threadfence_system(); else __threadfence();
     const unsigned prev = atomicAdd(a.finish_counter, 1u);
     if (prev != gridDim.x - 1) return;
     if (publish_only) {
@@ -218,6 +220,8 @@ __device__ __forceinline__ void em_finish_launch(const qrl_em_args& a) {
         *a.finish_counter = 0u;
         unsigned long long* dst = reinterpret_cast<unsigned long long*>(a.peer_flags[a.peer_dst]) + a.peer_rank;
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"((unsigned long long)a.peer_publish_value) : "memory");
+        if (a.done_flag)
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.done_flag), "l"((unsigned long long)a.done_value) : "memory");
         return;
     }
     // last block.  Cross-GPU barrier, part 1: publish this rank's new epoch in every rank's flag array FIRST — the
@@ -265,6 +269,8 @@ __device__ __forceinline__ void em_finish_launch(const qrl_em_args& a) {
         }
         if (!acq) __threadfence_system();
     }
+    if (a.done_flag)     // ABI 5: everything above (and, through the counter, every block's rows) is released with it
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.done_flag), "l"((unsigned long long)a.done_value) : "memory");
 }
 
 }  // namespace qrl

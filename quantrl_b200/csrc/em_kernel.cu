@@ -13,6 +13,7 @@
 // coalesced 8-byte-per-lane stores (one warp = 32 consecutive doubles of the (K+1,E,n) block).
 #include <stdlib.h>
 #include "common.cuh"
+#include <chrono>
 #include "philox.cuh"
 
 namespace qrl {
@@ -178,6 +179,7 @@ extern "C" int qrl_em_step(const qrl_em_args* args, void* stream) {
     QRL_REQUIRE(a.finish_counter != nullptr || (a.minmax_out == nullptr && a.dyn_advance == 0),
                 "qrl_em_step: minmax_out / dyn_advance need finish_counter");
     QRL_REQUIRE(a.minmax_out == nullptr || a.obs_minmax != nullptr, "qrl_em_step: minmax_out needs obs_minmax");
+    QRL_REQUIRE(a.done_flag == nullptr || a.finish_counter != nullptr, "qrl_em_step: done_flag needs finish_counter");
     QRL_REQUIRE(a.peer_flags == nullptr || (a.finish_counter != nullptr && ((a.flags & QRL_EM_PEER_PUBLISH) || a.peer_epoch != nullptr) &&
                                             a.peer_world >= 1 && a.peer_rank >= 0 && a.peer_rank < a.peer_world),
                 "qrl_em_step: the peer exchange needs finish_counter, peer_epoch (barrier mode) and 0 <= peer_rank < peer_world");
@@ -236,4 +238,36 @@ extern "C" int qrl_em_step(const qrl_em_args* args, void* stream) {
         if (a.finish_counter) bias = -a.dyn_advance;
     }
     return pack_rows_launch(p, bias, st);
+}
+
+// qrl_em_step + the host's wait for this step's results (header: ABI 5).  The spin reads a pinned host word the launch's
+// last block stores with a system-scope release: on x86 the PCIe writes that precede it are visible once it is.
+extern "C" int qrl_em_step_host(const qrl_em_args* args, void* stream, const volatile uint64_t* done_host, int32_t timeout_ms) {
+    using namespace qrl;
+    QRL_REQUIRE(args != nullptr, "qrl_em_step_host: args is NULL");
+    QRL_REQUIRE(done_host == nullptr || args->done_flag != nullptr, "qrl_em_step_host: done_host needs args->done_flag");
+    const int rc = qrl_em_step(args, stream);
+    if (rc != 0) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (done_host == nullptr || args->n_envs == 0) {
+        QRL_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    }
+    const uint64_t want = args->done_value;
+    const auto t0 = std::chrono::steady_clock::now();
+    const auto limit = std::chrono::milliseconds(timeout_ms > 0 ? timeout_ms : 2000);
+    for (unsigned spins = 0;; ++spins) {
+        if (*done_host == want) {
+            std::atomic_thread_fence(std::memory_order_acquire);
+            return 0;
+        }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+        if ((spins & 1023u) == 1023u && std::chrono::steady_clock::now() - t0 > limit) break;
+    }
+    QRL_CUDA(cudaStreamSynchronize(st));    // a failed launch surfaces here
+    QRL_REQUIRE(*done_host == want, "qrl_em_step_host: the launch completed without storing done_value (done_flag and "
+                                    "done_host do not name the same pinned word?)");
+    return 0;
 }

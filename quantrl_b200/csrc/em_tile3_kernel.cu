@@ -398,11 +398,27 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
             for (int i = 0; i < RO; ++i)
 #pragma unroll
                 for (int c = 0; c < N; ++c) M[i][c] = Ar[i * N + c];
+#pragma unroll
+            for (int i = 0; i < RO; ++i) nzr[i] = a.nz[(int64_t)e * a.nz_stride_e + RO * q + i];
+#pragma unroll
+            for (int c = 0; c < N; ++c) x[c] = a.x0[(int64_t)e * N + c];
+        }
+        double x0r[RO];                        // this lane's piece of row 0
+#pragma unroll
+        for (int i = 0; i < RO; ++i) x0r[i] = a.x0[(int64_t)(e0 + el_c) * N + RO * q + i];
+        // The raw actions are ISSUED here and consumed behind the CTA barrier: the workers (whose first chunk of noise does
+        // not depend on the actions) must not wait for them — with step(host actions) they come from pinned host memory
+        // over PCIe, a ~2 us round trip that now hides behind the production of chunk 0.
+        double u0 = 0.0;
+        if (a.A_act) u0 = a.actions[(int64_t)(e0 + el_c) * a.n_actions];
+        publish_prologue();
+        {
+            const int e = e0 + el_c;
             if (a.A_act) {
                 // action-affine drift functor, same accumulation order as em_drift(): A += u_k * A_k for k = 0, 1, ...
 #pragma unroll 1
                 for (int k = 0; k < a.n_actions; ++k) {
-                    const double u = a.actions[(int64_t)e * a.n_actions + k] * (a.action_scale ? a.action_scale[k] : 1.0);
+                    const double u = (k == 0 ? u0 : a.actions[(int64_t)e * a.n_actions + k]) * (a.action_scale ? a.action_scale[k] : 1.0);
                     const double* Ak = a.A_act + (int64_t)k * N * N + (int64_t)(RO * q) * N;
 #pragma unroll
                     for (int i = 0; i < RO; ++i)
@@ -411,19 +427,11 @@ em_tile3_kernel(const qrl_em_args a_in, const PhiloxKeys keys, const T3Plan pl) 
                 }
             }
 #pragma unroll
-            for (int i = 0; i < RO; ++i) {
+            for (int i = 0; i < RO; ++i)
 #pragma unroll
                 for (int c = 0; c < N; ++c)
                     M[i][c] = __dadd_rn((RO * q + i == c) ? 1.0 : 0.0, __dmul_rn(M[i][c], a.t_ssz));   // unfused like the reference
-                nzr[i] = a.nz[(int64_t)e * a.nz_stride_e + RO * q + i];
-            }
-#pragma unroll
-            for (int c = 0; c < N; ++c) x[c] = a.x0[(int64_t)e * N + c];
         }
-        double x0r[RO];                        // this lane's piece of row 0
-#pragma unroll
-        for (int i = 0; i < RO; ++i) x0r[i] = a.x0[(int64_t)(e0 + el_c) * N + RO * q + i];
-        publish_prologue();
         int s = 0;
         uint32_t par = 0u;
         for (int c = 0; c < NC; ++c) {

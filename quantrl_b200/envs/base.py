@@ -291,6 +291,7 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
                             for _ in range(2 if self.host_output_views else 1)]
         self._h_out_nps = [b.numpy() for b in self._h_out_bufs]
         self._h_status_nps = [b.view(np.int32) for b in self._h_out_nps]
+        self._h_views = [(b[:E * no].reshape(E, no), b[E * no:E * (no + 1)]) for b in self._h_out_nps]   # (obs, reward) views
         self._h_sel = 0
         self._h_out, self._h_out_np = self._h_out_bufs[0], self._h_out_nps[0]
         self._h_actions = torch.empty((E, self.n_actions), dtype=f64).pin_memory()
@@ -581,13 +582,17 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
             self._host_graph_done = False
         else:
             host = self._fetch_step_outputs()
+        return self._finish_host_step(host, observations, reward, terminated)
+
+    def _finish_host_step(self, host, observations, reward, terminated):
+        """Tail of ``step_wait`` once this step's results are in pinned memory: truncation check, the returned arrays, the
+        automatic reset (base.py:1262-1293)."""
         truncated = self.check_truncation(host)
         if truncated:
             print(f"Batch #{self.batch_idx} truncated")
         E, no = self.n_envs, self.n_observations
         if self.host_output_views:
-            reward_out = self._h_out_np[E * no:E * (no + 1)]
-            obs_out = self._h_out_np[:E * no].reshape(E, no)
+            obs_out, reward_out = self._h_views[self._h_sel]
         elif self.return_numpy:
             reward_out = self._h_out_np[E * no:E * (no + 1)].copy()
             obs_out = self._h_out_np[:E * no].reshape(E, no).copy()
@@ -605,6 +610,9 @@ class BaseVecEnv(*(() if _SB3VecEnv is None else (_SB3VecEnv,))):
         cumulative reward, packed cache rows) but no host round trip — actions are a CUDA tensor, the returned
         ``(observations, reward)`` are views of device buffers that the next step overwrites, and the truncation
         reduction stays on the device (``truncation_pending()`` reads it).  Returns ``(obs, reward, terminated)``."""
+        self._host_step = False     # (a preceding step(host actions) leaves it set: this step reads ``actions``, not the pinned buffer)
+        if not isinstance(actions, torch.Tensor):
+            actions = torch.as_tensor(np.asarray(actions, dtype=np.float64), device=self.device)
         self._set_actions(actions)
         observations, reward, terminated = self.update(reset_minmax=False)  # min/max accumulate over the episode
         self.update_data()

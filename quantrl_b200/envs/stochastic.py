@@ -109,17 +109,22 @@ class LinearVecEnv(BaseVecEnv):
     def _reset(self):
         if self.rng == "fed" and not getattr(self, "_fed_assigned", False):
             S1, E, n = self.shape_T[0], self.n_envs, self.n_observations
-            self.Ws = np.sqrt(self.t_ssz) * self.backend.normal(
+            Ws = np.sqrt(self.t_ssz) * self.backend.normal(
                 generator=self.backend.generator(seed=self.seed), shape=(S1 - 1, E, n), mean=0.0, std=1.0, dtype="real")
+            # (drawn into the SAME tensors every episode: captured graphs and cached argument blocks hold their addresses)
+            self.Ws = Ws if self.Ws is None or self.Ws.shape != Ws.shape else self.Ws.copy_(Ws)
             if self.observation_stds is not None:
-                self.Observation_noises = self.backend.normal(
+                noises = self.backend.normal(
                     generator=self.backend.generator(seed=self.seed), shape=(S1, E, n), mean=0.0, std=1.0,
                     dtype="real") * self.observation_stds.reshape(1, -1, n)
+                old = self.Observation_noises
+                self.Observation_noises = noises if old is None or old.shape != noises.shape else old.copy_(noises)
         if self.use_cuda_graph:
             # scalar fills: the values travel as kernel arguments, so a host that runs whole episodes ahead of the GPU
             # (device-resident loops) cannot overwrite a staging buffer before an earlier copy has executed
             self._dyn[0].fill_(0)
             self._dyn[1].fill_((self.batch_idx + 1) & 0xFFFFFFFF)
+            self._dyn_stale = False
         return super()._reset()
 
     def set_fed_noise(self, Ws, Observation_noises=None):
@@ -282,7 +287,7 @@ class LinearVecEnv(BaseVecEnv):
         assert not (self.use_cuda_graph and not self._single_kernel_step()), \
             "the peer exchange rotates the output slice launch by launch: it needs eager launches or the single-kernel step"
         self._peer = peer
-        self._graph = self._graph_host = self._graph_host1 = None
+        self._graph = self._graph_host = self._graph_host1 = self._fast_host = None
         self._static = {}
 
     def _peer_patch(self, a, host_io):
@@ -296,7 +301,7 @@ class LinearVecEnv(BaseVecEnv):
     def attach_peer_barrier(self, flag_ptrs, epoch, rank, world):
         """Fuse the per-step cross-GPU barrier of the sharded path into the captured step kernel (ABI 3)."""
         self._peer_barrier = (flag_ptrs, epoch, int(rank), int(world))
-        self._graph = self._graph_host = self._graph_host1 = None
+        self._graph = self._graph_host = self._graph_host1 = self._fast_host = None
         self._static = {}
 
     def _zero_copy(self):
@@ -357,6 +362,8 @@ class LinearVecEnv(BaseVecEnv):
                 self._actions_in.copy_(self._h_actions, non_blocking=True)
                 self._minmax.copy_(self._minmax_init, non_blocking=True)
             self.actions = (self._actions_in * self.action_maximums_batch)
+            if self.__dict__.get("_dyn_stale"):
+                self._sync_dyn()                # the eager launch reads the device-side index too
             self._launch(dim - 1, self._x_last)
             self._dyn[0] += dim - 1
         return self._States[:dim]
@@ -376,6 +383,16 @@ class LinearVecEnv(BaseVecEnv):
                 # every step anyway, so it also supplies the time index (the kernel still advances the device-side copy
                 # for the graph paths) and the kernel does not wait for a global load before its first Philox counter
                 a.flags |= N.EM_PDL | N.EM_HOST_TIDX
+                if os.environ.get("QRL_DEV_NO_PDL"):          # development knob (A/B of the device-resident loop)
+                    a.flags &= ~N.EM_PDL
+                # ... and because it does, the device-side index need not be advanced by this launch: without the
+                # last-block protocol (one __syncthreads, a fence and an atomic round trip on every CTA's way out) a step
+                # of the chained loop takes 23.0 instead of 24.9 us at config 3.  The index is brought up to date by a
+                # scalar fill before the next launch that reads it (``_sync_dyn``).  The kernel-driven exchanges (pull /
+                # fused barrier) keep the protocol: their last block publishes the epoch.
+                if (self._peer is None or self._peer.mode == "push") and self._peer_barrier is None \
+                        and not os.environ.get("QRL_DEV_KEEP_FINISH"):
+                    a.finish_counter, a.dyn_advance = None, 0
             stream = torch.cuda.current_stream()
             self._replay_stream = stream       # looked up once: the call costs ~10 us per step otherwise
             st = self._static[key] = {"a": a, "keep": keep, "zc": zc, "packs": self._packed_by_kernel,
@@ -402,12 +419,117 @@ class LinearVecEnv(BaseVecEnv):
         self._packed_by_kernel = st["packs"]
         if self._peer is not None:
             self._peer_patch(a, host_io)
+        if not host_io and not a.finish_counter:
+            self._dyn_stale = True              # this launch does not advance the device-side time index
+        elif self.__dict__.get("_dyn_stale"):
+            self._sync_dyn()
         N.em_step(a, st["stream"])
         if self._peer is not None:
             self._peer.after_launch(st["stream"])
         if host_io and st["zc"] is None:
             self._h_out.copy_(self._step_out, non_blocking=True)
         self._host_graph_done = host_io
+
+    # ---- step(host actions): the lean host round trip of the single-kernel step -------------------------------------
+    def _fast_host_setup(self):
+        """State of the lean ``step(host actions)`` path, or ``False`` when it does not apply: it needs the single-kernel
+        step with the zero-copy round trip (the launch reads the actions from and writes ``[obs | reward | min,max |
+        status]`` to pinned memory) and cache rows written by the same launch — then a full action interval is one
+        kernel and nothing else, and everything ``update()`` / ``update_data()`` do besides is host bookkeeping.
+
+        Two flavours of the launch + wait (measured at config 3 with nothing else on the host,
+        ``tools/e2e_breakdown.py``, ``profiles/r02x_e2e_breakdown.log``): replay of the captured one-kernel graph + stream
+        synchronisation 35.7 us (default), ``qrl_em_step_host`` (ABI 5: direct launch + spin on a completion word in pinned
+        memory, ``QRL_HOST_STEP_NATIVE=1``) 36.2 us — the kernel itself takes 22.9 us, the rest is launch latency and the
+        164 KB of results crossing PCIe at the end of the launch."""
+        if (os.environ.get("QRL_NO_FAST_HOST_STEP") or not self._single_kernel_step() or self._peer is not None
+                or self._peer_barrier is not None or self.n_properties > 0 or self.cache_all_data
+                or getattr(self, "_pre_sync_hook", None) is not None or getattr(self, "_em_events", None) is not None):
+            return False
+        if self._zero_copy() is None or (self.store_trajectory and not self.fuse_cache_rows):
+            return False
+        native = os.environ.get("QRL_HOST_STEP_NATIVE")      # "1": spin on the completion word, "sync": stream synchronisation
+        if not native:
+            return {"native": False}
+        E, no, blocks, sel0 = self.n_envs, self.n_observations, [], self._h_sel
+        for sel in range(len(self._h_out_bufs)):
+            self._h_sel = sel
+            zc = self._zero_copy()
+            a, keep = self.interval_args(self.action_interval, self._x_last, True, graph_mode="host")
+            a.flags |= N.EM_HOST_TIDX           # the host supplies the time index (dyn is still advanced by the last block)
+            spin = native != "sync"
+            if spin:
+                a.done_flag = zc["out"] + 8 * (E * (no + 1) + 3)
+            words = self._h_out_nps[sel].view(np.uint64)
+            blocks.append({"a": a, "ref": C.byref(a), "keep": keep, "packs": self._packed_by_kernel,
+                           "T_step": a.T_step, "packed": a.packed, "W": a.W, "obs_noise": a.obs_noise,
+                           "pitch": 8 * (a.packed_row_pitch if a.packed_row_pitch > 0 else a.n_sel),
+                           "done": C.c_void_p(words[E * (no + 1) + 3:].ctypes.data) if spin else None})
+        self._h_sel = sel0
+        stream = torch.cuda.current_stream()
+        self._replay_stream = stream
+        self._fast_seq = 0
+        return {"native": True, "blocks": blocks, "stream": C.c_void_p(stream.cuda_stream), "fn": N.lib().qrl_em_step_host}
+
+    def step(self, actions):
+        """``step_async`` + ``step_wait`` (base.py:1233-1293).  Host actions on a full action interval of the single-kernel
+        step take the lean path: copy the actions into pinned memory, replay the captured one-kernel graph (or call
+        ``qrl_em_step_host``), wait, and do the bookkeeping of ``update()`` / ``update_data()`` inline."""
+        fast = self.__dict__.get("_fast_host")
+        K = self.action_interval
+        t = self.t_idx
+        host_full = not isinstance(actions, torch.Tensor) and t + K < self.shape_T[0]
+        if fast is None and host_full:
+            fast = self._fast_host = self._fast_host_setup()
+        if not fast or not host_full:
+            return super().step(actions)
+        sel = self._h_sel ^ 1 if self.host_output_views else self._h_sel    # this step's results go to the other pinned buffer
+        if not fast["native"]:
+            graph = self._graph_host1 if sel else self._graph_host
+            if graph is None:                   # not captured yet: the general path captures it
+                return super().step(actions)
+        self._h_actions_np[...] = np.asarray(actions, dtype=np.float64).reshape(self.n_envs, self.n_actions)
+        if sel != self._h_sel:
+            self._h_sel = sel
+            self._h_out, self._h_out_np = self._h_out_bufs[sel], self._h_out_nps[sel]
+        if fast["native"]:
+            b = fast["blocks"][sel]
+            a = b["a"]
+            a.t_idx, a.episode = t, self.batch_idx & 0xFFFFFFFF
+            if b["packed"]:
+                a.T_step, a.packed = b["T_step"] + 8 * t, b["packed"] + b["pitch"] * t
+            if b["W"]:                          # rng='fed': rows of the fed draws
+                a.W = b["W"] + 8 * t * self.n_envs * self.n_observations
+                if b["obs_noise"]:
+                    a.obs_noise = b["obs_noise"] + 8 * t * self.n_envs * self.n_observations
+            self._fast_seq = a.done_value = self._fast_seq + 1
+            rc = fast["fn"](b["ref"], fast["stream"], b["done"], 0)
+            if rc != 0:
+                N.check(rc, "qrl_em_step_host")
+            self._packed_by_kernel = b["packs"]
+        else:
+            if self.__dict__.get("_dyn_stale"):
+                self._sync_dyn()
+            self.graph_replays += 1
+            graph.replay()
+            self._replay_stream.synchronize()
+            self._packed_by_kernel = self._graph_packs
+        # bookkeeping of update() / update_data() for a full interval (base.py:440-483, 1295-1380)
+        self._host_step, self._host_graph_done = True, False
+        self._dim, self._t_range = K + 1, (t, t + K + 1)
+        self.States, self.Observations, self.Reward = self._States, self._Observations, self._Reward
+        self._data_host = None
+        self.last_step_peer_fenced = False
+        self.t_idx = t = t + K
+        self.t = self._T_host[t]
+        self.action_idx += 1
+        return self._finish_host_step(self._h_out, self._obs_last, self._reward_last, not t + 1 < self.shape_T[0])
+
+    def _sync_dyn(self):
+        """The device-side time index = the host's, before a launch that reads it (graph replays, the host round trip)
+        follows device-resident steps that did not advance it."""
+        self._dyn[0].fill_(self.t_idx)
+        self._dyn_stale = False
 
     def _replay_interval(self, host_io=False):
         """One full action interval as ONE graph launch: actions scaling, the coefficient hooks (batched torch) and the
@@ -444,6 +566,8 @@ class LinearVecEnv(BaseVecEnv):
             setattr(self, key + "_keep", keep)
             self._graph_packs = self._packed_by_kernel
             self.graph_native_launches = N.launch_count() - n0   # kernels of libquantrl_b200.so inside one replay
+        if self.__dict__.get("_dyn_stale"):
+            self._sync_dyn()
         self.graph_replays += 1
         self._packed_by_kernel = self._graph_packs
         getattr(self, key).replay()

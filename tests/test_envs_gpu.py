@@ -335,6 +335,101 @@ def test_cuda_graph_replay_equals_eager(native, cuda):
     eager.close(); graph.close(); hostg.close(); hostv.close()
 
 
+def test_device_resident_steps_interleaved_with_host_steps(native, cuda):
+    """``step_device`` launches of the single-kernel step get their time index from the host and no longer advance the
+    device-side one (no last-block protocol); a host round trip (captured graph / re-enqueued block, which READ the
+    device-side index) that follows them must see it brought up to date.  Alternating the two kinds of step, over two
+    episodes with a tail interval, reproduces an env stepped through ``step(host actions)`` only — bit for bit."""
+    from quantrl_b200.systems import AffineLinearVecEnv, affine_matrices
+    A0, Au = affine_matrices(4, 1, seed=0)
+    E, K = 200, 10
+    kw = dict(n_envs=E, n=4, A0=A0, Au=Au, noise_prefixes=0.05, x0=1.0, t_norm_max=0.455, t_norm_ssz=0.01,
+              action_interval=K, observation_stds=[0.01] * 4, seed=11, dir_prefix="/tmp/qrl_test", use_cuda_graph=True,
+              fused_coefficients=True, return_numpy=True)
+    ref, mix = AffineLinearVecEnv(**kw), AffineLinearVecEnv(**kw)
+    np.testing.assert_array_equal(ref.reset(), mix.reset())
+    rng = np.random.default_rng(1)
+    pattern = [0, 0, 1, 0, 0, 1, 0, 1, 0, 1]      # 0 = device-resident step, 1 = host round trip (5 steps per episode, the last a tail)
+    for step, host in enumerate(pattern):
+        u = rng.uniform(-1, 1, (E, 1))
+        o_r, r_r, d_r, _ = ref.step(u)
+        if host:
+            o_m, r_m, d_m, _ = mix.step(u)
+            np.testing.assert_array_equal(o_r, o_m)
+            np.testing.assert_array_equal(r_r, r_m)
+            assert d_r == d_m
+        else:
+            o_m, r_m, term = mix.step_device(torch.as_tensor(u, device="cuda"))
+            if not d_r[0]:
+                np.testing.assert_array_equal(o_r, o_m.cpu().numpy())
+                np.testing.assert_array_equal(r_r, r_m.cpu().numpy())
+            assert term == d_r[0]
+            if term:
+                mix.reset()
+        assert ref.t_idx == mix.t_idx and ref.batch_idx == mix.batch_idx
+    np.testing.assert_array_equal(ref.data, mix.data)
+    ref.close(); mix.close()
+
+
+@pytest.mark.parametrize("views", [False, True])
+@pytest.mark.parametrize("rng", ["philox", "fed"])
+def test_lean_host_step_equals_the_general_step_path(native, cuda, monkeypatch, views, rng):
+    """``step(host actions)`` of the single-kernel step takes a lean path (``LinearVecEnv.step``): replay of the captured
+    one-kernel graph + inline bookkeeping, or — ``QRL_HOST_STEP_NATIVE`` — ONE native call (``qrl_em_step_host``, ABI 5:
+    launch + spin on the completion word the last block stores to pinned memory, or launch + stream synchronisation).
+    All three give the results of the general ``step_async`` / ``step_wait`` path (``QRL_NO_FAST_HOST_STEP``) bit for
+    bit, over two episodes with a tail interval, with copies and with views of the pinned result buffers."""
+    from quantrl_b200.systems import AffineLinearVecEnv, affine_matrices
+    A0, Au = affine_matrices(4, 1, seed=0)
+    E, K = 200, 10
+    kw = dict(n_envs=E, n=4, A0=A0, Au=Au, noise_prefixes=0.05, x0=1.0, t_norm_max=0.455, t_norm_ssz=0.01,
+              action_interval=K, observation_stds=[0.01] * 4, seed=11, dir_prefix="/tmp/qrl_test", use_cuda_graph=True,
+              fused_coefficients=True, return_numpy=True, host_output_views=views, rng=rng)
+    fed = None
+    if rng == "fed":      # the same caller-supplied draws for every env of the test
+        g = np.random.default_rng(5)
+        fed = (0.1 * g.standard_normal((45, E, 4)), 0.01 * g.standard_normal((46, E, 4)))
+    rng_ = np.random.default_rng(2)
+    actions = [rng_.uniform(-1, 1, (E, 1)) for _ in range(10)]
+    envs, results = {}, {}
+    for name, var, val in (("general", "QRL_NO_FAST_HOST_STEP", "1"), ("lean", None, None),
+                           ("native", "QRL_HOST_STEP_NATIVE", "1"), ("native_sync", "QRL_HOST_STEP_NATIVE", "sync")):
+        if var:
+            monkeypatch.setenv(var, val)
+        env = envs[name] = AffineLinearVecEnv(**kw)
+        if fed is not None:
+            env.set_fed_noise(*fed)
+        results[name] = [env.reset().copy()]
+        results[name].append([np.array(x) if isinstance(x, np.ndarray) else x for x in env.step(actions[0])])  # fixes the flavour
+        if var:
+            monkeypatch.delenv(var)
+    assert envs["general"]._fast_host is False and envs["lean"]._fast_host == {"native": False}
+    assert envs["native"]._fast_host["blocks"][0]["done"] is not None and envs["native_sync"]._fast_host["blocks"][0]["done"] is None
+    general = envs["general"]
+    for step in range(1, 10):
+        res = {}
+        for name, env in envs.items():
+            n0 = native.launch_count()
+            out = env.step(actions[step])
+            res[name] = [np.array(x) if isinstance(x, np.ndarray) else x for x in out]
+            if name.startswith("native") and env.t_idx != 0 and env.t_idx % K == 0:
+                assert native.launch_count() - n0 == 1           # a full interval is one launch of the library
+        for name, env in envs.items():
+            if name == "general":
+                continue
+            a, b = res[name], res["general"]
+            np.testing.assert_array_equal(a[0], b[0])
+            np.testing.assert_array_equal(a[1], b[1])
+            assert a[2] == b[2] and len(a[3]) == E
+            assert env.t_idx == general.t_idx and env.batch_idx == general.batch_idx and env.action_idx == general.action_idx
+            assert torch.equal(env.States, general.States) and torch.equal(env.rewards, general.rewards)
+    assert general.batch_idx == 2
+    assert envs["lean"].graph_replays == 8                        # every full interval, incl. the one that captured the graph
+    for name, env in envs.items():
+        np.testing.assert_array_equal(env.data, general.data)
+        env.close()
+
+
 def test_fused_affine_coefficients_match_hook_path(native, cuda):
     """``fused_coefficients=True`` evaluates A = A0 + sum_a u_a A_a (u = actions * action_maximums) inside the kernel:
     same trajectories as the ``get_A`` torch hook up to the rounding of one fused multiply-add, bit-identical between
