@@ -347,6 +347,11 @@ __device__ constexpr double P[7][4] = {
     {0.0, 127303824393.0 / 49829197408.0, -318862633887.0 / 49829197408.0, 701980252875.0 / 199316789632.0},
     {0.0, -282668133.0 / 205662961.0, 2019193451.0 / 616988883.0, -1453857185.0 / 822651844.0},
     {0.0, 40617522.0 / 29380423.0, -110615467.0 / 29380423.0, 69997945.0 / 29380423.0}};
+// the same coefficients as rows (stage arguments 2..6, then the 5th-order solution) for kernels that LOOP over the stages
+// (dopri5_rows_kernel: the unrolled step did not fit the instruction cache)
+static __constant__ double AS[6][6] = {{A21, 0, 0, 0, 0, 0}, {A31, A32, 0, 0, 0, 0}, {A41, A42, A43, 0, 0, 0},
+                                       {A51, A52, A53, A54, 0, 0}, {A61, A62, A63, A64, A65, 0}, {B1, 0, B3, B4, B5, B6}};
+static __constant__ double CS[6] = {C2, C3, C4, C5, 1.0, 1.0};
 constexpr double SAFETY = 0.9, MIN_FACTOR = 0.2, MAX_FACTOR = 10.0;
 constexpr int MAX_STEPS = 1000000;
 }  // namespace dp
@@ -837,6 +842,292 @@ __global__ void __launch_bounds__(BLOCK) rk4_rows_kernel(const __grid_constant__
         }
         emit(row, row == K);
     }
+    if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// DOPRI5 with q LANES per environment (num_quads 6 and 8): the layout of rk4_rows_kernel — lane i of an environment owns
+// row i of the covariance V and of the drift matrix A, the rows meet in padded shared-memory tiles once per right-hand
+// side — with the method, controller and dense output of dopri5_kernel, element by element in the same order of
+// operations.  One thread per environment keeps 7 d stage derivatives in shared memory (129 KB per warp at q = 8: ONE warp
+// per SM) next to 255 registers and 1.2 KB of spills; here a lane keeps the seven derivatives of its own row (7 q shared-
+// memory columns) and of ONE mode component (7 registers: lane c < 2m owns mode component c; the stage arguments of the
+// modes are computed by their owners and gathered with 2m shuffles), 99 KB per 128-thread block = 8 warps per SM, nothing
+// spills.  The per-env controller is uniform over the q lanes of an environment; the 32 / q environments of a warp
+// diverge only against each other, and every warp-level primitive carries the environment's lane mask.  The error norm is
+// the one reduction across the lanes (q shuffles, the same order in every lane; the thread kernel sums over d
+// sequentially, so the two agree to rounding, not bit for bit — like dopri5_lanes_kernel).
+// ------------------------------------------------------------------------------------------------------------------
+template <class Sys, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) dopri5_rows_kernel(const __grid_constant__ qrl_ode_args a) {
+    constexpr int M = Sys::M, Q = Sys::Q, D = Dim<Sys>::D;
+    constexpr int M2 = 2 * M > 0 ? 2 * M : 1;
+    static_assert(Q % 2 == 0 && Q <= 8 && BLOCK % 32 == 0 && 2 * M <= Q, "row lanes: even q <= 8, one mode component per lane");
+    constexpr int EPW = 32 / Q, EPB = (BLOCK / 32) * EPW;              // envs per warp / per block
+    constexpr int RPITCH = Q + 2, EPITCH = Q * RPITCH + 2;             // padded exchange tiles (see rk4_rows_kernel)
+    __shared__ __align__(16) double sA[2][EPB * EPITCH], sV[2][EPB * EPITCH];
+    extern __shared__ double ks_rows[];                                // [7][Q + 1][BLOCK]: stage derivatives of my row (+ my mode component)
+#define KS(s, j) ks_rows[((s) * Q + (j)) * BLOCK + threadIdx.x]
+    const int E = a.n_envs, K = a.K;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gw = lane / Q, i = lane - gw * Q;                        // env within the warp, my row
+    const bool lane_used = gw < EPW;
+    const int g = warp * EPW + (lane_used ? gw : 0);                   // env slot within the block
+    const int e = blockIdx.x * EPB + g;
+    const bool live = lane_used && e < E;
+    const int lane0 = gw * Q;                                          // first lane of my environment
+    const unsigned emask = lane_used ? (((1u << Q) - 1u) << lane0) : 0u;
+    double lo = INFINITY, hi = -INFINITY;
+
+    if (live) {
+        RowSys<Sys> s;
+        {
+            const double* prm = a.params ? a.params + (int64_t)e * a.params_stride_e : nullptr;
+            double us[4] = {0.0, 0.0, 0.0, 0.0};
+            if (a.actions) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k < a.n_actions) us[k] = a.actions[(int64_t)e * a.n_actions + k] * (a.action_scale ? a.action_scale[k] : 1.0);
+            }
+            s.load(prm, us, a.A ? a.A + (int64_t)e * a.A_stride_e : nullptr, a.D ? a.D + (int64_t)e * a.D_stride_e : nullptr, i);
+        }
+        double ym[M2], v[Q], drow[Q];
+#pragma unroll
+        for (int c = 0; c < M2; ++c) ym[c] = 2 * M > 0 ? a.y0[(int64_t)e * D + c] : 0.0;
+#pragma unroll
+        for (int j = 0; j < Q; ++j) { v[j] = a.y0[(int64_t)e * D + 2 * M + i * Q + j]; drow[j] = s.Drow(j); }
+        const int noise = a.obs_noise ? 1 : (a.obs_std ? 2 : 0);
+        const bool mode_lane = i < 2 * M;
+        const int64_t col_v = (int64_t)e * D + 2 * M + i * Q, col_m = (int64_t)e * D + i, row_pitch = (int64_t)E * D;
+        auto my_mode = [&](const double* m) {
+            double mv = 0.0;
+#pragma unroll
+            for (int c = 0; c < 2 * M; ++c) mv = (i == c) ? m[c] : mv;
+            return mv;
+        };
+        // the mode amplitudes of a stage argument: every owner lane holds its component, all lanes of the env need all
+        auto gather_modes = [&](double own, double* out) {
+#pragma unroll
+            for (int c = 0; c < 2 * M; ++c) out[c] = __shfl_sync(emask, own, lane0 + c);
+        };
+        auto emit = [&](int row, const double (&vv)[Q], double mv) {
+            double ov[Q], om = mv;
+#pragma unroll
+            for (int j = 0; j < Q; ++j) ov[j] = noise ? vv[j] + obs_noise_at(a, row, e, 2 * M + i * Q + j, D) : vv[j];
+            if (noise && mode_lane) om = mv + obs_noise_at(a, row, e, i, D);
+            const int64_t r0 = (int64_t)row * row_pitch;
+            if (a.states) {
+#pragma unroll
+                for (int j = 0; j < Q; j += 2) *reinterpret_cast<double2*>(a.states + r0 + col_v + j) = make_double2(vv[j], vv[j + 1]);
+                if (mode_lane) a.states[r0 + col_m] = mv;
+            }
+            if (a.observations) {
+#pragma unroll
+                for (int j = 0; j < Q; j += 2) *reinterpret_cast<double2*>(a.observations + r0 + col_v + j) = make_double2(ov[j], ov[j + 1]);
+                if (mode_lane) a.observations[r0 + col_m] = om;
+            }
+#pragma unroll
+            for (int j = 0; j < Q; ++j) { lo = fmin(lo, ov[j]); hi = fmax(hi, ov[j]); }
+            if (mode_lane) { lo = fmin(lo, om); hi = fmax(hi, om); }
+            if (row == K && a.obs_last) {
+#pragma unroll
+                for (int j = 0; j < Q; j += 2) *reinterpret_cast<double2*>(a.obs_last + col_v + j) = make_double2(ov[j], ov[j + 1]);
+                if (mode_lane) a.obs_last[col_m] = om;
+            }
+        };
+        // one right-hand side at (modes ymt, my row vt) through exchange buffer `buf`: dv = my row of dV/dt, dm = d(modes)/dt
+        int buf = 0;
+        auto rhs_row = [&](double t, const double* ymt, const double (&vt)[Q], double (&dv)[Q], double* dm) {
+            double Arow[Q];
+            s.rates(t, ymt, dm);
+            s.row(t, ymt, Arow);
+#pragma unroll
+            for (int j = 0; j < Q; j += 2) {
+                *reinterpret_cast<double2*>(&sV[buf][g * EPITCH + i * RPITCH + j]) = make_double2(vt[j], vt[j + 1]);
+                *reinterpret_cast<double2*>(&sA[buf][g * EPITCH + i * RPITCH + j]) = make_double2(Arow[j], Arow[j + 1]);
+            }
+            __syncwarp(emask);
+            double av[Q];
+#pragma unroll
+            for (int j = 0; j < Q; ++j) av[j] = 0.0;
+#pragma unroll
+            for (int k = 0; k < Q; ++k) {          // (A V)_ij: row k of V, broadcast to the lanes of the env
+                double vk[Q];
+#pragma unroll
+                for (int j = 0; j < Q; j += 2) {
+                    const double2 t2 = *reinterpret_cast<const double2*>(&sV[buf][g * EPITCH + k * RPITCH + j]);
+                    vk[j] = t2.x; vk[j + 1] = t2.y;
+                }
+#pragma unroll
+                for (int j = 0; j < Q; ++j) av[j] = fma(Arow[k], vk[j], av[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {          // (V A^T)_ij: row j of A
+                double aj[Q];
+#pragma unroll
+                for (int k = 0; k < Q; k += 2) {
+                    const double2 t2 = *reinterpret_cast<const double2*>(&sA[buf][g * EPITCH + j * RPITCH + k]);
+                    aj[k] = t2.x; aj[k + 1] = t2.y;
+                }
+                double va = 0.0;
+#pragma unroll
+                for (int k = 0; k < Q; ++k) va = fma(vt[k], aj[k], va);
+                dv[j] = (av[j] + va) + drow[j];    // same association as deterministic.py:713-732
+            }
+            buf ^= 1;     // the next right-hand side writes the other pair of tiles: its __syncwarp orders this one's reads
+        };
+
+        emit(0, v, my_mode(ym));
+        const double t_end = a.t0 + (double)K * a.t_ssz;
+        double t = a.t0;
+        double h = (a.h_state && a.h_state[e] > 0.0) ? a.h_state[e] : a.t_ssz;
+        int next_row = 1, n_acc = 0, n_rej = 0, guard = 0;
+        bool rejected = false;
+        double ymo = my_mode(ym);              // MY mode component (lanes i < 2m) ...
+#define KMO(s) ks_rows[((7 * Q) + (s)) * BLOCK + threadIdx.x]   /* ... and its stage derivatives */
+        {
+            double dv[Q], dm[M2];
+            rhs_row(t, ym, v, dv, dm);
+#pragma unroll
+            for (int j = 0; j < Q; ++j) KS(0, j) = dv[j];
+            KMO(0) = my_mode(dm);
+        }
+#define KV(s) KS(s, j)
+#define DP_ERR(KK) (ht * fma(dp::E7, KK(6), fma(dp::E6, KK(5), fma(dp::E5, KK(4), fma(dp::E4, KK(3), fma(dp::E3, KK(2), dp::E1 * KK(0)))))))
+        while (next_row <= K && guard++ < dp::MAX_STEPS) {
+            const double remaining = t_end - t;
+            const bool last = h >= remaining * (1.0 - 1e-12);
+            const double ht = last ? remaining : h;
+            double vt[Q], ymt[M2];
+            // Stage arguments 2 .. 6 and the 5th-order solution (= stage-7 argument, FSAL) as ONE loop body over the rows of
+            // the tableau: y + ht (((a_s0 k_0) + a_s1 k_1) + ...) accumulated in the order of dopri5_kernel's nested FMAs
+            // (zero coefficients add exact zeros; stage 2 keeps its own form fma(ht a_21, k_0, y)).  Fully unrolled, the step
+            // was 11 400 instructions (183 KB) and the warps spent 3.2 stall cycles per issue waiting for instruction fetch
+            // (profiles/r02z_ode_ncu_summary.md); the loop is a third of that.
+#pragma unroll 1
+            for (int st = 1; st <= 6; ++st) {
+                double acc[Q], accm = dp::AS[st - 1][0] * KMO(0);
+#pragma unroll
+                for (int j = 0; j < Q; ++j) acc[j] = dp::AS[st - 1][0] * KS(0, j);
+#pragma unroll 1
+                for (int r = 1; r < st; ++r) {
+                    const double c = dp::AS[st - 1][r];
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) acc[j] = fma(c, KS(r, j), acc[j]);
+                    accm = fma(c, KMO(r), accm);
+                }
+                if (st == 1) {
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) vt[j] = fma(ht * dp::A21, KS(0, j), v[j]);
+                    accm = fma(ht * dp::A21, KMO(0), ymo);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) vt[j] = fma(ht, acc[j], v[j]);
+                    accm = fma(ht, accm, ymo);
+                }
+                if (2 * M > 0) gather_modes(accm, ymt);
+                double dv[Q], dm[M2];
+                rhs_row(t + dp::CS[st - 1] * ht, ymt, vt, dv, dm);
+#pragma unroll
+                for (int j = 0; j < Q; ++j) KS(st, j) = dv[j];
+                KMO(st) = my_mode(dm);
+            }
+            const double ymo_new = my_mode(ymt);
+            // error estimate, RMS norm with scale atol + rtol * max(|y|, |y_new|): my row (+ my mode component), then the
+            // sum over the env's lanes in lane order
+            double sq = 0.0;
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+                const double ev = DP_ERR(KV);
+                const double sc = fma(a.rtol, fmax(fabs(v[j]), fabs(vt[j])), a.atol);
+                const double r = ev / sc;
+                sq = fma(r, r, sq);
+            }
+            if (mode_lane) {
+                const double ev = DP_ERR(KMO);
+                const double sc = fma(a.rtol, fmax(fabs(ymo), fabs(ymo_new)), a.atol);
+                const double r = ev / sc;
+                sq = fma(r, r, sq);
+            }
+            double tot = 0.0;
+#pragma unroll
+            for (int c = 0; c < Q; ++c) tot += __shfl_sync(emask, sq, lane0 + c);
+            const double err = sqrt(tot / (double)D);
+            if (err <= 1.0) {
+                double fac = (err == 0.0) ? dp::MAX_FACTOR : fmin(dp::MAX_FACTOR, fmax(dp::MIN_FACTOR, dp::SAFETY * pow(err, -0.2)));
+                if (rejected) fac = fmin(1.0, fac);
+                rejected = false;
+                ++n_acc;
+                const double t_new = last ? t_end : t + ht;
+                // dense output on every grid point inside (t, t_new]
+                while (next_row <= K) {
+                    const double tg = (next_row == K) ? t_end : a.t0 + (double)next_row * a.t_ssz;
+                    if (tg > t_new) break;
+                    if (tg == t_new) {
+                        emit(next_row, vt, ymo_new);
+                    } else {
+                        const double x = (tg - t) / ht;
+                        double pw[7];
+#pragma unroll
+                        for (int st = 0; st < 7; ++st)
+                            pw[st] = fma(fma(fma(dp::P[st][3], x, dp::P[st][2]), x, dp::P[st][1]), x, dp::P[st][0]);
+                        double vo[Q], mo = 0.0;
+#pragma unroll
+                        for (int j = 0; j < Q; ++j) {
+                            double q = 0.0;
+#pragma unroll
+                            for (int st = 0; st < 7; ++st) {
+                                if (st == 1) continue;
+                                q = fma(KS(st, j), pw[st], q);
+                            }
+                            vo[j] = fma(ht * x, q, v[j]);
+                        }
+                        if (mode_lane) {
+                            double qm = 0.0;
+#pragma unroll
+                            for (int st = 0; st < 7; ++st) {
+                                if (st == 1) continue;
+                                qm = fma(KMO(st), pw[st], qm);
+                            }
+                            mo = fma(ht * x, qm, ymo);
+                        }
+                        emit(next_row, vo, mo);
+                    }
+                    ++next_row;
+                }
+                t = t_new;
+#pragma unroll
+                for (int j = 0; j < Q; ++j) { v[j] = vt[j]; KS(0, j) = KS(6, j); }
+#pragma unroll
+                for (int c = 0; c < 2 * M; ++c) ym[c] = ymt[c];
+                ymo = ymo_new;
+                KMO(0) = KMO(6);
+                // a step that was clipped to the interval end does not shrink the carried step size
+                h = (last && fac >= 1.0) ? fmax(h, ht * fac) : ht * fac;
+            } else {
+                h = ht * fmax(dp::MIN_FACTOR, dp::SAFETY * pow(err, -0.2));
+                rejected = true;
+                ++n_rej;
+            }
+        }
+#undef DP_ERR
+#undef KV
+#undef KMO
+        if (a.y_last) {
+#pragma unroll
+            for (int j = 0; j < Q; j += 2) *reinterpret_cast<double2*>(a.y_last + col_v + j) = make_double2(v[j], v[j + 1]);
+            if (mode_lane) a.y_last[col_m] = ymo;
+        }
+        if (i == 0) {
+            if (a.h_state) a.h_state[e] = h;
+            if (a.n_steps) { a.n_steps[2 * e] += n_acc; a.n_steps[2 * e + 1] += n_rej; }
+        }
+        bool bad = next_row <= K || !isfinite(ymo);   // step budget exhausted / non-finite state
+#pragma unroll
+        for (int j = 0; j < Q; ++j) bad |= !isfinite(v[j]);
+        if (a.nan_flag && bad) atomicOr(a.nan_flag, QRL_STATUS_NONFINITE);
+    }
+#undef KS
     if (a.obs_minmax) block_minmax_commit(lo, hi, a.obs_minmax);
 }
 
@@ -1418,6 +1709,22 @@ int launch_ode(const qrl_ode_args& a, cudaStream_t st) {
             constexpr int BL = 64;
             dopri5_lanes_kernel<Sys, BL><<<(a.n_envs + BL / 16 - 1) / (BL / 16), BL, 0, st>>>(a);
             return after_launch("dopri5_lanes_kernel");
+        }
+    }
+    if constexpr (Sys::Q > 4 && Sys::Q % 2 == 0) {
+        // q = 6, 8: q lanes per environment (dopri5_rows_kernel), every batch size.  Measured on B200 (tools/prof_ode.py,
+        // kerr_chain, 100 grid rows, default tolerances = 5.4 steps per interval; ms per interval, row lanes vs one thread per
+        // env, which keeps 7 d stage derivatives per env in shared memory = 1 (q = 8) / 3 (q = 6) warps per SM):
+        //   q = 8: E = 1024 0.21 vs 3.46, 4096 0.37 vs 3.77, 16384 1.38 vs 12.97 (1.19e9 sub-steps/s)
+        //   q = 6: E = 1024 0.18 vs 2.30, 4096 0.24 vs 2.51, 16384 0.68 vs 4.46 (2.41e9 sub-steps/s)
+        if (!(a.flags & QRL_ODE_FORCE_THREAD)) {
+            constexpr int BR = 128, EPB = (BR / 32) * (32 / Sys::Q);
+            const size_t smem_rows = (size_t)7 * (Sys::Q + 1) * BR * sizeof(double);
+            static OncePerDevice attr_rows;
+            if (attr_rows.first())
+                QRL_CUDA(cudaFuncSetAttribute(dopri5_rows_kernel<Sys, BR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+            dopri5_rows_kernel<Sys, BR><<<(a.n_envs + EPB - 1) / EPB, BR, smem_rows, st>>>(a);
+            return after_launch("dopri5_rows_kernel");
         }
     }
     constexpr int BLOCK = 32;

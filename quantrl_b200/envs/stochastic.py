@@ -438,7 +438,7 @@ class LinearVecEnv(BaseVecEnv):
         kernel and nothing else, and everything ``update()`` / ``update_data()`` do besides is host bookkeeping.
 
         Two flavours of the launch + wait (measured at config 3 with nothing else on the host,
-        ``tools/e2e_breakdown.py``, ``profiles/r02x_e2e_breakdown.log``): replay of the captured one-kernel graph + stream
+        ``tools/e2e_breakdown.py``, ``profiles/r02y_e2e_breakdown.log``): replay of the captured one-kernel graph + stream
         synchronisation 35.7 us (default), ``qrl_em_step_host`` (ABI 5: direct launch + spin on a completion word in pinned
         memory, ``QRL_HOST_STEP_NATIVE=1``) 36.2 us — the kernel itself takes 22.9 us, the rest is launch latency and the
         164 KB of results crossing PCIe at the end of the launch."""

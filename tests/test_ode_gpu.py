@@ -73,7 +73,7 @@ def _single_rhs(osys, p, m, q):
 
 
 @pytest.mark.parametrize("flags", [0, 1])   # 0: default (q = 4, small batch: 16 lanes per env), 1: one thread per env
-@pytest.mark.parametrize("fname,tag,osys,system", CASES[:2])
+@pytest.mark.parametrize("fname,tag,osys,system", CASES)    # (N4: q = 8 -> the row-lanes kernel by default)
 def test_dopri5_default_tolerance_follows_oracle_controller(native, cuda, golden_dir, fname, tag, osys, system, flags):
     """Same controller, same accept/reject sequence: both dopri5 kernels == oracle/lyap_oracle.py:dopri5_dense_interval
     at the reference's default tolerances (atol 1e-9, rtol 1e-6), including the carried step size and the step counts."""
