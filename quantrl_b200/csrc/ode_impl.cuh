@@ -985,13 +985,7 @@ __global__ void __launch_bounds__(BLOCK) dopri5_rows_kernel(const __grid_constan
         bool rejected = false;
         double ymo = my_mode(ym);              // MY mode component (lanes i < 2m) ...
 #define KMO(s) ks_rows[((7 * Q) + (s)) * BLOCK + threadIdx.x]   /* ... and its stage derivatives */
-        {
-            double dv[Q], dm[M2];
-            rhs_row(t, ym, v, dv, dm);
-#pragma unroll
-            for (int j = 0; j < Q; ++j) KS(0, j) = dv[j];
-            KMO(0) = my_mode(dm);
-        }
+        int st0 = 0;                           // the first step of the launch also evaluates k_1 = f(t, y) (stage "0")
 #define KV(s) KS(s, j)
 #define DP_ERR(KK) (ht * fma(dp::E7, KK(6), fma(dp::E6, KK(5), fma(dp::E5, KK(4), fma(dp::E4, KK(3), fma(dp::E3, KK(2), dp::E1 * KK(0)))))))
         while (next_row <= K && guard++ < dp::MAX_STEPS) {
@@ -1005,33 +999,42 @@ __global__ void __launch_bounds__(BLOCK) dopri5_rows_kernel(const __grid_constan
             // was 11 400 instructions (183 KB) and the warps spent 3.2 stall cycles per issue waiting for instruction fetch
             // (profiles/r02z_ode_ncu_summary.md); the loop is a third of that.
 #pragma unroll 1
-            for (int st = 1; st <= 6; ++st) {
-                double acc[Q], accm = dp::AS[st - 1][0] * KMO(0);
+            for (int st = st0; st <= 6; ++st) {
+                double accm = ymo, ts = t;
+                if (st == 0) {                 // (one inlined copy of the right-hand side for all seven evaluations)
 #pragma unroll
-                for (int j = 0; j < Q; ++j) acc[j] = dp::AS[st - 1][0] * KS(0, j);
-#pragma unroll 1
-                for (int r = 1; r < st; ++r) {
-                    const double c = dp::AS[st - 1][r];
-#pragma unroll
-                    for (int j = 0; j < Q; ++j) acc[j] = fma(c, KS(r, j), acc[j]);
-                    accm = fma(c, KMO(r), accm);
-                }
-                if (st == 1) {
-#pragma unroll
-                    for (int j = 0; j < Q; ++j) vt[j] = fma(ht * dp::A21, KS(0, j), v[j]);
-                    accm = fma(ht * dp::A21, KMO(0), ymo);
+                    for (int j = 0; j < Q; ++j) vt[j] = v[j];
                 } else {
+                    double acc[Q];
+                    accm = dp::AS[st - 1][0] * KMO(0);
 #pragma unroll
-                    for (int j = 0; j < Q; ++j) vt[j] = fma(ht, acc[j], v[j]);
-                    accm = fma(ht, accm, ymo);
+                    for (int j = 0; j < Q; ++j) acc[j] = dp::AS[st - 1][0] * KS(0, j);
+#pragma unroll 1
+                    for (int r = 1; r < st; ++r) {
+                        const double c = dp::AS[st - 1][r];
+#pragma unroll
+                        for (int j = 0; j < Q; ++j) acc[j] = fma(c, KS(r, j), acc[j]);
+                        accm = fma(c, KMO(r), accm);
+                    }
+                    if (st == 1) {
+#pragma unroll
+                        for (int j = 0; j < Q; ++j) vt[j] = fma(ht * dp::A21, KS(0, j), v[j]);
+                        accm = fma(ht * dp::A21, KMO(0), ymo);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < Q; ++j) vt[j] = fma(ht, acc[j], v[j]);
+                        accm = fma(ht, accm, ymo);
+                    }
+                    ts = t + dp::CS[st - 1] * ht;
                 }
                 if (2 * M > 0) gather_modes(accm, ymt);
                 double dv[Q], dm[M2];
-                rhs_row(t + dp::CS[st - 1] * ht, ymt, vt, dv, dm);
+                rhs_row(ts, ymt, vt, dv, dm);
 #pragma unroll
                 for (int j = 0; j < Q; ++j) KS(st, j) = dv[j];
                 KMO(st) = my_mode(dm);
             }
+            st0 = 1;
             const double ymo_new = my_mode(ymt);
             // error estimate, RMS norm with scale atol + rtol * max(|y|, |y_new|): my row (+ my mode component), then the
             // sum over the env's lanes in lane order
@@ -1063,15 +1066,15 @@ __global__ void __launch_bounds__(BLOCK) dopri5_rows_kernel(const __grid_constan
                 while (next_row <= K) {
                     const double tg = (next_row == K) ? t_end : a.t0 + (double)next_row * a.t_ssz;
                     if (tg > t_new) break;
-                    if (tg == t_new) {
-                        emit(next_row, vt, ymo_new);
-                    } else {
+                    double vo[Q], mo = ymo_new;
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) vo[j] = vt[j];
+                    if (tg != t_new) {
                         const double x = (tg - t) / ht;
                         double pw[7];
 #pragma unroll
                         for (int st = 0; st < 7; ++st)
                             pw[st] = fma(fma(fma(dp::P[st][3], x, dp::P[st][2]), x, dp::P[st][1]), x, dp::P[st][0]);
-                        double vo[Q], mo = 0.0;
 #pragma unroll
                         for (int j = 0; j < Q; ++j) {
                             double q = 0.0;
@@ -1091,8 +1094,8 @@ __global__ void __launch_bounds__(BLOCK) dopri5_rows_kernel(const __grid_constan
                             }
                             mo = fma(ht * x, qm, ymo);
                         }
-                        emit(next_row, vo, mo);
                     }
+                    emit(next_row, vo, mo);
                     ++next_row;
                 }
                 t = t_new;
