@@ -260,7 +260,19 @@ class PeerGather:
                 a.flag_src = self._epoch_words.data_ptr() + 8 * s
                 a.flag_dst = self._flag_dst
                 a.step_done, a.copy_done = self._ev_step[s].cuda_event, self._ev_copy[s].cuda_event
+                # destination of slot s: SLOTS is even, so the parity of an epoch is the parity of its slot
+                base = self._g_dst + 8 * (s % 2) * self._gwords
+                a.dst = base + 8 * self.offset * n
+                a.dst2 = base + 8 * (n_envs_total * n + self.offset)
+                if self.is_learner:
+                    a.bytes = a.bytes2 = 0      # rows already in place; only the epoch word follows the launch
                 self._push.append(a)
+            assert self.SLOTS % 2 == 0
+            # what next_launch returns for the learner, per epoch parity (its launch writes straight into the gathered block)
+            self._learner_out = [(self.gathered.data_ptr() + 8 * par * self._gwords + 8 * self.offset * n,
+                                  self.gathered.data_ptr() + 8 * par * self._gwords + 8 * (n_envs_total * n + self.offset))
+                                 for par in (0, 1)]
+            self._slot_ptrs = [(o.data_ptr(), r.data_ptr()) for o, r in self._slot_views]
         elif self.is_learner:
             i64 = dict(dtype=torch.int64, device=device)
             self.gathered = torch.zeros((self._gwords,), dtype=torch.float64, device=device)
@@ -310,19 +322,21 @@ class PeerGather:
     # ---- called by the env around every integration launch it enqueues ------------------------------------------------------
     def next_launch(self):
         """``(epoch, obs_ptr, reward_ptr, pulled_min)`` of the ring slice the next launch writes."""
-        self.epoch += 1
-        e = self.epoch
+        self.epoch = e = self.epoch + 1
         s = e % self.SLOTS
-        if self.mode == "push" and self._slot_seq[s]:
-            # the copy that last read this slice (epoch e - SLOTS) has long finished; this returns at once
-            self._N.peer_ctx_wait(self._ctx, self._slot_seq[s])
-        if self.mode == "push" and self.is_learner:
-            # the learner's own rows need no transfer: its launch writes them straight into its slice of the gathered block
-            # (a local device-to-device copy would run on SMs and hold up the next step's CTAs: measured 36.6 vs 27.6 us)
-            base = self.gathered.data_ptr() + 8 * (e % 2) * self._gwords
-            return e, base + 8 * self.offset * self.n_obs, base + 8 * (self.E * self.n_obs + self.offset), 0
+        if self.mode == "push":
+            if self._slot_seq[s]:
+                # the copy that last read this slice (epoch e - SLOTS) has long finished; this returns at once
+                self._N.peer_ctx_wait(self._ctx, self._slot_seq[s])
+            if self.is_learner:
+                # the learner's own rows need no transfer: its launch writes them straight into its slice of the gathered
+                # block (a local device-to-device copy would run on SMs and hold up the next step's CTAs: 36.6 vs 27.6 us)
+                o, r = self._learner_out[e & 1]
+            else:
+                o, r = self._slot_ptrs[s]
+            return e, o, r, 0
         obs_v, rew_v = self._slot_views[s]
-        return e, obs_v.data_ptr(), rew_v.data_ptr(), (max(0, e - self.SLOTS) if self.mode == "pull" else 0)
+        return e, obs_v.data_ptr(), rew_v.data_ptr(), max(0, e - self.SLOTS)
 
     def after_launch(self, main_stream_raw):
         """push mode: enqueue the transfer of the epoch just launched (events + copy engine, no kernel)."""
@@ -330,14 +344,8 @@ class PeerGather:
             return
         e = self.epoch
         s = e % self.SLOTS
-        a = self._push[s]
-        self._epoch_np[s] = e
-        base = self._g_dst + 8 * (e % 2) * self._gwords
-        a.dst = base + 8 * self.offset * self.n_obs
-        a.dst2 = base + 8 * (self.E * self.n_obs + self.offset)
-        if self.is_learner:
-            a.bytes = a.bytes2 = 0          # rows already in place; only the epoch word follows the launch
-        self._slot_seq[s] = self._N.peer_ctx_push(self._ctx, a, main_stream_raw)
+        self._epoch_np[s] = e               # (source, destination and sizes of slot s were fixed at construction)
+        self._slot_seq[s] = self._N.peer_ctx_push(self._ctx, self._push[s], main_stream_raw)
 
     # ---- learner ------------------------------------------------------------------------------------------------------
     def gather(self):

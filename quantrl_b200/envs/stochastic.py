@@ -525,6 +525,68 @@ class LinearVecEnv(BaseVecEnv):
         self.action_idx += 1
         return self._finish_host_step(self._h_out, self._obs_last, self._reward_last, not t + 1 < self.shape_T[0])
 
+    def step_device(self, actions):
+        """Device-resident step (``BaseVecEnv.step_device``).  A full action interval of the single-kernel step whose
+        actions are a contiguous float64 CUDA tensor takes a lean path: the cached argument block of ``_relaunch_interval``
+        is patched and enqueued here and the bookkeeping of ``update()`` / ``update_data()`` is done inline — the host side
+        of a step is what limits a multi-GPU loop once the kernel takes 23 us (8 ranks on one box share its cores)."""
+        st = self._static.get("device")
+        K, t = self.action_interval, self.t_idx
+        if (st is None or not st.get("lean") or t + K >= self.shape_T[0] or not isinstance(actions, torch.Tensor)
+                or not actions.is_cuda or actions.dtype != torch.float64 or not actions.is_contiguous()
+                or actions.numel() != self.n_envs * self.n_actions):
+            out = super().step_device(actions)
+            st = self._static.get("device")
+            if st is not None and "lean" not in st:     # the general path has just built the block: does the lean path apply?
+                st["lean"] = (self.n_properties == 0 and not self.cache_all_data and self._cum_fused
+                              and (st["packs"] or not self.store_trajectory) and getattr(self, "_em_events", None) is None
+                              and not os.environ.get("QRL_NO_FAST_DEVICE_STEP"))
+                st["ref"], st["fn"] = C.byref(st["a"]), N.lib().qrl_em_step
+                st["no_finish"] = not st["a"].finish_counter
+                st["pitch"] = 8 * (st["a"].packed_row_pitch if st["a"].packed_row_pitch > 0 else st["a"].n_sel)
+                st["episode"] = None
+            return out
+        a = st["a"]
+        a.actions, a.t_idx = actions.data_ptr(), t
+        if st["episode"] != self.batch_idx:
+            st["episode"] = self.batch_idx
+            a.episode = self.batch_idx & 0xFFFFFFFF
+        if st["packed"]:
+            a.T_step, a.packed = st["T_step"] + 8 * t, st["packed"] + st["pitch"] * t
+        if st["W"]:                             # rng='fed': rows of the fed draws
+            rows = 8 * t * self.n_envs * self.n_observations
+            a.W = st["W"] + rows
+            if st["obs_noise"]:
+                a.obs_noise = st["obs_noise"] + rows
+        peer = self._peer
+        if peer is not None:
+            e, a.obs_last_b, a.reward_last_b, pulled_min = peer.next_launch()
+            if pulled_min or peer.mode != "push":
+                a.peer_publish_value, a.peer_pulled_min = e, pulled_min
+        if st["no_finish"]:
+            self._dyn_stale = True              # this launch does not advance the device-side time index
+        elif self.__dict__.get("_dyn_stale"):
+            self._sync_dyn()
+        rc = st["fn"](st["ref"], st["stream"])
+        if rc != 0:
+            N.check(rc, "qrl_em_step")
+        if peer is not None:
+            peer.after_launch(st["stream"])
+        # bookkeeping of update() / update_data() for a full interval (base.py:440-483, 1295-1380)
+        self._host_step = self._host_graph_done = False
+        self._actions_src = None
+        self._dim, self._t_range = K + 1, (t, t + K + 1)
+        self.States, self.Observations, self.Reward = self._States, self._Observations, self._Reward
+        self._packed_by_kernel, self._data_host = st["packs"], None
+        self.last_step_peer_fenced = self._peer_barrier is not None
+        self.t_idx = t = t + K
+        self.t = self._T_host[t]
+        self.action_idx += 1
+        terminated = not t + 1 < self.shape_T[0]
+        if terminated:
+            self.data_rewards.append(self.rewards.clone())
+        return self._obs_last, self._reward_last, terminated
+
     def _sync_dyn(self):
         """The device-side time index = the host's, before a launch that reads it (graph replays, the host round trip)
         follows device-resident steps that did not advance it."""

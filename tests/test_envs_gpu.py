@@ -430,6 +430,39 @@ def test_lean_host_step_equals_the_general_step_path(native, cuda, monkeypatch, 
         env.close()
 
 
+def test_lean_device_step_equals_the_general_device_step(native, cuda, monkeypatch):
+    """``step_device`` on a full interval of the single-kernel step patches and enqueues the cached argument block itself
+    and does the bookkeeping of ``update()`` / ``update_data()`` inline; same States, rewards, cache rows and counters as the
+    general path (``QRL_NO_FAST_DEVICE_STEP``), bit for bit, over two episodes with a tail interval."""
+    from quantrl_b200.systems import AffineLinearVecEnv, affine_matrices
+    A0, Au = affine_matrices(4, 1, seed=0)
+    E, K = 200, 10
+    kw = dict(n_envs=E, n=4, A0=A0, Au=Au, noise_prefixes=0.05, x0=1.0, t_norm_max=0.455, t_norm_ssz=0.01,
+              action_interval=K, observation_stds=[0.01] * 4, seed=11, dir_prefix="/tmp/qrl_test", use_cuda_graph=True,
+              fused_coefficients=True, return_numpy=True)
+    lean = AffineLinearVecEnv(**kw)
+    monkeypatch.setenv("QRL_NO_FAST_DEVICE_STEP", "1")
+    gen = AffineLinearVecEnv(**kw)
+    lean.reset(); gen.reset()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for step in range(10):
+        u = torch.rand((E, 1), generator=g, device="cuda", dtype=torch.float64) * 2 - 1
+        o_g, r_g, t_g = gen.step_device(u)          # (the first call builds the block and decides the flavour)
+        if step == 0:
+            monkeypatch.delenv("QRL_NO_FAST_DEVICE_STEP")
+        o_l, r_l, t_l = lean.step_device(u)
+        assert torch.equal(o_l, o_g) and torch.equal(r_l, r_g) and t_l == t_g
+        assert torch.equal(lean.States, gen.States) and torch.equal(lean.rewards, gen.rewards)
+        assert (lean.t_idx, lean.action_idx, lean.batch_idx) == (gen.t_idx, gen.action_idx, gen.batch_idx)
+        assert lean.truncation_pending() == gen.truncation_pending()
+        if t_l:
+            np.testing.assert_array_equal(lean.data, gen.data)
+            assert len(lean.data_rewards) == len(gen.data_rewards)
+            lean.reset(); gen.reset()
+    assert lean._static["device"]["lean"] is True and gen._static["device"]["lean"] is False and lean.batch_idx == 2
+    lean.close(); gen.close()
+
+
 def test_fused_affine_coefficients_match_hook_path(native, cuda):
     """``fused_coefficients=True`` evaluates A = A0 + sum_a u_a A_a (u = actions * action_maximums) inside the kernel:
     same trajectories as the ``get_A`` torch hook up to the rounding of one fused multiply-add, bit-identical between
