@@ -246,13 +246,19 @@ def time_device_loop(torch, dist, world, dev, env, peer, actions, steps, warmup,
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def region():
-        barrier()
-        e0.record()
-        t_host0 = time.perf_counter()
-        device_loop(env, peer, actions, steps)
-        host_us = (time.perf_counter() - t_host0) * 1e6 / steps   # host time to ENQUEUE one step (no sync)
-        e1.record()
-        barrier()
+        import gc
+        gc.collect()
+        gc.disable()              # a collector pause on ONE rank is an idle GPU in a max-over-ranks number
+        try:
+            barrier()
+            e0.record()
+            t_host0 = time.perf_counter()
+            device_loop(env, peer, actions, steps)
+            host_us = (time.perf_counter() - t_host0) * 1e6 / steps   # host time to ENQUEUE one step (no sync)
+            e1.record()
+            barrier()
+        finally:
+            gc.enable()
         return host_us
     if sampler is not None:
         with sampler:
@@ -329,7 +335,7 @@ def bench_config4(torch, dist, N, world, rank, dev, args, clocks):
         peer = PeerGather(E_C4, N_C4, dev, dst=0, mode=args.gather if args.gather != "none" else "push")
         peer.attach(env)
     steps, warmup = max(10, min(args.steps, 200)), 5
-    ms, host_us = time_device_loop(torch, dist, world, dev, env, peer, actions, steps, warmup, clocks)
+    ms, host_us = time_device_loop(torch, dist, world, dev, env, peer, actions, steps, warmup, clocks if rank == 0 else None)
     res = {"workload": "BASELINE config 4: 65536 stochastic linear envs (n=8, 8x8 drift A0+u*A1), K=100, S=1000, FP64, sharded "
                        f"over {world} GPU(s) ({E} envs each)", "scaling": "strong", "steps": steps,
            "value": E_C4 * K_SUB * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps}
@@ -497,7 +503,9 @@ def main():
     # ---- value: device-resident ----
     clocks = ClockSampler(local)
     launches0 = N.launch_count()
-    ms_max, host_enqueue_us = time_device_loop(torch, dist, world, dev, env, peer, actions_dev, args.steps, args.warmup, clocks)
+    # (the clock sampler is a thread of this process: only rank 0 runs it; its numbers go into the line)
+    ms_max, host_enqueue_us = time_device_loop(torch, dist, world, dev, env, peer, actions_dev, args.steps, args.warmup,
+                                               clocks if rank == 0 else None)
     print(f"[bench] rank {rank}: host enqueue {host_enqueue_us:.1f} us/step, device {ms_max * 1e3 / args.steps:.1f} us/step (max over ranks)",
           file=sys.stderr)
     # kernels of libquantrl_b200.so launched by this rank since the warm-up began, scaled to the timed region
@@ -533,6 +541,9 @@ def main():
             # wait_in_step=True) — so the sync that ends step() also covers "every rank's rows of this step have arrived")
             env2.step(host_actions[i % 8])
     e2e_loop(args.warmup)
+    import gc
+    gc.collect()
+    gc.disable()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -540,6 +551,7 @@ def main():
     e2e_loop(e2e_steps)
     torch.cuda.synchronize()
     e2e_ms = 1e3 * (time.perf_counter() - t0)   # wall clock: every step already ends with a host sync
+    gc.enable()
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.barrier()

@@ -197,7 +197,7 @@ class PeerGather:
     The NCCL path (``LearnerLink.gather_step``) stays as the fallback and as the measured comparison.
     """
 
-    SLOTS = 16          # ring depth = how many steps the host may run ahead of the copies (jitter tolerance), 16 x 164 KB at config 3
+    SLOTS = 32          # ring depth = how many steps the host may run ahead of the copies (jitter tolerance: 0.7 ms at config 3), 32 x 164 KB
 
     def __init__(self, n_envs_total, n_observations, device, dst=0, group=None, mode="push"):
         import ctypes as C
@@ -226,6 +226,7 @@ class PeerGather:
         self.flag_ptrs = torch.tensor([int(p) for p in self.flags_hdl.buffer_ptrs], dtype=torch.int64, device=device)
         self.pulled_ptr = self.flags.data_ptr() + 8 * self.world
         self.epoch = 0                                              # launches published by this rank
+        self._direct = False                                        # set by attach(..., wait_in_step=True)
         self._slot_views = []
         for s in range(self.SLOTS):
             base = s * self.slot_words
@@ -313,6 +314,20 @@ class PeerGather:
         covers "every rank's rows of this step have arrived" (one sync instead of two)."""
         assert env.n_envs == self.count and env.n_observations == self.n_obs
         env.attach_peer(self)
+        # step(host actions) with the learner waiting for the rows of the SAME step: the transfer is latency critical, so the
+        # rank enqueues it itself right behind its launch (the worker thread polls with 20 us sleeps; its driver calls are
+        # hidden behind the running step kernel here anyway)
+        self._direct = bool(wait_in_step) and self.mode == "push"
+        if self._direct and not self.is_learner:
+            # ... and the rows do not take the copy engine at all: the launch's second copy of the last rows goes straight
+            # into this rank's slice of the LEARNER's gathered block (peer-mapped stores over NVLink, complete when the kernel
+            # is), so only the 8-byte epoch word follows the launch — one copy-engine operation between "kernel done" and "the
+            # learner sees the step" instead of three (measured at 2 GPUs: the learner waited ~10 us per step for the chain)
+            n = self.n_obs
+            self._learner_out = [(self._g_dst + 8 * par * self._gwords + 8 * self.offset * n,
+                                  self._g_dst + 8 * par * self._gwords + 8 * (self.E * n + self.offset)) for par in (0, 1)]
+            for a in self._push:
+                a.bytes = a.bytes2 = 0
         if wait_in_step and self.is_learner:
             def hook():
                 self.gather()
@@ -327,10 +342,14 @@ class PeerGather:
         if self.mode == "push":
             if self._slot_seq[s]:
                 # the copy that last read this slice (epoch e - SLOTS) has long finished; this returns at once
-                self._N.peer_ctx_wait(self._ctx, self._slot_seq[s])
-            if self.is_learner:
+                if self._slot_seq[s] < 0:
+                    self._N.peer_event_wait(self._ev_copy[s].cuda_event)      # (a direct push: its copy_done event)
+                else:
+                    self._N.peer_ctx_wait(self._ctx, self._slot_seq[s])
+            if self.is_learner or self._direct:
                 # the learner's own rows need no transfer: its launch writes them straight into its slice of the gathered
-                # block (a local device-to-device copy would run on SMs and hold up the next step's CTAs: 36.6 vs 27.6 us)
+                # block (a local device-to-device copy would run on SMs and hold up the next step's CTAs: 36.6 vs 27.6 us);
+                # host-step mode: every rank's launch does (see attach)
                 o, r = self._learner_out[e & 1]
             else:
                 o, r = self._slot_ptrs[s]
@@ -345,7 +364,11 @@ class PeerGather:
         e = self.epoch
         s = e % self.SLOTS
         self._epoch_np[s] = e               # (source, destination and sizes of slot s were fixed at construction)
-        self._slot_seq[s] = self._N.peer_ctx_push(self._ctx, self._push[s], main_stream_raw)
+        if self._direct:
+            self._N.peer_push(self._push[s], main_stream_raw, self._side_raw)
+            self._slot_seq[s] = -1
+        else:
+            self._slot_seq[s] = self._N.peer_ctx_push(self._ctx, self._push[s], main_stream_raw)
 
     # ---- learner ------------------------------------------------------------------------------------------------------
     def gather(self):
@@ -368,7 +391,7 @@ class PeerGather:
 
     def close(self):
         if self.mode == "push" and getattr(self, "_ctx", None) is not None:
-            self._N.peer_ctx_wait(self._ctx, max(self._slot_seq))
+            self._N.peer_ctx_wait(self._ctx, max(0, max(self._slot_seq)))
             self._N.peer_ctx_destroy(self._ctx)
             self._ctx = None
 
@@ -381,7 +404,7 @@ class PeerGather:
     def check(self):
         """Synchronise and raise if an exchange step timed out (a rank never delivered)."""
         if self.mode == "push" and getattr(self, "_ctx", None) is not None:
-            self._N.peer_ctx_wait(self._ctx, max(self._slot_seq))   # every queued transfer has been issued
+            self._N.peer_ctx_wait(self._ctx, max(0, max(self._slot_seq)))   # every queued transfer has been issued
         self.side.synchronize()
         torch.cuda.current_stream().synchronize()
         if int(self._status.item()) & self._N.STATUS_PEER_TIMEOUT:

@@ -38,10 +38,15 @@ def _worker(rank, world, port, out, mode):
         env = make_sharded_env(AffineLinearVecEnv, E, **kw)
         env_d = make_sharded_env(AffineLinearVecEnv, E, use_cuda_graph=True, fused_coefficients=True, **kw)
         env_h = make_sharded_env(AffineLinearVecEnv, E, use_cuda_graph=True, fused_coefficients=True, return_numpy=True, **kw)
-        peers = [PeerGather(E, n, dev, dst=0, mode=mode) for _ in range(3)]
+        # ... and the host round trip whose learner step also waits for every rank's rows of the same step (wait_in_step: in
+        # push mode the launches store their last rows straight into the learner's block and only the epoch word is copied)
+        env_w = make_sharded_env(AffineLinearVecEnv, E, use_cuda_graph=True, fused_coefficients=True, return_numpy=True, **kw)
+        peers = [PeerGather(E, n, dev, dst=0, mode=mode) for _ in range(4)]
         for e_, p_ in zip((env, env_d, env_h), peers):
             p_.attach(e_)
             e_.reset()
+        peers[3].attach(env_w, wait_in_step=True)
+        env_w.reset()
         full = AffineLinearVecEnv(n_envs=E, **kw) if rank == 0 else None   # the unsharded twin on the learner
         if full is not None:
             full.reset()
@@ -54,18 +59,24 @@ def _worker(rank, world, port, out, mode):
             o_h, r_h, done_h, _ = env_h.step(a_loc.cpu().numpy())
             torch.testing.assert_close(o_d, o_loc, rtol=1e-12, atol=1e-14)                      # in-kernel affine drift
             np.testing.assert_allclose(o_h, o_loc.cpu().numpy() if not done_h[0] else o_h, rtol=1e-12, atol=1e-14)
+            o_w, r_w, done_w, _ = env_w.step(a_loc.cpu().numpy())      # (the learner's call returns with everybody's rows in place)
+            if rank == 0:
+                ow_all, rw_all = peers[3].obs_all.clone(), peers[3].reward_all.clone()
+            np.testing.assert_array_equal(o_w, o_h)
             res = link.gather_step(env.Observations[-1], env.Reward[-1])
             if rank == 0:
-                for p_ in peers:
+                for p_ in peers[:3]:
                     p_.gather()
                     p_.wait()
                 o_full, r_full, term = full.step_device(actions)
                 torch.cuda.synchronize()
                 assert torch.equal(peers[0].obs_all, res[0]) and torch.equal(peers[0].reward_all, res[1])
                 assert torch.equal(peers[0].obs_all, o_full) and torch.equal(peers[0].reward_all, r_full)   # bit for bit
-                for p_ in peers[1:]:
+                for p_ in peers[1:3]:
                     torch.testing.assert_close(p_.obs_all, o_full, rtol=1e-12, atol=1e-14)
                     torch.testing.assert_close(p_.reward_all, r_full, rtol=1e-12, atol=1e-14)
+                torch.testing.assert_close(ow_all, o_full, rtol=1e-12, atol=1e-14)
+                torch.testing.assert_close(rw_all, r_full, rtol=1e-12, atol=1e-14)
                 if term:
                     full.reset()
             if env.t_idx + 1 >= env.shape_T[0]:
