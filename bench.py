@@ -16,8 +16,9 @@ trajectory blocks (> L2) — the kernel is issue bound, the two agree.
            LinearizedHOVecEnv.step), c4 (65536 stochastic envs, n = 8: STRONG scaling over the ranks), c5 (PPO on 8192
            stochastic envs, rollouts on the device, sharded over the ranks)
   N > 1  : environments are sharded (weak scaling of config 3: 4096 per GPU); the only exchange is the learner gather of
-           [obs | reward] per step — every rank publishes an epoch flag, the learner's qrl_peer_pull copies the slices over
-           NVLink on a side stream.  After the timed loop rank 0 replays the whole run UNSHARDED and checks that the
+           [obs | reward] per step — behind each step launch every rank's copy engine moves its rows into the learner's block
+           over NVLink and stores an epoch word (`--gather push`, default; `pull`: flag stored by the step kernel + gather
+           kernel on the learner).  After the timed loop rank 0 replays the whole run UNSHARDED and checks that the
            gathered block equals it bit for bit (`sharded_equals_unsharded`).
   --impl reference : the reference algorithm's CPU path on all host cores: the UNMODIFIED reference LinearEnv when it has
            been staged into oracle/_ref (oracle/stage_ref.py), else the oracle port of it
